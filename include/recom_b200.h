@@ -1,0 +1,223 @@
+/* recom_b200.h — C ABI of the B200-native fused embedding-column path.
+ *
+ * This header is the drop-in boundary. Each entry point replaces one piece of
+ * the plugin ABI the reference's TF ops bind with dlopen/dlsym
+ * (paths relative to the reference root):
+ *
+ *   recom_plan_create / recom_plan_create_from_blob / recom_plan_destroy
+ *       replace dlopen(dlpath) + dlsym("CreateConstBuffers") and the cudaFree in
+ *       the op destructor
+ *       (tensorflow_addons/custom_ops/feature_column_process/feature_column_process_op_gpu.cu.cc:51-62,
+ *        feature_column_process_ops.h:47,
+ *        tensorflow_addons/graph_optimizers/cuda_emitter.cc:2260-2301).
+ *       The plan is what the reference's generated .cu file is: the per-column
+ *       description of transform -> lookup -> combine -> concat slot.
+ *   recom_plan_workspace_bytes
+ *       replaces the arena sizing `buffer_size_sum = sum alignmem(expr*sizeof)`
+ *       (cuda_emitter.cc:2151-2179) and the malloc_temp/malloc_buff callbacks
+ *       (feature_column_process_op_gpu.cu.cc:99-111): the caller owns memory.
+ *   recom_plan_run
+ *       replaces dlsym("ProcessFeatureColumns")
+ *       (feature_column_process_ops.h:37-43, cuda_emitter.cc:2306-2494) AND
+ *       dlsym("ConcatOutputs")
+ *       (tensorflow_addons/custom_ops/concat_outputs/concat_outputs_ops.h:35,
+ *        concat_outputs_op_gpu.cu.cc:133-140): it writes the final row-major
+ *       [batch, out_width] tensor directly, stream ordered, no host sync.
+ *   recom_scatter_columns
+ *       keeps ConcatOutputs' `host_inputs` capability
+ *       (concat_outputs_op_gpu.cu.cc:186-232): columns computed elsewhere are
+ *       scattered into their concat slices.
+ *   recom_segment_ids_to_row_splits
+ *       replaces experiment::ComputeSegmentOffsets (cuda_emitter.cc:768-818).
+ *
+ * No C++ types, no torch types: plain pointers and sizes only. Every function
+ * returns a recom_status; recom_last_error() gives a thread-local message. The
+ * library never calls exit() (the reference does, via CubDebugExit).
+ */
+#ifndef RECOM_B200_H_
+#define RECOM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RECOM_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RECOM_API __attribute__((visibility("default")))
+#else
+#define RECOM_API
+#endif
+
+typedef enum recom_status {
+  RECOM_OK = 0,
+  RECOM_ERR_INVALID_ARGUMENT = 1,
+  RECOM_ERR_CUDA = 2,
+  RECOM_ERR_WORKSPACE_TOO_SMALL = 3,
+  RECOM_ERR_UNSUPPORTED = 4,
+  RECOM_ERR_OUT_OF_MEMORY = 5,
+  RECOM_ERR_ID_OUT_OF_RANGE = 6
+} recom_status;
+
+typedef enum recom_dtype {
+  RECOM_F32 = 0,
+  RECOM_BF16 = 1,
+  RECOM_I32 = 2,
+  RECOM_I64 = 3,
+  RECOM_STR = 4, /* wire format: int32 offsets[n+1] slot + uint8 bytes slot */
+  RECOM_F64 = 5
+} recom_dtype;
+
+/* The three lookup shapes LookupOptimizer produces
+ * (tensorflow_addons/graph_optimizers/lookup_optimizer.cc:137-155,270-440). */
+typedef enum recom_lookup {
+  RECOM_LOOKUP_DENSE = 0,          /* exactly one id per sample: GatherV2 */
+  RECOM_LOOKUP_GATHER_SCATTER = 1, /* <=1 id per sample: ScatterNd(Gather) */
+  RECOM_LOOKUP_SEGMENT = 2         /* multi-hot: SparseSegment*WithNumSegments */
+} recom_lookup;
+
+typedef enum recom_combiner {
+  RECOM_COMBINE_SUM = 0,
+  RECOM_COMBINE_MEAN = 1,
+  RECOM_COMBINE_SQRTN = 2
+} recom_combiner;
+
+/* What is fused ahead of the gather. */
+typedef enum recom_transform {
+  RECOM_XFORM_NONE = 0,      /* values are row ids already (i32 / i64) */
+  RECOM_XFORM_BUCKETIZE = 1, /* TF Bucketize: upper_bound over float boundaries */
+  RECOM_XFORM_HASH_STR = 2,  /* TF StringToHashBucketFast: Fingerprint64 % n */
+  RECOM_XFORM_HASH_INT = 3   /* AsString(int) then StringToHashBucketFast */
+} recom_transform;
+
+/* How the sample (segment) of each id is given for non-DENSE lookups. */
+typedef enum recom_seg_format {
+  RECOM_SEG_NONE = 0,
+  RECOM_SEG_ROW_SPLITS_I32 = 1, /* int32[batch+1], CSR */
+  RECOM_SEG_COO_I64 = 2 /* int64[nnz, seg_stride] SparseTensor.indices, row id in
+                           column 0, row-major sorted: what the reference reads in
+                           place (cuda_emitter.cc:1836-1873) */
+} recom_seg_format;
+
+/* One embedding column ("FC" in the reference, graph_info.h:41-42). */
+typedef struct recom_column_desc {
+  int32_t lookup;      /* recom_lookup */
+  int32_t combiner;    /* recom_combiner (ignored for DENSE / GATHER_SCATTER) */
+  int32_t transform;   /* recom_transform */
+  int32_t value_dtype; /* recom_dtype of the values slot */
+  int32_t table;       /* index into recom_request.tables */
+  int32_t table_dtype; /* RECOM_F32 or RECOM_BF16 */
+  int64_t table_rows;
+  int32_t dim;         /* embedding width D */
+  int32_t out_offset;  /* element offset of this column's slice in the concat row */
+  int32_t value_slot;  /* blob slot of the values (for STR: of the int32 offsets) */
+  int32_t bytes_slot;  /* STR only: blob slot of the uint8 payload, else -1 */
+  int32_t seg_slot;    /* blob slot of row_splits / COO indices, -1 for DENSE */
+  int32_t seg_format;  /* recom_seg_format */
+  int32_t seg_stride;  /* COO only: int64s per entry (sparse rank) */
+  int32_t num_boundaries;    /* BUCKETIZE only */
+  int64_t boundaries_offset; /* BUCKETIZE only: first boundary in `boundaries` */
+  int64_t num_buckets;       /* HASH_* only */
+} recom_column_desc;
+
+typedef struct recom_plan_config {
+  int32_t out_dtype;    /* RECOM_F32 or RECOM_BF16: dtype of the concat tensor */
+  int32_t out_width;    /* sum of dims (row length of the concat tensor), elements */
+  int32_t num_slots;    /* number of blob slots a request carries */
+  int32_t num_tables;   /* number of table pointers a request carries */
+  int32_t check_ids;    /* !=0: bounds-check every row id; bad ids read row 0 and
+                           raise the request's status word */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t max_ctas_per_sm; /* 0 = library default */
+  int32_t reserved;
+} recom_plan_config;
+
+typedef struct recom_plan recom_plan;
+typedef struct CUstream_st *recom_stream_t; /* == cudaStream_t */
+
+/* One inference request. All device pointers are borrowed for the duration of
+ * the stream-ordered work; host arrays are consumed before the call returns. */
+typedef struct recom_request {
+  int64_t batch;               /* B: rows of the concat tensor */
+  const void *blob;            /* device: ConcatInputs blob (one H2D copy) */
+  const int64_t *slot_offsets; /* host [num_slots]: byte offset of each slot */
+  const int64_t *slot_elems;   /* host [num_slots]: element count of each slot */
+  const void *const *tables;   /* host [num_tables]: device pointers, row-major */
+  void *out;                   /* device [batch, out_width] of out_dtype */
+  void *workspace;             /* device, >= recom_plan_workspace_bytes() */
+  size_t workspace_bytes;
+  int32_t *ids_out;   /* optional device [sum over columns of their id count], in
+                         column order: the row id every gather used (parity hook) */
+  int32_t *status_out; /* optional device int32: set !=0 on id-range violation */
+  recom_stream_t stream;
+} recom_request;
+
+RECOM_API const char *recom_last_error(void);
+RECOM_API int recom_abi_version(void);
+
+/* `boundaries` holds exact float bits (the reference embeds std::to_string
+ * literals, cuda_emitter.cc:1806-1810). Arrays are copied; caller may free. */
+RECOM_API recom_status recom_plan_create(const recom_column_desc *cols, int32_t num_cols,
+                               const float *boundaries, int64_t num_boundaries,
+                               const recom_plan_config *cfg, recom_plan **out);
+RECOM_API recom_status recom_plan_destroy(recom_plan *plan);
+
+/* Serialized plan: the payload that replaces the reference's `dlpath` attr. */
+RECOM_API recom_status recom_plan_serialize(const recom_plan *plan, void *buf,
+                                  size_t buf_bytes, size_t *needed);
+RECOM_API recom_status recom_plan_create_from_blob(const void *buf, size_t bytes,
+                                         int32_t device, recom_plan **out);
+
+RECOM_API recom_status recom_plan_num_columns(const recom_plan *plan, int32_t *out);
+RECOM_API recom_status recom_plan_out_width(const recom_plan *plan, int32_t *out);
+
+/* Upper bound of the per-request scratch for a batch of `batch` rows carrying
+ * `total_ids` ids over all non-DENSE columns. */
+RECOM_API recom_status recom_plan_workspace_bytes(const recom_plan *plan, int64_t batch,
+                                        int64_t total_ids, size_t *out);
+
+/* Enqueue the whole fused stage on req->stream. Re-entrant per plan. */
+RECOM_API recom_status recom_plan_run(const recom_plan *plan, const recom_request *req);
+
+/* Number of kernels the last recom_plan_run on this thread launched. */
+RECOM_API int recom_last_launch_count(void);
+
+/* Algorithmic bytes of the request just described:
+ * inputs consumed + row-splits + compulsory table rows + output written. */
+RECOM_API recom_status recom_plan_algorithmic_bytes(const recom_plan *plan,
+                                          const recom_request *req,
+                                          int64_t *bytes_out);
+
+/* out[p, col_offsets[i] + e] = cols[i][p, e] for e < col_dims[i]. `cols` is a
+ * host array of device pointers; dtype is the plan-independent element size. */
+RECOM_API recom_status recom_scatter_columns(const void *const *cols,
+                                   const int32_t *col_dims,
+                                   const int32_t *col_offsets, int32_t num_cols,
+                                   int64_t batch, int32_t out_width,
+                                   int32_t elem_bytes, void *out,
+                                   recom_stream_t stream);
+
+/* Sorted COO row ids (int64, stride in int64s) -> int32 row_splits[batch+1]. */
+RECOM_API recom_status recom_segment_ids_to_row_splits(const int64_t *coo, int64_t nnz,
+                                             int32_t stride, int64_t batch,
+                                             int32_t *row_splits,
+                                             recom_stream_t stream);
+
+/* Device-side TF StringToHashBucketFast over a packed string slot (parity hook
+ * and stand-alone op): out[i] = Fingerprint64(bytes[off[i]:off[i+1]]) % n. */
+RECOM_API recom_status recom_string_to_hash_bucket_fast(const uint8_t *bytes,
+                                              const int32_t *offsets, int64_t n,
+                                              int64_t num_buckets, int64_t *out,
+                                              recom_stream_t stream);
+/* Raw device Fingerprint64 (uint64 written as int64 bits). */
+RECOM_API recom_status recom_fingerprint64(const uint8_t *bytes, const int32_t *offsets,
+                                 int64_t n, uint64_t *out,
+                                 recom_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECOM_B200_H_ */

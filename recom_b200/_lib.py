@@ -1,0 +1,113 @@
+"""ctypes binding of librecom_b200.so (the C ABI in include/recom_b200.h).
+
+There is no fallback: if the shared library (hand-written sm_100a kernels + C++ host
+code) is missing or fails to load, importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librecom_b200.so")
+
+# enums (include/recom_b200.h)
+OK = 0
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WORKSPACE_TOO_SMALL = 1, 2, 3
+ERR_UNSUPPORTED, ERR_OUT_OF_MEMORY, ERR_ID_OUT_OF_RANGE = 4, 5, 6
+F32, BF16, I32, I64, STR, F64 = 0, 1, 2, 3, 4, 5
+LOOKUP_DENSE, LOOKUP_GATHER_SCATTER, LOOKUP_SEGMENT = 0, 1, 2
+COMBINE_SUM, COMBINE_MEAN, COMBINE_SQRTN = 0, 1, 2
+XFORM_NONE, XFORM_BUCKETIZE, XFORM_HASH_STR, XFORM_HASH_INT = 0, 1, 2, 3
+SEG_NONE, SEG_ROW_SPLITS_I32, SEG_COO_I64 = 0, 1, 2
+
+DTYPE_BYTES = {F32: 4, BF16: 2, I32: 4, I64: 8, STR: 4, F64: 8}
+
+# numpy mirror of struct recom_column_desc (natural C alignment)
+COLUMN_DESC = np.dtype(
+    [
+        ("lookup", "<i4"), ("combiner", "<i4"), ("transform", "<i4"), ("value_dtype", "<i4"),
+        ("table", "<i4"), ("table_dtype", "<i4"), ("table_rows", "<i8"),
+        ("dim", "<i4"), ("out_offset", "<i4"), ("value_slot", "<i4"), ("bytes_slot", "<i4"),
+        ("seg_slot", "<i4"), ("seg_format", "<i4"), ("seg_stride", "<i4"),
+        ("num_boundaries", "<i4"), ("boundaries_offset", "<i8"), ("num_buckets", "<i8"),
+    ],
+    align=True,
+)
+assert COLUMN_DESC.itemsize == 80
+
+
+class PlanConfig(C.Structure):
+    _fields_ = [
+        ("out_dtype", C.c_int32), ("out_width", C.c_int32), ("num_slots", C.c_int32),
+        ("num_tables", C.c_int32), ("check_ids", C.c_int32), ("device", C.c_int32),
+        ("max_ctas_per_sm", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Request(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int64), ("blob", C.c_void_p), ("slot_offsets", C.c_void_p),
+        ("slot_elems", C.c_void_p), ("tables", C.c_void_p), ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("ids_out", C.c_void_p),
+        ("status_out", C.c_void_p), ("stream", C.c_void_p),
+    ]
+
+
+class RecomError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"recom_b200 status {status}: {message}")
+        self.status = status
+
+
+EXPORTS = [
+    "recom_last_error", "recom_abi_version", "recom_plan_create", "recom_plan_destroy",
+    "recom_plan_serialize", "recom_plan_create_from_blob", "recom_plan_num_columns",
+    "recom_plan_out_width", "recom_plan_workspace_bytes", "recom_plan_run",
+    "recom_last_launch_count", "recom_plan_algorithmic_bytes", "recom_scatter_columns",
+    "recom_segment_ids_to_row_splits", "recom_string_to_hash_bucket_fast", "recom_fingerprint64",
+]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make -C recom_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "recom_b200 has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.recom_last_error.restype = C.c_char_p
+    lib.recom_abi_version.restype = C.c_int
+    lib.recom_last_launch_count.restype = C.c_int
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    sigs = {
+        "recom_plan_create": [vp, i32, vp, i64, C.POINTER(PlanConfig), C.POINTER(vp)],
+        "recom_plan_destroy": [vp],
+        "recom_plan_serialize": [vp, vp, sz, C.POINTER(sz)],
+        "recom_plan_create_from_blob": [vp, sz, i32, C.POINTER(vp)],
+        "recom_plan_num_columns": [vp, C.POINTER(i32)],
+        "recom_plan_out_width": [vp, C.POINTER(i32)],
+        "recom_plan_workspace_bytes": [vp, i64, i64, C.POINTER(sz)],
+        "recom_plan_run": [vp, C.POINTER(Request)],
+        "recom_plan_algorithmic_bytes": [vp, C.POINTER(Request), C.POINTER(i64)],
+        "recom_scatter_columns": [vp, vp, vp, i32, i64, i32, i32, vp, vp],
+        "recom_segment_ids_to_row_splits": [vp, i64, i32, i64, vp, vp],
+        "recom_string_to_hash_bucket_fast": [vp, vp, i64, i64, vp, vp],
+        "recom_fingerprint64": [vp, vp, i64, vp, vp],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int) -> None:
+    if status != OK:
+        raise RecomError(status, lib.recom_last_error().decode("utf-8", "replace"))

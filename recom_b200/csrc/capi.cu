@@ -1,0 +1,788 @@
+// capi.cu — the C ABI (include/recom_b200.h): plan construction, per-request
+// argument marshalling and kernel enqueue. Host code only; kernels live in
+// kernels.cu.
+//
+// Reference counterparts (reference root relative):
+//   plan create  <-> generated CreateConstBuffers + the code generator's per-column
+//                    bookkeeping (graph_optimizers/cuda_emitter.cc:975-1038,2260-2301)
+//   plan run     <-> generated ProcessFeatureColumns + kernel caller
+//                    (cuda_emitter.cc:2139-2258,2303-2494) and the op's Compute
+//                    (custom_ops/feature_column_process/feature_column_process_op_gpu.cu.cc:65-131)
+// Differences by design: no host<->device synchronisation anywhere (the reference
+// has three per request), one small H2D upload per request from pinned memory,
+// errors are returned instead of exit().
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "plan.h"
+
+using namespace recom;
+
+namespace {
+
+thread_local std::string g_last_error;
+thread_local int g_last_launches = 0;
+
+recom_status fail(recom_status st, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return st;
+}
+
+#define CUDA_TRY(expr)                                                             \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess)                                                         \
+      return fail(RECOM_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int kRing = 16;
+
+struct ArgSlot {
+  std::mutex mu;
+  uint8_t* pinned = nullptr;
+  size_t cap = 0;
+  cudaEvent_t done = nullptr;
+  bool in_flight = false;
+};
+
+int dtype_bytes(int32_t dt) {
+  switch (dt) {
+    case RECOM_F32: return 4;
+    case RECOM_BF16: return 2;
+    case RECOM_I32: return 4;
+    case RECOM_I64: return 8;
+    case RECOM_F64: return 8;
+    case RECOM_STR: return 4;  // the offsets slot
+    default: return 0;
+  }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct recom_plan {
+  recom_plan_config cfg{};
+  std::vector<recom_column_desc> descs;  // as given (for serialisation)
+  std::vector<float> boundaries_in;      // as given
+  // host mirrors of the device arrays
+  std::vector<DevColumn> cols;
+  std::vector<DevSlab> slabs;
+  std::vector<DevChunk> chunks;
+  std::vector<int32_t> slab_cols;
+  std::vector<float> boundary_pool;
+  std::vector<int32_t> sparse_cols;  // column index of each non-DENSE column
+  std::vector<int32_t> coo_cols;     // column index of each COO column
+  std::vector<int32_t> slab_order;   // slabs sorted for scheduling (heavy first)
+  // device
+  void* d_block = nullptr;
+  DevPlan dev{};
+  int elem_bytes = 4;
+  int num_sms = 148;
+  int ctas_per_sm = 4;
+  // pinned argument ring
+  ArgSlot ring[kRing];
+  std::atomic<uint32_t> ring_next{0};
+};
+
+namespace {
+
+recom_status validate_columns(const recom_column_desc* cols, int32_t n, const recom_plan_config& cfg,
+                              int64_t num_boundaries) {
+  if (cfg.out_dtype != RECOM_F32 && cfg.out_dtype != RECOM_BF16)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "out_dtype must be F32 or BF16");
+  if (cfg.out_width <= 0) return fail(RECOM_ERR_INVALID_ARGUMENT, "out_width must be > 0");
+  for (int32_t i = 0; i < n; ++i) {
+    const recom_column_desc& c = cols[i];
+    if (c.dim <= 0 || c.out_offset < 0 || (int64_t)c.out_offset + c.dim > cfg.out_width)
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: slice [%d,+%d) outside out_width %d", i,
+                  c.out_offset, c.dim, cfg.out_width);
+    if (c.table < 0 || c.table >= cfg.num_tables)
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: table index %d out of range", i, c.table);
+    if (c.table_dtype != cfg.out_dtype)
+      return fail(RECOM_ERR_UNSUPPORTED,
+                  "column %d: table dtype must equal the concat dtype (got %d vs %d)", i,
+                  c.table_dtype, cfg.out_dtype);
+    if (c.table_rows <= 0 || c.table_rows > 0x7fffffffLL)
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: table_rows %lld unsupported", i,
+                  (long long)c.table_rows);
+    if ((int64_t)c.dim * dtype_bytes(c.table_dtype) > (1 << 20))
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: dim too large", i);
+    if (c.value_slot < 0 || c.value_slot >= cfg.num_slots)
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: value_slot out of range", i);
+    switch (c.transform) {
+      case RECOM_XFORM_NONE:
+        if (c.value_dtype != RECOM_I32 && c.value_dtype != RECOM_I64)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: ids must be I32 or I64", i);
+        break;
+      case RECOM_XFORM_BUCKETIZE:
+        if (c.value_dtype != RECOM_F32 && c.value_dtype != RECOM_I32 &&
+            c.value_dtype != RECOM_I64 && c.value_dtype != RECOM_F64)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: bad bucketize input dtype", i);
+        if (c.num_boundaries < 0 || c.boundaries_offset < 0 ||
+            c.boundaries_offset + c.num_boundaries > num_boundaries)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: boundaries out of range", i);
+        break;
+      case RECOM_XFORM_HASH_STR:
+        if (c.value_dtype != RECOM_STR || c.bytes_slot < 0 || c.bytes_slot >= cfg.num_slots)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: HASH_STR needs STR values + bytes_slot", i);
+        if (c.num_buckets <= 0 || c.num_buckets > 0x7fffffffLL)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: num_buckets unsupported", i);
+        break;
+      case RECOM_XFORM_HASH_INT:
+        if (c.value_dtype != RECOM_I32 && c.value_dtype != RECOM_I64)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: HASH_INT needs I32/I64 values", i);
+        if (c.num_buckets <= 0 || c.num_buckets > 0x7fffffffLL)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: num_buckets unsupported", i);
+        break;
+      default:
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: unknown transform %d", i, c.transform);
+    }
+    if (c.lookup == RECOM_LOOKUP_DENSE) {
+      // nothing
+    } else if (c.lookup == RECOM_LOOKUP_GATHER_SCATTER || c.lookup == RECOM_LOOKUP_SEGMENT) {
+      if (c.seg_slot < 0 || c.seg_slot >= cfg.num_slots)
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: seg_slot out of range", i);
+      if (c.seg_format == RECOM_SEG_COO_I64) {
+        if (c.seg_stride < 1)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: COO seg_stride must be >= 1", i);
+      } else if (c.seg_format != RECOM_SEG_ROW_SPLITS_I32) {
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: unknown seg_format", i);
+      }
+      if (c.lookup == RECOM_LOOKUP_SEGMENT && c.combiner != RECOM_COMBINE_SUM &&
+          c.combiner != RECOM_COMBINE_MEAN && c.combiner != RECOM_COMBINE_SQRTN)
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: unknown combiner", i);
+    } else {
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: unknown lookup kind", i);
+    }
+  }
+  // output slices must not overlap
+  std::vector<std::pair<int32_t, int32_t>> spans(n);
+  for (int32_t i = 0; i < n; ++i) spans[i] = {cols[i].out_offset, cols[i].dim};
+  std::sort(spans.begin(), spans.end());
+  for (int32_t i = 1; i < n; ++i)
+    if (spans[i].first < spans[i - 1].first + spans[i - 1].second)
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "output slices overlap at offset %d", spans[i].first);
+  return RECOM_OK;
+}
+
+// Build DevColumn/DevSlab/DevChunk arrays from the descriptors.
+void build_layout(recom_plan* p) {
+  const int n = (int)p->descs.size();
+  const int es = p->elem_bytes;
+  std::map<std::vector<float>, int32_t> pool_index;  // dedup identical boundary sets
+  p->cols.resize(n);
+  for (int i = 0; i < n; ++i) {
+    const recom_column_desc& d = p->descs[i];
+    DevColumn& c = p->cols[i];
+    memset(&c, 0, sizeof c);
+    c.table_rows = d.table_rows;
+    c.num_buckets = d.num_buckets;
+    c.table = d.table;
+    c.dim = d.dim;
+    c.row_bytes = d.dim * es;
+    c.transform = d.transform;
+    c.value_dtype = d.value_dtype;
+    c.value_slot = d.value_slot;
+    c.bytes_slot = d.bytes_slot;
+    c.seg_slot = d.seg_slot;
+    c.seg_format = d.seg_format;
+    c.seg_stride = d.seg_stride;
+    c.lookup = d.lookup;
+    // GATHER_SCATTER == SEGMENT(sum) with <=1 id per row (lookup_optimizer.cc:324-440)
+    c.combiner = d.lookup == RECOM_LOOKUP_SEGMENT ? d.combiner : RECOM_COMBINE_SUM;
+    c.sparse_index = -1;
+    c.coo_index = -1;
+    if (d.lookup != RECOM_LOOKUP_DENSE) {
+      c.sparse_index = (int32_t)p->sparse_cols.size();
+      p->sparse_cols.push_back(i);
+      if (d.seg_format == RECOM_SEG_COO_I64) {
+        c.coo_index = (int32_t)p->coo_cols.size();
+        p->coo_cols.push_back(i);
+      }
+    }
+    if (d.transform == RECOM_XFORM_BUCKETIZE) {
+      std::vector<float> b(p->boundaries_in.begin() + d.boundaries_offset,
+                           p->boundaries_in.begin() + d.boundaries_offset + d.num_boundaries);
+      auto it = pool_index.find(b);
+      if (it == pool_index.end()) {
+        it = pool_index.emplace(b, (int32_t)p->boundary_pool.size()).first;
+        p->boundary_pool.insert(p->boundary_pool.end(), b.begin(), b.end());
+      }
+      c.boundaries_offset = it->second;
+      c.num_boundaries = d.num_boundaries;
+    }
+  }
+  if (p->boundary_pool.empty()) p->boundary_pool.push_back(0.f);
+
+  // slabs: walk columns in concat order, group same-class neighbours up to 32 chunks
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    return p->descs[a].out_offset < p->descs[b].out_offset;
+  });
+  const bool row_aligned = ((int64_t)p->cfg.out_width * es) % 16 == 0;
+  auto open_slab = [&](int cls, int vec) {
+    DevSlab s{};
+    s.cls = cls;
+    s.vec_bytes = vec;
+    s.first_chunk = (int32_t)p->chunks.size();
+    s.first_col = (int32_t)p->slab_cols.size();
+    s.tile_rows = cls == kSlabDense ? kDenseTileRows : kSparseTileRows;
+    p->slabs.push_back(s);
+  };
+  int prev_end = -1;
+  for (int oi = 0; oi < n; ++oi) {
+    const int i = order[oi];
+    const recom_column_desc& d = p->descs[i];
+    const int cls = d.lookup == RECOM_LOOKUP_DENSE ? kSlabDense : kSlabSparse;
+    const bool vec16 = row_aligned && (d.dim * es) % 16 == 0 && ((int64_t)d.out_offset * es) % 16 == 0;
+    const int vec = vec16 ? 16 : es;
+    const int nchunks = d.dim * es / vec;
+    int done = 0;
+    while (done < nchunks) {
+      bool need_new = p->slabs.empty();
+      if (!need_new) {
+        const DevSlab& s = p->slabs.back();
+        need_new = s.cls != cls || s.vec_bytes != vec || s.num_chunks >= kMaxChunks ||
+                   (done == 0 && d.out_offset != prev_end) ||
+                   // keep a column inside one slab when it fits in an empty one
+                   (done == 0 && nchunks <= kMaxChunks && s.num_chunks + nchunks > kMaxChunks);
+      }
+      if (need_new) open_slab(cls, vec);
+      DevSlab& s = p->slabs.back();
+      const int take = std::min(nchunks - done, kMaxChunks - s.num_chunks);
+      const int col_local = s.num_cols;
+      p->slab_cols.push_back(i);
+      s.num_cols++;
+      for (int k = 0; k < take; ++k) {
+        DevChunk ch;
+        ch.col = i;
+        ch.col_local = col_local;
+        ch.table_byte = (done + k) * vec;
+        ch.out_byte = d.out_offset * es + (done + k) * vec;
+        p->chunks.push_back(ch);
+      }
+      s.num_chunks += take;
+      done += take;
+    }
+    prev_end = d.out_offset + d.dim;
+  }
+}
+
+recom_status upload_plan(recom_plan* p) {
+  const size_t b_cols = align_up(p->cols.size() * sizeof(DevColumn), 256);
+  const size_t b_slabs = align_up(p->slabs.size() * sizeof(DevSlab), 256);
+  const size_t b_chunks = align_up(p->chunks.size() * sizeof(DevChunk), 256);
+  const size_t b_sc = align_up(p->slab_cols.size() * sizeof(int32_t), 256);
+  const size_t b_bnd = align_up(p->boundary_pool.size() * sizeof(float), 256);
+  const size_t total = b_cols + b_slabs + b_chunks + b_sc + b_bnd;
+  std::vector<uint8_t> host(total, 0);
+  size_t o = 0;
+  memcpy(host.data() + o, p->cols.data(), p->cols.size() * sizeof(DevColumn));
+  const size_t o_cols = o; o += b_cols;
+  memcpy(host.data() + o, p->slabs.data(), p->slabs.size() * sizeof(DevSlab));
+  const size_t o_slabs = o; o += b_slabs;
+  memcpy(host.data() + o, p->chunks.data(), p->chunks.size() * sizeof(DevChunk));
+  const size_t o_chunks = o; o += b_chunks;
+  memcpy(host.data() + o, p->slab_cols.data(), p->slab_cols.size() * sizeof(int32_t));
+  const size_t o_sc = o; o += b_sc;
+  memcpy(host.data() + o, p->boundary_pool.data(), p->boundary_pool.size() * sizeof(float));
+  const size_t o_bnd = o;
+  CUDA_TRY(cudaMalloc(&p->d_block, total));
+  CUDA_TRY(cudaMemcpy(p->d_block, host.data(), total, cudaMemcpyHostToDevice));
+  uint8_t* base = (uint8_t*)p->d_block;
+  p->dev.cols = (const DevColumn*)(base + o_cols);
+  p->dev.slabs = (const DevSlab*)(base + o_slabs);
+  p->dev.chunks = (const DevChunk*)(base + o_chunks);
+  p->dev.slab_cols = (const int32_t*)(base + o_sc);
+  p->dev.boundaries = (const float*)(base + o_bnd);
+  p->dev.num_cols = (int32_t)p->cols.size();
+  p->dev.num_slabs = (int32_t)p->slabs.size();
+  p->dev.elem_bytes = p->elem_bytes;
+  p->dev.check_ids = p->cfg.check_ids;
+  return RECOM_OK;
+}
+
+int64_t column_num_ids(const recom_plan* p, int ci, const recom_request* req) {
+  const recom_column_desc& d = p->descs[ci];
+  if (d.lookup == RECOM_LOOKUP_DENSE) return req->batch;
+  const int64_t e = req->slot_elems[d.value_slot];
+  return d.value_dtype == RECOM_STR ? e - 1 : e;
+}
+
+recom_status validate_request(const recom_plan* p, const recom_request* req) {
+  if (!req->slot_offsets || !req->slot_elems || !req->tables)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "request host arrays must not be null");
+  if (req->batch < 0 || req->batch > 0x7fffffffLL)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "batch out of range");
+  if (req->batch > 0 && (!req->out || (!req->blob && p->cfg.num_slots > 0)))
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "blob/out device pointers must not be null");
+  if (((uintptr_t)req->blob & 15) || ((uintptr_t)req->out & 15) || ((uintptr_t)req->workspace & 255))
+    return fail(RECOM_ERR_INVALID_ARGUMENT,
+                "blob/out must be 16-byte aligned and workspace 256-byte aligned");
+  for (int t = 0; t < p->cfg.num_tables; ++t)
+    if (!req->tables[t] || ((uintptr_t)req->tables[t] & 15))
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "table %d pointer is null or not 16-byte aligned", t);
+  const int n = (int)p->descs.size();
+  for (int i = 0; i < n; ++i) {
+    const recom_column_desc& d = p->descs[i];
+    const int64_t voff = req->slot_offsets[d.value_slot];
+    const int valign = dtype_bytes(d.value_dtype);
+    if (voff < 0 || voff % valign)
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: value slot offset %lld not %d-byte aligned",
+                  i, (long long)voff, valign);
+    const int64_t velems = req->slot_elems[d.value_slot];
+    if (d.lookup == RECOM_LOOKUP_DENSE) {
+      const int64_t want = d.value_dtype == RECOM_STR ? req->batch + 1 : req->batch;
+      if (velems != want)
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: value slot has %lld elements, want %lld",
+                    i, (long long)velems, (long long)want);
+    } else {
+      const int64_t nnz = d.value_dtype == RECOM_STR ? velems - 1 : velems;
+      if (nnz < 0) return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: empty STR offsets slot", i);
+      const int64_t soff = req->slot_offsets[d.seg_slot];
+      const int64_t selems = req->slot_elems[d.seg_slot];
+      if (d.seg_format == RECOM_SEG_ROW_SPLITS_I32) {
+        if (soff % 4 || selems != req->batch + 1)
+          return fail(RECOM_ERR_INVALID_ARGUMENT,
+                      "column %d: row_splits slot must hold batch+1 int32 (has %lld)", i,
+                      (long long)selems);
+      } else {
+        if (soff % 8 || selems != nnz * d.seg_stride)
+          return fail(RECOM_ERR_INVALID_ARGUMENT,
+                      "column %d: COO slot must hold nnz*stride int64 (has %lld, nnz %lld)", i,
+                      (long long)selems, (long long)nnz);
+      }
+    }
+  }
+  return RECOM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* recom_last_error(void) { return g_last_error.c_str(); }
+int recom_abi_version(void) { return RECOM_B200_ABI_VERSION; }
+int recom_last_launch_count(void) { return g_last_launches; }
+
+recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
+                               const float* boundaries, int64_t num_boundaries,
+                               const recom_plan_config* cfg, recom_plan** out) {
+  if (!cols || num_cols <= 0 || !cfg || !out)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "null or empty argument");
+  if (num_boundaries < 0 || (num_boundaries > 0 && !boundaries))
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "bad boundaries array");
+  recom_status st = validate_columns(cols, num_cols, *cfg, num_boundaries);
+  if (st != RECOM_OK) return st;
+  for (int32_t i = 0; i < num_cols; ++i) {
+    if (cols[i].transform != RECOM_XFORM_BUCKETIZE) continue;
+    const float* b = boundaries + cols[i].boundaries_offset;
+    for (int32_t k = 1; k < cols[i].num_boundaries; ++k)
+      if (b[k] < b[k - 1])  // bucketize_op.cc:57-59 "Expected sorted boundaries"
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: boundaries not sorted", i);
+  }
+  int n_dev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n_dev));
+  if (cfg->device < 0 || cfg->device >= n_dev)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "device %d not present (%d visible)", cfg->device, n_dev);
+  int prev_dev = 0;
+  CUDA_TRY(cudaGetDevice(&prev_dev));
+  CUDA_TRY(cudaSetDevice(cfg->device));
+
+  recom_plan* p = new (std::nothrow) recom_plan();
+  if (!p) return fail(RECOM_ERR_OUT_OF_MEMORY, "host allocation failed");
+  p->cfg = *cfg;
+  p->descs.assign(cols, cols + num_cols);
+  if (num_boundaries) p->boundaries_in.assign(boundaries, boundaries + num_boundaries);
+  p->elem_bytes = cfg->out_dtype == RECOM_BF16 ? 2 : 4;
+  build_layout(p);
+  st = upload_plan(p);
+  if (st == RECOM_OK) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) p->num_sms = prop.multiProcessorCount;
+    int occ = fused_kernel_max_ctas_per_sm(p->elem_bytes == 2);
+    if (occ < 1) occ = 1;
+    p->ctas_per_sm = cfg->max_ctas_per_sm > 0 ? std::min(cfg->max_ctas_per_sm, occ) : occ;
+    for (int i = 0; i < kRing && st == RECOM_OK; ++i) {
+      cudaError_t e = cudaEventCreateWithFlags(&p->ring[i].done, cudaEventDisableTiming);
+      if (e != cudaSuccess) st = fail(RECOM_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+    }
+  }
+  cudaSetDevice(prev_dev);
+  if (st != RECOM_OK) {
+    recom_plan_destroy(p);
+    return st;
+  }
+  *out = p;
+  return RECOM_OK;
+}
+
+recom_status recom_plan_destroy(recom_plan* p) {
+  if (!p) return RECOM_OK;
+  for (int i = 0; i < kRing; ++i) {
+    if (p->ring[i].done) {
+      cudaEventSynchronize(p->ring[i].done);
+      cudaEventDestroy(p->ring[i].done);
+    }
+    if (p->ring[i].pinned) cudaFreeHost(p->ring[i].pinned);
+  }
+  if (p->d_block) cudaFree(p->d_block);
+  delete p;
+  return RECOM_OK;
+}
+
+// ---- serialisation: the payload that replaces the reference's `dlpath` attr ----
+struct BlobHeader {
+  char magic[8];  // "RECOMB2\0"
+  int32_t version;
+  int32_t num_cols;
+  int64_t num_boundaries;
+  recom_plan_config cfg;
+  int32_t desc_bytes;
+  int32_t pad;
+};
+
+recom_status recom_plan_serialize(const recom_plan* p, void* buf, size_t buf_bytes, size_t* needed) {
+  if (!p || !needed) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  const size_t total = sizeof(BlobHeader) + p->descs.size() * sizeof(recom_column_desc) +
+                       p->boundaries_in.size() * sizeof(float);
+  *needed = total;
+  if (!buf) return RECOM_OK;
+  if (buf_bytes < total) return fail(RECOM_ERR_INVALID_ARGUMENT, "buffer too small");
+  BlobHeader h{};
+  memcpy(h.magic, "RECOMB2", 8);
+  h.version = RECOM_B200_ABI_VERSION;
+  h.num_cols = (int32_t)p->descs.size();
+  h.num_boundaries = (int64_t)p->boundaries_in.size();
+  h.cfg = p->cfg;
+  h.desc_bytes = (int32_t)sizeof(recom_column_desc);
+  uint8_t* o = (uint8_t*)buf;
+  memcpy(o, &h, sizeof h);
+  o += sizeof h;
+  memcpy(o, p->descs.data(), p->descs.size() * sizeof(recom_column_desc));
+  o += p->descs.size() * sizeof(recom_column_desc);
+  if (!p->boundaries_in.empty())
+    memcpy(o, p->boundaries_in.data(), p->boundaries_in.size() * sizeof(float));
+  return RECOM_OK;
+}
+
+recom_status recom_plan_create_from_blob(const void* buf, size_t bytes, int32_t device,
+                                         recom_plan** out) {
+  if (!buf || bytes < sizeof(BlobHeader) || !out)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "blob too small");
+  BlobHeader h;
+  memcpy(&h, buf, sizeof h);
+  if (memcmp(h.magic, "RECOMB2", 8) != 0 || h.version != RECOM_B200_ABI_VERSION ||
+      h.desc_bytes != (int32_t)sizeof(recom_column_desc) || h.num_cols <= 0 || h.num_boundaries < 0)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "not a recom_b200 plan blob (or ABI mismatch)");
+  const size_t want = sizeof(BlobHeader) + (size_t)h.num_cols * sizeof(recom_column_desc) +
+                      (size_t)h.num_boundaries * sizeof(float);
+  if (bytes < want) return fail(RECOM_ERR_INVALID_ARGUMENT, "plan blob truncated");
+  std::vector<recom_column_desc> descs(h.num_cols);
+  std::vector<float> bnd((size_t)h.num_boundaries);
+  const uint8_t* o = (const uint8_t*)buf + sizeof h;
+  memcpy(descs.data(), o, descs.size() * sizeof(recom_column_desc));
+  o += descs.size() * sizeof(recom_column_desc);
+  if (!bnd.empty()) memcpy(bnd.data(), o, bnd.size() * sizeof(float));
+  recom_plan_config cfg = h.cfg;
+  cfg.device = device;
+  return recom_plan_create(descs.data(), h.num_cols, bnd.data(), h.num_boundaries, &cfg, out);
+}
+
+recom_status recom_plan_num_columns(const recom_plan* p, int32_t* out) {
+  if (!p || !out) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  *out = (int32_t)p->descs.size();
+  return RECOM_OK;
+}
+recom_status recom_plan_out_width(const recom_plan* p, int32_t* out) {
+  if (!p || !out) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  *out = p->cfg.out_width;
+  return RECOM_OK;
+}
+
+static size_t arg_block_bytes(const recom_plan* p, int64_t num_tiles) {
+  size_t b = align_up(sizeof(ReqHeader), 16);
+  b += align_up((size_t)p->cfg.num_slots * 8, 16);
+  b += align_up((size_t)p->cfg.num_tables * 8, 16);
+  b += align_up((p->descs.size() + 1) * 4, 16);
+  b += align_up((p->sparse_cols.size() + 1) * 4, 16);
+  b += align_up((size_t)num_tiles * sizeof(Tile), 16);
+  b += align_up(p->coo_cols.size() * 4 + 4, 16);
+  return b;
+}
+
+static int64_t max_tiles(const recom_plan* p, int64_t batch) {
+  // smallest tile is 32 rows
+  return (int64_t)p->slabs.size() * ((batch + 31) / 32) + 1;
+}
+
+recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int64_t total_ids,
+                                        size_t* out) {
+  if (!p || !out || batch < 0 || total_ids < 0)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  size_t b = align_up(arg_block_bytes(p, max_tiles(p, batch)), 256);
+  b += align_up((size_t)total_ids * 4 + 16, 256);                            // ws_ids
+  b += align_up(p->coo_cols.size() * (size_t)(batch + 1) * 4 + 16, 256);     // ws_row_splits
+  *out = b;
+  return RECOM_OK;
+}
+
+recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
+  g_last_launches = 0;
+  if (!cp || !req) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  recom_plan* p = const_cast<recom_plan*>(cp);  // only the internally locked arg ring mutates
+  recom_status st = validate_request(p, req);
+  if (st != RECOM_OK) return st;
+  if (req->batch == 0) return RECOM_OK;
+  const int n = (int)p->descs.size();
+  const int64_t B = req->batch;
+  cudaStream_t stream = (cudaStream_t)req->stream;
+
+  // per-column id counts
+  std::vector<int32_t> ids_base(n + 1, 0);
+  std::vector<int32_t> sparse_base(p->sparse_cols.size() + 1, 0);
+  int64_t total = 0, sparse_total = 0, max_coo_nnz = 0;
+  for (int i = 0; i < n; ++i) {
+    const int64_t cnt = column_num_ids(p, i, req);
+    ids_base[i] = (int32_t)total;
+    total += cnt;
+    if (p->cols[i].sparse_index >= 0) {
+      sparse_base[p->cols[i].sparse_index] = (int32_t)sparse_total;
+      sparse_total += cnt;
+      if (p->cols[i].coo_index >= 0) max_coo_nnz = std::max(max_coo_nnz, cnt);
+    }
+    if (total > 0x7fffffffLL) return fail(RECOM_ERR_INVALID_ARGUMENT, "too many ids in one request");
+  }
+  ids_base[n] = (int32_t)total;
+  sparse_base[p->sparse_cols.size()] = (int32_t)sparse_total;
+
+  // tile table: heavy (multi-hot) slabs first, then dense; tile rows shrink for small
+  // batches so that every SM has work.
+  const int target_ctas = p->num_sms * p->ctas_per_sm;
+  int dense_rows = kDenseTileRows, sparse_rows = kSparseTileRows;
+  auto count_tiles = [&](int dr, int sr) {
+    int64_t t = 0;
+    for (const DevSlab& s : p->slabs) t += (B + (s.cls == kSlabDense ? dr : sr) - 1) / (s.cls == kSlabDense ? dr : sr);
+    return t;
+  };
+  while (count_tiles(dense_rows, sparse_rows) < 2 * (int64_t)target_ctas &&
+         (dense_rows > 32 || sparse_rows > 32)) {
+    if (dense_rows > 32) dense_rows /= 2;
+    if (sparse_rows > 32 && sparse_rows > dense_rows / 2) sparse_rows /= 2;
+  }
+  std::vector<std::pair<double, int>> order;  // (cost per row, slab)
+  order.reserve(p->slabs.size());
+  for (int s = 0; s < (int)p->slabs.size(); ++s) {
+    const DevSlab& sl = p->slabs[s];
+    double cost = 0;
+    if (sl.cls == kSlabSparse) {
+      for (int k = 0; k < sl.num_chunks; ++k) {
+        const int ci = p->chunks[sl.first_chunk + k].col;
+        cost += (double)(ids_base[ci + 1] - ids_base[ci]) / (double)B * sl.vec_bytes;
+      }
+      cost += 1e6;  // all sparse slabs ahead of all dense slabs
+    } else {
+      cost = (double)sl.num_chunks * sl.vec_bytes;
+    }
+    order.push_back({-cost, s});
+  }
+  std::sort(order.begin(), order.end());
+  std::vector<Tile> tiles;
+  tiles.reserve((size_t)count_tiles(dense_rows, sparse_rows));
+  for (auto& os : order) {
+    const DevSlab& sl = p->slabs[os.second];
+    const int tr = sl.cls == kSlabDense ? dense_rows : sparse_rows;
+    for (int64_t b = 0; b < B; b += tr) {
+      Tile t;
+      t.slab = os.second;
+      t.row_begin = (int32_t)b;
+      t.rows = (int32_t)std::min<int64_t>(tr, B - b);
+      t.pad = 0;
+      tiles.push_back(t);
+    }
+  }
+  const int num_tiles = (int)tiles.size();
+  const int grid = std::max(1, std::min(num_tiles, target_ctas));
+
+  // workspace carve-up
+  const size_t args_bytes = arg_block_bytes(p, num_tiles);
+  size_t off = align_up(args_bytes, 256);
+  const size_t off_ws_ids = off;
+  off += align_up((size_t)sparse_total * 4 + 16, 256);
+  const size_t off_rs = off;
+  off += align_up(p->coo_cols.size() * (size_t)(B + 1) * 4 + 16, 256);
+  if (!req->workspace || req->workspace_bytes < off)
+    return fail(RECOM_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes, got %zu", off,
+                req->workspace_bytes);
+  uint8_t* ws = (uint8_t*)req->workspace;
+
+  // pinned staging slot
+  ArgSlot& slot = p->ring[p->ring_next.fetch_add(1) % kRing];
+  std::lock_guard<std::mutex> lock(slot.mu);
+  if (slot.in_flight) {
+    CUDA_TRY(cudaEventSynchronize(slot.done));
+    slot.in_flight = false;
+  }
+  if (slot.cap < args_bytes) {
+    if (slot.pinned) cudaFreeHost(slot.pinned);
+    slot.pinned = nullptr;
+    slot.cap = 0;
+    const size_t cap = align_up(args_bytes * 2, 4096);
+    CUDA_TRY(cudaHostAlloc((void**)&slot.pinned, cap, cudaHostAllocDefault));
+    slot.cap = cap;
+  }
+  uint8_t* h = slot.pinned;
+  ReqHeader* hdr = (ReqHeader*)h;
+  memset(hdr, 0, sizeof *hdr);
+  hdr->blob = (const uint8_t*)req->blob;
+  hdr->out = (uint8_t*)req->out;
+  hdr->ids_out = req->ids_out;
+  hdr->status = req->status_out;
+  hdr->ws_ids = (int32_t*)(ws + off_ws_ids);
+  hdr->ws_row_splits = (int32_t*)(ws + off_rs);
+  hdr->batch = B;
+  hdr->out_row_bytes = (int64_t)p->cfg.out_width * p->elem_bytes;
+  hdr->num_tiles = num_tiles;
+  hdr->tile_counter = grid;
+  hdr->num_coo = (int32_t)p->coo_cols.size();
+  size_t o = align_up(sizeof(ReqHeader), 16);
+  hdr->off_slot_offsets = (uint32_t)o;
+  memcpy(h + o, req->slot_offsets, (size_t)p->cfg.num_slots * 8);
+  o += align_up((size_t)p->cfg.num_slots * 8, 16);
+  hdr->off_tables = (uint32_t)o;
+  memcpy(h + o, req->tables, (size_t)p->cfg.num_tables * 8);
+  o += align_up((size_t)p->cfg.num_tables * 8, 16);
+  hdr->off_ids_base = (uint32_t)o;
+  memcpy(h + o, ids_base.data(), ids_base.size() * 4);
+  o += align_up(ids_base.size() * 4, 16);
+  hdr->off_sparse_base = (uint32_t)o;
+  memcpy(h + o, sparse_base.data(), sparse_base.size() * 4);
+  o += align_up(sparse_base.size() * 4, 16);
+  hdr->off_tiles = (uint32_t)o;
+  memcpy(h + o, tiles.data(), tiles.size() * sizeof(Tile));
+  o += align_up(tiles.size() * sizeof(Tile), 16);
+  hdr->off_coo_cols = (uint32_t)o;
+  if (!p->coo_cols.empty()) memcpy(h + o, p->coo_cols.data(), p->coo_cols.size() * 4);
+  o += align_up(p->coo_cols.size() * 4 + 4, 16);
+  hdr->total_bytes = (uint32_t)o;
+
+  CUDA_TRY(cudaMemcpyAsync(ws, h, o, cudaMemcpyHostToDevice, stream));
+  ReqHeader* d_req = (ReqHeader*)ws;
+  if (!p->coo_cols.empty()) {
+    launch_coo_to_row_splits(p->dev, d_req, (int)p->coo_cols.size(), max_coo_nnz, stream);
+    g_last_launches++;
+  }
+  launch_fused_columns(p->dev, d_req, grid, p->elem_bytes == 2, stream);
+  g_last_launches++;
+  cudaError_t e = cudaGetLastError();
+  cudaEventRecord(slot.done, stream);
+  slot.in_flight = true;
+  if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return RECOM_OK;
+}
+
+recom_status recom_plan_algorithmic_bytes(const recom_plan* p, const recom_request* req,
+                                          int64_t* bytes_out) {
+  if (!p || !req || !bytes_out) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  const int64_t B = req->batch;
+  const int64_t s = p->elem_bytes;
+  int64_t total = 0;
+  for (size_t i = 0; i < p->descs.size(); ++i) {
+    const recom_column_desc& d = p->descs[i];
+    const int64_t nnz = column_num_ids(p, (int)i, req);
+    int64_t in_bytes;
+    if (d.value_dtype == RECOM_STR)
+      in_bytes = 4 * (nnz + 1) + req->slot_elems[d.bytes_slot];
+    else
+      in_bytes = (int64_t)dtype_bytes(d.value_dtype) * nnz;
+    const int64_t seg = d.lookup == RECOM_LOOKUP_DENSE ? 0 : 4 * (B + 1);
+    const int64_t tbl = (int64_t)d.dim * s * std::min<int64_t>(nnz, d.table_rows);
+    const int64_t outb = (int64_t)d.dim * s * B;
+    total += in_bytes + seg + tbl + outb;
+  }
+  *bytes_out = total;
+  return RECOM_OK;
+}
+
+recom_status recom_scatter_columns(const void* const* cols, const int32_t* col_dims,
+                                   const int32_t* col_offsets, int32_t num_cols, int64_t batch,
+                                   int32_t out_width, int32_t elem_bytes, void* out,
+                                   recom_stream_t stream_) {
+  if (num_cols == 0 || batch == 0) return RECOM_OK;
+  if (!cols || !col_dims || !col_offsets || !out || num_cols < 0 || batch < 0 ||
+      (elem_bytes != 4 && elem_bytes != 2))
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  for (int i = 0; i < num_cols; ++i)
+    if (!cols[i] || col_dims[i] <= 0 || col_offsets[i] < 0 || col_offsets[i] + col_dims[i] > out_width)
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: bad pointer/slice", i);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // descriptors travel through a small stream-ordered device allocation
+  const size_t bytes = (size_t)num_cols * (8 + 4 + 4);
+  uint8_t* d = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&d, bytes, stream));
+  std::vector<uint8_t> h(bytes);
+  memcpy(h.data(), cols, (size_t)num_cols * 8);
+  memcpy(h.data() + (size_t)num_cols * 8, col_dims, (size_t)num_cols * 4);
+  memcpy(h.data() + (size_t)num_cols * 12, col_offsets, (size_t)num_cols * 4);
+  CUDA_TRY(cudaMemcpyAsync(d, h.data(), bytes, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));  // h is pageable and about to die
+  launch_scatter_columns((const void* const*)d, (const int32_t*)(d + (size_t)num_cols * 8),
+                         (const int32_t*)(d + (size_t)num_cols * 12), num_cols, batch, out_width,
+                         elem_bytes, out, stream);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(d, stream);
+  if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "scatter launch failed: %s", cudaGetErrorString(e));
+  return RECOM_OK;
+}
+
+recom_status recom_segment_ids_to_row_splits(const int64_t* coo, int64_t nnz, int32_t stride,
+                                             int64_t batch, int32_t* row_splits,
+                                             recom_stream_t stream) {
+  if (nnz < 0 || batch < 0 || stride < 1 || !row_splits || (nnz > 0 && !coo) || nnz > 0x7fffffffLL)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  launch_segment_ids_to_row_splits(coo, nnz, stride, batch, row_splits, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
+  return RECOM_OK;
+}
+
+recom_status recom_string_to_hash_bucket_fast(const uint8_t* bytes, const int32_t* offsets,
+                                              int64_t n, int64_t num_buckets, int64_t* out,
+                                              recom_stream_t stream) {
+  if (n == 0) return RECOM_OK;
+  if (n < 0 || !offsets || !out || num_buckets < 1)  // op.cc:22-23 requires num_buckets >= 1
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  launch_fingerprint64(bytes, offsets, n, num_buckets, (uint64_t*)out, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
+  return RECOM_OK;
+}
+
+recom_status recom_fingerprint64(const uint8_t* bytes, const int32_t* offsets, int64_t n,
+                                 uint64_t* out, recom_stream_t stream) {
+  if (n == 0) return RECOM_OK;
+  if (n < 0 || !offsets || !out) return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  launch_fingerprint64(bytes, offsets, n, 0, out, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
+  return RECOM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+// plan.h — internal layout shared by the host planner and the device kernels.
+//
+// A plan is the B200-native counterpart of the CUDA file the reference generates
+// per graph (tensorflow_addons/graph_optimizers/cuda_emitter.cc:2057-2137): the
+// same information (per-column transform, lookup kind, table shape, concat
+// offset), but as data consumed by ONE precompiled persistent kernel instead of
+// as generated code with one 64-thread block per column.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/recom_b200.h"
+
+namespace recom {
+
+constexpr int kThreads = 256;          // threads per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxChunks = 32;         // a slab is at most one warp wide
+constexpr int kDenseTileRows = 128;    // rows per DENSE tile
+constexpr int kSparseTileRows = 64;    // rows per SPARSE tile
+constexpr int kIdPitch = kDenseTileRows + 1;  // smem pitch (bank-conflict free)
+
+enum SlabClass : int32_t { kSlabDense = 0, kSlabSparse = 1 };
+
+// Per-column constants, device resident for the life of the plan.
+struct DevColumn {
+  int64_t table_rows;
+  int64_t num_buckets;
+  int32_t table;          // index into the request's table pointer array
+  int32_t dim;
+  int32_t row_bytes;      // dim * sizeof(table element)
+  int32_t transform;
+  int32_t value_dtype;
+  int32_t value_slot;
+  int32_t bytes_slot;
+  int32_t seg_slot;
+  int32_t seg_format;
+  int32_t seg_stride;
+  int32_t combiner;
+  int32_t boundaries_offset;  // into the (deduplicated) boundary pool
+  int32_t num_boundaries;
+  int32_t sparse_index;   // rank among non-DENSE columns, -1 for DENSE
+  int32_t coo_index;      // rank among COO columns, -1 otherwise
+  int32_t lookup;
+};
+
+// One 16-byte (or element-sized) piece of a slab's output span, owned by a lane.
+struct DevChunk {
+  int32_t col;         // global column index
+  int32_t col_local;   // index of that column inside the slab
+  int32_t table_byte;  // byte offset of this chunk inside a table row
+  int32_t out_byte;    // byte offset of this chunk inside an output row
+};
+
+// A slab: a group of columns whose output slices are adjacent in the concat row
+// and together at most kMaxChunks chunks wide. Work is tiled as (slab, row block).
+struct DevSlab {
+  int32_t cls;          // SlabClass
+  int32_t num_chunks;   // W <= 32
+  int32_t first_chunk;  // into the chunk array
+  int32_t num_cols;
+  int32_t first_col;    // into the slab_cols array
+  int32_t vec_bytes;    // 16, or the element size when unaligned
+  int32_t tile_rows;
+  int32_t pad;
+};
+
+struct DevPlan {
+  const DevColumn* cols;
+  const DevSlab* slabs;
+  const DevChunk* chunks;
+  const int32_t* slab_cols;
+  const float* boundaries;
+  int32_t num_cols;
+  int32_t num_slabs;
+  int32_t elem_bytes;   // 4 (fp32) or 2 (bf16): table and output element size
+  int32_t check_ids;
+};
+
+// A unit of work pulled by a persistent CTA.
+struct Tile {
+  int32_t slab;
+  int32_t row_begin;
+  int32_t rows;
+  int32_t pad;
+};
+
+// Per-request argument block. Built on the host in pinned memory, uploaded with
+// one cudaMemcpyAsync into the workspace, read by every kernel of the request
+// (replaces the reference's KnlArgs + SymbolResults uploads,
+// cuda_emitter.cc:2182-2232).
+struct ReqHeader {
+  const uint8_t* blob;
+  uint8_t* out;
+  int32_t* ids_out;       // may be null
+  int32_t* status;        // may be null
+  int32_t* ws_ids;        // workspace: transformed ids of non-DENSE columns
+  int32_t* ws_row_splits; // workspace: row_splits built from COO columns
+  int64_t batch;
+  int64_t out_row_bytes;
+  int32_t num_tiles;
+  int32_t tile_counter;   // dynamic scheduler; starts at gridDim.x
+  int32_t num_coo;        // number of COO columns
+  int32_t pad;
+  // byte offsets from the start of this block
+  uint32_t off_slot_offsets;  // int64[num_slots]
+  uint32_t off_tables;        // const void*[num_tables]
+  uint32_t off_ids_base;      // int32[num_cols + 1] prefix of ids per column
+  uint32_t off_sparse_base;   // int32[num_sparse + 1] prefix of ids, non-DENSE only
+  uint32_t off_tiles;         // Tile[num_tiles]
+  uint32_t off_coo_cols;      // int32[num_coo] column index of each COO column
+  uint32_t total_bytes;
+  uint32_t pad2;
+};
+
+__host__ __device__ inline const int64_t* req_slot_offsets(const ReqHeader* r) {
+  return reinterpret_cast<const int64_t*>(reinterpret_cast<const uint8_t*>(r) +
+                                          r->off_slot_offsets);
+}
+__host__ __device__ inline const void* const* req_tables(const ReqHeader* r) {
+  return reinterpret_cast<const void* const*>(reinterpret_cast<const uint8_t*>(r) +
+                                              r->off_tables);
+}
+__host__ __device__ inline const int32_t* req_ids_base(const ReqHeader* r) {
+  return reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(r) +
+                                          r->off_ids_base);
+}
+__host__ __device__ inline const int32_t* req_sparse_base(const ReqHeader* r) {
+  return reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(r) +
+                                          r->off_sparse_base);
+}
+__host__ __device__ inline const Tile* req_tiles(const ReqHeader* r) {
+  return reinterpret_cast<const Tile*>(reinterpret_cast<const uint8_t*>(r) +
+                                       r->off_tiles);
+}
+__host__ __device__ inline const int32_t* req_coo_cols(const ReqHeader* r) {
+  return reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(r) +
+                                          r->off_coo_cols);
+}
+
+// kernels.cu
+void launch_fused_columns(const DevPlan& plan, ReqHeader* d_req, int grid, bool bf16,
+                          cudaStream_t stream);
+void launch_coo_to_row_splits(const DevPlan& plan, const ReqHeader* d_req, int num_coo,
+                              int64_t max_nnz, cudaStream_t stream);
+void launch_scatter_columns(const void* const* d_cols, const int32_t* d_dims,
+                            const int32_t* d_offsets, int32_t num_cols, int64_t batch,
+                            int32_t out_width, int32_t elem_bytes, void* out,
+                            cudaStream_t stream);
+void launch_segment_ids_to_row_splits(const int64_t* coo, int64_t nnz, int32_t stride,
+                                      int64_t batch, int32_t* row_splits,
+                                      cudaStream_t stream);
+void launch_fingerprint64(const uint8_t* bytes, const int32_t* offsets, int64_t n,
+                          int64_t num_buckets, uint64_t* out, cudaStream_t stream);
+int fused_kernel_max_ctas_per_sm(bool bf16);
+
+}  // namespace recom
