@@ -58,10 +58,14 @@ def assert_parity(model: Model, batch: int, feats, tables_np, check_ids=False):
     # ids: bit exact
     np.testing.assert_array_equal(got_ids.astype(np.int64), ref_ids)
     assert not np.isnan(got).any(), "some output element was never written"
-    if model.out_dtype == L.BF16:
-        np.testing.assert_allclose(got, ref, rtol=1e-2, atol=1e-2)  # BASELINE.json: 1e-2 (bf16)
-    else:
-        # BASELINE.json: 1e-5 relative (fp32). Sums of up to tens of N(0, 1/sqrt(D)) terms
-        # can cancel, so the relative bound is taken against the row scale via atol.
-        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6)
+    # Tolerance (BASELINE.json): 1e-5 relative for fp32, 1e-2 for bf16. "Relative" is taken
+    # against the magnitude of what was summed (the oracle re-run on |table|), the standard
+    # forward bound for a sum whose order differs (TF-CPU adds 8-blocks, the GPU adds in
+    # sequence); a plain |got-ref|/|ref| is meaningless where terms cancel.
+    scale, _ = run_oracle(model, req, [np.abs(t) for t in tables_np])
+    rtol = 1e-2 if model.out_dtype == L.BF16 else 1e-5
+    err = np.abs(got - ref)
+    bound = rtol * scale + 1e-30
+    worst = float((err / bound).max()) if err.size else 0.0
+    assert worst <= 1.0, f"max err/bound = {worst:.3g} (max abs err {err.max():.3g})"
     return req, got, ref
