@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the fused embedding-column stage.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload model_E|model_F|micro100|large_table] [--batch B]
+
+One step = one pass of the hot path (hash/bucketize -> gather -> combine -> concat) over
+one batch of synthetic features of the AE synthesized model E (1000 columns,
+examples/python/dlrm.py:202 of the reference) at batch 2048, the configuration
+BASELINE.json's metric is quoted on. Prints ONE JSON line (rank 0).
+
+  value      samples/s with the request blob already resident in HBM; CUDA events on the
+             launch stream around K back-to-back recom_plan_run calls, max over ranks.
+  e2e        the same metric through the C-ABI call with HOST buffers: per step a pinned
+             host blob -> device copy, recom_plan_run, and a device -> host read of the
+             last output row, all inside the timed region.
+  roofline   algorithmic bytes per launch / average step duration,
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (a C restatement of the TF-CPU path the reference runs,
+             OpenMP over columns) on the box's host cores, same workload, bounded sample.
+
+N > 1: model E fits one GPU, columns and batches are independent, so ranks are replicas
+(one process per GPU, own batch, no data-path collective): weak scaling. The sharded
+large-table configuration is `--workload large_table` (NCCL all-gather of partial rows).
+
+--impl reference times the reference's CPU implementation of the path. TensorFlow cannot
+be installed here, so that arm is the oracle port with all host threads (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "embedding_column_stage_samples_per_sec"
+UNIT = "samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="model_E",
+                    choices=["model_E", "model_F", "micro100", "large_table"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--sets", type=int, default=4, help="rotating request/output buffer sets")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def build_model(workload: str, world: int = 1, rank: int = 0):
+    from recom_b200 import synth
+
+    if workload == "model_E":
+        return synth.model_E(), 2048
+    if workload == "model_F":
+        return synth.model_F(), 2048
+    if workload == "micro100":
+        return synth.microbenchmark_model(100), 256
+    raise ValueError(workload)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"  # /opt/skills/guides/B200_PROFILING.md
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_tables(model, seed=0):
+    """Random-init fp32 tables in host memory (same distribution as the device tables)."""
+    import torch
+
+    g = torch.Generator()
+    g.manual_seed(seed + 12345)
+    out = []
+    for rows, dim in model.table_shapes:
+        t = torch.empty((rows, dim), dtype=torch.float32)
+        t.normal_(0.0, 1.0 / float(np.sqrt(dim)), generator=g)
+        out.append(t.numpy())
+    return out
+
+
+def time_oracle(model, batch, n_sets, seconds, warmup, steps=None):
+    """Times the CPU oracle on `model` at `batch`. -> dict(samples_per_s, p50_ms, p99_ms, ...)."""
+    from oracle import oracle as O
+    from recom_b200 import synth
+    from recom_b200.schema import pack_request
+
+    descs, bnd = model.descs()
+    tabs = host_tables(model)
+    ptrs = np.array([t.ctypes.data for t in tabs], dtype=np.uint64)
+    reqs = [pack_request(model, batch, synth.make_features(model, batch, seed=100 + s))
+            for s in range(n_sets)]
+    out = np.zeros((batch, model.out_width), np.float32)
+    threads = O.num_threads()
+
+    def one(r):
+        rc = O.lib.oracle_run_model(descs.ctypes.data, len(descs), bnd.ctypes.data if bnd.size else None,
+                                    model.out_width, model.out_dtype, batch, r.blob.ctypes.data,
+                                    r.slot_offsets.ctypes.data, r.slot_elems.ctypes.data,
+                                    ptrs.ctypes.data, out.ctypes.data, None, threads)
+        assert rc == 0
+
+    for i in range(max(warmup, 1)):
+        one(reqs[i % n_sets])
+    lat = []
+    t0 = time.perf_counter()
+    i = 0
+    while True:
+        t1 = time.perf_counter()
+        one(reqs[i % n_sets])
+        t2 = time.perf_counter()
+        lat.append(t2 - t1)
+        i += 1
+        if steps is not None:
+            if i >= steps:
+                break
+        elif t2 - t0 >= seconds:
+            break
+    total = time.perf_counter() - t0
+    lat_ms = np.array(lat) * 1e3
+    return {"samples_per_s": batch * len(lat) / total, "steps": len(lat), "cores": threads,
+            "ms_per_step": total / len(lat) * 1e3, "p50_ms": float(np.percentile(lat_ms, 50)),
+            "p99_ms": float(np.percentile(lat_ms, 99))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model, batch = build_model(args.workload)
+    batch = args.batch or batch
+    r = time_oracle(model, batch, args.sets, 0.0, args.warmup, steps=args.steps)
+    sample = f"{r['steps']} batches of {batch} samples of {args.workload}, all {len(model.columns)} columns"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["samples_per_s"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "p50_ms": r["p50_ms"], "p99_ms": r["p99_ms"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}_b{batch}", "columns": len(model.columns),
+                   "batch": batch, "out_width": model.out_width},
+        "cpu_baseline": {"value": r["samples_per_s"], "unit": UNIT, "cores": r["cores"],
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": r["samples_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": "reference arm = CPU oracle port (TensorFlow 2.6 is not installable here): "
+                "un-fused per-column TF-CPU kernels restated in C, OpenMP over columns",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from recom_b200 import _lib as L
+    from recom_b200 import runtime as R
+    from recom_b200 import synth
+    from recom_b200.schema import algorithmic_bytes, pack_request
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    if args.workload == "large_table":
+        from recom_b200 import sharding
+        return sharding.bench_large_table(args, world, rank, local)
+
+    model, batch = build_model(args.workload)
+    batch = args.batch or batch
+    K, W, S = args.steps, max(args.warmup, 3), max(args.sets, 2)
+
+    plan = R.Plan(model, device=local)
+    tables = R.make_tables(model, device=local, seed=0)
+    ptrs = R.table_pointers(tables)
+    reqs = [pack_request(model, batch, synth.make_features(model, batch, seed=1000 * rank + s))
+            for s in range(S)]
+    blobs = [R.upload_blob(r, local) for r in reqs]
+    outs = [plan.alloc_out(batch) for _ in range(S)]
+    wss = [plan.alloc_workspace(batch, r.sparse_ids) for r in reqs]
+    stream = torch.cuda.Stream(device=local)
+    creqs = [plan._request(reqs[s], blobs[s], ptrs, outs[s], wss[s], None, None, stream) for s in range(S)]
+    alg_bytes = [plan.algorithmic_bytes(reqs[s], blobs[s], ptrs, outs[s], wss[s]) for s in range(S)]
+    assert alg_bytes[0] == algorithmic_bytes(model, reqs[0])
+    run = L.lib.recom_plan_run
+    h = plan._h
+    refs = [C.byref(c) for c in creqs]
+
+    def barrier():
+        torch.cuda.synchronize(local)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(local)
+
+    # rotating sets: S x (blob + [B, out_width] output) exceeds the 126 MB L2
+    rot_bytes = sum(b.numel() for b in blobs) + sum(o.numel() * o.element_size() for o in outs)
+
+    with torch.cuda.stream(stream):
+        for i in range(W):
+            L.check(run(h, refs[i % S]))
+    launches_per_step = plan.last_launch_count()
+    barrier()
+
+    # ---- device-resident timing: K back-to-back steps -----------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        st = run(h, refs[i % S])
+        if st:
+            L.check(st)
+    e1.record(stream)
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+
+    # per-step latency distribution (event pair per step)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        evs[i][0].record(stream)
+        L.check(run(h, refs[i % S]))
+        evs[i][1].record(stream)
+    barrier()
+    lat = np.array([a.elapsed_time(b) for a, b in evs])
+
+    # ---- end to end: host blob -> H2D -> run -> D2H of the last output row ---------
+    pinned = [torch.from_numpy(r.blob).pin_memory() for r in reqs]
+    last_row = torch.empty(model.out_width, dtype=outs[0].dtype).pin_memory()
+    h2d = int(np.mean([r.blob.nbytes for r in reqs]))
+    d2h = last_row.numel() * last_row.element_size()
+
+    def e2e_step(i):
+        s = i % S
+        blobs[s].copy_(pinned[s], non_blocking=True)
+        st = run(h, refs[s])
+        if st:
+            L.check(st)
+        last_row.copy_(outs[s][batch - 1], non_blocking=True)
+
+    with torch.cuda.stream(stream):
+        for i in range(W):
+            e2e_step(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        f0.record(stream)
+        for i in range(K):
+            e2e_step(i)
+        f1.record(stream)
+        stream.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), wall_ms)
+    clocks = sampler.stop()
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / K
+    value = world * batch * K / (total_ms * 1e-3)
+    e2e_value = world * batch * K / (e2e_ms * 1e-3)
+
+    peak, peak_src = peaks()
+    mean_alg = float(np.mean(alg_bytes))
+    achieved = mean_alg / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(f"{args.workload}_b{batch}")
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "p50_ms": float(np.percentile(lat, 50)),
+        "p99_ms": float(np.percentile(lat, 99)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}_b{batch}", "columns": len(model.columns),
+                   "batch": batch, "out_width": model.out_width,
+                   "table_bytes": model.table_bytes(), "parallelism": f"replicas x{world}",
+                   "l2": f"rotating {S} request/output sets = {rot_bytes / 1e6:.0f} MB > 126 MB L2",
+                   "hashing": "fused on device (Fingerprint64)", "segments": "int32 row_splits"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": mean_alg, "kernel": "fused_columns_kernel"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+        "gpu_launches": launches_per_step * K,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del tables
+        torch.cuda.empty_cache()
+        r = time_oracle(model, batch, 2, args.cpu_seconds, 2)
+        line["cpu_baseline"] = {
+            "value": r["samples_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "p50_ms": r["p50_ms"], "p99_ms": r["p99_ms"],
+            "sample": f"{r['steps']} batches of {batch} samples of {args.workload} "
+                      f"(all {len(model.columns)} columns), {args.cpu_seconds:.0f} s of CPU work",
+        }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

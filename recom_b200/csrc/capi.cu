@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -74,6 +75,11 @@ int dtype_bytes(int32_t dt) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+struct TileTable {
+  std::vector<Tile> tiles;
+  int grid = 1;
+};
+
 }  // namespace
 
 struct recom_plan {
@@ -95,6 +101,9 @@ struct recom_plan {
   int elem_bytes = 4;
   int num_sms = 148;
   int ctas_per_sm = 4;
+  // tile tables depend only on the batch size: cached (read-mostly)
+  std::mutex tiles_mu;
+  std::map<int64_t, std::shared_ptr<const TileTable>> tiles_by_batch;
   // pinned argument ring
   ArgSlot ring[kRing];
   std::atomic<uint32_t> ring_next{0};
@@ -283,6 +292,63 @@ void build_layout(recom_plan* p) {
     }
     prev_end = d.out_offset + d.dim;
   }
+  // scheduling order: multi-hot slabs first (their tiles chase several dependent DRAM
+  // round trips), widest rows first; then the dense slabs.
+  std::vector<std::pair<double, int>> order2;
+  for (int s = 0; s < (int)p->slabs.size(); ++s) {
+    const DevSlab& sl = p->slabs[s];
+    double cost = (double)sl.num_chunks * sl.vec_bytes;
+    if (sl.cls == kSlabSparse) {
+      cost = 0;
+      for (int k = 0; k < sl.num_chunks; ++k)
+        cost += p->cols[p->chunks[sl.first_chunk + k].col].row_bytes;
+      cost += 1e9;
+    }
+    order2.push_back({-cost, s});
+  }
+  std::sort(order2.begin(), order2.end());
+  for (auto& o : order2) p->slab_order.push_back(o.second);
+}
+
+// Tile table of a batch size: heavy slabs first; tile rows shrink for small batches so
+// that every SM has work.
+std::shared_ptr<const TileTable> tiles_for_batch(recom_plan* p, int64_t B) {
+  std::lock_guard<std::mutex> lock(p->tiles_mu);
+  auto it = p->tiles_by_batch.find(B);
+  if (it != p->tiles_by_batch.end()) return it->second;
+  const int target_ctas = p->num_sms * p->ctas_per_sm;
+  int dense_rows = kDenseTileRows, sparse_rows = kSparseTileRows;
+  auto count_tiles = [&](int dr, int sr) {
+    int64_t t = 0;
+    for (const DevSlab& s : p->slabs) {
+      const int tr = s.cls == kSlabDense ? dr : sr;
+      t += (B + tr - 1) / tr;
+    }
+    return t;
+  };
+  while (count_tiles(dense_rows, sparse_rows) < 2 * (int64_t)target_ctas &&
+         (dense_rows > 32 || sparse_rows > 32)) {
+    if (dense_rows > 32) dense_rows /= 2;
+    if (sparse_rows > 32 && sparse_rows > dense_rows / 2) sparse_rows /= 2;
+  }
+  auto tt = std::make_shared<TileTable>();
+  tt->tiles.reserve((size_t)count_tiles(dense_rows, sparse_rows));
+  for (int s : p->slab_order) {
+    const DevSlab& sl = p->slabs[s];
+    const int tr = sl.cls == kSlabDense ? dense_rows : sparse_rows;
+    for (int64_t b = 0; b < B; b += tr) {
+      Tile t;
+      t.slab = s;
+      t.row_begin = (int32_t)b;
+      t.rows = (int32_t)std::min<int64_t>(tr, B - b);
+      t.pad = 0;
+      tt->tiles.push_back(t);
+    }
+  }
+  tt->grid = std::max(1, std::min((int)tt->tiles.size(), target_ctas));
+  if (p->tiles_by_batch.size() > 64) p->tiles_by_batch.clear();
+  p->tiles_by_batch[B] = tt;
+  return tt;
 }
 
 recom_status upload_plan(recom_plan* p) {
@@ -573,53 +639,10 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   ids_base[n] = (int32_t)total;
   sparse_base[p->sparse_cols.size()] = (int32_t)sparse_total;
 
-  // tile table: heavy (multi-hot) slabs first, then dense; tile rows shrink for small
-  // batches so that every SM has work.
-  const int target_ctas = p->num_sms * p->ctas_per_sm;
-  int dense_rows = kDenseTileRows, sparse_rows = kSparseTileRows;
-  auto count_tiles = [&](int dr, int sr) {
-    int64_t t = 0;
-    for (const DevSlab& s : p->slabs) t += (B + (s.cls == kSlabDense ? dr : sr) - 1) / (s.cls == kSlabDense ? dr : sr);
-    return t;
-  };
-  while (count_tiles(dense_rows, sparse_rows) < 2 * (int64_t)target_ctas &&
-         (dense_rows > 32 || sparse_rows > 32)) {
-    if (dense_rows > 32) dense_rows /= 2;
-    if (sparse_rows > 32 && sparse_rows > dense_rows / 2) sparse_rows /= 2;
-  }
-  std::vector<std::pair<double, int>> order;  // (cost per row, slab)
-  order.reserve(p->slabs.size());
-  for (int s = 0; s < (int)p->slabs.size(); ++s) {
-    const DevSlab& sl = p->slabs[s];
-    double cost = 0;
-    if (sl.cls == kSlabSparse) {
-      for (int k = 0; k < sl.num_chunks; ++k) {
-        const int ci = p->chunks[sl.first_chunk + k].col;
-        cost += (double)(ids_base[ci + 1] - ids_base[ci]) / (double)B * sl.vec_bytes;
-      }
-      cost += 1e6;  // all sparse slabs ahead of all dense slabs
-    } else {
-      cost = (double)sl.num_chunks * sl.vec_bytes;
-    }
-    order.push_back({-cost, s});
-  }
-  std::sort(order.begin(), order.end());
-  std::vector<Tile> tiles;
-  tiles.reserve((size_t)count_tiles(dense_rows, sparse_rows));
-  for (auto& os : order) {
-    const DevSlab& sl = p->slabs[os.second];
-    const int tr = sl.cls == kSlabDense ? dense_rows : sparse_rows;
-    for (int64_t b = 0; b < B; b += tr) {
-      Tile t;
-      t.slab = os.second;
-      t.row_begin = (int32_t)b;
-      t.rows = (int32_t)std::min<int64_t>(tr, B - b);
-      t.pad = 0;
-      tiles.push_back(t);
-    }
-  }
+  const std::shared_ptr<const TileTable> tt = tiles_for_batch(p, B);
+  const std::vector<Tile>& tiles = tt->tiles;
   const int num_tiles = (int)tiles.size();
-  const int grid = std::max(1, std::min(num_tiles, target_ctas));
+  const int grid = tt->grid;
 
   // workspace carve-up
   const size_t args_bytes = arg_block_bytes(p, num_tiles);
