@@ -52,7 +52,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="model_E",
-                    choices=["model_E", "model_F", "micro100", "large_table"])
+                    choices=["model_E", "model_F", "micro100", "large_table",
+                             # diagnostic slices of model E (not headline workloads)
+                             "model_E_dense", "model_E_bucketize", "model_E_sparse"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--sets", type=int, default=4, help="rotating request/output buffer sets")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -69,6 +71,12 @@ def build_model(workload: str, world: int = 1, rank: int = 0):
         return synth.model_F(), 2048
     if workload == "micro100":
         return synth.microbenchmark_model(100), 256
+    if workload == "model_E_dense":
+        return synth.dlrm_model(880, 50, 50, 0, 0, name="E_dense"), 2048
+    if workload == "model_E_bucketize":
+        return synth.dlrm_model(880, 0, 0, 0, 0, name="E_bucketize"), 2048
+    if workload == "model_E_sparse":
+        return synth.dlrm_model(0, 0, 0, 15, 5, name="E_sparse"), 2048
     raise ValueError(workload)
 
 

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librecom_b200.so")
+# RECOM_B200_LIB selects another build of the same library (e.g. the phase-timer build)
+LIB_PATH = os.environ.get("RECOM_B200_LIB") or os.path.join(_HERE, "librecom_b200.so")
 
 # enums (include/recom_b200.h)
 OK = 0

@@ -17,6 +17,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -75,9 +76,20 @@ int dtype_bytes(int32_t dt) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Schedule of one batch size (see TileCursor in kernels.cu). Layout of `tiles`:
+// [sparse pool | static runs of CTA 0, 1, ... | dense pool].
 struct TileTable {
   std::vector<Tile> tiles;
+  std::vector<int32_t> static_begin;  // [grid + 1]
   int grid = 1;
+  int num_sparse = 0;
+  int dyn_begin = 0;
+  void* d_block = nullptr;            // device copy: tiles, then static_begin (cached tables only)
+  ~TileTable() {
+    if (d_block) cudaFree(d_block);
+  }
+  size_t tiles_bytes() const { return (tiles.size() * sizeof(Tile) + 15) / 16 * 16; }
+  size_t bytes() const { return tiles_bytes() + (static_begin.size() * 4 + 15) / 16 * 16; }
 };
 
 }  // namespace
@@ -90,7 +102,8 @@ struct recom_plan {
   std::vector<DevColumn> cols;
   std::vector<DevSlab> slabs;
   std::vector<DevChunk> chunks;
-  std::vector<int32_t> slab_cols;
+  std::vector<DevSlabCol> slab_cols;
+  std::vector<DevSlabBnd> slab_bnds;
   std::vector<float> boundary_pool;
   std::vector<int32_t> sparse_cols;  // column index of each non-DENSE column
   std::vector<int32_t> coo_cols;     // column index of each COO column
@@ -100,10 +113,16 @@ struct recom_plan {
   DevPlan dev{};
   int elem_bytes = 4;
   int num_sms = 148;
-  int ctas_per_sm = 4;
+  int ctas_per_sm = 3;
+  double pool_frac = 0.15;  // share of the dense tiles kept in the dynamic pool
   // tile tables depend only on the batch size: cached (read-mostly)
   std::mutex tiles_mu;
   std::map<int64_t, std::shared_ptr<const TileTable>> tiles_by_batch;
+  bool stage_tables = true;
+  // profiling builds only (RECOM_B200_PROF_DUMP=<file>): per-CTA phase timers of the last run
+  uint64_t* d_prof = nullptr;
+  int prof_grid = 0;
+  std::string prof_path;
   // pinned argument ring
   ArgSlot ring[kRing];
   std::atomic<uint32_t> ring_next{0};
@@ -202,6 +221,10 @@ void build_layout(recom_plan* p) {
     memset(&c, 0, sizeof c);
     c.table_rows = d.table_rows;
     c.num_buckets = d.num_buckets;
+    if (d.num_buckets > 1) {
+      const uint64_t nb = (uint64_t)d.num_buckets;
+      c.bucket_magic = ~0ull / nb + ((nb & (nb - 1)) == 0 ? 1 : 0);  // floor(2^64 / nb)
+    }
     c.table = d.table;
     c.dim = d.dim;
     c.row_bytes = d.dim * es;
@@ -230,14 +253,16 @@ void build_layout(recom_plan* p) {
                            p->boundaries_in.begin() + d.boundaries_offset + d.num_boundaries);
       auto it = pool_index.find(b);
       if (it == pool_index.end()) {
+        // every set starts 16-byte aligned and is padded to 16 bytes (TMA bulk copies)
         it = pool_index.emplace(b, (int32_t)p->boundary_pool.size()).first;
         p->boundary_pool.insert(p->boundary_pool.end(), b.begin(), b.end());
+        while (p->boundary_pool.size() % 4) p->boundary_pool.push_back(0.f);
       }
       c.boundaries_offset = it->second;
       c.num_boundaries = d.num_boundaries;
     }
   }
-  if (p->boundary_pool.empty()) p->boundary_pool.push_back(0.f);
+  while (p->boundary_pool.size() < 4) p->boundary_pool.push_back(0.f);
 
   // slabs: walk columns in concat order, group same-class neighbours up to 32 chunks
   std::vector<int> order(n);
@@ -246,20 +271,37 @@ void build_layout(recom_plan* p) {
     return p->descs[a].out_offset < p->descs[b].out_offset;
   });
   const bool row_aligned = ((int64_t)p->cfg.out_width * es) % 16 == 0;
+  auto column_class = [&](const recom_column_desc& d) {
+    if (d.lookup != RECOM_LOOKUP_DENSE) return (int)kSlabSparse;
+    const int64_t bytes = d.table_rows * d.dim * es;
+    const bool stage = p->stage_tables && d.table_rows <= kStageTableRows &&
+                       bytes <= kStageTableBytes && bytes % 16 == 0;
+    return stage ? (int)kSlabDenseStaged : (int)kSlabDense;
+  };
   auto open_slab = [&](int cls, int vec) {
     DevSlab s{};
     s.cls = cls;
     s.vec_bytes = vec;
     s.first_chunk = (int32_t)p->chunks.size();
     s.first_col = (int32_t)p->slab_cols.size();
-    s.tile_rows = cls == kSlabDense ? kDenseTileRows : kSparseTileRows;
+    s.first_bnd = (int32_t)p->slab_bnds.size();
+    s.tile_rows = cls == kSlabSparse ? kSparseTileRowsL2 : kDenseTileRows;
     p->slabs.push_back(s);
+  };
+  // smem offset of a table already staged by the open slab, or -1
+  auto staged_offset = [&](const DevSlab& s, int table) {
+    for (int k = 0; k < s.num_cols; ++k) {
+      const DevSlabCol& sc = p->slab_cols[s.first_col + k];
+      if (sc.stage_off >= 0 && p->descs[sc.col].table == table) return sc.stage_off;
+    }
+    return -1;
   };
   int prev_end = -1;
   for (int oi = 0; oi < n; ++oi) {
     const int i = order[oi];
     const recom_column_desc& d = p->descs[i];
-    const int cls = d.lookup == RECOM_LOOKUP_DENSE ? kSlabDense : kSlabSparse;
+    const int cls = column_class(d);
+    const int64_t table_bytes = d.table_rows * d.dim * es;
     const bool vec16 = row_aligned && (d.dim * es) % 16 == 0 && ((int64_t)d.out_offset * es) % 16 == 0;
     const int vec = vec16 ? 16 : es;
     const int nchunks = d.dim * es / vec;
@@ -271,13 +313,66 @@ void build_layout(recom_plan* p) {
         need_new = s.cls != cls || s.vec_bytes != vec || s.num_chunks >= kMaxChunks ||
                    (done == 0 && d.out_offset != prev_end) ||
                    // keep a column inside one slab when it fits in an empty one
-                   (done == 0 && nchunks <= kMaxChunks && s.num_chunks + nchunks > kMaxChunks);
+                   (done == 0 && nchunks <= kMaxChunks && s.num_chunks + nchunks > kMaxChunks) ||
+                   (cls == kSlabDenseStaged && staged_offset(s, d.table) < 0 &&
+                    s.stage_bytes + table_bytes > kStageSlabBytes);
       }
       if (need_new) open_slab(cls, vec);
       DevSlab& s = p->slabs.back();
       const int take = std::min(nchunks - done, kMaxChunks - s.num_chunks);
       const int col_local = s.num_cols;
-      p->slab_cols.push_back(i);
+      DevSlabCol sc{};
+      sc.col = i;
+      sc.stage_off = -1;
+      sc.stage_copy = 0;
+      sc.bnd_off = -1;
+      {
+        const DevColumn& c = p->cols[i];
+        sc.transform = c.transform;
+        sc.value_dtype = c.value_dtype;
+        sc.value_slot = c.value_slot;
+        sc.bytes_slot = c.bytes_slot;
+        sc.table = c.table;
+        sc.row_bytes = c.row_bytes;
+        sc.table_rows = (int32_t)c.table_rows;
+        sc.num_boundaries = c.num_boundaries;
+        sc.boundaries_offset = c.boundaries_offset;
+        sc.num_buckets = (int32_t)c.num_buckets;
+        sc.bucket_magic = c.bucket_magic;
+        sc.seg_slot = c.seg_slot;
+        sc.coo_index = c.coo_index;
+        sc.sparse_index = c.sparse_index;
+        sc.combiner = c.combiner;
+      }
+      if (cls == kSlabDenseStaged) {
+        const int have = staged_offset(s, d.table);
+        if (have >= 0) {
+          sc.stage_off = have;
+        } else {
+          sc.stage_off = s.stage_bytes;
+          sc.stage_copy = 1;
+          s.stage_bytes += (int32_t)table_bytes;
+        }
+      }
+      if (cls != kSlabSparse && d.transform == RECOM_XFORM_BUCKETIZE && d.num_boundaries > 0) {
+        const int32_t pool_off = p->cols[i].boundaries_offset;
+        const int32_t floats = (d.num_boundaries + 3) / 4 * 4;
+        for (int k = 0; k < s.num_bnds; ++k)
+          if (p->slab_bnds[s.first_bnd + k].pool_off == pool_off)
+            sc.bnd_off = p->slab_bnds[s.first_bnd + k].smem_off;
+        if (sc.bnd_off < 0 && s.bnd_bytes / 4 + floats <= kStageBndFloats) {
+          DevSlabBnd sb{};
+          sb.pool_off = pool_off;
+          sb.floats = floats;
+          sb.smem_off = s.bnd_bytes / 4;
+          p->slab_bnds.push_back(sb);
+          s.num_bnds++;
+          s.bnd_bytes += floats * 4;
+          sc.bnd_off = sb.smem_off;
+        }
+      }
+      if (cls == kSlabSparse && table_bytes > kHbmTableBytes) s.tile_rows = kSparseTileRowsHbm;
+      p->slab_cols.push_back(sc);
       s.num_cols++;
       for (int k = 0; k < take; ++k) {
         DevChunk ch;
@@ -292,17 +387,32 @@ void build_layout(recom_plan* p) {
     }
     prev_end = d.out_offset + d.dim;
   }
+  // shared memory layout: [staged tables | staged boundaries | 2 x ids]
+  int max_stage = 0, max_bnd = 0, max_cols = 1;
+  for (const DevSlab& s : p->slabs) {
+    max_stage = std::max(max_stage, s.stage_bytes);
+    max_bnd = std::max(max_bnd, s.bnd_bytes);
+    if (s.cls != kSlabSparse) max_cols = std::max(max_cols, s.num_cols);
+  }
+  p->dev.smem_off_bnd = (int32_t)align_up((size_t)max_stage, 128);
+  p->dev.smem_off_ids = p->dev.smem_off_bnd + (int32_t)align_up((size_t)max_bnd, 128);
+  p->dev.smem_ids_cols = max_cols;
+  p->dev.smem_bytes = p->dev.smem_off_ids + 2 * max_cols * kIdPitch * 4;
+
   // scheduling order: multi-hot slabs first (their tiles chase several dependent DRAM
-  // round trips), widest rows first; then the dense slabs.
+  // round trips), widest rows first; then the dense slabs in concat order.
   std::vector<std::pair<double, int>> order2;
   for (int s = 0; s < (int)p->slabs.size(); ++s) {
     const DevSlab& sl = p->slabs[s];
-    double cost = (double)sl.num_chunks * sl.vec_bytes;
+    double cost = 0;
     if (sl.cls == kSlabSparse) {
-      cost = 0;
-      for (int k = 0; k < sl.num_chunks; ++k)
-        cost += p->cols[p->chunks[sl.first_chunk + k].col].row_bytes;
+      for (int k = 0; k < sl.num_chunks; ++k) {
+        const recom_column_desc& d = p->descs[p->chunks[sl.first_chunk + k].col];
+        cost += (double)sl.vec_bytes * (d.table_rows * d.dim * es > kHbmTableBytes ? 64.0 : 1.0);
+      }
       cost += 1e9;
+    } else {
+      cost = -(double)s;
     }
     order2.push_back({-cost, s});
   }
@@ -310,32 +420,22 @@ void build_layout(recom_plan* p) {
   for (auto& o : order2) p->slab_order.push_back(o.second);
 }
 
-// Tile table of a batch size: heavy slabs first; tile rows shrink for small batches so
-// that every SM has work.
-std::shared_ptr<const TileTable> tiles_for_batch(recom_plan* p, int64_t B) {
-  std::lock_guard<std::mutex> lock(p->tiles_mu);
-  auto it = p->tiles_by_batch.find(B);
-  if (it != p->tiles_by_batch.end()) return it->second;
+// Schedule of a batch size: SPARSE tiles in a shared pool (heavy first); DENSE tiles in
+// slab-major order, the first (1 - pool_frac) of them split into one contiguous static run
+// per CTA (equal output bytes), the rest in a second shared pool. Tile rows shrink for
+// small batches so that every CTA has work.
+std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   const int target_ctas = p->num_sms * p->ctas_per_sm;
-  int dense_rows = kDenseTileRows, sparse_rows = kSparseTileRows;
-  auto count_tiles = [&](int dr, int sr) {
+  auto tt = std::make_shared<TileTable>();
+  int dense_rows = kDenseTileRows;
+  auto count_dense = [&](int dr) {
     int64_t t = 0;
-    for (const DevSlab& s : p->slabs) {
-      const int tr = s.cls == kSlabDense ? dr : sr;
-      t += (B + tr - 1) / tr;
-    }
+    for (const DevSlab& s : p->slabs)
+      if (s.cls != kSlabSparse) t += (B + dr - 1) / dr;
     return t;
   };
-  while (count_tiles(dense_rows, sparse_rows) < 2 * (int64_t)target_ctas &&
-         (dense_rows > 32 || sparse_rows > 32)) {
-    if (dense_rows > 32) dense_rows /= 2;
-    if (sparse_rows > 32 && sparse_rows > dense_rows / 2) sparse_rows /= 2;
-  }
-  auto tt = std::make_shared<TileTable>();
-  tt->tiles.reserve((size_t)count_tiles(dense_rows, sparse_rows));
-  for (int s : p->slab_order) {
-    const DevSlab& sl = p->slabs[s];
-    const int tr = sl.cls == kSlabDense ? dense_rows : sparse_rows;
+  while (dense_rows > 16 && count_dense(dense_rows) < 2 * (int64_t)target_ctas) dense_rows /= 2;
+  auto push = [&](int s, int tr) {
     for (int64_t b = 0; b < B; b += tr) {
       Tile t;
       t.slab = s;
@@ -344,40 +444,92 @@ std::shared_ptr<const TileTable> tiles_for_batch(recom_plan* p, int64_t B) {
       t.pad = 0;
       tt->tiles.push_back(t);
     }
+  };
+  for (int s : p->slab_order)
+    if (p->slabs[s].cls == kSlabSparse) push(s, p->slabs[s].tile_rows);
+  tt->num_sparse = (int)tt->tiles.size();
+  for (int s : p->slab_order)
+    if (p->slabs[s].cls != kSlabSparse) push(s, dense_rows);
+  const int num_tiles = (int)tt->tiles.size();
+  const int num_dense = num_tiles - tt->num_sparse;
+  tt->grid = std::max(1, std::min(num_tiles, target_ctas));
+  tt->static_begin.assign(tt->grid + 1, tt->num_sparse);
+  int num_static = 0;
+  if (num_dense >= 3 * tt->grid) num_static = (int)((1.0 - p->pool_frac) * num_dense);
+  if (num_static > 0) {
+    std::vector<double> cum(num_static + 1, 0.0);
+    for (int i = 0; i < num_static; ++i) {
+      const Tile& t = tt->tiles[tt->num_sparse + i];
+      const DevSlab& sl = p->slabs[t.slab];
+      cum[i + 1] = cum[i] + (double)t.rows * sl.num_chunks * sl.vec_bytes;
+    }
+    int cursor = 0;
+    for (int c = 0; c < tt->grid; ++c) {
+      tt->static_begin[c] = tt->num_sparse + cursor;
+      const double want = cum[num_static] * (c + 1) / tt->grid;
+      while (cursor < num_static && 0.5 * (cum[cursor] + cum[cursor + 1]) < want) ++cursor;
+    }
+    tt->static_begin[tt->grid] = tt->num_sparse + num_static;
   }
-  tt->grid = std::max(1, std::min((int)tt->tiles.size(), target_ctas));
-  if (p->tiles_by_batch.size() > 64) p->tiles_by_batch.clear();
+  tt->dyn_begin = tt->num_sparse + num_static;
+  return tt;
+}
+
+constexpr size_t kMaxCachedTileTables = 512;
+
+// Cached (device resident) schedule of a batch size, or nullptr when the cache is full:
+// the caller then ships the schedule inside the request's argument block.
+std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, recom_status* st) {
+  *st = RECOM_OK;
+  std::lock_guard<std::mutex> lock(p->tiles_mu);
+  auto it = p->tiles_by_batch.find(B);
+  if (it != p->tiles_by_batch.end()) return it->second;
+  if (p->tiles_by_batch.size() >= kMaxCachedTileTables) return nullptr;
+  std::shared_ptr<TileTable> tt = build_tiles(p, B);
+  std::vector<uint8_t> host(tt->bytes(), 0);
+  memcpy(host.data(), tt->tiles.data(), tt->tiles.size() * sizeof(Tile));
+  memcpy(host.data() + tt->tiles_bytes(), tt->static_begin.data(), tt->static_begin.size() * 4);
+  // first use of a batch size (warm-up): a blocking allocation + copy
+  if (cudaMalloc(&tt->d_block, host.size()) != cudaSuccess ||
+      cudaMemcpy(tt->d_block, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    *st = fail(RECOM_ERR_CUDA, "tile table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
   p->tiles_by_batch[B] = tt;
   return tt;
 }
 
 recom_status upload_plan(recom_plan* p) {
-  const size_t b_cols = align_up(p->cols.size() * sizeof(DevColumn), 256);
-  const size_t b_slabs = align_up(p->slabs.size() * sizeof(DevSlab), 256);
-  const size_t b_chunks = align_up(p->chunks.size() * sizeof(DevChunk), 256);
-  const size_t b_sc = align_up(p->slab_cols.size() * sizeof(int32_t), 256);
-  const size_t b_bnd = align_up(p->boundary_pool.size() * sizeof(float), 256);
-  const size_t total = b_cols + b_slabs + b_chunks + b_sc + b_bnd;
+  struct Part {
+    const void* src;
+    size_t bytes;
+    size_t off;
+  };
+  Part parts[6] = {
+      {p->cols.data(), p->cols.size() * sizeof(DevColumn), 0},
+      {p->slabs.data(), p->slabs.size() * sizeof(DevSlab), 0},
+      {p->chunks.data(), p->chunks.size() * sizeof(DevChunk), 0},
+      {p->slab_cols.data(), p->slab_cols.size() * sizeof(DevSlabCol), 0},
+      {p->slab_bnds.data(), p->slab_bnds.size() * sizeof(DevSlabBnd), 0},
+      {p->boundary_pool.data(), p->boundary_pool.size() * sizeof(float), 0},
+  };
+  size_t total = 0;
+  for (Part& pt : parts) {
+    pt.off = total;
+    total += align_up(pt.bytes + 16, 256);
+  }
   std::vector<uint8_t> host(total, 0);
-  size_t o = 0;
-  memcpy(host.data() + o, p->cols.data(), p->cols.size() * sizeof(DevColumn));
-  const size_t o_cols = o; o += b_cols;
-  memcpy(host.data() + o, p->slabs.data(), p->slabs.size() * sizeof(DevSlab));
-  const size_t o_slabs = o; o += b_slabs;
-  memcpy(host.data() + o, p->chunks.data(), p->chunks.size() * sizeof(DevChunk));
-  const size_t o_chunks = o; o += b_chunks;
-  memcpy(host.data() + o, p->slab_cols.data(), p->slab_cols.size() * sizeof(int32_t));
-  const size_t o_sc = o; o += b_sc;
-  memcpy(host.data() + o, p->boundary_pool.data(), p->boundary_pool.size() * sizeof(float));
-  const size_t o_bnd = o;
+  for (const Part& pt : parts)
+    if (pt.bytes) memcpy(host.data() + pt.off, pt.src, pt.bytes);
   CUDA_TRY(cudaMalloc(&p->d_block, total));
   CUDA_TRY(cudaMemcpy(p->d_block, host.data(), total, cudaMemcpyHostToDevice));
   uint8_t* base = (uint8_t*)p->d_block;
-  p->dev.cols = (const DevColumn*)(base + o_cols);
-  p->dev.slabs = (const DevSlab*)(base + o_slabs);
-  p->dev.chunks = (const DevChunk*)(base + o_chunks);
-  p->dev.slab_cols = (const int32_t*)(base + o_sc);
-  p->dev.boundaries = (const float*)(base + o_bnd);
+  p->dev.cols = (const DevColumn*)(base + parts[0].off);
+  p->dev.slabs = (const DevSlab*)(base + parts[1].off);
+  p->dev.chunks = (const DevChunk*)(base + parts[2].off);
+  p->dev.slab_cols = (const DevSlabCol*)(base + parts[3].off);
+  p->dev.slab_bnds = (const DevSlabBnd*)(base + parts[4].off);
+  p->dev.boundaries = (const float*)(base + parts[5].off);
   p->dev.num_cols = (int32_t)p->cols.size();
   p->dev.num_slabs = (int32_t)p->slabs.size();
   p->dev.elem_bytes = p->elem_bytes;
@@ -478,14 +630,26 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
   p->descs.assign(cols, cols + num_cols);
   if (num_boundaries) p->boundaries_in.assign(boundaries, boundaries + num_boundaries);
   p->elem_bytes = cfg->out_dtype == RECOM_BF16 ? 2 : 4;
+  // tuning knobs (the reference's counterpart: its RECOM_* env flags, fc_optimize_pass.cc:41-69)
+  if (const char* e = getenv("RECOM_B200_STAGE_TABLES")) p->stage_tables = atoi(e) != 0;
+  if (const char* e = getenv("RECOM_B200_POOL_PCT"))
+    p->pool_frac = std::min(100, std::max(0, atoi(e))) / 100.0;
   build_layout(p);
   st = upload_plan(p);
   if (st == RECOM_OK) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) p->num_sms = prop.multiProcessorCount;
-    int occ = fused_kernel_max_ctas_per_sm(p->elem_bytes == 2);
-    if (occ < 1) occ = 1;
+    int occ = fused_kernel_configure(p->elem_bytes == 2, p->dev.smem_bytes);
+    if (occ < 1) {
+      st = fail(RECOM_ERR_CUDA, "fused kernel does not fit (smem %d bytes): %s", p->dev.smem_bytes,
+                cudaGetErrorString(cudaGetLastError()));
+      occ = 1;
+    }
     p->ctas_per_sm = cfg->max_ctas_per_sm > 0 ? std::min(cfg->max_ctas_per_sm, occ) : occ;
+    if (const char* e = getenv("RECOM_B200_PROF_DUMP")) {
+      p->prof_path = e;
+      if (cudaMalloc((void**)&p->d_prof, (size_t)p->num_sms * 16 * 16 * 8) != cudaSuccess) p->d_prof = nullptr;
+    }
     for (int i = 0; i < kRing && st == RECOM_OK; ++i) {
       cudaError_t e = cudaEventCreateWithFlags(&p->ring[i].done, cudaEventDisableTiming);
       if (e != cudaSuccess) st = fail(RECOM_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
@@ -502,6 +666,19 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
 
 recom_status recom_plan_destroy(recom_plan* p) {
   if (!p) return RECOM_OK;
+  if (p->d_prof && p->prof_grid > 0) {
+    cudaDeviceSynchronize();
+    std::vector<uint64_t> h((size_t)p->prof_grid * 16);
+    if (cudaMemcpy(h.data(), p->d_prof, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (FILE* f = fopen(p->prof_path.c_str(), "w")) {
+        for (int c = 0; c < p->prof_grid; ++c) {
+          for (int i = 0; i < 16; ++i) fprintf(f, "%llu%c", (unsigned long long)h[(size_t)c * 16 + i], i == 15 ? '\n' : ' ');
+        }
+        fclose(f);
+      }
+    }
+  }
+  if (p->d_prof) cudaFree(p->d_prof);
   for (int i = 0; i < kRing; ++i) {
     if (p->ring[i].done) {
       cudaEventSynchronize(p->ring[i].done);
@@ -583,27 +760,31 @@ recom_status recom_plan_out_width(const recom_plan* p, int32_t* out) {
   return RECOM_OK;
 }
 
-static size_t arg_block_bytes(const recom_plan* p, int64_t num_tiles) {
+// Bytes of the per-request argument block; `sched_bytes` > 0 only when the schedule is not
+// cached on the device and travels with the request.
+static size_t arg_block_bytes(const recom_plan* p, size_t sched_bytes) {
   size_t b = align_up(sizeof(ReqHeader), 16);
   b += align_up((size_t)p->cfg.num_slots * 8, 16);
   b += align_up((size_t)p->cfg.num_tables * 8, 16);
   b += align_up((p->descs.size() + 1) * 4, 16);
   b += align_up((p->sparse_cols.size() + 1) * 4, 16);
-  b += align_up((size_t)num_tiles * sizeof(Tile), 16);
   b += align_up(p->coo_cols.size() * 4 + 4, 16);
+  b += sched_bytes;
   return b;
 }
 
-static int64_t max_tiles(const recom_plan* p, int64_t batch) {
-  // smallest tile is 32 rows
-  return (int64_t)p->slabs.size() * ((batch + 31) / 32) + 1;
+static size_t max_sched_bytes(const recom_plan* p, int64_t batch) {
+  // smallest tile is 8 rows (HBM-resident multi-hot) resp. 16 rows (dense)
+  const size_t tiles = p->slabs.size() * (size_t)((batch + 7) / 8) + 1;
+  return align_up(tiles * sizeof(Tile), 16) +
+         align_up(((size_t)p->num_sms * p->ctas_per_sm + 2) * 4, 16);
 }
 
 recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int64_t total_ids,
                                         size_t* out) {
   if (!p || !out || batch < 0 || total_ids < 0)
     return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
-  size_t b = align_up(arg_block_bytes(p, max_tiles(p, batch)), 256);
+  size_t b = align_up(arg_block_bytes(p, max_sched_bytes(p, batch)), 256);
   b += align_up((size_t)total_ids * 4 + 16, 256);                            // ws_ids
   b += align_up(p->coo_cols.size() * (size_t)(batch + 1) * 4 + 16, 256);     // ws_row_splits
   *out = b;
@@ -613,7 +794,7 @@ recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int6
 recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   g_last_launches = 0;
   if (!cp || !req) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
-  recom_plan* p = const_cast<recom_plan*>(cp);  // only the internally locked arg ring mutates
+  recom_plan* p = const_cast<recom_plan*>(cp);  // only internally locked caches mutate
   recom_status st = validate_request(p, req);
   if (st != RECOM_OK) return st;
   if (req->batch == 0) return RECOM_OK;
@@ -639,13 +820,14 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   ids_base[n] = (int32_t)total;
   sparse_base[p->sparse_cols.size()] = (int32_t)sparse_total;
 
-  const std::shared_ptr<const TileTable> tt = tiles_for_batch(p, B);
-  const std::vector<Tile>& tiles = tt->tiles;
-  const int num_tiles = (int)tiles.size();
+  std::shared_ptr<const TileTable> tt = cached_tiles(p, B, &st);
+  if (st != RECOM_OK) return st;
+  const bool sched_in_args = !tt;
+  if (sched_in_args) tt = build_tiles(p, B);
   const int grid = tt->grid;
 
   // workspace carve-up
-  const size_t args_bytes = arg_block_bytes(p, num_tiles);
+  const size_t args_bytes = arg_block_bytes(p, sched_in_args ? tt->bytes() : 0);
   size_t off = align_up(args_bytes, 256);
   const size_t off_ws_ids = off;
   off += align_up((size_t)sparse_total * 4 + 16, 256);
@@ -682,9 +864,14 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   hdr->ws_row_splits = (int32_t*)(ws + off_rs);
   hdr->batch = B;
   hdr->out_row_bytes = (int64_t)p->cfg.out_width * p->elem_bytes;
-  hdr->num_tiles = num_tiles;
-  hdr->tile_counter = grid;
+  hdr->num_tiles = (int32_t)tt->tiles.size();
+  hdr->num_sparse_tiles = tt->num_sparse;
+  hdr->dyn_begin = tt->dyn_begin;
+  hdr->ctr_sparse = 0;
+  hdr->ctr_dense = 0;
   hdr->num_coo = (int32_t)p->coo_cols.size();
+  hdr->prof = p->d_prof;
+  if (p->d_prof) p->prof_grid = grid;
   size_t o = align_up(sizeof(ReqHeader), 16);
   hdr->off_slot_offsets = (uint32_t)o;
   memcpy(h + o, req->slot_offsets, (size_t)p->cfg.num_slots * 8);
@@ -698,12 +885,19 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   hdr->off_sparse_base = (uint32_t)o;
   memcpy(h + o, sparse_base.data(), sparse_base.size() * 4);
   o += align_up(sparse_base.size() * 4, 16);
-  hdr->off_tiles = (uint32_t)o;
-  memcpy(h + o, tiles.data(), tiles.size() * sizeof(Tile));
-  o += align_up(tiles.size() * sizeof(Tile), 16);
   hdr->off_coo_cols = (uint32_t)o;
   if (!p->coo_cols.empty()) memcpy(h + o, p->coo_cols.data(), p->coo_cols.size() * 4);
   o += align_up(p->coo_cols.size() * 4 + 4, 16);
+  if (sched_in_args) {
+    hdr->tiles = (const Tile*)(ws + o);
+    memcpy(h + o, tt->tiles.data(), tt->tiles.size() * sizeof(Tile));
+    hdr->static_begin = (const int32_t*)(ws + o + tt->tiles_bytes());
+    memcpy(h + o + tt->tiles_bytes(), tt->static_begin.data(), tt->static_begin.size() * 4);
+    o += tt->bytes();
+  } else {
+    hdr->tiles = (const Tile*)tt->d_block;
+    hdr->static_begin = (const int32_t*)((const uint8_t*)tt->d_block + tt->tiles_bytes());
+  }
   hdr->total_bytes = (uint32_t)o;
 
   CUDA_TRY(cudaMemcpyAsync(ws, h, o, cudaMemcpyHostToDevice, stream));

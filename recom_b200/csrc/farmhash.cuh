@@ -33,17 +33,29 @@ __device__ __forceinline__ uint64_t hash_len16(uint64_t u, uint64_t v, uint64_t 
   return b * mul;
 }
 
-// Bytes in global memory at an arbitrary alignment.
+// Bytes in global memory at an arbitrary alignment. fetch32/fetch64 read the aligned
+// words that cover the requested bytes and funnel-shift them: every word read holds at
+// least one byte of the string, so reads stay inside the string's slot as long as the
+// slot is padded to an 8-byte boundary (include/recom_b200.h: blob slots are padded).
 struct MemBytes {
   const uint8_t* p;
   __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return __ldg(p + pos); }
   __device__ __forceinline__ uint32_t fetch32(uint32_t pos) const {
-    const uint8_t* q = p + pos;
-    return (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) |
-           ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) + pos;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t lo = __ldg(w);
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, __ldg(w + 1), sh);
   }
   __device__ __forceinline__ uint64_t fetch64(uint32_t pos) const {
-    return (uint64_t)fetch32(pos) | ((uint64_t)fetch32(pos + 4) << 32);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) + pos;
+    const unsigned long long* w =
+        reinterpret_cast<const unsigned long long*>(a & ~uintptr_t(7));
+    const uint32_t sh = (uint32_t)(a & 7) * 8;
+    const uint64_t lo = __ldg(w);
+    if (sh == 0) return lo;
+    return (lo >> sh) | ((uint64_t)__ldg(w + 1) << (64 - sh));
   }
 };
 
@@ -246,6 +258,18 @@ __device__ __forceinline__ uint64_t fingerprint64_of_decimal_u32small(uint32_t v
   }
   const RegBytes s{w, 0, 0};
   return hash_len_0_16(s, nd);
+}
+
+// h % n for 1 <= n < 2^31 with magic = floor(2^64 / n) (0 when n == 1):
+// q = mulhi(h, magic) is floor(h / n) or one less, so one conditional subtract
+// finishes; bit-exact with the `%` TF uses (string_to_hash_bucket_fast_op.h:47-55).
+__device__ __forceinline__ uint64_t mod_bucket(uint64_t h, uint64_t n, uint64_t magic) {
+  if (n == 1) return 0;
+  const uint64_t q = __umul64hi(h, magic);
+  uint64_t r = h - q * n;
+  if (r >= n) r -= n;
+  if (r >= n) r -= n;
+  return r;
 }
 
 }  // namespace fh

@@ -12,19 +12,27 @@
 //   * the TF-CPU ops the reference leaves upstream: StringToHashBucketFast and
 //     AsString.
 //
-// Work decomposition: the host builds a per-request table of tiles
-// (slab, row block). A slab is a run of columns whose output slices are adjacent
-// in the concat row and at most 32 16-byte chunks wide, so one warp store covers
-// up to 512 contiguous bytes of one output row. CTAs (256 threads, several per
-// SM) pull tiles through an atomic counter, heavy multi-hot tiles first.
+// Work decomposition: a table of tiles (slab, row block) per batch size, cached on
+// the device. A slab is a run of columns whose output slices are adjacent in the
+// concat row and at most 32 16-byte chunks wide, so one warp store covers up to
+// 512 contiguous bytes of one output row. Persistent CTAs (256 threads, 3 per SM)
+// first drain a shared pool of multi-hot tiles, then walk a static run of dense
+// tiles of ONE slab (so what they staged in shared memory is reused), then drain
+// a shared pool of left-over dense tiles (load balance).
 //
 // Per tile:
+//   stage    (dense, on slab change) the slab's small tables and bucket boundaries
+//            are copied into shared memory with TMA bulk copies (cp.async.bulk,
+//            mbarrier completion), overlapping phase 1.
 //   phase 1  transform raw inputs to row ids (bucketize / hash / cast), one warp
 //            per column with lanes along the batch so input reads are coalesced;
 //            ids go to shared memory (DENSE) or to the workspace (multi-hot).
-//   phase 2  lane = chunk of the slab; per output row: read id(s), 128-bit
-//            read-only gathers of the table row chunk, fp32 accumulation,
-//            combiner scaling, one 128-bit streaming store into the concat row.
+//   phase 2  lane = chunk of the slab; per output row: read id(s), 128-bit gathers
+//            of the table row chunk (from shared memory when staged, else
+//            ld.global.nc), fp32 accumulation, combiner scaling, one 128-bit
+//            streaming store into the concat row.
+// One __syncthreads per dense tile (ids and the next tile index are double
+// buffered), so fast warps start the next tile's phase 1 while others still store.
 //
 // The path is HBM / L2 bound integer+copy work: no tensor cores by design.
 #include <cuda_bf16.h>
@@ -167,47 +175,130 @@ struct Acc<2, true> {
 };
 
 // ---------------------------------------------------------------------------
+// shared-memory / TMA helpers (sm_100a)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared (UBLKCP), completion counted in bytes on `bar`.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// A chunk read from shared memory.
+template <int VEC>
+__device__ __forceinline__ Chunk<VEC> lds_chunk(const uint8_t* p);
+template <>
+__device__ __forceinline__ Chunk<16> lds_chunk<16>(const uint8_t* p) {
+  Chunk<16> c;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(c.v.x), "=r"(c.v.y), "=r"(c.v.z), "=r"(c.v.w)
+               : "r"(smem_u32(p)));
+  return c;
+}
+template <>
+__device__ __forceinline__ Chunk<4> lds_chunk<4>(const uint8_t* p) {
+  Chunk<4> c;
+  c.v = *reinterpret_cast<const uint32_t*>(p);
+  return c;
+}
+template <>
+__device__ __forceinline__ Chunk<2> lds_chunk<2>(const uint8_t* p) {
+  Chunk<2> c;
+  c.v = *reinterpret_cast<const uint16_t*>(p);
+  return c;
+}
+
+// ---------------------------------------------------------------------------
 // phase 1: raw value -> table row id
 // ---------------------------------------------------------------------------
 // TF Bucketize == std::upper_bound over float boundaries with `value < boundary`
 // (bucketize_op.cc:42-44; the reference's device Bucketize, cuda_emitter.cc:233-247).
-template <typename T>
-__device__ __forceinline__ int32_t bucketize(const float* __restrict__ bnd, int32_t nb, T v) {
-  int32_t lo = 0, n = nb;
+// N independent searches run in lock step (same boundary array) for ILP. `bnd` may
+// point to shared or global memory.
+template <typename T, int N>
+__device__ __forceinline__ void bucketize_n(const float* __restrict__ bnd, int32_t nb,
+                                            const T (&v)[N], int32_t (&out)[N]) {
+  int32_t lo[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) lo[k] = 0;
+  int32_t n = nb;
+  // Every search sees the same sequence of range lengths: with len = n, the left part has
+  // `half` elements and the right part n - half - 1 <= half; using `half` for both keeps the
+  // searches in lock step and is still a correct upper_bound (the probe is clamped).
   while (n > 0) {
     const int32_t half = n >> 1;
-    const int32_t mid = lo + half;
-    const bool right = !(v < __ldg(bnd + mid));
-    lo = right ? mid + 1 : lo;
-    n = right ? n - half - 1 : half;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int32_t mid = min(lo[k] + half, nb - 1);
+      const bool right = (lo[k] + half < nb) && !(v[k] < bnd[mid]);
+      lo[k] = right ? lo[k] + half + 1 : lo[k];
+    }
+    n = half;
   }
-  return lo;
+#pragma unroll
+  for (int k = 0; k < N; ++k) out[k] = min(lo[k], nb);
 }
 
-__device__ __forceinline__ int32_t column_id(const DevColumn& c, const uint8_t* __restrict__ blob,
-                                             const int64_t* __restrict__ slot_off,
-                                             const float* __restrict__ boundaries, int64_t i) {
-  const uint8_t* vals = blob + slot_off[c.value_slot];
+template <typename T>
+__device__ __forceinline__ int32_t bucketize(const float* __restrict__ bnd, int32_t nb, T v) {
+  const T vv[1] = {v};
+  int32_t o[1];
+  bucketize_n<T, 1>(bnd, nb, vv, o);
+  return o[0];
+}
+
+// Any transform, one element. `bnd` = this column's boundaries (shared or global).
+__device__ __forceinline__ int32_t column_id(const ColCtx& c, const float* __restrict__ bnd,
+                                             int64_t i) {
+  const uint8_t* vals = c.values;
   switch (c.transform) {
     case RECOM_XFORM_NONE:
       if (c.value_dtype == RECOM_I32) return __ldg((const int32_t*)vals + i);
       return (int32_t)__ldg((const long long*)vals + i);
     case RECOM_XFORM_BUCKETIZE: {
-      const float* b = boundaries + c.boundaries_offset;
       switch (c.value_dtype) {
-        case RECOM_F32: return bucketize<float>(b, c.num_boundaries, __ldg((const float*)vals + i));
-        case RECOM_I32: return bucketize<int32_t>(b, c.num_boundaries, __ldg((const int32_t*)vals + i));
+        case RECOM_F32: return bucketize<float>(bnd, c.num_boundaries, __ldg((const float*)vals + i));
+        case RECOM_I32: return bucketize<int32_t>(bnd, c.num_boundaries, __ldg((const int32_t*)vals + i));
         case RECOM_I64:
-          return bucketize<long long>(b, c.num_boundaries, __ldg((const long long*)vals + i));
-        default: return bucketize<double>(b, c.num_boundaries, __ldg((const double*)vals + i));
+          return bucketize<long long>(bnd, c.num_boundaries, __ldg((const long long*)vals + i));
+        default: return bucketize<double>(bnd, c.num_boundaries, __ldg((const double*)vals + i));
       }
     }
     case RECOM_XFORM_HASH_STR: {
       const int32_t* off = (const int32_t*)vals;
       const int32_t o0 = __ldg(off + i), o1 = __ldg(off + i + 1);
-      const uint64_t h =
-          fh::fingerprint64(blob + slot_off[c.bytes_slot] + o0, (uint32_t)(o1 - o0));
-      return (int32_t)(h % (uint64_t)c.num_buckets);
+      const uint64_t h = fh::fingerprint64(c.bytes + o0, (uint32_t)(o1 - o0));
+      return (int32_t)fh::mod_bucket(h, (uint64_t)c.num_buckets, c.bucket_magic);
     }
     default: {  // RECOM_XFORM_HASH_INT
       uint64_t h;
@@ -218,169 +309,318 @@ __device__ __forceinline__ int32_t column_id(const DevColumn& c, const uint8_t* 
       } else {
         h = fh::fingerprint64_of_decimal((int64_t)__ldg((const long long*)vals + i));
       }
-      return (int32_t)(h % (uint64_t)c.num_buckets);
+      return (int32_t)fh::mod_bucket(h, (uint64_t)c.num_buckets, c.bucket_magic);
     }
   }
 }
 
-__device__ __forceinline__ int32_t checked_id(int32_t id, int64_t rows, int32_t* status) {
-  if ((uint64_t)(int64_t)id >= (uint64_t)rows) {
+__device__ __forceinline__ int32_t checked_id(int32_t id, int32_t rows, int32_t* status) {
+  if ((uint32_t)id >= (uint32_t)rows) {
     if (status) atomicExch(status, RECOM_ERR_ID_OUT_OF_RANGE);
     return 0;
   }
   return id;
 }
 
-struct __align__(16) TileSmem {
-  int32_t ids[kMaxChunks * kIdPitch];
-  int32_t next_tile;
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// Static shared state of a CTA (the dynamic part holds tables | boundaries | ids).
+struct __align__(16) CtaShared {
+  Tile next[2];            // the tile two steps ahead (slab < 0: none), double buffered
+  uint64_t mbar_bnd;       // boundaries of the staged slab have landed
+  uint64_t mbar_tbl;       // tables of the staged slab have landed
+  ColCtx ctx[kMaxChunks];  // the columns of the slab the CTA is working on
 };
+
+// Request-wide values every tile needs, read once per CTA.
+struct ReqRegs {
+  uint8_t* out;
+  int64_t out_row_bytes;
+  int32_t* status;
+};
+
+// ---------------------------------------------------------------------------
+// entering a slab: resolve its columns against the request (one thread per column), start
+// the TMA bulk copies of its small tables and bucket boundaries into shared memory
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void enter_slab(const DevPlan& P, const ReqHeader* __restrict__ R,
+                                           const DevSlab& slab, CtaShared& cs, uint8_t* s_tables,
+                                           float* s_bnd) {
+  const int tid = threadIdx.x;
+  if (tid < slab.num_cols) {
+    const DevSlabCol sc = P.slab_cols[slab.first_col + tid];
+    const int64_t* slot_off = req_slot_offsets(R);
+    ColCtx x;
+    x.values = R->blob + slot_off[sc.value_slot];
+    x.bytes = sc.bytes_slot >= 0 ? R->blob + slot_off[sc.bytes_slot] : nullptr;
+    x.table = (const uint8_t*)req_tables(R)[sc.table];
+    x.row_splits = nullptr;
+    x.ws_ids = nullptr;
+    if (sc.sparse_index >= 0) {
+      x.row_splits = sc.coo_index >= 0
+                         ? R->ws_row_splits + (int64_t)sc.coo_index * (R->batch + 1)
+                         : (const int32_t*)(R->blob + slot_off[sc.seg_slot]);
+      x.ws_ids = R->ws_ids + req_sparse_base(R)[sc.sparse_index];
+    }
+    x.ids_out = R->ids_out ? R->ids_out + req_ids_base(R)[sc.col] : nullptr;
+    x.bucket_magic = sc.bucket_magic;
+    x.num_buckets = sc.num_buckets;
+    x.table_rows = sc.table_rows;
+    x.row_bytes = sc.row_bytes;
+    x.transform = sc.transform;
+    x.value_dtype = sc.value_dtype;
+    x.num_boundaries = sc.num_boundaries;
+    x.bnd_off = sc.bnd_off;
+    x.bnd_pool_off = sc.boundaries_offset;
+    x.stage_off = sc.stage_off;
+    x.combiner = sc.combiner;
+    cs.ctx[tid] = x;
+    if (sc.stage_off >= 0 && sc.stage_copy) {
+      fence_proxy_async();  // the region was read through the generic proxy by the last slab
+      bulk_g2s(s_tables + sc.stage_off, x.table, (uint32_t)sc.table_rows * (uint32_t)sc.row_bytes,
+               &cs.mbar_tbl);
+    }
+  } else if (tid >= 32 && tid - 32 < slab.num_bnds) {
+    const DevSlabBnd b = P.slab_bnds[slab.first_bnd + tid - 32];
+    fence_proxy_async();
+    bulk_g2s(s_bnd + b.smem_off, P.boundaries + b.pool_off, (uint32_t)b.floats * 4, &cs.mbar_bnd);
+  }
+  if (tid == 0 && slab.stage_bytes + slab.bnd_bytes > 0) {
+    // complete_tx of a copy issued above may precede this expect_tx: the phase cannot
+    // complete before this (the only) arrival
+    mbar_expect_tx(&cs.mbar_bnd, (uint32_t)slab.bnd_bytes);
+    mbar_expect_tx(&cs.mbar_tbl, (uint32_t)slab.stage_bytes);
+  }
+}
 
 // ---------------------------------------------------------------------------
 // DENSE slab: exactly one id per (column, row)
 // ---------------------------------------------------------------------------
-template <int VEC, bool CHECK>
-__device__ __forceinline__ void dense_tile(const DevPlan& P, const ReqHeader* __restrict__ R,
-                                           const DevSlab& slab, const Tile& tile,
-                                           TileSmem& sm) {
+// Is this column on the fast path: float32 input bucketized against boundaries staged in smem?
+__device__ __forceinline__ bool fast_bucketize(const ColCtx& c) {
+  return c.transform == RECOM_XFORM_BUCKETIZE && c.value_dtype == RECOM_F32 && c.bnd_off >= 0;
+}
+
+// phase 1: one warp per column, lanes along the batch (coalesced input reads). The smem id
+// slot receives the byte offset of the row inside the smem table region when the table is
+// staged, else the raw row id.
+template <bool CHECK>
+__device__ __forceinline__ void dense_phase1(const DevPlan& P, const ReqRegs& Q, const CtaShared& cs,
+                                             int num_cols, const Tile& tile, const float* s_bnd,
+                                             int32_t* s_ids) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t* slot_off = req_slot_offsets(R);
-  const int32_t* ids_base = req_ids_base(R);
   const int rows = tile.rows;
   const int64_t b0 = tile.row_begin;
-
-  // phase 1: one warp per column, lanes along the batch
-  for (int cl = warp; cl < slab.num_cols; cl += kWarps) {
-    const int ci = P.slab_cols[slab.first_col + cl];
-    const DevColumn c = P.cols[ci];
-    for (int r = lane; r < rows; r += 32) {
-      int32_t id = column_id(c, R->blob, slot_off, P.boundaries, b0 + r);
-      if (CHECK) id = checked_id(id, c.table_rows, R->status);
-      sm.ids[cl * kIdPitch + r] = id;
-      if (R->ids_out) R->ids_out[ids_base[ci] + b0 + r] = id;
+  for (int cl0 = warp; cl0 < num_cols; cl0 += 2 * kWarps) {
+    // a warp takes columns cl0 and cl0 + kWarps together: every global load of both is in
+    // flight before the first search step
+    const int ncol = cl0 + kWarps < num_cols ? 2 : 1;
+    const ColCtx& c0 = cs.ctx[cl0];
+    const ColCtx& c1 = cs.ctx[ncol == 2 ? cl0 + kWarps : cl0];
+    if (rows == kDenseTileRows && ncol == 2 && fast_bucketize(c0) && fast_bucketize(c1)) {
+      const float* in0 = (const float*)c0.values + b0;
+      const float* in1 = (const float*)c1.values + b0;
+      const float v[4] = {__ldg(in0 + lane), __ldg(in0 + lane + 32), __ldg(in1 + lane),
+                          __ldg(in1 + lane + 32)};
+      const int32_t nb[2] = {c0.num_boundaries, c1.num_boundaries};
+      const uint32_t bp[2] = {smem_u32(s_bnd + c0.bnd_off), smem_u32(s_bnd + c1.bnd_off)};
+      int32_t lo[4] = {0, 0, 0, 0};
+      // four upper_bound searches in lock step (see bucketize_n for why `half` serves both sides)
+      for (int32_t n = max(nb[0], nb[1]); n > 0; n >>= 1) {
+        const int32_t half = n >> 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int32_t idx = lo[k] + half;
+          const float b = lds_f32(bp[k >> 1] + 4u * (uint32_t)min(idx, nb[k >> 1] - 1));
+          const bool right = idx < nb[k >> 1] && !(v[k] < b);
+          lo[k] = right ? idx + 1 : lo[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const ColCtx& c = k < 2 ? c0 : c1;
+        const int cl = k < 2 ? cl0 : cl0 + kWarps;
+        const int r = lane + 32 * (k & 1);
+        int32_t id = lo[k];
+        if (CHECK) id = checked_id(id, c.table_rows, Q.status);
+        s_ids[cl * kIdPitch + r] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
+        if (c.ids_out) c.ids_out[b0 + r] = id;
+      }
+      continue;
+    }
+    for (int j = 0; j < ncol; ++j) {
+      const ColCtx& c = j ? c1 : c0;
+      const int cl = j ? cl0 + kWarps : cl0;
+      const float* bnd = c.bnd_off >= 0 ? s_bnd + c.bnd_off : P.boundaries + c.bnd_pool_off;
+      for (int r = lane; r < rows; r += 32) {
+        int32_t id = column_id(c, bnd, b0 + r);
+        if (CHECK) id = checked_id(id, c.table_rows, Q.status);
+        s_ids[cl * kIdPitch + r] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
+        if (c.ids_out) c.ids_out[b0 + r] = id;
+      }
     }
   }
-  __syncthreads();
+}
 
-  // phase 2: lane = chunk; rows_per_pass rows per warp pass
-  const int W = slab.num_chunks;
+// Pull the input lines of a later tile of the SAME dense slab into L2.
+__device__ __forceinline__ void prefetch_tile_inputs(const CtaShared& cs, int num_cols,
+                                                     const Tile& tile) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int cl = warp; cl < num_cols; cl += kWarps) {
+    const ColCtx& c = cs.ctx[cl];
+    const int es = (c.value_dtype == RECOM_I64 || c.value_dtype == RECOM_F64) ? 8 : 4;
+    const uint8_t* p = c.values + (int64_t)tile.row_begin * es;
+    const int bytes = (tile.rows + 1) * es;  // + 1: string offsets read one past
+    const uint8_t* line = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)127) + lane * 128;
+    if (line < p + bytes) prefetch_l2(line);
+  }
+}
+
+// phase 2: lane = chunk; 32 / W rows per warp pass; UNROLL independent rows in flight.
+template <int VEC, bool STAGED>
+__device__ __forceinline__ void dense_phase2(const ReqRegs& Q, const CtaShared& cs, int W,
+                                             const DevChunk& ch, const Tile& tile,
+                                             const uint8_t* s_tables, const int32_t* s_ids) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rpp = 32 / W;  // rows handled by one warp per pass
   const int sub = lane / W;
-  const int chunk = lane - sub * W;
-  if (sub < rpp) {
-    const DevChunk ch = P.chunks[slab.first_chunk + chunk];
-    const DevColumn& c = P.cols[ch.col];
-    const uint8_t* tbl = (const uint8_t*)req_tables(R)[c.table] + ch.table_byte;
-    const int64_t row_bytes = c.row_bytes;
-    const int32_t* ids = sm.ids + ch.col_local * kIdPitch;
-    uint8_t* outp = R->out + b0 * R->out_row_bytes + ch.out_byte;
-    const int64_t orb = R->out_row_bytes;
-    const int step = kWarps * rpp;
-    int r = warp * rpp + sub;
-    // 4 independent gathers in flight per lane
-    for (; r + 3 * step < rows; r += 4 * step) {
-      Chunk<VEC> v0, v1, v2, v3;
-      v0.load(tbl + (int64_t)ids[r] * row_bytes);
-      v1.load(tbl + (int64_t)ids[r + step] * row_bytes);
-      v2.load(tbl + (int64_t)ids[r + 2 * step] * row_bytes);
-      v3.load(tbl + (int64_t)ids[r + 3 * step] * row_bytes);
-      v0.store(outp + (int64_t)r * orb);
-      v1.store(outp + (int64_t)(r + step) * orb);
-      v2.store(outp + (int64_t)(r + 2 * step) * orb);
-      v3.store(outp + (int64_t)(r + 3 * step) * orb);
+  if (sub >= rpp) return;
+  const int rows = tile.rows;
+  const uint8_t* tbl;
+  int64_t row_bytes = 0;
+  if (STAGED) {
+    tbl = s_tables + ch.table_byte;
+  } else {
+    const ColCtx& c = cs.ctx[ch.col_local];
+    tbl = c.table + ch.table_byte;
+    row_bytes = c.row_bytes;
+  }
+  const int32_t* ids = s_ids + ch.col_local * kIdPitch;
+  const int64_t orb = Q.out_row_bytes;
+  const int step = kWarps * rpp;
+  int r = warp * rpp + sub;
+  uint8_t* outp = Q.out + ((int64_t)tile.row_begin + r) * orb + ch.out_byte;
+  const int64_t ostep = (int64_t)step * orb;
+  constexpr int UNROLL = 8;
+  for (; r + (UNROLL - 1) * step < rows; r += UNROLL * step) {
+    Chunk<VEC> v[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) {
+      const int32_t o = ids[r + k * step];
+      if (STAGED) v[k] = lds_chunk<VEC>(tbl + o);
+      else v[k].load(tbl + (int64_t)o * row_bytes);
     }
-    for (; r < rows; r += step) {
-      Chunk<VEC> v;
-      v.load(tbl + (int64_t)ids[r] * row_bytes);
-      v.store(outp + (int64_t)r * orb);
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) {
+      v[k].store(outp);
+      outp += ostep;
     }
   }
-  __syncthreads();  // ids are reused by the next tile
+  for (; r < rows; r += step) {
+    const int32_t o = ids[r];
+    Chunk<VEC> v;
+    if (STAGED) v = lds_chunk<VEC>(tbl + o);
+    else v.load(tbl + (int64_t)o * row_bytes);
+    v.store(outp);
+    outp += ostep;
+  }
 }
 
 // ---------------------------------------------------------------------------
 // SPARSE slab: row b owns ids [row_splits[b], row_splits[b+1])
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ const int32_t* column_row_splits(const DevColumn& c,
-                                                            const ReqHeader* R,
-                                                            const int64_t* slot_off) {
-  if (c.coo_index >= 0) return R->ws_row_splits + (int64_t)c.coo_index * (R->batch + 1);
-  return (const int32_t*)(R->blob + slot_off[c.seg_slot]);
+// phase 1: materialise the row ids of transformed columns for this row block (workspace).
+// One warp per column, so the dependent chains (row_splits -> offsets -> bytes -> hash) of
+// different columns overlap.
+template <bool CHECK>
+__device__ __forceinline__ void sparse_phase1(const DevPlan& P, const ReqRegs& Q, const CtaShared& cs,
+                                              int num_cols, const Tile& tile) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = tile.rows;
+  const int64_t b0 = tile.row_begin;
+  for (int cl = warp; cl < num_cols; cl += kWarps) {
+    const ColCtx& c = cs.ctx[cl];
+    const bool xform = c.transform != RECOM_XFORM_NONE;
+    if (!xform && !c.ids_out && !CHECK) continue;
+    const int32_t e0 = c.row_splits[b0], e1 = c.row_splits[b0 + rows];
+    const float* bnd = P.boundaries + c.bnd_pool_off;
+    for (int32_t e = e0 + lane; e < e1; e += 32) {
+      int32_t id = column_id(c, bnd, e);
+      if (CHECK) id = checked_id(id, c.table_rows, Q.status);
+      if (xform || CHECK) c.ws_ids[e] = id;
+      if (c.ids_out) c.ids_out[e] = id;
+    }
+  }
 }
 
 template <int VEC, bool BF16, bool CHECK>
-__device__ __forceinline__ void sparse_tile(const DevPlan& P, const ReqHeader* __restrict__ R,
-                                            const DevSlab& slab, const Tile& tile) {
+__device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const CtaShared& cs, int W,
+                                              const DevChunk& ch, const Tile& tile) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t* slot_off = req_slot_offsets(R);
-  const int32_t* ids_base = req_ids_base(R);
-  const int32_t* sparse_base = req_sparse_base(R);
   const int rows = tile.rows;
   const int64_t b0 = tile.row_begin;
-
-  // phase 1: materialise row ids of transformed columns for this row block
-  bool wrote = false;
-  for (int cl = 0; cl < slab.num_cols; ++cl) {
-    const int ci = P.slab_cols[slab.first_col + cl];
-    const DevColumn c = P.cols[ci];
-    const bool xform = c.transform != RECOM_XFORM_NONE;
-    if (!xform && !R->ids_out && !CHECK) continue;
-    const int32_t* rs = column_row_splits(c, R, slot_off);
-    const int32_t e0 = rs[b0], e1 = rs[b0 + rows];
-    int32_t* ws = R->ws_ids + sparse_base[c.sparse_index];
-    for (int32_t e = e0 + (int)threadIdx.x; e < e1; e += kThreads) {
-      int32_t id = column_id(c, R->blob, slot_off, P.boundaries, e);
-      if (CHECK) id = checked_id(id, c.table_rows, R->status);
-      if (xform || CHECK) ws[e] = id;
-      if (R->ids_out) R->ids_out[ids_base[ci] + e] = id;
-    }
-    wrote |= (xform || CHECK);
-  }
-  if (wrote) __syncthreads();  // block-scope visibility of the global writes above
-
-  // phase 2
-  const int W = slab.num_chunks;
   const int rpp = 32 / W;
   const int sub = lane / W;
-  const int chunk = lane - sub * W;
   if (sub >= rpp) return;
-  const DevChunk ch = P.chunks[slab.first_chunk + chunk];
-  const DevColumn& c = P.cols[ch.col];
-  const uint8_t* tbl = (const uint8_t*)req_tables(R)[c.table] + ch.table_byte;
+  const ColCtx& c = cs.ctx[ch.col_local];
+  const uint8_t* tbl = c.table + ch.table_byte;
   const int64_t row_bytes = c.row_bytes;
-  const int32_t* rs = column_row_splits(c, R, slot_off) + b0;
+  const int32_t* rs = c.row_splits + b0;
   const bool from_ws = (c.transform != RECOM_XFORM_NONE) || CHECK;
-  const int32_t* ids32 = from_ws ? R->ws_ids + sparse_base[c.sparse_index]
-                                 : (const int32_t*)(R->blob + slot_off[c.value_slot]);
+  const int32_t* ids32 = from_ws ? c.ws_ids : (const int32_t*)c.values;
   const bool ids64 = !from_ws && c.value_dtype == RECOM_I64;
   const long long* idsll = (const long long*)ids32;
-  uint8_t* outp = R->out + b0 * R->out_row_bytes + ch.out_byte;
+  uint8_t* outp = Q.out + b0 * Q.out_row_bytes + ch.out_byte;
   const int combiner = c.combiner;
+  auto id_at = [&](int32_t e) -> int64_t {
+    return ids64 ? (int64_t)idsll[e] : (int64_t)ids32[e];
+  };
+  constexpr int U = BF16 ? 4 : 8;  // independent row gathers in flight per lane
 
   for (int r = warp * rpp + sub; r < rows; r += kWarps * rpp) {
     const int32_t beg = rs[r], end = rs[r + 1];
     Acc<VEC, BF16> acc;
     acc.clear();
     int32_t e = beg;
-    for (; e + 3 < end; e += 4) {  // 4 independent row gathers in flight
-      int64_t i0, i1, i2, i3;
-      if (ids64) {
-        i0 = idsll[e]; i1 = idsll[e + 1]; i2 = idsll[e + 2]; i3 = idsll[e + 3];
-      } else {
-        i0 = ids32[e]; i1 = ids32[e + 1]; i2 = ids32[e + 2]; i3 = ids32[e + 3];
-      }
-      Chunk<VEC> v0, v1, v2, v3;
-      v0.load(tbl + i0 * row_bytes);
-      v1.load(tbl + i1 * row_bytes);
-      v2.load(tbl + i2 * row_bytes);
-      v3.load(tbl + i3 * row_bytes);
-      acc.add(v0); acc.add(v1); acc.add(v2); acc.add(v3);
+    for (; e + U - 1 < end; e += U) {
+      Chunk<VEC> v[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) v[k].load(tbl + id_at(e + k) * row_bytes);
+#pragma unroll
+      for (int k = 0; k < U; ++k) acc.add(v[k]);
     }
-    for (; e < end; ++e) {
-      const int64_t i0 = ids64 ? (int64_t)idsll[e] : (int64_t)ids32[e];
-      Chunk<VEC> v;
-      v.load(tbl + i0 * row_bytes);
-      acc.add(v);
+    if (U == 8 && e + 3 < end) {
+      Chunk<VEC> v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k].load(tbl + id_at(e + k) * row_bytes);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc.add(v[k]);
+      e += 4;
+    }
+    {
+      // up to 3 left: issue them together as well
+      Chunk<VEC> v[3];
+      const int left = end - e;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (k < left) v[k].load(tbl + id_at(e + k) * row_bytes);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (k < left) acc.add(v[k]);
     }
     const int32_t n = end - beg;
     if (n > 1 && combiner != RECOM_COMBINE_SUM) {
@@ -391,57 +631,228 @@ __device__ __forceinline__ void sparse_tile(const DevPlan& P, const ReqHeader* _
       if (n < 10) acc.mul(__fdiv_rn(1.0f, m));
       else acc.div(m);
     }
-    acc.pack().store(outp + (int64_t)r * R->out_row_bytes);
+    acc.pack().store(outp + (int64_t)r * Q.out_row_bytes);
   }
 }
 
 // ---------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------
-template <bool BF16, bool CHECK>
-__global__ void __launch_bounds__(kThreads, 4)
-fused_columns_kernel(const DevPlan P, ReqHeader* __restrict__ R) {
-  __shared__ TileSmem sm;
-  constexpr int ELEM = BF16 ? 2 : 4;
-  const Tile* tiles = req_tiles(R);
-  int t = blockIdx.x;
-  while (t < R->num_tiles) {
-    const Tile tile = tiles[t];
-    const DevSlab slab = P.slabs[tile.slab];
-    if (threadIdx.x == 0) sm.next_tile = atomicAdd(&R->tile_counter, 1);
-    if (slab.cls == kSlabDense) {
-      if (slab.vec_bytes == 16) dense_tile<16, CHECK>(P, R, slab, tile, sm);
-      else dense_tile<ELEM, CHECK>(P, R, slab, tile, sm);
-    } else {
-      if (slab.vec_bytes == 16) sparse_tile<16, BF16, CHECK>(P, R, slab, tile);
-      else sparse_tile<ELEM, BF16, CHECK>(P, R, slab, tile);
-      __syncthreads();
-    }
-    t = sm.next_tile;
-    __syncthreads();
+// Tile source of a CTA: first the shared pool of SPARSE tiles (long DRAM-latency chains:
+// start them early), then the CTA's own static run of DENSE tiles (consecutive row blocks
+// of one slab, so staged tables are reused), then the shared pool of left-over DENSE tiles.
+// Lives in thread 0. Returns a tile index or -1.
+struct TileCursor {
+  int phase;
+  int cur, cur_end;
+  int num_sparse, dyn_begin, num_tiles;
+  __device__ __forceinline__ void init(const ReqHeader* R) {
+    phase = 0;
+    cur = R->static_begin[blockIdx.x];
+    cur_end = R->static_begin[blockIdx.x + 1];
+    num_sparse = R->num_sparse_tiles;
+    dyn_begin = R->dyn_begin;
+    num_tiles = R->num_tiles;
   }
+  __device__ __forceinline__ int next(ReqHeader* R) {
+    if (phase == 0) {
+      if (num_sparse > 0) {
+        const int t = atomicAdd(&R->ctr_sparse, 1);
+        if (t < num_sparse) return t;
+      }
+      phase = 1;
+    }
+    if (phase == 1) {
+      if (cur < cur_end) return cur++;
+      phase = 2;
+    }
+    if (phase == 2) {
+      if (dyn_begin < num_tiles) {
+        const int t = dyn_begin + atomicAdd(&R->ctr_dense, 1);
+        if (t < num_tiles) return t;
+      }
+      phase = 3;
+    }
+    return -1;
+  }
+};
+
+// Optional per-CTA phase timing (thread 0's view, %globaltimer ns), compiled in only with
+// -DRECOM_PROFILE (make prof): slots are summed over the CTA's tiles and written to R->prof.
+#ifdef RECOM_PROFILE
+__device__ __forceinline__ uint64_t gtimer() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// phase slots count SM cycles (clock64: cheap, exact); slots 14 / 15 hold the CTA's start /
+// end in globaltimer ns
+#define PROF_DECL uint64_t prof_acc[16] = {0}; prof_acc[14] = gtimer(); uint64_t prof_last = clock64();
+#define PROF_T(i)                                   \
+  if (threadIdx.x == 0) {                           \
+    const uint64_t now_ = clock64();                \
+    prof_acc[i] += now_ - prof_last;                \
+    prof_last = now_;                               \
+  }
+#define PROF_COUNT(i) if (threadIdx.x == 0) prof_acc[i] += 1;
+#define PROF_END                                                        \
+  if (threadIdx.x == 0 && R->prof) {                                    \
+    prof_acc[15] = gtimer();                                            \
+    for (int i_ = 0; i_ < 16; ++i_) R->prof[blockIdx.x * 16 + i_] = prof_acc[i_]; \
+  }
+#else
+#define PROF_DECL
+#define PROF_T(i)
+#define PROF_COUNT(i)
+#define PROF_END
+#endif
+
+template <bool BF16, bool CHECK>
+__global__ void __launch_bounds__(kThreads, 3)
+fused_columns_kernel(const DevPlan P, ReqHeader* __restrict__ R) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ CtaShared cs;
+  constexpr int ELEM = BF16 ? 2 : 4;
+  uint8_t* s_tables = smem;
+  float* s_bnd = reinterpret_cast<float*>(smem + P.smem_off_bnd);
+  int32_t* s_ids = reinterpret_cast<int32_t*>(smem + P.smem_off_ids);
+  const int ids_buf = P.smem_ids_cols * kIdPitch;
+  const Tile* tiles = R->tiles;
+  ReqRegs Q;
+  Q.out = R->out;
+  Q.out_row_bytes = R->out_row_bytes;
+  Q.status = R->status;
+
+  PROF_DECL
+  // Thread 0 claims tile indices three steps ahead (the atomic's latency is never waited
+  // for) and copies the Tile record two steps ahead into cs.next with cp.async.
+  TileCursor cursor;
+  int pending = -1;
+  if (threadIdx.x == 0) {
+    mbar_init(&cs.mbar_bnd, 1);
+    mbar_init(&cs.mbar_tbl, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cursor.init(R);
+    const int i0 = cursor.next(R);
+    const int i1 = i0 >= 0 ? cursor.next(R) : -1;
+    pending = i1 >= 0 ? cursor.next(R) : -1;
+    Tile none;
+    none.slab = -1;
+    none.row_begin = none.rows = none.pad = 0;
+    cs.next[0] = i0 >= 0 ? tiles[i0] : none;
+    cs.next[1] = i1 >= 0 ? tiles[i1] : none;
+  }
+  __syncthreads();
+  Tile tile = cs.next[0];   // this tile
+  Tile tile1 = cs.next[1];  // the next one
+  __syncthreads();          // both read before thread 0 reuses the slots
+
+  PROF_T(13)
+  int cur_slab = -1;
+  uint32_t stage_parity = 1;  // parity of the phase completed by the latest staging
+  DevSlab slab;
+  DevChunk ch;
+  slab.cls = kSlabSparse;
+  slab.num_cols = slab.num_chunks = 0;
+  slab.vec_bytes = 16;
+  slab.stage_bytes = slab.bnd_bytes = 0;
+  ch.col = ch.col_local = ch.table_byte = ch.out_byte = 0;
+
+  for (int k = 0; tile.slab >= 0; ++k) {
+    const int buf = k & 1;
+    if (threadIdx.x == 0) {
+      if (pending >= 0) {
+        cp_async_16(&cs.next[buf], tiles + pending);
+        pending = cursor.next(R);
+      } else {
+        cs.next[buf].slab = -1;
+      }
+    }
+    PROF_T(0)
+    PROF_COUNT(11)
+    if (tile.slab != cur_slab) {
+      // every warp has finished with the previous slab's context, tables and boundaries
+      __syncthreads();
+      slab = P.slabs[tile.slab];
+      cur_slab = tile.slab;
+      if (slab.stage_bytes + slab.bnd_bytes > 0) stage_parity ^= 1;
+      enter_slab(P, R, slab, cs, s_tables, s_bnd);
+      {
+        const int lane = threadIdx.x & 31;
+        const int chunk = lane % slab.num_chunks;
+        ch = P.chunks[slab.first_chunk + chunk];
+      }
+      __syncthreads();  // the column contexts are visible
+      PROF_COUNT(12)
+    }
+    PROF_T(1)
+    if (slab.cls == kSlabSparse) {
+      sparse_phase1<CHECK>(P, Q, cs, slab.num_cols, tile);
+      PROF_T(8)
+      if (threadIdx.x == 0) cp_async_wait_all();
+      __syncthreads();  // block-scope visibility of the workspace ids (and of cs.next)
+      PROF_T(9)
+      if (slab.vec_bytes == 16) sparse_phase2<16, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile);
+      else sparse_phase2<ELEM, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile);
+      PROF_T(10)
+    } else {
+      int32_t* ids = s_ids + buf * ids_buf;
+      if (slab.bnd_bytes > 0) mbar_wait(&cs.mbar_bnd, stage_parity);
+      PROF_T(2)
+      dense_phase1<CHECK>(P, Q, cs, slab.num_cols, tile, s_bnd, ids);
+      PROF_T(3)
+      if (threadIdx.x == 0) cp_async_wait_all();
+      __syncthreads();  // the only barrier of a DENSE tile: ids (and cs.next) are visible
+      PROF_T(4)
+      if (slab.cls == kSlabDenseStaged) {
+        mbar_wait(&cs.mbar_tbl, stage_parity);
+        PROF_T(5)
+        if (slab.vec_bytes == 16) dense_phase2<16, true>(Q, cs, slab.num_chunks, ch, tile, s_tables, ids);
+        else dense_phase2<ELEM, true>(Q, cs, slab.num_chunks, ch, tile, s_tables, ids);
+      } else {
+        if (slab.vec_bytes == 16) dense_phase2<16, false>(Q, cs, slab.num_chunks, ch, tile, s_tables, ids);
+        else dense_phase2<ELEM, false>(Q, cs, slab.num_chunks, ch, tile, s_tables, ids);
+      }
+      PROF_T(6)
+    }
+    const Tile tile2 = cs.next[buf];
+    if (tile2.slab == cur_slab && slab.cls != kSlabSparse)
+      prefetch_tile_inputs(cs, slab.num_cols, tile2);
+    PROF_T(7)
+    tile = tile1;
+    tile1 = tile2;
+  }
+  PROF_END
 }
 
-int fused_kernel_max_ctas_per_sm(bool bf16) {
+template <bool BF16, bool CHECK>
+static int configure_one(int smem_bytes) {
+  auto fn = fused_columns_kernel<BF16, CHECK>;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
+      cudaSuccess)
+    return -1;
   int n = 0;
-  if (bf16)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_columns_kernel<true, false>,
-                                                  kThreads, 0);
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_columns_kernel<false, false>,
-                                                  kThreads, 0);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kThreads, smem_bytes) != cudaSuccess)
+    return -1;
   return n;
+}
+
+int fused_kernel_configure(bool bf16, int smem_bytes) {
+  const int a = bf16 ? configure_one<true, false>(smem_bytes) : configure_one<false, false>(smem_bytes);
+  const int b = bf16 ? configure_one<true, true>(smem_bytes) : configure_one<false, true>(smem_bytes);
+  return a < b ? a : b;
 }
 
 void launch_fused_columns(const DevPlan& plan, ReqHeader* d_req, int grid, bool bf16,
                           cudaStream_t stream) {
   const bool check = plan.check_ids != 0;
+  const size_t sm = (size_t)plan.smem_bytes;
   if (bf16) {
-    if (check) fused_columns_kernel<true, true><<<grid, kThreads, 0, stream>>>(plan, d_req);
-    else fused_columns_kernel<true, false><<<grid, kThreads, 0, stream>>>(plan, d_req);
+    if (check) fused_columns_kernel<true, true><<<grid, kThreads, sm, stream>>>(plan, d_req);
+    else fused_columns_kernel<true, false><<<grid, kThreads, sm, stream>>>(plan, d_req);
   } else {
-    if (check) fused_columns_kernel<false, true><<<grid, kThreads, 0, stream>>>(plan, d_req);
-    else fused_columns_kernel<false, false><<<grid, kThreads, 0, stream>>>(plan, d_req);
+    if (check) fused_columns_kernel<false, true><<<grid, kThreads, sm, stream>>>(plan, d_req);
+    else fused_columns_kernel<false, false><<<grid, kThreads, sm, stream>>>(plan, d_req);
   }
 }
 
@@ -541,7 +952,7 @@ fingerprint64_kernel(const uint8_t* __restrict__ bytes, const int32_t* __restric
        i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t o0 = offsets[i], o1 = offsets[i + 1];
     const uint64_t h = fh::fingerprint64(bytes + o0, (uint32_t)(o1 - o0));
-    out[i] = num_buckets ? h % num_buckets : h;
+    out[i] = num_buckets ? h % num_buckets : h;  // plain 64-bit modulo: checks mod_bucket
   }
 }
 

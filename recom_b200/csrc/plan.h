@@ -15,16 +15,28 @@ namespace recom {
 constexpr int kThreads = 256;          // threads per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxChunks = 32;         // a slab is at most one warp wide
-constexpr int kDenseTileRows = 128;    // rows per DENSE tile
-constexpr int kSparseTileRows = 64;    // rows per SPARSE tile
+constexpr int kDenseTileRows = 64;     // rows per DENSE tile (ids of one tile live in smem)
 constexpr int kIdPitch = kDenseTileRows + 1;  // smem pitch (bank-conflict free)
+constexpr int kSparseTileRowsL2 = 32;  // rows per SPARSE tile, tables that fit in L2
+constexpr int kSparseTileRowsHbm = 8;  // rows per SPARSE tile, HBM-resident tables
+constexpr int64_t kHbmTableBytes = 32ll << 20;  // a table beyond this is "HBM resident"
+// shared-memory staging limits (per CTA)
+constexpr int kStageTableRows = 256;       // only tables with few rows are staged
+constexpr int kStageTableBytes = 16 << 10; // ... and at most this large
+constexpr int kStageSlabBytes = 56 << 10;  // staged tables of one slab
+constexpr int kStageBndFloats = 2048;      // staged bucket boundaries of one slab
 
-enum SlabClass : int32_t { kSlabDense = 0, kSlabSparse = 1 };
+enum SlabClass : int32_t {
+  kSlabDenseStaged = 0,  // DENSE lookups, every table staged in shared memory
+  kSlabDense = 1,        // DENSE lookups, rows gathered from global memory
+  kSlabSparse = 2        // GATHER_SCATTER / SEGMENT lookups
+};
 
 // Per-column constants, device resident for the life of the plan.
 struct DevColumn {
   int64_t table_rows;
   int64_t num_buckets;
+  uint64_t bucket_magic;  // floor(2^64 / num_buckets): multiply-high modulo
   int32_t table;          // index into the request's table pointer array
   int32_t dim;
   int32_t row_bytes;      // dim * sizeof(table element)
@@ -36,7 +48,7 @@ struct DevColumn {
   int32_t seg_format;
   int32_t seg_stride;
   int32_t combiner;
-  int32_t boundaries_offset;  // into the (deduplicated) boundary pool
+  int32_t boundaries_offset;  // into the (deduplicated, 16-byte aligned) boundary pool
   int32_t num_boundaries;
   int32_t sparse_index;   // rank among non-DENSE columns, -1 for DENSE
   int32_t coo_index;      // rank among COO columns, -1 otherwise
@@ -51,6 +63,61 @@ struct DevChunk {
   int32_t out_byte;    // byte offset of this chunk inside an output row
 };
 
+// A column's membership in a slab, with everything static the kernel needs about the
+// column, so that a CTA entering a slab resolves a column with one read of this record
+// plus one read of the request's slot / table arrays.
+struct DevSlabCol {
+  int32_t col;         // global column index
+  int32_t stage_off;   // byte offset of its table in the smem table region, -1: global
+  int32_t stage_copy;  // 1 if this entry issues the bulk copy (shared tables copy once)
+  int32_t bnd_off;     // float offset of its boundaries in the smem region, -1: global
+  int32_t transform;
+  int32_t value_dtype;
+  int32_t value_slot;
+  int32_t bytes_slot;
+  int32_t table;       // index into the request's table pointer array
+  int32_t row_bytes;
+  int32_t table_rows;  // < 2^31 (validated)
+  int32_t num_boundaries;
+  int32_t boundaries_offset;  // float offset in the boundary pool
+  int32_t num_buckets;        // < 2^31 (validated)
+  uint64_t bucket_magic;
+  int32_t seg_slot;     // non-DENSE only
+  int32_t coo_index;    // rank among COO columns, -1 otherwise
+  int32_t sparse_index; // rank among non-DENSE columns, -1 for DENSE
+  int32_t combiner;
+};
+
+// The same column resolved against one request; lives in shared memory while a CTA works
+// on the slab (built once per slab change, one thread per column).
+struct ColCtx {
+  const uint8_t* values;      // blob + slot_offsets[value_slot]
+  const uint8_t* bytes;       // STR payload, else null
+  const uint8_t* table;       // request table pointer
+  const int32_t* row_splits;  // non-DENSE only
+  int32_t* ws_ids;            // non-DENSE only: transformed ids of this column
+  int32_t* ids_out;           // parity hook: where this column's ids go, or null
+  uint64_t bucket_magic;
+  int32_t num_buckets;
+  int32_t table_rows;
+  int32_t row_bytes;
+  int32_t transform;
+  int32_t value_dtype;
+  int32_t num_boundaries;
+  int32_t bnd_off;            // smem float offset, -1: read the pool in global memory
+  int32_t bnd_pool_off;
+  int32_t stage_off;          // smem byte offset of the staged table, -1: global
+  int32_t combiner;
+};
+
+// A distinct boundary set staged by a slab.
+struct DevSlabBnd {
+  int32_t pool_off;    // float offset in the boundary pool (multiple of 4)
+  int32_t floats;      // padded to a multiple of 4
+  int32_t smem_off;    // float offset in the smem boundary region
+  int32_t pad;
+};
+
 // A slab: a group of columns whose output slices are adjacent in the concat row
 // and together at most kMaxChunks chunks wide. Work is tiled as (slab, row block).
 struct DevSlab {
@@ -61,6 +128,10 @@ struct DevSlab {
   int32_t first_col;    // into the slab_cols array
   int32_t vec_bytes;    // 16, or the element size when unaligned
   int32_t tile_rows;
+  int32_t stage_bytes;  // total bytes of staged tables
+  int32_t first_bnd;    // into the slab_bnds array
+  int32_t num_bnds;
+  int32_t bnd_bytes;    // total bytes of staged boundaries
   int32_t pad;
 };
 
@@ -68,12 +139,18 @@ struct DevPlan {
   const DevColumn* cols;
   const DevSlab* slabs;
   const DevChunk* chunks;
-  const int32_t* slab_cols;
+  const DevSlabCol* slab_cols;
+  const DevSlabBnd* slab_bnds;
   const float* boundaries;
   int32_t num_cols;
   int32_t num_slabs;
   int32_t elem_bytes;   // 4 (fp32) or 2 (bf16): table and output element size
   int32_t check_ids;
+  // dynamic shared memory layout (bytes from the start)
+  int32_t smem_off_bnd;
+  int32_t smem_off_ids;
+  int32_t smem_ids_cols;  // columns per ids buffer (max columns of a DENSE slab)
+  int32_t smem_bytes;
 };
 
 // A unit of work pulled by a persistent CTA.
@@ -87,7 +164,8 @@ struct Tile {
 // Per-request argument block. Built on the host in pinned memory, uploaded with
 // one cudaMemcpyAsync into the workspace, read by every kernel of the request
 // (replaces the reference's KnlArgs + SymbolResults uploads,
-// cuda_emitter.cc:2182-2232).
+// cuda_emitter.cc:2182-2232). The tile table is NOT part of it: it depends only
+// on the batch size and is cached on the device by the plan.
 struct ReqHeader {
   const uint8_t* blob;
   uint8_t* out;
@@ -95,21 +173,26 @@ struct ReqHeader {
   int32_t* status;        // may be null
   int32_t* ws_ids;        // workspace: transformed ids of non-DENSE columns
   int32_t* ws_row_splits; // workspace: row_splits built from COO columns
+  const Tile* tiles;      // device tile table of this batch size
+  const int32_t* static_begin;  // [grid + 1] static tile range of every CTA
+  uint64_t* prof;         // profiling builds only (make prof): [grid, 16] phase timers, else null
   int64_t batch;
   int64_t out_row_bytes;
+  // schedule: tiles [0, num_sparse_tiles) are pulled through ctr_sparse, then each
+  // CTA walks its static range, then tiles [dyn_begin, num_tiles) through ctr_dense
   int32_t num_tiles;
-  int32_t tile_counter;   // dynamic scheduler; starts at gridDim.x
+  int32_t num_sparse_tiles;
+  int32_t dyn_begin;
+  int32_t ctr_sparse;
+  int32_t ctr_dense;
   int32_t num_coo;        // number of COO columns
-  int32_t pad;
   // byte offsets from the start of this block
   uint32_t off_slot_offsets;  // int64[num_slots]
   uint32_t off_tables;        // const void*[num_tables]
   uint32_t off_ids_base;      // int32[num_cols + 1] prefix of ids per column
   uint32_t off_sparse_base;   // int32[num_sparse + 1] prefix of ids, non-DENSE only
-  uint32_t off_tiles;         // Tile[num_tiles]
   uint32_t off_coo_cols;      // int32[num_coo] column index of each COO column
   uint32_t total_bytes;
-  uint32_t pad2;
 };
 
 __host__ __device__ inline const int64_t* req_slot_offsets(const ReqHeader* r) {
@@ -127,10 +210,6 @@ __host__ __device__ inline const int32_t* req_ids_base(const ReqHeader* r) {
 __host__ __device__ inline const int32_t* req_sparse_base(const ReqHeader* r) {
   return reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(r) +
                                           r->off_sparse_base);
-}
-__host__ __device__ inline const Tile* req_tiles(const ReqHeader* r) {
-  return reinterpret_cast<const Tile*>(reinterpret_cast<const uint8_t*>(r) +
-                                       r->off_tiles);
 }
 __host__ __device__ inline const int32_t* req_coo_cols(const ReqHeader* r) {
   return reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(r) +
@@ -151,6 +230,7 @@ void launch_segment_ids_to_row_splits(const int64_t* coo, int64_t nnz, int32_t s
                                       cudaStream_t stream);
 void launch_fingerprint64(const uint8_t* bytes, const int32_t* offsets, int64_t n,
                           int64_t num_buckets, uint64_t* out, cudaStream_t stream);
-int fused_kernel_max_ctas_per_sm(bool bf16);
+// configures the dynamic shared memory of the fused kernel; returns resident CTAs per SM
+int fused_kernel_configure(bool bf16, int smem_bytes);
 
 }  // namespace recom
