@@ -84,6 +84,7 @@ struct TileTable {
   int grid = 1;
   int num_sparse = 0;
   int dyn_begin = 0;
+  int sparse_first = 0;               // CTAs [0, sparse_first) start with the sparse pool
   void* d_block = nullptr;            // device copy: tiles, then static_begin (cached tables only)
   ~TileTable() {
     if (d_block) cudaFree(d_block);
@@ -285,7 +286,8 @@ void build_layout(recom_plan* p) {
     s.first_chunk = (int32_t)p->chunks.size();
     s.first_col = (int32_t)p->slab_cols.size();
     s.first_bnd = (int32_t)p->slab_bnds.size();
-    s.tile_rows = cls == kSlabSparse ? kSparseTileRowsL2 : kDenseTileRows;
+    s.first_bnd_pool = -1;
+    s.tile_rows = cls == kSlabSparse ? kSparseTileRowsL2 : kPoolTileRows;
     p->slabs.push_back(s);
   };
   // smem offset of a table already staged by the open slab, or -1
@@ -366,6 +368,7 @@ void build_layout(recom_plan* p) {
           sb.floats = floats;
           sb.smem_off = s.bnd_bytes / 4;
           p->slab_bnds.push_back(sb);
+          if (s.num_bnds == 0) s.first_bnd_pool = pool_off;
           s.num_bnds++;
           s.bnd_bytes += floats * 4;
           sc.bnd_off = sb.smem_off;
@@ -397,7 +400,13 @@ void build_layout(recom_plan* p) {
   p->dev.smem_off_bnd = (int32_t)align_up((size_t)max_stage, 128);
   p->dev.smem_off_ids = p->dev.smem_off_bnd + (int32_t)align_up((size_t)max_bnd, 128);
   p->dev.smem_ids_cols = max_cols;
-  p->dev.smem_bytes = p->dev.smem_off_ids + 2 * max_cols * kIdPitch * 4;
+  p->dev.smem_bytes = p->dev.smem_off_ids + max_cols * kIdPitch * 4;
+  // a SPARSE tile stages its row_splits and ids in the same memory: room for 16 ids per row
+  for (const DevSlab& s : p->slabs)
+    if (s.cls == kSlabSparse) {
+      const int need = s.num_cols * (s.tile_rows + 1 + s.tile_rows * 16 + 4) * 4;
+      p->dev.smem_bytes = std::max(p->dev.smem_bytes, std::min(need, 48 << 10));
+    }
 
   // scheduling order: multi-hot slabs first (their tiles chase several dependent DRAM
   // round trips), widest rows first; then the dense slabs in concat order.
@@ -420,58 +429,108 @@ void build_layout(recom_plan* p) {
   for (auto& o : order2) p->slab_order.push_back(o.second);
 }
 
-// Schedule of a batch size: SPARSE tiles in a shared pool (heavy first); DENSE tiles in
-// slab-major order, the first (1 - pool_frac) of them split into one contiguous static run
-// per CTA (equal output bytes), the rest in a second shared pool. Tile rows shrink for
-// small batches so that every CTA has work.
+// Schedule of a batch size.
+//   * SPARSE tiles go to a shared pool (heavy slabs first).
+//   * The CTAs are split into "sparse first" CTAs (a share proportional to the estimated
+//     cost of the SPARSE tiles) and dense CTAs. Every dense CTA owns ONE static macro tile:
+//     up to kMaxTileRows consecutive rows of one slab, so the slab's staged tables, the
+//     column contexts and the input latency are paid once per CTA. Dense CTAs are
+//     apportioned to the DENSE slabs by output bytes.
+//   * What the macro tiles leave over (about pool_frac of the rows) goes to a second shared
+//     pool of small tiles that evens out the finish.
+// Layout of `tiles`: [sparse pool | static tiles (CTA order) | dense pool].
 std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
-  const int target_ctas = p->num_sms * p->ctas_per_sm;
+  const int cap_ctas = p->num_sms * p->ctas_per_sm;
   auto tt = std::make_shared<TileTable>();
-  int dense_rows = kDenseTileRows;
-  auto count_dense = [&](int dr) {
-    int64_t t = 0;
-    for (const DevSlab& s : p->slabs)
-      if (s.cls != kSlabSparse) t += (B + dr - 1) / dr;
-    return t;
+  auto push = [&](std::vector<Tile>& v, int s, int64_t b, int64_t rows) {
+    Tile t;
+    t.slab = s;
+    t.row_begin = (int32_t)b;
+    t.rows = (int32_t)rows;
+    t.pad = 0;
+    v.push_back(t);
   };
-  while (dense_rows > 16 && count_dense(dense_rows) < 2 * (int64_t)target_ctas) dense_rows /= 2;
-  auto push = [&](int s, int tr) {
-    for (int64_t b = 0; b < B; b += tr) {
-      Tile t;
-      t.slab = s;
-      t.row_begin = (int32_t)b;
-      t.rows = (int32_t)std::min<int64_t>(tr, B - b);
-      t.pad = 0;
-      tt->tiles.push_back(t);
-    }
-  };
-  for (int s : p->slab_order)
-    if (p->slabs[s].cls == kSlabSparse) push(s, p->slabs[s].tile_rows);
-  tt->num_sparse = (int)tt->tiles.size();
-  for (int s : p->slab_order)
-    if (p->slabs[s].cls != kSlabSparse) push(s, dense_rows);
-  const int num_tiles = (int)tt->tiles.size();
-  const int num_dense = num_tiles - tt->num_sparse;
-  tt->grid = std::max(1, std::min(num_tiles, target_ctas));
-  tt->static_begin.assign(tt->grid + 1, tt->num_sparse);
-  int num_static = 0;
-  if (num_dense >= 3 * tt->grid) num_static = (int)((1.0 - p->pool_frac) * num_dense);
-  if (num_static > 0) {
-    std::vector<double> cum(num_static + 1, 0.0);
-    for (int i = 0; i < num_static; ++i) {
-      const Tile& t = tt->tiles[tt->num_sparse + i];
-      const DevSlab& sl = p->slabs[t.slab];
-      cum[i + 1] = cum[i] + (double)t.rows * sl.num_chunks * sl.vec_bytes;
-    }
-    int cursor = 0;
-    for (int c = 0; c < tt->grid; ++c) {
-      tt->static_begin[c] = tt->num_sparse + cursor;
-      const double want = cum[num_static] * (c + 1) / tt->grid;
-      while (cursor < num_static && 0.5 * (cum[cursor] + cum[cursor + 1]) < want) ++cursor;
-    }
-    tt->static_begin[tt->grid] = tt->num_sparse + num_static;
+  // sparse pool
+  double sparse_cost = 0, dense_cost = 0;
+  for (int s : p->slab_order) {
+    const DevSlab& sl = p->slabs[s];
+    if (sl.cls != kSlabSparse) continue;
+    for (int64_t b = 0; b < B; b += sl.tile_rows)
+      push(tt->tiles, s, b, std::min<int64_t>(sl.tile_rows, B - b));
+    // guess: 5 ids per row, latency-bound gathers weigh 3x their bytes
+    sparse_cost += (double)B * sl.num_chunks * sl.vec_bytes * 5.0 * 3.0;
   }
-  tt->dyn_begin = tt->num_sparse + num_static;
+  tt->num_sparse = (int)tt->tiles.size();
+  std::vector<int> dense;
+  for (int s : p->slab_order)
+    if (p->slabs[s].cls != kSlabSparse) {
+      dense.push_back(s);
+      dense_cost += (double)B * p->slabs[s].num_chunks * p->slabs[s].vec_bytes;
+    }
+  // grid: never more CTAs than 32-row units of work
+  int64_t units = tt->num_sparse;
+  for (size_t i = 0; i < dense.size(); ++i) units += (B + 31) / 32;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cap_ctas, units));
+  tt->grid = grid;
+  int sparse_ctas = 0;
+  if (tt->num_sparse > 0 && !dense.empty()) {
+    sparse_ctas = (int)(grid * sparse_cost / (sparse_cost + dense_cost) + 0.5);
+    sparse_ctas = std::max(1, std::min({sparse_ctas, grid - 1, tt->num_sparse}));
+  } else if (tt->num_sparse > 0) {
+    sparse_ctas = grid;
+  }
+  tt->sparse_first = sparse_ctas;
+  const int dense_ctas = grid - sparse_ctas;
+  // apportion the dense CTAs to the dense slabs by cost (largest remainder)
+  std::vector<int> n_ctas(dense.size(), 0);
+  if (dense_ctas > 0 && !dense.empty()) {
+    std::vector<std::pair<double, int>> rem;
+    int given = 0;
+    for (size_t i = 0; i < dense.size(); ++i) {
+      const DevSlab& sl = p->slabs[dense[i]];
+      const double share = dense_ctas * ((double)B * sl.num_chunks * sl.vec_bytes) / dense_cost;
+      n_ctas[i] = (int)share;
+      given += n_ctas[i];
+      rem.push_back({-(share - n_ctas[i]), (int)i});
+    }
+    std::sort(rem.begin(), rem.end());
+    for (int k = 0; given < dense_ctas && k < (int)rem.size(); ++k, ++given) n_ctas[rem[k].second]++;
+  }
+  // static macro tiles, then the pool
+  std::vector<Tile> statics, pool;
+  int pool_rows = kPoolTileRows;
+  {
+    // small batches: shrink pool tiles until every CTA can have one
+    int64_t est = 0;
+    for (size_t i = 0; i < dense.size(); ++i) est += (B + pool_rows - 1) / pool_rows;
+    while (pool_rows > 16 && est < grid) {
+      pool_rows /= 2;
+      est = 0;
+      for (size_t i = 0; i < dense.size(); ++i) est += (B + pool_rows - 1) / pool_rows;
+    }
+  }
+  for (size_t i = 0; i < dense.size(); ++i) {
+    int64_t static_rows = 0;
+    if (n_ctas[i] > 0) {
+      int64_t per = (int64_t)((1.0 - p->pool_frac) * (double)B / n_ctas[i]);
+      per = std::min<int64_t>(per / 32 * 32, kMaxTileRows);
+      if (per >= 64) {
+        for (int c = 0; c < n_ctas[i]; ++c) push(statics, dense[i], c * per, per);
+        static_rows = per * n_ctas[i];
+      }
+    }
+    for (int64_t b = static_rows; b < B; b += pool_rows)
+      push(pool, dense[i], b, std::min<int64_t>(pool_rows, B - b));
+  }
+  // CTA c >= sparse_ctas owns static tile (c - sparse_ctas), if there is one
+  tt->static_begin.assign(grid + 1, 0);
+  for (int c = 0; c <= grid; ++c) {
+    const int k = std::max(0, std::min((int)statics.size(), c - sparse_ctas));
+    tt->static_begin[c] = tt->num_sparse + k;
+  }
+  tt->tiles.insert(tt->tiles.end(), statics.begin(), statics.end());
+  tt->dyn_begin = (int)tt->tiles.size();
+  tt->tiles.insert(tt->tiles.end(), pool.begin(), pool.end());
   return tt;
 }
 
@@ -774,8 +833,8 @@ static size_t arg_block_bytes(const recom_plan* p, size_t sched_bytes) {
 }
 
 static size_t max_sched_bytes(const recom_plan* p, int64_t batch) {
-  // smallest tile is 8 rows (HBM-resident multi-hot) resp. 16 rows (dense)
-  const size_t tiles = p->slabs.size() * (size_t)((batch + 7) / 8) + 1;
+  // smallest tile is 8 rows (HBM-resident multi-hot) resp. 16 rows (dense pool)
+  const size_t tiles = p->slabs.size() * (size_t)((batch + 7) / 8 + 1) + 1;
   return align_up(tiles * sizeof(Tile), 16) +
          align_up(((size_t)p->num_sms * p->ctas_per_sm + 2) * 4, 16);
 }
@@ -867,6 +926,7 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   hdr->num_tiles = (int32_t)tt->tiles.size();
   hdr->num_sparse_tiles = tt->num_sparse;
   hdr->dyn_begin = tt->dyn_begin;
+  hdr->sparse_first_ctas = tt->sparse_first;
   hdr->ctr_sparse = 0;
   hdr->ctr_dense = 0;
   hdr->num_coo = (int32_t)p->coo_cols.size();

@@ -338,12 +338,15 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-// Static shared state of a CTA (the dynamic part holds tables | boundaries | ids).
+// Static shared state of a CTA. The dynamic part holds, for a DENSE slab,
+// [staged tables | staged boundaries | ids of the tile]; a SPARSE tile reuses all of it for
+// the tile's row_splits and row ids.
 struct __align__(16) CtaShared {
   Tile next[2];            // the tile two steps ahead (slab < 0: none), double buffered
   uint64_t mbar_bnd;       // boundaries of the staged slab have landed
   uint64_t mbar_tbl;       // tables of the staged slab have landed
   ColCtx ctx[kMaxChunks];  // the columns of the slab the CTA is working on
+  int32_t sp_cnt[kMaxChunks];  // SPARSE tile: ids of the tile per column, -1: not staged
 };
 
 // Request-wide values every tile needs, read once per CTA.
@@ -359,7 +362,7 @@ struct ReqRegs {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void enter_slab(const DevPlan& P, const ReqHeader* __restrict__ R,
                                            const DevSlab& slab, CtaShared& cs, uint8_t* s_tables,
-                                           float* s_bnd) {
+                                           float* s_bnd, bool keep_bnd) {
   const int tid = threadIdx.x;
   if (tid < slab.num_cols) {
     const DevSlabCol sc = P.slab_cols[slab.first_col + tid];
@@ -394,15 +397,16 @@ __device__ __forceinline__ void enter_slab(const DevPlan& P, const ReqHeader* __
       bulk_g2s(s_tables + sc.stage_off, x.table, (uint32_t)sc.table_rows * (uint32_t)sc.row_bytes,
                &cs.mbar_tbl);
     }
-  } else if (tid >= 32 && tid - 32 < slab.num_bnds) {
+  } else if (!keep_bnd && tid >= 32 && tid - 32 < slab.num_bnds) {
     const DevSlabBnd b = P.slab_bnds[slab.first_bnd + tid - 32];
     fence_proxy_async();
     bulk_g2s(s_bnd + b.smem_off, P.boundaries + b.pool_off, (uint32_t)b.floats * 4, &cs.mbar_bnd);
   }
-  if (tid == 0 && slab.stage_bytes + slab.bnd_bytes > 0) {
+  const int bnd_bytes = keep_bnd ? 0 : slab.bnd_bytes;
+  if (tid == 0 && slab.stage_bytes + bnd_bytes > 0) {
     // complete_tx of a copy issued above may precede this expect_tx: the phase cannot
     // complete before this (the only) arrival
-    mbar_expect_tx(&cs.mbar_bnd, (uint32_t)slab.bnd_bytes);
+    mbar_expect_tx(&cs.mbar_bnd, (uint32_t)bnd_bytes);
     mbar_expect_tx(&cs.mbar_tbl, (uint32_t)slab.stage_bytes);
   }
 }
@@ -413,6 +417,26 @@ __device__ __forceinline__ void enter_slab(const DevPlan& P, const ReqHeader* __
 // Is this column on the fast path: float32 input bucketized against boundaries staged in smem?
 __device__ __forceinline__ bool fast_bucketize(const ColCtx& c) {
   return c.transform == RECOM_XFORM_BUCKETIZE && c.value_dtype == RECOM_F32 && c.bnd_off >= 0;
+}
+
+// K upper_bound searches in lock step over boundaries in shared memory; search k uses the
+// boundary set k / (K / 2) (see bucketize_n for why `half` serves both sides of a probe).
+template <int K>
+__device__ __forceinline__ void search_smem(const uint32_t (&bp)[2], const int32_t (&nb)[2],
+                                            const float (&v)[K], int32_t (&lo)[K]) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) lo[k] = 0;
+  for (int32_t n = max(nb[0], nb[1]); n > 0; n >>= 1) {
+    const int32_t half = n >> 1;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      constexpr int H = K / 2;
+      const int32_t idx = lo[k] + half;
+      const float b = lds_f32(bp[k / H] + 4u * (uint32_t)min(idx, nb[k / H] - 1));
+      const bool right = idx < nb[k / H] && !(v[k] < b);
+      lo[k] = right ? idx + 1 : lo[k];
+    }
+  }
 }
 
 // phase 1: one warp per column, lanes along the batch (coalesced input reads). The smem id
@@ -431,34 +455,38 @@ __device__ __forceinline__ void dense_phase1(const DevPlan& P, const ReqRegs& Q,
     const int ncol = cl0 + kWarps < num_cols ? 2 : 1;
     const ColCtx& c0 = cs.ctx[cl0];
     const ColCtx& c1 = cs.ctx[ncol == 2 ? cl0 + kWarps : cl0];
-    if (rows == kDenseTileRows && ncol == 2 && fast_bucketize(c0) && fast_bucketize(c1)) {
+    if (ncol == 2 && fast_bucketize(c0) && fast_bucketize(c1)) {
       const float* in0 = (const float*)c0.values + b0;
       const float* in1 = (const float*)c1.values + b0;
-      const float v[4] = {__ldg(in0 + lane), __ldg(in0 + lane + 32), __ldg(in1 + lane),
-                          __ldg(in1 + lane + 32)};
+      // all (up to 2 x 8) coalesced input loads first
+      float v0[kMaxTileRows / 32], v1[kMaxTileRows / 32];
+#pragma unroll
+      for (int j = 0; j < kMaxTileRows / 32; ++j) {
+        const int r = lane + 32 * j;
+        v0[j] = r < rows ? __ldg(in0 + r) : 0.f;
+        v1[j] = r < rows ? __ldg(in1 + r) : 0.f;
+      }
       const int32_t nb[2] = {c0.num_boundaries, c1.num_boundaries};
       const uint32_t bp[2] = {smem_u32(s_bnd + c0.bnd_off), smem_u32(s_bnd + c1.bnd_off)};
-      int32_t lo[4] = {0, 0, 0, 0};
-      // four upper_bound searches in lock step (see bucketize_n for why `half` serves both sides)
-      for (int32_t n = max(nb[0], nb[1]); n > 0; n >>= 1) {
-        const int32_t half = n >> 1;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int32_t idx = lo[k] + half;
-          const float b = lds_f32(bp[k >> 1] + 4u * (uint32_t)min(idx, nb[k >> 1] - 1));
-          const bool right = idx < nb[k >> 1] && !(v[k] < b);
-          lo[k] = right ? idx + 1 : lo[k];
+      for (int g = 0; g < kMaxTileRows / 128; ++g) {  // 128 rows of both columns per round
+        if (g * 128 >= rows) break;
+        const float v[8] = {v0[4 * g], v0[4 * g + 1], v0[4 * g + 2], v0[4 * g + 3],
+                            v1[4 * g], v1[4 * g + 1], v1[4 * g + 2], v1[4 * g + 3]};
+        int32_t lo[8];
+        search_smem<8>(bp, nb, v, lo);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const ColCtx& c = k < 4 ? c0 : c1;
+          const int cl = k < 4 ? cl0 : cl0 + kWarps;
+          const int r = g * 128 + lane + 32 * (k & 3);
+          if (r < rows) {
+            int32_t id = lo[k];
+            if (CHECK) id = checked_id(id, c.table_rows, Q.status);
+            s_ids[cl * kIdPitch + r] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
+            if (c.ids_out) c.ids_out[b0 + r] = id;
+          }
         }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const ColCtx& c = k < 2 ? c0 : c1;
-        const int cl = k < 2 ? cl0 : cl0 + kWarps;
-        const int r = lane + 32 * (k & 1);
-        int32_t id = lo[k];
-        if (CHECK) id = checked_id(id, c.table_rows, Q.status);
-        s_ids[cl * kIdPitch + r] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
-        if (c.ids_out) c.ids_out[b0 + r] = id;
       }
       continue;
     }
@@ -543,25 +571,37 @@ __device__ __forceinline__ void dense_phase2(const ReqRegs& Q, const CtaShared& 
 // ---------------------------------------------------------------------------
 // SPARSE slab: row b owns ids [row_splits[b], row_splits[b+1])
 // ---------------------------------------------------------------------------
-// phase 1: materialise the row ids of transformed columns for this row block (workspace).
-// One warp per column, so the dependent chains (row_splits -> offsets -> bytes -> hash) of
-// different columns overlap.
+// The tile's row_splits and row ids are staged in shared memory (`sp`, `stride` ints per
+// column: rows + 1 splits, then the ids), so that phase 2's only global accesses are the
+// table rows. A column whose ids do not fit (very long rows) falls back to the workspace.
+//
+// phase 1: one warp per column, so the dependent chains (row_splits -> offsets -> bytes ->
+// hash) of different columns overlap.
 template <bool CHECK>
-__device__ __forceinline__ void sparse_phase1(const DevPlan& P, const ReqRegs& Q, const CtaShared& cs,
-                                              int num_cols, const Tile& tile) {
+__device__ __forceinline__ void sparse_phase1(const DevPlan& P, const ReqRegs& Q, CtaShared& cs,
+                                              int num_cols, const Tile& tile, int32_t* sp,
+                                              int stride) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = tile.rows;
   const int64_t b0 = tile.row_begin;
+  const int cap = stride - (rows + 1);
   for (int cl = warp; cl < num_cols; cl += kWarps) {
     const ColCtx& c = cs.ctx[cl];
+    int32_t* rs_s = sp + cl * stride;
+    int32_t* ids_s = rs_s + rows + 1;
+    for (int r = lane; r <= rows; r += 32) rs_s[r] = c.row_splits[b0 + r];
+    __syncwarp();
+    const int32_t e0 = rs_s[0], e1 = rs_s[rows];
+    const bool staged = e1 - e0 <= cap;
+    if (lane == 0) cs.sp_cnt[cl] = staged ? e1 - e0 : -1;
     const bool xform = c.transform != RECOM_XFORM_NONE;
-    if (!xform && !c.ids_out && !CHECK) continue;
-    const int32_t e0 = c.row_splits[b0], e1 = c.row_splits[b0 + rows];
+    if (!staged && !xform && !c.ids_out && !CHECK) continue;
     const float* bnd = P.boundaries + c.bnd_pool_off;
     for (int32_t e = e0 + lane; e < e1; e += 32) {
       int32_t id = column_id(c, bnd, e);
       if (CHECK) id = checked_id(id, c.table_rows, Q.status);
-      if (xform || CHECK) c.ws_ids[e] = id;
+      if (staged) ids_s[e - e0] = id;
+      else if (xform || CHECK) c.ws_ids[e] = id;
       if (c.ids_out) c.ids_out[e] = id;
     }
   }
@@ -569,7 +609,8 @@ __device__ __forceinline__ void sparse_phase1(const DevPlan& P, const ReqRegs& Q
 
 template <int VEC, bool BF16, bool CHECK>
 __device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const CtaShared& cs, int W,
-                                              const DevChunk& ch, const Tile& tile) {
+                                              const DevChunk& ch, const Tile& tile,
+                                              const int32_t* sp, int stride) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = tile.rows;
   const int64_t b0 = tile.row_begin;
@@ -579,11 +620,14 @@ __device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const CtaShared&
   const ColCtx& c = cs.ctx[ch.col_local];
   const uint8_t* tbl = c.table + ch.table_byte;
   const int64_t row_bytes = c.row_bytes;
-  const int32_t* rs = c.row_splits + b0;
+  const int32_t* rs = sp + ch.col_local * stride;
+  const bool staged = cs.sp_cnt[ch.col_local] >= 0;
+  // id source: smem (relative to the tile's first id), the workspace, or the raw input slot
   const bool from_ws = (c.transform != RECOM_XFORM_NONE) || CHECK;
-  const int32_t* ids32 = from_ws ? c.ws_ids : (const int32_t*)c.values;
-  const bool ids64 = !from_ws && c.value_dtype == RECOM_I64;
-  const long long* idsll = (const long long*)ids32;
+  const int32_t* ids32 = staged ? rs + rows + 1 - rs[0]
+                                : (from_ws ? c.ws_ids : (const int32_t*)c.values);
+  const bool ids64 = !staged && !from_ws && c.value_dtype == RECOM_I64;
+  const long long* idsll = (const long long*)c.values;
   uint8_t* outp = Q.out + b0 * Q.out_row_bytes + ch.out_byte;
   const int combiner = c.combiner;
   auto id_at = [&](int32_t e) -> int64_t {
@@ -638,47 +682,65 @@ __device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const CtaShared&
 // ---------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------
-// Tile source of a CTA: first the shared pool of SPARSE tiles (long DRAM-latency chains:
-// start them early), then the CTA's own static run of DENSE tiles (consecutive row blocks
-// of one slab, so staged tables are reused), then the shared pool of left-over DENSE tiles.
-// Lives in thread 0. Returns a tile index or -1.
+// Tile sources of a CTA: SP = the shared pool of SPARSE tiles (long DRAM-latency chains),
+// ST = the CTA's own static DENSE macro tile(s), DP = the shared pool of small left-over
+// DENSE tiles (load balance). "Sparse first" CTAs walk SP, ST, DP; the others ST, SP, DP, so
+// that latency-bound gathers and bandwidth-bound dense stores overlap on every SM.
+// Claims are issued one step before they are looked at, so the latency of a pool's atomic
+// is never waited for (except once, when a pool runs dry). Lives in thread 0.
 struct TileCursor {
-  int phase;
-  int cur, cur_end;
-  int num_sparse, dyn_begin, num_tiles;
+  enum Kind : int { SP = 0, ST = 1, DP = 2, DONE = 3 };
+  struct Claim {
+    int kind;
+    int raw;
+  };
+  int step;          // position in this CTA's order of sources
+  bool sparse_first;
+  int cur, cur_end, num_sparse, dyn_begin, num_tiles;
+
   __device__ __forceinline__ void init(const ReqHeader* R) {
-    phase = 0;
+    step = 0;
+    sparse_first = (int)blockIdx.x < R->sparse_first_ctas;
     cur = R->static_begin[blockIdx.x];
     cur_end = R->static_begin[blockIdx.x + 1];
     num_sparse = R->num_sparse_tiles;
     dyn_begin = R->dyn_begin;
     num_tiles = R->num_tiles;
   }
-  __device__ __forceinline__ int next(ReqHeader* R) {
-    if (phase == 0) {
-      if (num_sparse > 0) {
-        const int t = atomicAdd(&R->ctr_sparse, 1);
-        if (t < num_sparse) return t;
+  __device__ __forceinline__ int kind_at(int s) const {
+    if (s >= 3) return DONE;
+    if (s == 2) return DP;
+    return (s == 0) == sparse_first ? SP : ST;
+  }
+  __device__ __forceinline__ Claim issue(ReqHeader* R) {
+    for (;;) {
+      const int kind = kind_at(step);
+      if (kind == ST) {
+        if (cur < cur_end) return Claim{ST, cur++};
+      } else if (kind == SP) {
+        if (num_sparse > 0) return Claim{SP, atomicAdd(&R->ctr_sparse, 1)};
+      } else if (kind == DP) {
+        if (dyn_begin < num_tiles) return Claim{DP, dyn_begin + atomicAdd(&R->ctr_dense, 1)};
+      } else {
+        return Claim{DONE, -1};
       }
-      phase = 1;
+      ++step;
     }
-    if (phase == 1) {
-      if (cur < cur_end) return cur++;
-      phase = 2;
+  }
+  // -> tile index, or -1 when every source is exhausted
+  __device__ __forceinline__ int resolve(ReqHeader* R, Claim c) {
+    for (;;) {
+      if (c.kind == ST) return c.raw;
+      if (c.kind == DONE) return -1;
+      if (c.raw < (c.kind == SP ? num_sparse : num_tiles)) return c.raw;
+      if (kind_at(step) == c.kind) ++step;  // that pool is dry
+      c = issue(R);
     }
-    if (phase == 2) {
-      if (dyn_begin < num_tiles) {
-        const int t = dyn_begin + atomicAdd(&R->ctr_dense, 1);
-        if (t < num_tiles) return t;
-      }
-      phase = 3;
-    }
-    return -1;
   }
 };
 
-// Optional per-CTA phase timing (thread 0's view, %globaltimer ns), compiled in only with
-// -DRECOM_PROFILE (make prof): slots are summed over the CTA's tiles and written to R->prof.
+// Optional per-CTA phase timing (thread 0's view), compiled in only with -DRECOM_PROFILE
+// (make prof): slots are summed over the CTA's tiles and written to R->prof.
 #ifdef RECOM_PROFILE
 __device__ __forceinline__ uint64_t gtimer() {
   uint64_t t;
@@ -716,7 +778,6 @@ fused_columns_kernel(const DevPlan P, ReqHeader* __restrict__ R) {
   uint8_t* s_tables = smem;
   float* s_bnd = reinterpret_cast<float*>(smem + P.smem_off_bnd);
   int32_t* s_ids = reinterpret_cast<int32_t*>(smem + P.smem_off_ids);
-  const int ids_buf = P.smem_ids_cols * kIdPitch;
   const Tile* tiles = R->tiles;
   ReqRegs Q;
   Q.out = R->out;
@@ -724,18 +785,18 @@ fused_columns_kernel(const DevPlan P, ReqHeader* __restrict__ R) {
   Q.status = R->status;
 
   PROF_DECL
-  // Thread 0 claims tile indices three steps ahead (the atomic's latency is never waited
-  // for) and copies the Tile record two steps ahead into cs.next with cp.async.
+  // Thread 0 claims tiles three steps ahead and copies the Tile record two steps ahead into
+  // cs.next with cp.async.
   TileCursor cursor;
-  int pending = -1;
+  TileCursor::Claim pend{TileCursor::DONE, -1};
   if (threadIdx.x == 0) {
     mbar_init(&cs.mbar_bnd, 1);
     mbar_init(&cs.mbar_tbl, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     cursor.init(R);
-    const int i0 = cursor.next(R);
-    const int i1 = i0 >= 0 ? cursor.next(R) : -1;
-    pending = i1 >= 0 ? cursor.next(R) : -1;
+    const int i0 = cursor.resolve(R, cursor.issue(R));
+    const int i1 = i0 >= 0 ? cursor.resolve(R, cursor.issue(R)) : -1;
+    if (i1 >= 0) pend = cursor.issue(R);
     Tile none;
     none.slab = -1;
     none.row_begin = none.rows = none.pad = 0;
@@ -746,9 +807,10 @@ fused_columns_kernel(const DevPlan P, ReqHeader* __restrict__ R) {
   Tile tile = cs.next[0];   // this tile
   Tile tile1 = cs.next[1];  // the next one
   __syncthreads();          // both read before thread 0 reuses the slots
-
   PROF_T(13)
+
   int cur_slab = -1;
+  int staged_bnd = -1;        // pool offset of the single boundary set resident in smem, or -1
   uint32_t stage_parity = 1;  // parity of the phase completed by the latest staging
   DevSlab slab;
   DevChunk ch;
@@ -757,67 +819,78 @@ fused_columns_kernel(const DevPlan P, ReqHeader* __restrict__ R) {
   slab.vec_bytes = 16;
   slab.stage_bytes = slab.bnd_bytes = 0;
   ch.col = ch.col_local = ch.table_byte = ch.out_byte = 0;
+  int sp_stride = 0;
 
   for (int k = 0; tile.slab >= 0; ++k) {
     const int buf = k & 1;
     if (threadIdx.x == 0) {
-      if (pending >= 0) {
-        cp_async_16(&cs.next[buf], tiles + pending);
-        pending = cursor.next(R);
+      const int idx = cursor.resolve(R, pend);
+      if (idx >= 0) {
+        cp_async_16(&cs.next[buf], tiles + idx);
+        pend = cursor.issue(R);
       } else {
         cs.next[buf].slab = -1;
+        pend = TileCursor::Claim{TileCursor::DONE, -1};
       }
     }
     PROF_T(0)
     PROF_COUNT(11)
     if (tile.slab != cur_slab) {
-      // every warp has finished with the previous slab's context, tables and boundaries
-      __syncthreads();
+      // (every warp has passed the barrier that ends the previous tile)
       slab = P.slabs[tile.slab];
       cur_slab = tile.slab;
-      if (slab.stage_bytes + slab.bnd_bytes > 0) stage_parity ^= 1;
-      enter_slab(P, R, slab, cs, s_tables, s_bnd);
+      // a slab whose only boundary set is already resident keeps it (model E/F: one set for all)
+      const bool keep_bnd = slab.num_bnds == 1 && slab.first_bnd_pool == staged_bnd;
+      if (slab.cls == kSlabSparse) staged_bnd = -1;  // a sparse tile overwrites the whole region
+      else if (slab.num_bnds == 1) staged_bnd = slab.first_bnd_pool;
+      else if (slab.num_bnds > 1) staged_bnd = -1;
+      if (slab.stage_bytes + (keep_bnd ? 0 : slab.bnd_bytes) > 0) stage_parity ^= 1;
+      enter_slab(P, R, slab, cs, s_tables, s_bnd, keep_bnd);
       {
         const int lane = threadIdx.x & 31;
-        const int chunk = lane % slab.num_chunks;
-        ch = P.chunks[slab.first_chunk + chunk];
+        ch = P.chunks[slab.first_chunk + lane % slab.num_chunks];
       }
+      if (slab.cls == kSlabSparse)
+        sp_stride = (P.smem_bytes / 4 / slab.num_cols) & ~3;
       __syncthreads();  // the column contexts are visible
       PROF_COUNT(12)
     }
     PROF_T(1)
     if (slab.cls == kSlabSparse) {
-      sparse_phase1<CHECK>(P, Q, cs, slab.num_cols, tile);
+      int32_t* sp = reinterpret_cast<int32_t*>(smem);
+      sparse_phase1<CHECK>(P, Q, cs, slab.num_cols, tile, sp, sp_stride);
       PROF_T(8)
       if (threadIdx.x == 0) cp_async_wait_all();
-      __syncthreads();  // block-scope visibility of the workspace ids (and of cs.next)
+      __syncthreads();  // staged splits / ids (and cs.next) are visible
       PROF_T(9)
-      if (slab.vec_bytes == 16) sparse_phase2<16, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile);
-      else sparse_phase2<ELEM, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile);
+      if (slab.vec_bytes == 16)
+        sparse_phase2<16, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile, sp, sp_stride);
+      else
+        sparse_phase2<ELEM, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile, sp, sp_stride);
       PROF_T(10)
     } else {
-      int32_t* ids = s_ids + buf * ids_buf;
       if (slab.bnd_bytes > 0) mbar_wait(&cs.mbar_bnd, stage_parity);
       PROF_T(2)
-      dense_phase1<CHECK>(P, Q, cs, slab.num_cols, tile, s_bnd, ids);
+      dense_phase1<CHECK>(P, Q, cs, slab.num_cols, tile, s_bnd, s_ids);
       PROF_T(3)
       if (threadIdx.x == 0) cp_async_wait_all();
-      __syncthreads();  // the only barrier of a DENSE tile: ids (and cs.next) are visible
+      __syncthreads();  // ids (and cs.next) are visible
       PROF_T(4)
       if (slab.cls == kSlabDenseStaged) {
         mbar_wait(&cs.mbar_tbl, stage_parity);
         PROF_T(5)
-        if (slab.vec_bytes == 16) dense_phase2<16, true>(Q, cs, slab.num_chunks, ch, tile, s_tables, ids);
-        else dense_phase2<ELEM, true>(Q, cs, slab.num_chunks, ch, tile, s_tables, ids);
+        if (slab.vec_bytes == 16) dense_phase2<16, true>(Q, cs, slab.num_chunks, ch, tile, s_tables, s_ids);
+        else dense_phase2<ELEM, true>(Q, cs, slab.num_chunks, ch, tile, s_tables, s_ids);
       } else {
-        if (slab.vec_bytes == 16) dense_phase2<16, false>(Q, cs, slab.num_chunks, ch, tile, s_tables, ids);
-        else dense_phase2<ELEM, false>(Q, cs, slab.num_chunks, ch, tile, s_tables, ids);
+        if (slab.vec_bytes == 16) dense_phase2<16, false>(Q, cs, slab.num_chunks, ch, tile, s_tables, s_ids);
+        else dense_phase2<ELEM, false>(Q, cs, slab.num_chunks, ch, tile, s_tables, s_ids);
       }
       PROF_T(6)
     }
     const Tile tile2 = cs.next[buf];
     if (tile2.slab == cur_slab && slab.cls != kSlabSparse)
       prefetch_tile_inputs(cs, slab.num_cols, tile2);
+    __syncthreads();  // the tile's ids / staged splits may be overwritten from here on
     PROF_T(7)
     tile = tile1;
     tile1 = tile2;

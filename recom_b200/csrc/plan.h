@@ -15,9 +15,10 @@ namespace recom {
 constexpr int kThreads = 256;          // threads per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxChunks = 32;         // a slab is at most one warp wide
-constexpr int kDenseTileRows = 64;     // rows per DENSE tile (ids of one tile live in smem)
-constexpr int kIdPitch = kDenseTileRows + 1;  // smem pitch (bank-conflict free)
-constexpr int kSparseTileRowsL2 = 32;  // rows per SPARSE tile, tables that fit in L2
+constexpr int kMaxTileRows = 256;      // rows of a static DENSE macro tile (its ids live in smem)
+constexpr int kPoolTileRows = 64;      // rows of a DENSE tile in the load-balancing pool
+constexpr int kIdPitch = kMaxTileRows + 1;  // smem pitch (bank-conflict free)
+constexpr int kSparseTileRowsL2 = 16;  // rows per SPARSE tile, tables that fit in L2
 constexpr int kSparseTileRowsHbm = 8;  // rows per SPARSE tile, HBM-resident tables
 constexpr int64_t kHbmTableBytes = 32ll << 20;  // a table beyond this is "HBM resident"
 // shared-memory staging limits (per CTA)
@@ -132,7 +133,7 @@ struct DevSlab {
   int32_t first_bnd;    // into the slab_bnds array
   int32_t num_bnds;
   int32_t bnd_bytes;    // total bytes of staged boundaries
-  int32_t pad;
+  int32_t first_bnd_pool;  // pool offset of the first staged boundary set (-1: none)
 };
 
 struct DevPlan {
@@ -178,14 +179,16 @@ struct ReqHeader {
   uint64_t* prof;         // profiling builds only (make prof): [grid, 16] phase timers, else null
   int64_t batch;
   int64_t out_row_bytes;
-  // schedule: tiles [0, num_sparse_tiles) are pulled through ctr_sparse, then each
-  // CTA walks its static range, then tiles [dyn_begin, num_tiles) through ctr_dense
+  // schedule: tiles [0, num_sparse_tiles) are pulled through ctr_sparse, each CTA owns
+  // a static range, tiles [dyn_begin, num_tiles) are pulled through ctr_dense
   int32_t num_tiles;
   int32_t num_sparse_tiles;
   int32_t dyn_begin;
+  int32_t sparse_first_ctas;  // CTAs below this index start with the SPARSE pool
   int32_t ctr_sparse;
   int32_t ctr_dense;
   int32_t num_coo;        // number of COO columns
+  int32_t pad0;
   // byte offsets from the start of this block
   uint32_t off_slot_offsets;  // int64[num_slots]
   uint32_t off_tables;        // const void*[num_tables]
