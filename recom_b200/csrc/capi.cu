@@ -76,21 +76,29 @@ int dtype_bytes(int32_t dt) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Schedule of one batch size (see TileCursor in kernels.cu). Layout of `tiles`:
-// [sparse pool | static runs of CTA 0, 1, ... | dense pool].
+// Schedule of one batch size (see TileCursor in kernels.cu): `tiles` = [sparse pool |
+// dense pool], `start` = the static macro tile of every CTA.
 struct TileTable {
   std::vector<Tile> tiles;
-  std::vector<int32_t> static_begin;  // [grid + 1]
+  std::vector<Tile> start;  // [grid]
   int grid = 1;
   int num_sparse = 0;
-  int dyn_begin = 0;
-  int sparse_first = 0;               // CTAs [0, sparse_first) start with the sparse pool
-  void* d_block = nullptr;            // device copy: tiles, then static_begin (cached tables only)
+  int sparse_first = 0;     // CTAs [0, sparse_first) start with the sparse pool
+  void* d_block = nullptr;  // device copy: tiles, then start (cached tables only)
   ~TileTable() {
     if (d_block) cudaFree(d_block);
   }
-  size_t tiles_bytes() const { return (tiles.size() * sizeof(Tile) + 15) / 16 * 16; }
-  size_t bytes() const { return tiles_bytes() + (static_begin.size() * 4 + 15) / 16 * 16; }
+  size_t tiles_bytes() const { return tiles.size() * sizeof(Tile); }
+  size_t bytes() const { return tiles_bytes() + start.size() * sizeof(Tile); }
+  Sched sched(const void* base) const {
+    Sched s{};
+    s.tiles = (const Tile*)base;
+    s.start = (const Tile*)((const uint8_t*)base + tiles_bytes());
+    s.num_tiles = (int32_t)tiles.size();
+    s.num_sparse_tiles = num_sparse;
+    s.sparse_first_ctas = sparse_first;
+    return s;
+  }
 };
 
 }  // namespace
@@ -109,6 +117,7 @@ struct recom_plan {
   std::vector<int32_t> sparse_cols;  // column index of each non-DENSE column
   std::vector<int32_t> coo_cols;     // column index of each COO column
   std::vector<int32_t> slab_order;   // slabs sorted for scheduling (heavy first)
+  std::vector<double> slab_weight;   // relative cost of a slab's output byte (hashing costs ALU)
   // device
   void* d_block = nullptr;
   DevPlan dev{};
@@ -116,6 +125,7 @@ struct recom_plan {
   int num_sms = 148;
   int ctas_per_sm = 3;
   double pool_frac = 0.15;  // share of the dense tiles kept in the dynamic pool
+  double hash_weight = 5.0; // extra cost of a hashed column's output byte (schedule balance)
   // tile tables depend only on the batch size: cached (read-mostly)
   std::mutex tiles_mu;
   std::map<int64_t, std::shared_ptr<const TileTable>> tiles_by_batch;
@@ -400,13 +410,26 @@ void build_layout(recom_plan* p) {
   p->dev.smem_off_bnd = (int32_t)align_up((size_t)max_stage, 128);
   p->dev.smem_off_ids = p->dev.smem_off_bnd + (int32_t)align_up((size_t)max_bnd, 128);
   p->dev.smem_ids_cols = max_cols;
-  p->dev.smem_bytes = p->dev.smem_off_ids + max_cols * kIdPitch * 4;
+  p->dev.smem_bytes = p->dev.smem_off_ids + 2 * max_cols * kIdPitch * 4;  // two ring slots
   // a SPARSE tile stages its row_splits and ids in the same memory: room for 16 ids per row
   for (const DevSlab& s : p->slabs)
     if (s.cls == kSlabSparse) {
       const int need = s.num_cols * (s.tile_rows + 1 + s.tile_rows * 16 + 4) * 4;
       p->dev.smem_bytes = std::max(p->dev.smem_bytes, std::min(need, 48 << 10));
     }
+
+  // relative cost of a slab's output byte: hashing a value costs far more issue slots than a
+  // bucket search, so slabs of hashed columns get fewer rows per CTA
+  p->slab_weight.assign(p->slabs.size(), 1.0);
+  for (size_t si = 0; si < p->slabs.size(); ++si) {
+    const DevSlab& sl = p->slabs[si];
+    int hashed = 0;
+    for (int k = 0; k < sl.num_cols; ++k) {
+      const int t = p->slab_cols[sl.first_col + k].transform;
+      hashed += t == RECOM_XFORM_HASH_STR || t == RECOM_XFORM_HASH_INT;
+    }
+    p->slab_weight[si] = 1.0 + p->hash_weight * hashed / std::max(1, sl.num_cols);
+  }
 
   // scheduling order: multi-hot slabs first (their tiles chase several dependent DRAM
   // round trips), widest rows first; then the dense slabs in concat order.
@@ -433,22 +456,22 @@ void build_layout(recom_plan* p) {
 //   * SPARSE tiles go to a shared pool (heavy slabs first).
 //   * The CTAs are split into "sparse first" CTAs (a share proportional to the estimated
 //     cost of the SPARSE tiles) and dense CTAs. Every dense CTA owns ONE static macro tile:
-//     up to kMaxTileRows consecutive rows of one slab, so the slab's staged tables, the
-//     column contexts and the input latency are paid once per CTA. Dense CTAs are
-//     apportioned to the DENSE slabs by output bytes.
+//     a run of consecutive rows of one slab, so the slab's staged tables and the column
+//     contexts are paid once per CTA. Dense CTAs are apportioned to the DENSE slabs by
+//     output bytes.
 //   * What the macro tiles leave over (about pool_frac of the rows) goes to a second shared
 //     pool of small tiles that evens out the finish.
 // Layout of `tiles`: [sparse pool | static tiles (CTA order) | dense pool].
 std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   const int cap_ctas = p->num_sms * p->ctas_per_sm;
   auto tt = std::make_shared<TileTable>();
-  auto push = [&](std::vector<Tile>& v, int s, int64_t b, int64_t rows) {
-    Tile t;
-    t.slab = s;
+  auto make = [&](int s, int64_t b, int64_t rows) {
+    Tile t{};
+    t.slab_id = s;
     t.row_begin = (int32_t)b;
     t.rows = (int32_t)rows;
-    t.pad = 0;
-    v.push_back(t);
+    t.slab = p->slabs[s];
+    return t;
   };
   // sparse pool
   double sparse_cost = 0, dense_cost = 0;
@@ -456,16 +479,17 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     const DevSlab& sl = p->slabs[s];
     if (sl.cls != kSlabSparse) continue;
     for (int64_t b = 0; b < B; b += sl.tile_rows)
-      push(tt->tiles, s, b, std::min<int64_t>(sl.tile_rows, B - b));
+      tt->tiles.push_back(make(s, b, std::min<int64_t>(sl.tile_rows, B - b)));
     // guess: 5 ids per row, latency-bound gathers weigh 3x their bytes
     sparse_cost += (double)B * sl.num_chunks * sl.vec_bytes * 5.0 * 3.0;
   }
   tt->num_sparse = (int)tt->tiles.size();
   std::vector<int> dense;
+  auto slab_cost = [&](int s) { return (double)B * p->slabs[s].num_chunks * p->slabs[s].vec_bytes * p->slab_weight[s]; };
   for (int s : p->slab_order)
     if (p->slabs[s].cls != kSlabSparse) {
       dense.push_back(s);
-      dense_cost += (double)B * p->slabs[s].num_chunks * p->slabs[s].vec_bytes;
+      dense_cost += slab_cost(s);
     }
   // grid: never more CTAs than 32-row units of work
   int64_t units = tt->num_sparse;
@@ -487,8 +511,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     std::vector<std::pair<double, int>> rem;
     int given = 0;
     for (size_t i = 0; i < dense.size(); ++i) {
-      const DevSlab& sl = p->slabs[dense[i]];
-      const double share = dense_ctas * ((double)B * sl.num_chunks * sl.vec_bytes) / dense_cost;
+      const double share = dense_ctas * slab_cost(dense[i]) / dense_cost;
       n_ctas[i] = (int)share;
       given += n_ctas[i];
       rem.push_back({-(share - n_ctas[i]), (int)i});
@@ -497,7 +520,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     for (int k = 0; given < dense_ctas && k < (int)rem.size(); ++k, ++given) n_ctas[rem[k].second]++;
   }
   // static macro tiles, then the pool
-  std::vector<Tile> statics, pool;
+  std::vector<Tile> statics;
   int pool_rows = kPoolTileRows;
   {
     // small batches: shrink pool tiles until every CTA can have one
@@ -513,24 +536,21 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     int64_t static_rows = 0;
     if (n_ctas[i] > 0) {
       int64_t per = (int64_t)((1.0 - p->pool_frac) * (double)B / n_ctas[i]);
-      per = std::min<int64_t>(per / 32 * 32, kMaxTileRows);
+      per = per / 32 * 32;
       if (per >= 64) {
-        for (int c = 0; c < n_ctas[i]; ++c) push(statics, dense[i], c * per, per);
+        for (int c = 0; c < n_ctas[i]; ++c) statics.push_back(make(dense[i], c * per, per));
         static_rows = per * n_ctas[i];
       }
     }
     for (int64_t b = static_rows; b < B; b += pool_rows)
-      push(pool, dense[i], b, std::min<int64_t>(pool_rows, B - b));
+      tt->tiles.push_back(make(dense[i], b, std::min<int64_t>(pool_rows, B - b)));
   }
   // CTA c >= sparse_ctas owns static tile (c - sparse_ctas), if there is one
-  tt->static_begin.assign(grid + 1, 0);
-  for (int c = 0; c <= grid; ++c) {
-    const int k = std::max(0, std::min((int)statics.size(), c - sparse_ctas));
-    tt->static_begin[c] = tt->num_sparse + k;
-  }
-  tt->tiles.insert(tt->tiles.end(), statics.begin(), statics.end());
-  tt->dyn_begin = (int)tt->tiles.size();
-  tt->tiles.insert(tt->tiles.end(), pool.begin(), pool.end());
+  Tile none{};
+  none.slab_id = -1;
+  tt->start.assign(grid, none);
+  for (int k = 0; k < (int)statics.size() && sparse_ctas + k < grid; ++k)
+    tt->start[sparse_ctas + k] = statics[k];
   return tt;
 }
 
@@ -545,9 +565,9 @@ std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, recom_st
   if (it != p->tiles_by_batch.end()) return it->second;
   if (p->tiles_by_batch.size() >= kMaxCachedTileTables) return nullptr;
   std::shared_ptr<TileTable> tt = build_tiles(p, B);
-  std::vector<uint8_t> host(tt->bytes(), 0);
-  memcpy(host.data(), tt->tiles.data(), tt->tiles.size() * sizeof(Tile));
-  memcpy(host.data() + tt->tiles_bytes(), tt->static_begin.data(), tt->static_begin.size() * 4);
+  std::vector<uint8_t> host(tt->bytes() + 64, 0);
+  memcpy(host.data(), tt->tiles.data(), tt->tiles_bytes());
+  memcpy(host.data() + tt->tiles_bytes(), tt->start.data(), tt->start.size() * sizeof(Tile));
   // first use of a batch size (warm-up): a blocking allocation + copy
   if (cudaMalloc(&tt->d_block, host.size()) != cudaSuccess ||
       cudaMemcpy(tt->d_block, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -691,6 +711,7 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
   p->elem_bytes = cfg->out_dtype == RECOM_BF16 ? 2 : 4;
   // tuning knobs (the reference's counterpart: its RECOM_* env flags, fc_optimize_pass.cc:41-69)
   if (const char* e = getenv("RECOM_B200_STAGE_TABLES")) p->stage_tables = atoi(e) != 0;
+  if (const char* e = getenv("RECOM_B200_HASH_WEIGHT")) p->hash_weight = atof(e);
   if (const char* e = getenv("RECOM_B200_POOL_PCT"))
     p->pool_frac = std::min(100, std::max(0, atoi(e))) / 100.0;
   build_layout(p);
@@ -828,15 +849,17 @@ static size_t arg_block_bytes(const recom_plan* p, size_t sched_bytes) {
   b += align_up((p->descs.size() + 1) * 4, 16);
   b += align_up((p->sparse_cols.size() + 1) * 4, 16);
   b += align_up(p->coo_cols.size() * 4 + 4, 16);
-  b += sched_bytes;
+  b += sched_bytes + 64;
   return b;
 }
 
 static size_t max_sched_bytes(const recom_plan* p, int64_t batch) {
+  // only used when the schedule cache is full and the schedule travels with the request;
   // smallest tile is 8 rows (HBM-resident multi-hot) resp. 16 rows (dense pool)
-  const size_t tiles = p->slabs.size() * (size_t)((batch + 7) / 8 + 1) + 1;
-  return align_up(tiles * sizeof(Tile), 16) +
-         align_up(((size_t)p->num_sms * p->ctas_per_sm + 2) * 4, 16);
+  size_t tiles = 1;
+  for (const DevSlab& s : p->slabs)
+    tiles += (size_t)((batch + (s.cls == kSlabSparse ? 7 : 15)) / (s.cls == kSlabSparse ? 8 : 16) + 1);
+  return (tiles + (size_t)p->num_sms * p->ctas_per_sm + 2) * sizeof(Tile);
 }
 
 recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int64_t total_ids,
@@ -916,47 +939,50 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   ReqHeader* hdr = (ReqHeader*)h;
   memset(hdr, 0, sizeof *hdr);
   hdr->blob = (const uint8_t*)req->blob;
-  hdr->out = (uint8_t*)req->out;
-  hdr->ids_out = req->ids_out;
-  hdr->status = req->status_out;
-  hdr->ws_ids = (int32_t*)(ws + off_ws_ids);
   hdr->ws_row_splits = (int32_t*)(ws + off_rs);
   hdr->batch = B;
-  hdr->out_row_bytes = (int64_t)p->cfg.out_width * p->elem_bytes;
-  hdr->num_tiles = (int32_t)tt->tiles.size();
-  hdr->num_sparse_tiles = tt->num_sparse;
-  hdr->dyn_begin = tt->dyn_begin;
-  hdr->sparse_first_ctas = tt->sparse_first;
-  hdr->ctr_sparse = 0;
-  hdr->ctr_dense = 0;
   hdr->num_coo = (int32_t)p->coo_cols.size();
-  hdr->prof = p->d_prof;
+  ReqParams A{};
+  A.blob = (const uint8_t*)req->blob;
+  A.out = (uint8_t*)req->out;
+  A.ids_out = req->ids_out;
+  A.status = req->status_out;
+  A.ws_ids = (int32_t*)(ws + off_ws_ids);
+  A.ws_row_splits = (int32_t*)(ws + off_rs);
+  A.counters = (int32_t*)ws;  // ReqHeader::counters
+  A.prof = p->d_prof;
   if (p->d_prof) p->prof_grid = grid;
+  A.batch = B;
+  A.out_row_bytes = (int64_t)p->cfg.out_width * p->elem_bytes;
   size_t o = align_up(sizeof(ReqHeader), 16);
   hdr->off_slot_offsets = (uint32_t)o;
+  A.slot_offsets = (const int64_t*)(ws + o);
   memcpy(h + o, req->slot_offsets, (size_t)p->cfg.num_slots * 8);
   o += align_up((size_t)p->cfg.num_slots * 8, 16);
   hdr->off_tables = (uint32_t)o;
+  A.tables = (const void* const*)(ws + o);
   memcpy(h + o, req->tables, (size_t)p->cfg.num_tables * 8);
   o += align_up((size_t)p->cfg.num_tables * 8, 16);
   hdr->off_ids_base = (uint32_t)o;
+  A.ids_base = (const int32_t*)(ws + o);
   memcpy(h + o, ids_base.data(), ids_base.size() * 4);
   o += align_up(ids_base.size() * 4, 16);
   hdr->off_sparse_base = (uint32_t)o;
+  A.sparse_base = (const int32_t*)(ws + o);
   memcpy(h + o, sparse_base.data(), sparse_base.size() * 4);
   o += align_up(sparse_base.size() * 4, 16);
   hdr->off_coo_cols = (uint32_t)o;
   if (!p->coo_cols.empty()) memcpy(h + o, p->coo_cols.data(), p->coo_cols.size() * 4);
   o += align_up(p->coo_cols.size() * 4 + 4, 16);
+  Sched sched;
   if (sched_in_args) {
-    hdr->tiles = (const Tile*)(ws + o);
-    memcpy(h + o, tt->tiles.data(), tt->tiles.size() * sizeof(Tile));
-    hdr->static_begin = (const int32_t*)(ws + o + tt->tiles_bytes());
-    memcpy(h + o + tt->tiles_bytes(), tt->static_begin.data(), tt->static_begin.size() * 4);
+    o = align_up(o, 64);
+    memcpy(h + o, tt->tiles.data(), tt->tiles_bytes());
+    memcpy(h + o + tt->tiles_bytes(), tt->start.data(), tt->start.size() * sizeof(Tile));
+    sched = tt->sched(ws + o);
     o += tt->bytes();
   } else {
-    hdr->tiles = (const Tile*)tt->d_block;
-    hdr->static_begin = (const int32_t*)((const uint8_t*)tt->d_block + tt->tiles_bytes());
+    sched = tt->sched(tt->d_block);
   }
   hdr->total_bytes = (uint32_t)o;
 
@@ -966,7 +992,7 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
     launch_coo_to_row_splits(p->dev, d_req, (int)p->coo_cols.size(), max_coo_nnz, stream);
     g_last_launches++;
   }
-  launch_fused_columns(p->dev, d_req, grid, p->elem_bytes == 2, stream);
+  launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream);
   g_last_launches++;
   cudaError_t e = cudaGetLastError();
   cudaEventRecord(slot.done, stream);

@@ -188,18 +188,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// Waiting warps back off with nanosleep: a warp spinning on try_wait competes for issue slots
+// with the warps (often a single one doing serial work) that everybody is waiting for.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 // TMA bulk copy global -> shared (UBLKCP), completion counted in bytes on `bar`.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
@@ -345,6 +354,8 @@ struct __align__(16) CtaShared {
   Tile next[2];            // the tile two steps ahead (slab < 0: none), double buffered
   uint64_t mbar_bnd;       // boundaries of the staged slab have landed
   uint64_t mbar_tbl;       // tables of the staged slab have landed
+  uint64_t full[2];        // ids ring: slot filled by the producer warps
+  uint64_t empty[2];       // ids ring: slot released by the consumer warps
   ColCtx ctx[kMaxChunks];  // the columns of the slab the CTA is working on
   int32_t sp_cnt[kMaxChunks];  // SPARSE tile: ids of the tile per column, -1: not staged
 };
@@ -360,26 +371,25 @@ struct ReqRegs {
 // entering a slab: resolve its columns against the request (one thread per column), start
 // the TMA bulk copies of its small tables and bucket boundaries into shared memory
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void enter_slab(const DevPlan& P, const ReqHeader* __restrict__ R,
+__device__ __forceinline__ void enter_slab(const DevPlan& P, const ReqParams& A,
                                            const DevSlab& slab, CtaShared& cs, uint8_t* s_tables,
                                            float* s_bnd, bool keep_bnd) {
   const int tid = threadIdx.x;
   if (tid < slab.num_cols) {
     const DevSlabCol sc = P.slab_cols[slab.first_col + tid];
-    const int64_t* slot_off = req_slot_offsets(R);
     ColCtx x;
-    x.values = R->blob + slot_off[sc.value_slot];
-    x.bytes = sc.bytes_slot >= 0 ? R->blob + slot_off[sc.bytes_slot] : nullptr;
-    x.table = (const uint8_t*)req_tables(R)[sc.table];
+    x.values = A.blob + A.slot_offsets[sc.value_slot];
+    x.bytes = sc.bytes_slot >= 0 ? A.blob + A.slot_offsets[sc.bytes_slot] : nullptr;
+    x.table = (const uint8_t*)A.tables[sc.table];
     x.row_splits = nullptr;
     x.ws_ids = nullptr;
     if (sc.sparse_index >= 0) {
       x.row_splits = sc.coo_index >= 0
-                         ? R->ws_row_splits + (int64_t)sc.coo_index * (R->batch + 1)
-                         : (const int32_t*)(R->blob + slot_off[sc.seg_slot]);
-      x.ws_ids = R->ws_ids + req_sparse_base(R)[sc.sparse_index];
+                         ? A.ws_row_splits + (int64_t)sc.coo_index * (A.batch + 1)
+                         : (const int32_t*)(A.blob + A.slot_offsets[sc.seg_slot]);
+      x.ws_ids = A.ws_ids + A.sparse_base[sc.sparse_index];
     }
-    x.ids_out = R->ids_out ? R->ids_out + req_ids_base(R)[sc.col] : nullptr;
+    x.ids_out = A.ids_out ? A.ids_out + A.ids_base[sc.col] : nullptr;
     x.bucket_magic = sc.bucket_magic;
     x.num_buckets = sc.num_buckets;
     x.table_rows = sc.table_rows;
@@ -419,80 +429,76 @@ __device__ __forceinline__ bool fast_bucketize(const ColCtx& c) {
   return c.transform == RECOM_XFORM_BUCKETIZE && c.value_dtype == RECOM_F32 && c.bnd_off >= 0;
 }
 
-// K upper_bound searches in lock step over boundaries in shared memory; search k uses the
-// boundary set k / (K / 2) (see bucketize_n for why `half` serves both sides of a probe).
-template <int K>
-__device__ __forceinline__ void search_smem(const uint32_t (&bp)[2], const int32_t (&nb)[2],
-                                            const float (&v)[K], int32_t (&lo)[K]) {
+// 8 upper_bound searches in lock step over boundaries in shared memory; search k uses
+// boundary set k / 2 (see bucketize_n for why `half` serves both sides of a probe).
+__device__ __forceinline__ void search_smem8(const uint32_t (&bp)[4], const int32_t (&nb)[4],
+                                             const float (&v)[8], int32_t (&lo)[8]) {
 #pragma unroll
-  for (int k = 0; k < K; ++k) lo[k] = 0;
-  for (int32_t n = max(nb[0], nb[1]); n > 0; n >>= 1) {
+  for (int k = 0; k < 8; ++k) lo[k] = 0;
+  for (int32_t n = max(max(nb[0], nb[1]), max(nb[2], nb[3])); n > 0; n >>= 1) {
     const int32_t half = n >> 1;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      constexpr int H = K / 2;
+    for (int k = 0; k < 8; ++k) {
       const int32_t idx = lo[k] + half;
-      const float b = lds_f32(bp[k / H] + 4u * (uint32_t)min(idx, nb[k / H] - 1));
-      const bool right = idx < nb[k / H] && !(v[k] < b);
+      const float b = lds_f32(bp[k >> 1] + 4u * (uint32_t)min(idx, nb[k >> 1] - 1));
+      const bool right = idx < nb[k >> 1] && !(v[k] < b);
       lo[k] = right ? idx + 1 : lo[k];
     }
   }
 }
 
-// phase 1: one warp per column, lanes along the batch (coalesced input reads). The smem id
-// slot receives the byte offset of the row inside the smem table region when the table is
+// DENSE tiles are processed by two groups of warps that hand over 64-row sub-tiles through a
+// two-slot ring of row ids in shared memory (mbarrier full / empty per slot):
+//   producers (warps 0-3): inputs -> row ids (bucketize / hash), lanes along the batch;
+//   consumers (warps 4-7): lane = chunk; gather the table rows, store into the concat rows.
+// The stores, which bound this path, therefore never wait for id computation or input latency.
+//
+// Producer side of one sub-tile. A producer warp owns the columns pw, pw + 4, pw + 8, ... and
+// takes them four at a time: 8 coalesced loads in flight, then 8 searches in lock step. The
+// id slot receives the byte offset of the row inside the smem table region when the table is
 // staged, else the raw row id.
 template <bool CHECK>
-__device__ __forceinline__ void dense_phase1(const DevPlan& P, const ReqRegs& Q, const CtaShared& cs,
-                                             int num_cols, const Tile& tile, const float* s_bnd,
-                                             int32_t* s_ids) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows = tile.rows;
-  const int64_t b0 = tile.row_begin;
-  for (int cl0 = warp; cl0 < num_cols; cl0 += 2 * kWarps) {
-    // a warp takes columns cl0 and cl0 + kWarps together: every global load of both is in
-    // flight before the first search step
-    const int ncol = cl0 + kWarps < num_cols ? 2 : 1;
-    const ColCtx& c0 = cs.ctx[cl0];
-    const ColCtx& c1 = cs.ctx[ncol == 2 ? cl0 + kWarps : cl0];
-    if (ncol == 2 && fast_bucketize(c0) && fast_bucketize(c1)) {
-      const float* in0 = (const float*)c0.values + b0;
-      const float* in1 = (const float*)c1.values + b0;
-      // all (up to 2 x 8) coalesced input loads first
-      float v0[kMaxTileRows / 32], v1[kMaxTileRows / 32];
+__device__ __forceinline__ void produce_ids(const DevPlan& P, const ReqRegs& Q, const CtaShared& cs,
+                                            int num_cols, int64_t b0, int rows, const float* s_bnd,
+                                            int32_t* s_ids, int pw, int lane) {
+  for (int cbase = pw; cbase < num_cols; cbase += 4 * kProducerWarps) {
+    const int nq = min(4, (num_cols - cbase + kProducerWarps - 1) / kProducerWarps);
+    bool fast = nq == 4;
 #pragma unroll
-      for (int j = 0; j < kMaxTileRows / 32; ++j) {
-        const int r = lane + 32 * j;
-        v0[j] = r < rows ? __ldg(in0 + r) : 0.f;
-        v1[j] = r < rows ? __ldg(in1 + r) : 0.f;
+    for (int q = 0; q < 4; ++q)
+      if (q < nq) fast = fast && fast_bucketize(cs.ctx[cbase + q * kProducerWarps]);
+    if (fast) {
+      float v[8];
+      uint32_t bp[4];
+      int32_t nb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const ColCtx& c = cs.ctx[cbase + q * kProducerWarps];
+        const float* in = (const float*)c.values + b0;
+        v[2 * q] = lane < rows ? __ldg(in + lane) : 0.f;
+        v[2 * q + 1] = lane + 32 < rows ? __ldg(in + lane + 32) : 0.f;
+        bp[q] = smem_u32(s_bnd + c.bnd_off);
+        nb[q] = c.num_boundaries;
       }
-      const int32_t nb[2] = {c0.num_boundaries, c1.num_boundaries};
-      const uint32_t bp[2] = {smem_u32(s_bnd + c0.bnd_off), smem_u32(s_bnd + c1.bnd_off)};
+      int32_t lo[8];
+      search_smem8(bp, nb, v, lo);
 #pragma unroll
-      for (int g = 0; g < kMaxTileRows / 128; ++g) {  // 128 rows of both columns per round
-        if (g * 128 >= rows) break;
-        const float v[8] = {v0[4 * g], v0[4 * g + 1], v0[4 * g + 2], v0[4 * g + 3],
-                            v1[4 * g], v1[4 * g + 1], v1[4 * g + 2], v1[4 * g + 3]};
-        int32_t lo[8];
-        search_smem<8>(bp, nb, v, lo);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const ColCtx& c = k < 4 ? c0 : c1;
-          const int cl = k < 4 ? cl0 : cl0 + kWarps;
-          const int r = g * 128 + lane + 32 * (k & 3);
-          if (r < rows) {
-            int32_t id = lo[k];
-            if (CHECK) id = checked_id(id, c.table_rows, Q.status);
-            s_ids[cl * kIdPitch + r] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
-            if (c.ids_out) c.ids_out[b0 + r] = id;
-          }
+      for (int k = 0; k < 8; ++k) {
+        const int cl = cbase + (k >> 1) * kProducerWarps;
+        const ColCtx& c = cs.ctx[cl];
+        const int r = lane + 32 * (k & 1);
+        if (r < rows) {
+          int32_t id = lo[k];
+          if (CHECK) id = checked_id(id, c.table_rows, Q.status);
+          s_ids[cl * kIdPitch + r] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
+          if (c.ids_out) c.ids_out[b0 + r] = id;
         }
       }
       continue;
     }
-    for (int j = 0; j < ncol; ++j) {
-      const ColCtx& c = j ? c1 : c0;
-      const int cl = j ? cl0 + kWarps : cl0;
+    for (int q = 0; q < nq; ++q) {
+      const int cl = cbase + q * kProducerWarps;
+      const ColCtx& c = cs.ctx[cl];
       const float* bnd = c.bnd_off >= 0 ? s_bnd + c.bnd_off : P.boundaries + c.bnd_pool_off;
       for (int r = lane; r < rows; r += 32) {
         int32_t id = column_id(c, bnd, b0 + r);
@@ -504,30 +510,16 @@ __device__ __forceinline__ void dense_phase1(const DevPlan& P, const ReqRegs& Q,
   }
 }
 
-// Pull the input lines of a later tile of the SAME dense slab into L2.
-__device__ __forceinline__ void prefetch_tile_inputs(const CtaShared& cs, int num_cols,
-                                                     const Tile& tile) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int cl = warp; cl < num_cols; cl += kWarps) {
-    const ColCtx& c = cs.ctx[cl];
-    const int es = (c.value_dtype == RECOM_I64 || c.value_dtype == RECOM_F64) ? 8 : 4;
-    const uint8_t* p = c.values + (int64_t)tile.row_begin * es;
-    const int bytes = (tile.rows + 1) * es;  // + 1: string offsets read one past
-    const uint8_t* line = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)127) + lane * 128;
-    if (line < p + bytes) prefetch_l2(line);
-  }
-}
-
-// phase 2: lane = chunk; 32 / W rows per warp pass; UNROLL independent rows in flight.
+// Consumer side of one sub-tile: lane = chunk; 32 / W rows per warp pass; UNROLL independent
+// rows in flight.
 template <int VEC, bool STAGED>
-__device__ __forceinline__ void dense_phase2(const ReqRegs& Q, const CtaShared& cs, int W,
-                                             const DevChunk& ch, const Tile& tile,
-                                             const uint8_t* s_tables, const int32_t* s_ids) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void consume_ids(const ReqRegs& Q, const CtaShared& cs, int W,
+                                            const DevChunk& ch, int64_t b0, int rows,
+                                            const uint8_t* s_tables, const int32_t* s_ids, int cw,
+                                            int lane) {
   const int rpp = 32 / W;  // rows handled by one warp per pass
   const int sub = lane / W;
   if (sub >= rpp) return;
-  const int rows = tile.rows;
   const uint8_t* tbl;
   int64_t row_bytes = 0;
   if (STAGED) {
@@ -539,9 +531,9 @@ __device__ __forceinline__ void dense_phase2(const ReqRegs& Q, const CtaShared& 
   }
   const int32_t* ids = s_ids + ch.col_local * kIdPitch;
   const int64_t orb = Q.out_row_bytes;
-  const int step = kWarps * rpp;
-  int r = warp * rpp + sub;
-  uint8_t* outp = Q.out + ((int64_t)tile.row_begin + r) * orb + ch.out_byte;
+  const int step = kConsumerWarps * rpp;
+  int r = cw * rpp + sub;
+  uint8_t* outp = Q.out + (b0 + r) * orb + ch.out_byte;
   const int64_t ostep = (int64_t)step * orb;
   constexpr int UNROLL = 8;
   for (; r + (UNROLL - 1) * step < rows; r += UNROLL * step) {
@@ -566,6 +558,52 @@ __device__ __forceinline__ void dense_phase2(const ReqRegs& Q, const CtaShared& 
     v.store(outp);
     outp += ostep;
   }
+}
+
+// One DENSE tile (any number of rows), producers and consumers running concurrently.
+// `ring_it` counts the sub-tiles handed over since the kernel started (same value in every
+// thread); slot = ring_it & 1, and use u of a slot completes phase u of its barriers.
+template <int ELEM, bool CHECK>
+__device__ __forceinline__ void dense_tile(const DevPlan& P, const ReqRegs& Q, CtaShared& cs,
+                                           const DevSlab& slab, const DevChunk& ch, const Tile& tile,
+                                           const uint8_t* s_tables, const float* s_bnd,
+                                           int32_t* s_ids, int ids_slot, uint32_t stage_parity,
+                                           uint32_t& ring_it) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsub = (tile.rows + kSubRows - 1) / kSubRows;
+  uint32_t it = ring_it;
+  if (warp < kProducerWarps) {
+    if (slab.bnd_bytes > 0) mbar_wait(&cs.mbar_bnd, stage_parity);
+    for (int j = 0; j < nsub; ++j, ++it) {
+      const int slot = it & 1;
+      if (it >= 2) mbar_wait(&cs.empty[slot], ((it >> 1) - 1) & 1);
+      const int rows = min(kSubRows, tile.rows - j * kSubRows);
+      produce_ids<CHECK>(P, Q, cs, slab.num_cols, (int64_t)tile.row_begin + j * kSubRows, rows, s_bnd,
+                         s_ids + slot * ids_slot, warp, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cs.full[slot]);
+    }
+  } else {
+    if (slab.cls == kSlabDenseStaged) mbar_wait(&cs.mbar_tbl, stage_parity);
+    const int cw = warp - kProducerWarps;
+    for (int j = 0; j < nsub; ++j, ++it) {
+      const int slot = it & 1;
+      mbar_wait(&cs.full[slot], (it >> 1) & 1);
+      const int rows = min(kSubRows, tile.rows - j * kSubRows);
+      const int64_t b0 = (int64_t)tile.row_begin + j * kSubRows;
+      const int32_t* ids = s_ids + slot * ids_slot;
+      if (slab.cls == kSlabDenseStaged) {
+        if (slab.vec_bytes == 16) consume_ids<16, true>(Q, cs, slab.num_chunks, ch, b0, rows, s_tables, ids, cw, lane);
+        else consume_ids<ELEM, true>(Q, cs, slab.num_chunks, ch, b0, rows, s_tables, ids, cw, lane);
+      } else {
+        if (slab.vec_bytes == 16) consume_ids<16, false>(Q, cs, slab.num_chunks, ch, b0, rows, s_tables, ids, cw, lane);
+        else consume_ids<ELEM, false>(Q, cs, slab.num_chunks, ch, b0, rows, s_tables, ids, cw, lane);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cs.empty[slot]);
+    }
+  }
+  ring_it += (uint32_t)nsub;
 }
 
 // ---------------------------------------------------------------------------
@@ -656,15 +694,19 @@ __device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const CtaShared&
       e += 4;
     }
     {
-      // up to 3 left: issue them together as well
-      Chunk<VEC> v[3];
+      // up to 3 left: issue them together as well (named registers: a conditionally indexed
+      // array would live in local memory)
       const int left = end - e;
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (k < left) v[k].load(tbl + id_at(e + k) * row_bytes);
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (k < left) acc.add(v[k]);
+      Chunk<VEC> v0, v1, v2;
+      v0.zero();
+      v1.zero();
+      v2.zero();
+      if (left > 0) v0.load(tbl + id_at(e) * row_bytes);
+      if (left > 1) v1.load(tbl + id_at(e + 1) * row_bytes);
+      if (left > 2) v2.load(tbl + id_at(e + 2) * row_bytes);
+      acc.add(v0);
+      acc.add(v1);
+      acc.add(v2);
     }
     const int32_t n = end - beg;
     if (n > 1 && combiner != RECOM_COMBINE_SUM) {
@@ -682,59 +724,45 @@ __device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const CtaShared&
 // ---------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------
-// Tile sources of a CTA: SP = the shared pool of SPARSE tiles (long DRAM-latency chains),
-// ST = the CTA's own static DENSE macro tile(s), DP = the shared pool of small left-over
-// DENSE tiles (load balance). "Sparse first" CTAs walk SP, ST, DP; the others ST, SP, DP, so
-// that latency-bound gathers and bandwidth-bound dense stores overlap on every SM.
-// Claims are issued one step before they are looked at, so the latency of a pool's atomic
-// is never waited for (except once, when a pool runs dry). Lives in thread 0.
+// Tile sources of a CTA: ST = its own static DENSE macro tile (Sched::start), SP = the shared
+// pool of SPARSE tiles (long DRAM-latency chains), DP = the shared pool of small left-over
+// DENSE tiles (load balance). "Sparse first" CTAs walk SP, DP; the others ST, SP, DP, so that
+// latency-bound gathers and bandwidth-bound dense stores overlap on every SM.
+// Pool claims are issued one tile before they are looked at, so the atomic's latency is not
+// waited for (except when a pool runs dry). Lives in thread 0.
 struct TileCursor {
-  enum Kind : int { SP = 0, ST = 1, DP = 2, DONE = 3 };
+  enum Kind : int { SP = 0, DP = 1, DONE = 2 };
   struct Claim {
     int kind;
-    int raw;
+    int raw;  // the atomic's result, untouched until resolve()
   };
-  int step;          // position in this CTA's order of sources
-  bool sparse_first;
-  int cur, cur_end, num_sparse, dyn_begin, num_tiles;
+  int kind;
+  int num_sparse, num_tiles;
 
-  __device__ __forceinline__ void init(const ReqHeader* R) {
-    step = 0;
-    sparse_first = (int)blockIdx.x < R->sparse_first_ctas;
-    cur = R->static_begin[blockIdx.x];
-    cur_end = R->static_begin[blockIdx.x + 1];
-    num_sparse = R->num_sparse_tiles;
-    dyn_begin = R->dyn_begin;
-    num_tiles = R->num_tiles;
+  __device__ __forceinline__ void init(const Sched& S) {
+    kind = SP;
+    num_sparse = S.num_sparse_tiles;
+    num_tiles = S.num_tiles;
   }
-  __device__ __forceinline__ int kind_at(int s) const {
-    if (s >= 3) return DONE;
-    if (s == 2) return DP;
-    return (s == 0) == sparse_first ? SP : ST;
-  }
-  __device__ __forceinline__ Claim issue(ReqHeader* R) {
-    for (;;) {
-      const int kind = kind_at(step);
-      if (kind == ST) {
-        if (cur < cur_end) return Claim{ST, cur++};
-      } else if (kind == SP) {
-        if (num_sparse > 0) return Claim{SP, atomicAdd(&R->ctr_sparse, 1)};
-      } else if (kind == DP) {
-        if (dyn_begin < num_tiles) return Claim{DP, dyn_begin + atomicAdd(&R->ctr_dense, 1)};
-      } else {
-        return Claim{DONE, -1};
-      }
-      ++step;
+  __device__ __forceinline__ Claim issue(const ReqParams& A) {
+    if (kind == SP) {
+      if (num_sparse > 0) return Claim{SP, atomicAdd(A.counters, 1)};
+      kind = DP;
     }
+    if (kind == DP) {
+      if (num_sparse < num_tiles) return Claim{DP, atomicAdd(A.counters + 1, 1)};
+      kind = DONE;
+    }
+    return Claim{DONE, -1};
   }
   // -> tile index, or -1 when every source is exhausted
-  __device__ __forceinline__ int resolve(ReqHeader* R, Claim c) {
+  __device__ __forceinline__ int resolve(const ReqParams& A, Claim c) {
     for (;;) {
-      if (c.kind == ST) return c.raw;
       if (c.kind == DONE) return -1;
-      if (c.raw < (c.kind == SP ? num_sparse : num_tiles)) return c.raw;
-      if (kind_at(step) == c.kind) ++step;  // that pool is dry
-      c = issue(R);
+      if (c.kind == SP && c.raw < num_sparse) return c.raw;
+      if (c.kind == DP && num_sparse + c.raw < num_tiles) return num_sparse + c.raw;
+      if (kind == c.kind) ++kind;  // that pool is dry
+      c = issue(A);
     }
   }
 };
@@ -749,18 +777,23 @@ __device__ __forceinline__ uint64_t gtimer() {
 }
 // phase slots count SM cycles (clock64: cheap, exact); slots 14 / 15 hold the CTA's start /
 // end in globaltimer ns
-#define PROF_DECL uint64_t prof_acc[16] = {0}; prof_acc[14] = gtimer(); uint64_t prof_last = clock64();
+#define PROF_DECL                                                       \
+  uint32_t prof_acc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   \
+  const uint64_t prof_t0 = gtimer();                                    \
+  uint32_t prof_last = (uint32_t)clock64();
 #define PROF_T(i)                                   \
   if (threadIdx.x == 0) {                           \
-    const uint64_t now_ = clock64();                \
+    const uint32_t now_ = (uint32_t)clock64();      \
     prof_acc[i] += now_ - prof_last;                \
     prof_last = now_;                               \
   }
 #define PROF_COUNT(i) if (threadIdx.x == 0) prof_acc[i] += 1;
 #define PROF_END                                                        \
-  if (threadIdx.x == 0 && R->prof) {                                    \
-    prof_acc[15] = gtimer();                                            \
-    for (int i_ = 0; i_ < 16; ++i_) R->prof[blockIdx.x * 16 + i_] = prof_acc[i_]; \
+  if (threadIdx.x == 0 && A.prof) {                                     \
+    uint64_t* o_ = A.prof + blockIdx.x * 16;                            \
+    _Pragma("unroll") for (int i_ = 0; i_ < 14; ++i_) o_[i_] = prof_acc[i_]; \
+    o_[14] = prof_t0;                                                   \
+    o_[15] = gtimer();                                                  \
   }
 #else
 #define PROF_DECL
@@ -769,83 +802,81 @@ __device__ __forceinline__ uint64_t gtimer() {
 #define PROF_END
 #endif
 
+__device__ __forceinline__ void cp_async_tile(Tile* smem_dst, const Tile* gsrc) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    cp_async_16(reinterpret_cast<uint8_t*>(smem_dst) + 16 * i,
+                reinterpret_cast<const uint8_t*>(gsrc) + 16 * i);
+}
+
 template <bool BF16, bool CHECK>
 __global__ void __launch_bounds__(kThreads, 3)
-fused_columns_kernel(const DevPlan P, ReqHeader* __restrict__ R) {
+fused_columns_kernel(const DevPlan P, const Sched S, const ReqParams A) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ CtaShared cs;
   constexpr int ELEM = BF16 ? 2 : 4;
   uint8_t* s_tables = smem;
   float* s_bnd = reinterpret_cast<float*>(smem + P.smem_off_bnd);
   int32_t* s_ids = reinterpret_cast<int32_t*>(smem + P.smem_off_ids);
-  const Tile* tiles = R->tiles;
   ReqRegs Q;
-  Q.out = R->out;
-  Q.out_row_bytes = R->out_row_bytes;
-  Q.status = R->status;
+  Q.out = A.out;
+  Q.out_row_bytes = A.out_row_bytes;
+  Q.status = A.status;
 
   PROF_DECL
-  // Thread 0 claims tiles three steps ahead and copies the Tile record two steps ahead into
-  // cs.next with cp.async.
+  // The first tile: the CTA's static macro tile, read by every thread straight from the
+  // schedule (one global round trip, no hand-over), or a claim from the sparse pool.
+  Tile tile = S.start[blockIdx.x];
+  const bool sparse_first = (int)blockIdx.x < S.sparse_first_ctas || tile.slab_id < 0;
   TileCursor cursor;
   TileCursor::Claim pend{TileCursor::DONE, -1};
   if (threadIdx.x == 0) {
     mbar_init(&cs.mbar_bnd, 1);
     mbar_init(&cs.mbar_tbl, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&cs.full[i], kProducerWarps);
+      mbar_init(&cs.empty[i], kConsumerWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    cursor.init(R);
-    const int i0 = cursor.resolve(R, cursor.issue(R));
-    const int i1 = i0 >= 0 ? cursor.resolve(R, cursor.issue(R)) : -1;
-    if (i1 >= 0) pend = cursor.issue(R);
-    Tile none;
-    none.slab = -1;
-    none.row_begin = none.rows = none.pad = 0;
-    cs.next[0] = i0 >= 0 ? tiles[i0] : none;
-    cs.next[1] = i1 >= 0 ? tiles[i1] : none;
+    cursor.init(S);
+    if (sparse_first) {
+      const int i0 = cursor.resolve(A, cursor.issue(A));
+      if (i0 >= 0) cs.next[1] = S.tiles[i0];
+      else cs.next[1].slab_id = -1;
+    }
+    pend = cursor.issue(A);
   }
-  __syncthreads();
-  Tile tile = cs.next[0];   // this tile
-  Tile tile1 = cs.next[1];  // the next one
-  __syncthreads();          // both read before thread 0 reuses the slots
+  __syncthreads();  // mbarriers initialised (and cs.next[1] written)
+  if (sparse_first) {
+    tile = cs.next[1];
+    __syncthreads();  // read before thread 0 reuses the slot
+  }
   PROF_T(13)
 
   int cur_slab = -1;
   int staged_bnd = -1;        // pool offset of the single boundary set resident in smem, or -1
   uint32_t stage_parity = 1;  // parity of the phase completed by the latest staging
-  DevSlab slab;
   DevChunk ch;
-  slab.cls = kSlabSparse;
-  slab.num_cols = slab.num_chunks = 0;
-  slab.vec_bytes = 16;
-  slab.stage_bytes = slab.bnd_bytes = 0;
   ch.col = ch.col_local = ch.table_byte = ch.out_byte = 0;
   int sp_stride = 0;
+  uint32_t ring_it = 0;
+  const int ids_slot = P.smem_ids_cols * kIdPitch;
 
-  for (int k = 0; tile.slab >= 0; ++k) {
+  for (int k = 0; tile.slab_id >= 0; ++k) {
     const int buf = k & 1;
-    if (threadIdx.x == 0) {
-      const int idx = cursor.resolve(R, pend);
-      if (idx >= 0) {
-        cp_async_16(&cs.next[buf], tiles + idx);
-        pend = cursor.issue(R);
-      } else {
-        cs.next[buf].slab = -1;
-        pend = TileCursor::Claim{TileCursor::DONE, -1};
-      }
-    }
+    const DevSlab& slab = tile.slab;
     PROF_T(0)
     PROF_COUNT(11)
-    if (tile.slab != cur_slab) {
+    if (tile.slab_id != cur_slab) {
       // (every warp has passed the barrier that ends the previous tile)
-      slab = P.slabs[tile.slab];
-      cur_slab = tile.slab;
+      cur_slab = tile.slab_id;
       // a slab whose only boundary set is already resident keeps it (model E/F: one set for all)
       const bool keep_bnd = slab.num_bnds == 1 && slab.first_bnd_pool == staged_bnd;
       if (slab.cls == kSlabSparse) staged_bnd = -1;  // a sparse tile overwrites the whole region
       else if (slab.num_bnds == 1) staged_bnd = slab.first_bnd_pool;
       else if (slab.num_bnds > 1) staged_bnd = -1;
       if (slab.stage_bytes + (keep_bnd ? 0 : slab.bnd_bytes) > 0) stage_parity ^= 1;
-      enter_slab(P, R, slab, cs, s_tables, s_bnd, keep_bnd);
+      enter_slab(P, A, slab, cs, s_tables, s_bnd, keep_bnd);
       {
         const int lane = threadIdx.x & 31;
         ch = P.chunks[slab.first_chunk + lane % slab.num_chunks];
@@ -856,12 +887,27 @@ fused_columns_kernel(const DevPlan P, ReqHeader* __restrict__ R) {
       PROF_COUNT(12)
     }
     PROF_T(1)
+    // thread 0: look at the claim made one tile ago, start copying that tile's record into
+    // cs.next (read by everyone after the barrier that ends this tile), claim one more.
+    // Placed right after a barrier: a __syncthreads waits for outstanding atomics, so the
+    // claim must have the whole tile to come back.
+    if (threadIdx.x == 0) {
+      const int idx = cursor.resolve(A, pend);
+      PROF_T(2)
+      if (idx >= 0) {
+        cp_async_tile(&cs.next[buf], S.tiles + idx);
+        pend = cursor.issue(A);
+      } else {
+        cs.next[buf].slab_id = -1;
+        pend = TileCursor::Claim{TileCursor::DONE, -1};
+      }
+      PROF_T(3)
+    }
     if (slab.cls == kSlabSparse) {
       int32_t* sp = reinterpret_cast<int32_t*>(smem);
       sparse_phase1<CHECK>(P, Q, cs, slab.num_cols, tile, sp, sp_stride);
       PROF_T(8)
-      if (threadIdx.x == 0) cp_async_wait_all();
-      __syncthreads();  // staged splits / ids (and cs.next) are visible
+      __syncthreads();  // staged splits / ids are visible
       PROF_T(9)
       if (slab.vec_bytes == 16)
         sparse_phase2<16, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile, sp, sp_stride);
@@ -869,31 +915,14 @@ fused_columns_kernel(const DevPlan P, ReqHeader* __restrict__ R) {
         sparse_phase2<ELEM, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile, sp, sp_stride);
       PROF_T(10)
     } else {
-      if (slab.bnd_bytes > 0) mbar_wait(&cs.mbar_bnd, stage_parity);
-      PROF_T(2)
-      dense_phase1<CHECK>(P, Q, cs, slab.num_cols, tile, s_bnd, s_ids);
-      PROF_T(3)
-      if (threadIdx.x == 0) cp_async_wait_all();
-      __syncthreads();  // ids (and cs.next) are visible
-      PROF_T(4)
-      if (slab.cls == kSlabDenseStaged) {
-        mbar_wait(&cs.mbar_tbl, stage_parity);
-        PROF_T(5)
-        if (slab.vec_bytes == 16) dense_phase2<16, true>(Q, cs, slab.num_chunks, ch, tile, s_tables, s_ids);
-        else dense_phase2<ELEM, true>(Q, cs, slab.num_chunks, ch, tile, s_tables, s_ids);
-      } else {
-        if (slab.vec_bytes == 16) dense_phase2<16, false>(Q, cs, slab.num_chunks, ch, tile, s_tables, s_ids);
-        else dense_phase2<ELEM, false>(Q, cs, slab.num_chunks, ch, tile, s_tables, s_ids);
-      }
+      dense_tile<ELEM, CHECK>(P, Q, cs, slab, ch, tile, s_tables, s_bnd, s_ids, ids_slot, stage_parity,
+                              ring_it);
       PROF_T(6)
     }
-    const Tile tile2 = cs.next[buf];
-    if (tile2.slab == cur_slab && slab.cls != kSlabSparse)
-      prefetch_tile_inputs(cs, slab.num_cols, tile2);
-    __syncthreads();  // the tile's ids / staged splits may be overwritten from here on
+    if (threadIdx.x == 0) cp_async_wait_all();
+    __syncthreads();  // end of tile: the ids ring / staged splits may be reused, cs.next is visible
     PROF_T(7)
-    tile = tile1;
-    tile1 = tile2;
+    tile = cs.next[buf];
   }
   PROF_END
 }
@@ -916,16 +945,16 @@ int fused_kernel_configure(bool bf16, int smem_bytes) {
   return a < b ? a : b;
 }
 
-void launch_fused_columns(const DevPlan& plan, ReqHeader* d_req, int grid, bool bf16,
-                          cudaStream_t stream) {
+void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqParams& req, int grid,
+                          bool bf16, cudaStream_t stream) {
   const bool check = plan.check_ids != 0;
   const size_t sm = (size_t)plan.smem_bytes;
   if (bf16) {
-    if (check) fused_columns_kernel<true, true><<<grid, kThreads, sm, stream>>>(plan, d_req);
-    else fused_columns_kernel<true, false><<<grid, kThreads, sm, stream>>>(plan, d_req);
+    if (check) fused_columns_kernel<true, true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+    else fused_columns_kernel<true, false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
   } else {
-    if (check) fused_columns_kernel<false, true><<<grid, kThreads, sm, stream>>>(plan, d_req);
-    else fused_columns_kernel<false, false><<<grid, kThreads, sm, stream>>>(plan, d_req);
+    if (check) fused_columns_kernel<false, true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+    else fused_columns_kernel<false, false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
   }
 }
 

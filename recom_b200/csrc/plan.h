@@ -15,9 +15,11 @@ namespace recom {
 constexpr int kThreads = 256;          // threads per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxChunks = 32;         // a slab is at most one warp wide
-constexpr int kMaxTileRows = 256;      // rows of a static DENSE macro tile (its ids live in smem)
+constexpr int kProducerWarps = 4;      // DENSE tiles: warps 0-3 turn inputs into row ids ...
+constexpr int kConsumerWarps = kWarps - kProducerWarps;  // ... warps 4-7 gather and store
+constexpr int kSubRows = 64;           // rows of one hand-over between them (ids ring slot)
+constexpr int kIdPitch = kSubRows + 1; // smem pitch of a column's ids (bank-conflict free)
 constexpr int kPoolTileRows = 64;      // rows of a DENSE tile in the load-balancing pool
-constexpr int kIdPitch = kMaxTileRows + 1;  // smem pitch (bank-conflict free)
 constexpr int kSparseTileRowsL2 = 16;  // rows per SPARSE tile, tables that fit in L2
 constexpr int kSparseTileRowsHbm = 8;  // rows per SPARSE tile, HBM-resident tables
 constexpr int64_t kHbmTableBytes = 32ll << 20;  // a table beyond this is "HBM resident"
@@ -154,46 +156,61 @@ struct DevPlan {
   int32_t smem_bytes;
 };
 
-// A unit of work pulled by a persistent CTA.
+// A unit of work of a persistent CTA: a row block of a slab. The slab record travels with
+// the tile so that a CTA entering a new slab needs no further lookup.
 struct Tile {
-  int32_t slab;
+  int32_t slab_id;      // -1: none
   int32_t row_begin;
   int32_t rows;
   int32_t pad;
+  DevSlab slab;
+};
+static_assert(sizeof(Tile) == 64, "Tile is copied with four 16-byte cp.async");
+
+// The schedule of a batch size (cached on the device by the plan); a kernel parameter.
+struct Sched {
+  const Tile* tiles;   // [num_tiles]: SPARSE pool, then DENSE pool
+  const Tile* start;   // [grid]: the static DENSE macro tile of each CTA (slab_id -1: none)
+  int32_t num_tiles;
+  int32_t num_sparse_tiles;   // tiles [0, num_sparse_tiles) are the SPARSE pool
+  int32_t sparse_first_ctas;  // CTAs below this index start with the SPARSE pool
+  int32_t pad;
 };
 
-// Per-request argument block. Built on the host in pinned memory, uploaded with
-// one cudaMemcpyAsync into the workspace, read by every kernel of the request
-// (replaces the reference's KnlArgs + SymbolResults uploads,
-// cuda_emitter.cc:2182-2232). The tile table is NOT part of it: it depends only
-// on the batch size and is cached on the device by the plan.
-struct ReqHeader {
+// Per-request values known on the host at launch; a kernel parameter (no dependent loads).
+struct ReqParams {
   const uint8_t* blob;
   uint8_t* out;
-  int32_t* ids_out;       // may be null
-  int32_t* status;        // may be null
-  int32_t* ws_ids;        // workspace: transformed ids of non-DENSE columns
-  int32_t* ws_row_splits; // workspace: row_splits built from COO columns
-  const Tile* tiles;      // device tile table of this batch size
-  const int32_t* static_begin;  // [grid + 1] static tile range of every CTA
-  uint64_t* prof;         // profiling builds only (make prof): [grid, 16] phase timers, else null
+  int32_t* ids_out;        // may be null
+  int32_t* status;         // may be null
+  int32_t* ws_ids;         // workspace: transformed ids of non-DENSE columns
+  int32_t* ws_row_splits;  // workspace: row_splits built from COO columns
+  // arrays inside the uploaded argument block (device addresses)
+  const int64_t* slot_offsets;  // [num_slots]
+  const void* const* tables;    // [num_tables]
+  const int32_t* ids_base;      // [num_cols + 1] prefix of ids per column
+  const int32_t* sparse_base;   // [num_sparse + 1] prefix of ids, non-DENSE only
+  int32_t* counters;            // [2]: SPARSE pool, DENSE pool claim counters (start at 0)
+  uint64_t* prof;               // profiling builds only: [grid, 16] phase timers, else null
   int64_t batch;
   int64_t out_row_bytes;
-  // schedule: tiles [0, num_sparse_tiles) are pulled through ctr_sparse, each CTA owns
-  // a static range, tiles [dyn_begin, num_tiles) are pulled through ctr_dense
-  int32_t num_tiles;
-  int32_t num_sparse_tiles;
-  int32_t dyn_begin;
-  int32_t sparse_first_ctas;  // CTAs below this index start with the SPARSE pool
-  int32_t ctr_sparse;
-  int32_t ctr_dense;
-  int32_t num_coo;        // number of COO columns
+};
+
+// Per-request argument block: a header followed by the arrays ReqParams points to. Built on
+// the host in pinned memory, uploaded with one cudaMemcpyAsync into the workspace (replaces the
+// reference's KnlArgs + SymbolResults uploads, cuda_emitter.cc:2182-2232).
+struct ReqHeader {
+  int32_t counters[4];        // claim counters, zero on upload
+  const uint8_t* blob;        // (kept for the COO -> row_splits pre-pass)
+  int32_t* ws_row_splits;
+  int64_t batch;
+  int32_t num_coo;            // number of COO columns
   int32_t pad0;
   // byte offsets from the start of this block
   uint32_t off_slot_offsets;  // int64[num_slots]
   uint32_t off_tables;        // const void*[num_tables]
-  uint32_t off_ids_base;      // int32[num_cols + 1] prefix of ids per column
-  uint32_t off_sparse_base;   // int32[num_sparse + 1] prefix of ids, non-DENSE only
+  uint32_t off_ids_base;      // int32[num_cols + 1]
+  uint32_t off_sparse_base;   // int32[num_sparse + 1]
   uint32_t off_coo_cols;      // int32[num_coo] column index of each COO column
   uint32_t total_bytes;
 };
@@ -220,8 +237,8 @@ __host__ __device__ inline const int32_t* req_coo_cols(const ReqHeader* r) {
 }
 
 // kernels.cu
-void launch_fused_columns(const DevPlan& plan, ReqHeader* d_req, int grid, bool bf16,
-                          cudaStream_t stream);
+void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqParams& req, int grid,
+                          bool bf16, cudaStream_t stream);
 void launch_coo_to_row_splits(const DevPlan& plan, const ReqHeader* d_req, int num_coo,
                               int64_t max_nnz, cudaStream_t stream);
 void launch_scatter_columns(const void* const* d_cols, const int32_t* d_dims,

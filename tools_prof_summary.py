@@ -3,7 +3,7 @@
 import sys
 import numpy as np
 a = np.loadtxt(sys.argv[1], dtype=np.uint64).astype(np.float64)
-names = ["fetch", "stage_issue", "bnd_wait", "d_phase1", "d_barrier", "tbl_wait", "d_phase2", "prefetch",
+names = ["looptop", "enter+sync", "resolve", "cp+issue", "-", "-", "dense_tile", "end_sync",
          "s_phase1", "s_barrier", "s_phase2", "tiles", "stagings", "prologue", "t_start", "t_end"]
 CYC = 1.0 / 1.965  # ns per SM cycle at 1965 MHz
 t0 = a[:, 14].min()
