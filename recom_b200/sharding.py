@@ -1,0 +1,275 @@
+"""Multi-GPU partitioning of the fused embedding-column stage.
+
+The reference has no multi-GPU path (one process, one GPU, CPU spill for tables above
+256 MiB: cuda_emitter.cc:1080-1094). Columns are independent units, so the path shards
+with exactly one exchange step at the end:
+
+  Mode A  column-group sharding (`partition_columns`): every rank owns a CONTIGUOUS run of
+          the concat row (so rank order == concat order), holds only those tables, computes
+          out_g[B, W_g]; ranks exchange the slices. Used when the tables do not fit one GPU
+          or there are too many columns.
+  Mode B  table row-sharding (`RowShard`): rows r of a table live on rank r % G; every rank
+          reduces its local rows into partial sums [B, D] (+ counts), combined with
+          reduce-scatter / all-reduce; mean / sqrtn scaling is applied after the reduction.
+  Mode C  replicas: everything fits (models E, F): batch split, no collective.
+
+This module is host logic plus torch.distributed plumbing (one process per GPU). The
+exchange of Mode A is an NCCL all-gather of the padded slices followed by one
+concatenation copy; the kernel-side variant (stores straight into peer concat tensors over
+NVLink) is described in DESIGN.md.
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .schema import Column, Feature, Model
+
+
+# ---------------------------------------------------------------------------------------
+# Mode A: contiguous column groups
+# ---------------------------------------------------------------------------------------
+@dataclass
+class ColumnShard:
+    rank: int
+    first_col: int          # [first_col, last_col) of the global model, in concat order
+    last_col: int
+    out_begin: int          # element span of this shard in the global concat row
+    out_end: int
+    model: Model            # local model: local table indices, local slots, offsets from 0
+    table_ids: List[int]    # global table index of every local table
+
+    @property
+    def width(self) -> int:
+        return self.out_end - self.out_begin
+
+
+def column_cost(c: Column, es: int, ids_per_row: float = 5.5) -> float:
+    """Relative cost of a column per sample: bytes written + bytes gathered (multi-hot rows
+    gather ~ids_per_row table rows; latency-bound HBM gathers weigh more)."""
+    out_bytes = c.dim * es
+    if c.lookup == L.LOOKUP_DENSE:
+        return out_bytes + (2.0 * out_bytes if c.transform in (L.XFORM_HASH_STR, L.XFORM_HASH_INT) else 0.0)
+    big = c.table_rows * c.dim * es > (32 << 20)
+    return out_bytes + ids_per_row * out_bytes * (4.0 if big else 2.0)
+
+
+def partition_columns(model: Model, world: int, max_table_bytes: Optional[int] = None) -> List[ColumnShard]:
+    """Split the concat row into `world` contiguous runs of columns with balanced cost,
+    optionally bounded by table bytes per rank. Deterministic: every rank computes the same
+    partition from the same model."""
+    assert world >= 1
+    es = 2 if model.out_dtype == L.BF16 else 4
+    order = sorted(range(len(model.columns)), key=lambda i: model.columns[i].out_offset)
+    assert order == list(range(len(model.columns))), "model columns must be in concat order"
+    costs = np.array([column_cost(c, es) for c in model.columns])
+    cum = np.concatenate([[0.0], np.cumsum(costs)])
+    cuts = [0]
+    for g in range(1, world):
+        target = cum[-1] * g / world
+        k = int(np.searchsorted(cum, target, side="left"))
+        k = min(max(k, cuts[-1] + (1 if len(model.columns) - cuts[-1] > world - g else 0)), len(model.columns))
+        cuts.append(k)
+    cuts.append(len(model.columns))
+    shards = []
+    for g in range(world):
+        lo, hi = cuts[g], cuts[g + 1]
+        cols = [copy.copy(c) for c in model.columns[lo:hi]]
+        table_ids: List[int] = []
+        remap: Dict[int, int] = {}
+        for c in cols:
+            if c.table not in remap:
+                remap[c.table] = len(table_ids)
+                table_ids.append(c.table)
+            c.table = remap[c.table]
+        local = Model(cols, [model.table_shapes[t] for t in table_ids], out_dtype=model.out_dtype,
+                      name=f"{model.name}.shard{g}of{world}")
+        if cols:
+            local.finalize()
+        out_begin = model.columns[lo].out_offset if lo < hi else (shards[-1].out_end if shards else 0)
+        out_end = out_begin + sum(c.dim for c in cols)
+        sh = ColumnShard(g, lo, hi, out_begin, out_end, local, table_ids)
+        if max_table_bytes is not None:
+            assert local.table_bytes() <= max_table_bytes, (
+                f"shard {g}: {local.table_bytes()} table bytes exceed {max_table_bytes}")
+        shards.append(sh)
+    return shards
+
+
+def shard_features(shard: ColumnShard, features: Dict[str, Feature]) -> Dict[str, Feature]:
+    """Inputs are replicated (ids are small next to tables): a rank keeps what its columns read."""
+    keys = {c.key for c in shard.model.columns}
+    return {k: v for k, v in features.items() if k in keys}
+
+
+def assemble_host(shards: Sequence[ColumnShard], outs: Sequence[np.ndarray]) -> np.ndarray:
+    """Host "fake all-gather": concatenate shard outputs in rank (== concat) order."""
+    return np.concatenate([o[:, :s.width] for s, o in zip(shards, outs)], axis=1)
+
+
+def all_gather_columns(local_out, shards: Sequence[ColumnShard], group=None):
+    """torch.distributed exchange of Mode A: all-gather of the (padded) slices, then one
+    concatenation. local_out: [B, W_rank] tensor. Works with nccl (GPU) and gloo (CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    wmax = max(s.width for s in shards)
+    B = local_out.shape[0]
+    if local_out.shape[1] == wmax:
+        padded = local_out.contiguous()
+    else:
+        padded = torch.zeros((B, wmax), dtype=local_out.dtype, device=local_out.device)
+        padded[:, :local_out.shape[1]] = local_out
+    flat = torch.empty((world * B, wmax), dtype=local_out.dtype, device=local_out.device)
+    dist.all_gather_into_tensor(flat, padded, group=group)
+    gathered = flat.view(world, B, wmax)
+    return torch.cat([gathered[g, :, :shards[g].width] for g in range(world)], dim=1)
+
+
+# ---------------------------------------------------------------------------------------
+# Mode B: table row-sharding
+# ---------------------------------------------------------------------------------------
+@dataclass
+class RowShard:
+    """rows r of every table live on rank r % world, at local row r // world."""
+
+    rank: int
+    world: int
+
+    def local_rows(self, table_rows: int) -> int:
+        return (table_rows - self.rank + self.world - 1) // self.world
+
+    def local_table(self, table: np.ndarray) -> np.ndarray:
+        return np.ascontiguousarray(table[self.rank::self.world])
+
+    def local_model(self, model: Model) -> Model:
+        """Same columns, partial SUMs over local rows: combiners become SUM (the scaling is
+        applied after the cross-rank reduction), ids arrive pre-transformed."""
+        cols = []
+        for c in model.columns:
+            c2 = copy.copy(c)
+            c2.lookup = L.LOOKUP_SEGMENT
+            c2.combiner = L.COMBINE_SUM
+            c2.transform, c2.value_dtype, c2.boundaries, c2.num_buckets = L.XFORM_NONE, L.I64, None, 0
+            c2.seg_format = L.SEG_ROW_SPLITS_I32
+            c2.table_rows = max(self.local_rows(c.table_rows), 1)
+            c2.input_key = f"{c.name}@rowshard"
+            cols.append(c2)
+        shapes = [(max(self.local_rows(r), 1), d) for r, d in model.table_shapes]
+        return Model(cols, shapes, out_dtype=model.out_dtype, name=f"{model.name}.rows{self.rank}").finalize()
+
+    def local_feature(self, ids: np.ndarray, row_of: np.ndarray, batch: int) -> Tuple[Feature, np.ndarray]:
+        """Global row ids (already hashed / bucketized) + their sample -> the local ids this
+        rank owns, as row_splits; also returns the per-sample TOTAL id count (for mean/sqrtn)."""
+        mine = (ids % self.world) == self.rank
+        lids = (ids[mine] // self.world).astype(np.int64)
+        lrow = row_of[mine]
+        counts = np.bincount(lrow, minlength=batch).astype(np.int64)
+        rs = np.zeros(batch + 1, np.int32)
+        rs[1:] = np.cumsum(counts)
+        total = np.bincount(row_of, minlength=batch).astype(np.int64)
+        return Feature(lids, row_splits=rs), total
+
+
+def combine_scale(combiner: int, counts: np.ndarray) -> np.ndarray:
+    """Per-sample factor applied after the partial sums were reduced (TF semantics:
+    mean divides by n, sqrtn by sqrt(n); empty rows stay 0)."""
+    n = np.maximum(counts.astype(np.float64), 1.0)
+    if combiner == L.COMBINE_MEAN:
+        return (1.0 / n).astype(np.float32)
+    if combiner == L.COMBINE_SQRTN:
+        return (1.0 / np.sqrt(n)).astype(np.float32)
+    return np.ones_like(n, dtype=np.float32)
+
+
+# ---------------------------------------------------------------------------------------
+# bench leg: the >180 GB large-table configuration (BASELINE.json config 4)
+# ---------------------------------------------------------------------------------------
+def bench_large_table(args, world: int, rank: int, local: int):
+    """1000 multi-hot mean columns over [rows, 32] fp32 tables, column-group sharded over
+    `world` GPUs, NCCL all-gather of the slices. Prints one JSON line on rank 0."""
+    import ctypes as C
+    import json
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    from . import runtime as R
+    from . import synth
+    from .schema import algorithmic_bytes, pack_request
+
+    n_cols = int(getattr(args, "lt_columns", 0) or 1000)
+    rows = int(getattr(args, "lt_rows", 0) or 1_500_000)
+    batch = args.batch or 2048
+    model = synth.large_table_model(n_cols, rows, 32)
+    per_gpu_budget = 170 << 30
+    if model.table_bytes() / world > per_gpu_budget:
+        if rank == 0:
+            print(json.dumps({"metric": "embedding_column_stage_samples_per_sec", "unavailable":
+                              f"{model.table_bytes() / 1e9:.0f} GB of tables need more than {world} GPU(s)"}))
+        return
+    shards = partition_columns(model, world)
+    sh = shards[rank]
+    plan = R.Plan(sh.model, device=local)
+    tables = R.make_tables(sh.model, device=local, seed=rank)
+    ptrs = R.table_pointers(tables)
+    K, W, S = args.steps, max(args.warmup, 3), max(args.sets, 2)
+    reqs = []
+    for s in range(S):
+        feats = synth.make_features(model, batch, seed=100 + s)  # replicated inputs, same on all ranks
+        reqs.append(pack_request(sh.model, batch, shard_features(sh, feats)))
+    blobs = [R.upload_blob(r, local) for r in reqs]
+    outs = [plan.alloc_out(batch) for _ in range(S)]
+    wss = [plan.alloc_workspace(batch, r.sparse_ids) for r in reqs]
+    stream = torch.cuda.current_stream(local)
+    alg = float(np.mean([algorithmic_bytes(sh.model, r) for r in reqs]))
+
+    def step(i):
+        s = i % S
+        plan.run(reqs[s], blobs[s], ptrs, outs[s], wss[s], stream=stream)
+        return all_gather_columns(outs[s], shards) if world > 1 else outs[s]
+
+    def barrier():
+        torch.cuda.synchronize(local)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(local)
+
+    for i in range(W):
+        full = step(i)
+    assert full.shape == (batch, model.out_width)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        step(i)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    alg_t = torch.tensor([alg], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(alg_t, op=dist.ReduceOp.SUM)
+    ms = float(t[0]) / K
+    if rank == 0:
+        print(json.dumps({
+            "metric": "embedding_column_stage_samples_per_sec", "value": batch / (ms * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"large_table_{n_cols}x{rows}x32_b{batch}", "columns": n_cols,
+                       "batch": batch, "table_bytes": model.table_bytes(),
+                       "parallelism": f"column-group x{world}, NCCL all-gather of [B, W_g] slices",
+                       "l2": f"rotating {S} request/output sets"},
+            "roofline": {"bound": "hbm", "achieved": float(alg_t[0]) / (ms * 1e-3) / 1e9,
+                         "unit": "GB/s", "note": "aggregate algorithmic bytes over all ranks / step time"},
+            "gpu_launches": plan.last_launch_count() * K,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()

@@ -1,0 +1,45 @@
+"""torchrun worker of tests/test_gpu_sharding.py::test_nccl_all_gather_two_gpus."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from recom_b200 import runtime as R  # noqa: E402
+from recom_b200 import sharding, synth  # noqa: E402
+from recom_b200.schema import pack_request  # noqa: E402
+from tests.helpers import run_oracle  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    m = synth.mixed_model(64, seed=13, large_rows=1 << 14)
+    batch = 96
+    feats = synth.make_features(m, batch, seed=6, empty_frac=0.1)
+    tables = synth.make_tables_np(m)
+    shards = sharding.partition_columns(m, world)
+    s = shards[rank]
+    plan = R.Plan(s.model, device=local)
+    dev_tables = R.tables_from_numpy(s.model, [tables[t] for t in s.table_ids], local)
+    req = pack_request(s.model, batch, sharding.shard_features(s, feats))
+    out = plan.alloc_out(batch)
+    ws = plan.alloc_workspace(batch, req.sparse_ids)
+    plan.run(req, R.upload_blob(req, local), R.table_pointers(dev_tables), out, ws)
+    full = sharding.all_gather_columns(out, shards)
+    torch.cuda.synchronize()
+    ref, _ = run_oracle(m, pack_request(m, batch, feats), tables)
+    np.testing.assert_allclose(full.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+    dist.barrier()
+    if rank == 0:
+        print("SHARD_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
