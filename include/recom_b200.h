@@ -217,6 +217,30 @@ RECOM_API recom_status recom_fingerprint64(const uint8_t *bytes, const int32_t *
                                  int64_t n, uint64_t *out,
                                  recom_stream_t stream);
 
+/* ---- host-side pieces of the op surface (no GPU needed) ------------------------------ */
+
+/* Addons>ConcatInputs (tensorflow_addons/custom_ops/concat_inputs/concat_inputs_ops.cc:42-77):
+ * copies `num_inputs` host buffers into one blob, every slot 16-byte aligned and zero
+ * padded, and reports each slot's byte offset. `blob == NULL` only computes `*needed`. */
+RECOM_API recom_status recom_concat_inputs(const void *const *inputs, const int64_t *nbytes,
+                                 int32_t num_inputs, void *blob, size_t blob_bytes,
+                                 int64_t *offsets, size_t *needed);
+
+/* Addons>ShapeConstruct (tensorflow_addons/custom_ops/shape_construct/shape_construct_ops.cc:34-153):
+ * run-time evaluation of size expressions over named symbols (num_segments, reshape
+ * shapes, the `symbols` input of FeatureColumnProcessWithSymbols). The expression strings
+ * are the ones the reference stores in the op's `exprs` attr (C syntax as printed by
+ * SymEngine: + - * / %, parentheses, max/min/pow/abs/floor/ceiling); symbols are bound as C
+ * `int`, `/` truncates, exactly like the code the reference compiles with g++. */
+typedef struct recom_shape_construct recom_shape_construct;
+RECOM_API recom_status recom_shape_construct_create(const char *const *symbols, int32_t num_symbols,
+                                          const char *const *exprs, int32_t num_exprs,
+                                          recom_shape_construct **out);
+RECOM_API recom_status recom_shape_construct_eval(const recom_shape_construct *sc,
+                                        const int64_t *inputs, int32_t num_inputs,
+                                        int64_t *outputs, int32_t num_outputs);
+RECOM_API recom_status recom_shape_construct_destroy(recom_shape_construct *sc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,8 @@ EXPORTS = [
     "recom_plan_out_width", "recom_plan_workspace_bytes", "recom_plan_run",
     "recom_last_launch_count", "recom_plan_algorithmic_bytes", "recom_scatter_columns",
     "recom_segment_ids_to_row_splits", "recom_string_to_hash_bucket_fast", "recom_fingerprint64",
+    "recom_concat_inputs", "recom_shape_construct_create", "recom_shape_construct_eval",
+    "recom_shape_construct_destroy",
 ]
 
 
@@ -98,6 +100,10 @@ def _load() -> C.CDLL:
         "recom_segment_ids_to_row_splits": [vp, i64, i32, i64, vp, vp],
         "recom_string_to_hash_bucket_fast": [vp, vp, i64, i64, vp, vp],
         "recom_fingerprint64": [vp, vp, i64, vp, vp],
+        "recom_concat_inputs": [vp, vp, i32, vp, sz, vp, C.POINTER(sz)],
+        "recom_shape_construct_create": [vp, i32, vp, i32, C.POINTER(vp)],
+        "recom_shape_construct_eval": [vp, vp, i32, vp, i32],
+        "recom_shape_construct_destroy": [vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

@@ -45,6 +45,23 @@ recom_status fail(recom_status st, const char* fmt, ...) {
   return st;
 }
 
+}  // namespace
+
+namespace recom {
+// shared with host_ops.cc
+recom_status set_error(recom_status st, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return st;
+}
+}  // namespace recom
+
+namespace {
+
 #define CUDA_TRY(expr)                                                             \
   do {                                                                             \
     cudaError_t _e = (expr);                                                       \
