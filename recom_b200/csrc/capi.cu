@@ -69,7 +69,8 @@ namespace {
       return fail(RECOM_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
-constexpr int kRing = 16;
+constexpr int kRing = 16;       // pinned staging slots of the upload path
+constexpr int kArgCache = 16;   // device-resident argument blocks kept per plan
 
 struct ArgSlot {
   std::mutex mu;
@@ -77,6 +78,14 @@ struct ArgSlot {
   size_t cap = 0;
   cudaEvent_t done = nullptr;
   bool in_flight = false;
+};
+
+// A device-resident copy of a request's argument block, keyed by content. Entries are
+// immutable once published and live until the plan dies, so kernels in flight on any stream
+// may read them without further synchronisation.
+struct ArgEntry {
+  std::vector<uint8_t> host;
+  uint8_t* dev = nullptr;
 };
 
 int dtype_bytes(int32_t dt) {
@@ -93,27 +102,32 @@ int dtype_bytes(int32_t dt) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Schedule of one batch size (see TileCursor in kernels.cu): `tiles` = [sparse pool |
-// dense pool], `start` = the static macro tile of every CTA.
+// Static schedule of one batch size (see Sched in plan.h).
 struct TileTable {
-  std::vector<Tile> tiles;
-  std::vector<Tile> start;  // [grid]
+  std::vector<Tile> runs;      // DENSE runs grouped by CTA
+  std::vector<Tile> sparse;    // SPARSE warp tiles, heavy slabs first
+  std::vector<CtaWork> cta;    // [grid]
   int grid = 1;
-  int num_sparse = 0;
-  int sparse_first = 0;     // CTAs [0, sparse_first) start with the sparse pool
-  void* d_block = nullptr;  // device copy: tiles, then start (cached tables only)
+  int sparse_warps = 0;
+  void* d_block = nullptr;  // device copy: runs, sparse, cta (cached tables only)
   ~TileTable() {
     if (d_block) cudaFree(d_block);
   }
-  size_t tiles_bytes() const { return tiles.size() * sizeof(Tile); }
-  size_t bytes() const { return tiles_bytes() + start.size() * sizeof(Tile); }
+  size_t runs_bytes() const { return align_up(runs.size() * sizeof(Tile), 16); }
+  size_t sparse_bytes() const { return align_up(sparse.size() * sizeof(Tile), 16); }
+  size_t bytes() const { return runs_bytes() + sparse_bytes() + cta.size() * sizeof(CtaWork); }
+  void write(uint8_t* dst) const {
+    if (!runs.empty()) memcpy(dst, runs.data(), runs.size() * sizeof(Tile));
+    if (!sparse.empty()) memcpy(dst + runs_bytes(), sparse.data(), sparse.size() * sizeof(Tile));
+    memcpy(dst + runs_bytes() + sparse_bytes(), cta.data(), cta.size() * sizeof(CtaWork));
+  }
   Sched sched(const void* base) const {
     Sched s{};
-    s.tiles = (const Tile*)base;
-    s.start = (const Tile*)((const uint8_t*)base + tiles_bytes());
-    s.num_tiles = (int32_t)tiles.size();
-    s.num_sparse_tiles = num_sparse;
-    s.sparse_first_ctas = sparse_first;
+    s.runs = (const Tile*)base;
+    s.sparse_tiles = (const Tile*)((const uint8_t*)base + runs_bytes());
+    s.cta = (const CtaWork*)((const uint8_t*)base + runs_bytes() + sparse_bytes());
+    s.num_sparse_tiles = (int32_t)sparse.size();
+    s.sparse_warps = sparse_warps;
     return s;
   }
 };
@@ -140,9 +154,9 @@ struct recom_plan {
   DevPlan dev{};
   int elem_bytes = 4;
   int num_sms = 148;
-  int ctas_per_sm = 3;
-  double pool_frac = 0.15;  // share of the dense tiles kept in the dynamic pool
-  double hash_weight = 5.0; // extra cost of a hashed column's output byte (schedule balance)
+  int ctas_per_sm = 2;
+  double hash_weight = 2.0;   // extra cost of a hashed column's output byte (schedule balance)
+  double sparse_weight = 2.5; // cost of a SPARSE warp tile relative to a DENSE one
   // tile tables depend only on the batch size: cached (read-mostly)
   std::mutex tiles_mu;
   std::map<int64_t, std::shared_ptr<const TileTable>> tiles_by_batch;
@@ -151,7 +165,12 @@ struct recom_plan {
   uint64_t* d_prof = nullptr;
   int prof_grid = 0;
   std::string prof_path;
-  // pinned argument ring
+  // device-resident argument blocks, keyed by content (steady state: no upload at all)
+  std::mutex args_mu;
+  std::vector<std::unique_ptr<ArgEntry>> arg_cache;
+  std::vector<uint8_t> last_miss;  // a block is cached the second time it is seen in a row
+  bool cache_args = true;
+  // pinned argument ring of the upload path (first sight of a block, COO inputs, full caches)
   ArgSlot ring[kRing];
   std::atomic<uint32_t> ring_next{0};
 };
@@ -314,7 +333,7 @@ void build_layout(recom_plan* p) {
     s.first_col = (int32_t)p->slab_cols.size();
     s.first_bnd = (int32_t)p->slab_bnds.size();
     s.first_bnd_pool = -1;
-    s.tile_rows = cls == kSlabSparse ? kSparseTileRowsL2 : kPoolTileRows;
+    s.tile_rows = kDenseTileRows;
     p->slabs.push_back(s);
   };
   // smem offset of a table already staged by the open slab, or -1
@@ -401,7 +420,6 @@ void build_layout(recom_plan* p) {
           sc.bnd_off = sb.smem_off;
         }
       }
-      if (cls == kSlabSparse && table_bytes > kHbmTableBytes) s.tile_rows = kSparseTileRowsHbm;
       p->slab_cols.push_back(sc);
       s.num_cols++;
       for (int k = 0; k < take; ++k) {
@@ -417,23 +435,56 @@ void build_layout(recom_plan* p) {
     }
     prev_end = d.out_offset + d.dim;
   }
-  // shared memory layout: [staged tables | staged boundaries | 2 x ids]
+  // per-slab derived fields
+  for (DevSlab& sl : p->slabs) {
+    if (sl.cls == kSlabSparse) {
+      const int rpp = 32 / sl.num_chunks;
+      sl.tile_rows = std::min(32, rpp * kSparseRowsPerSub);
+      continue;
+    }
+    for (int g = 0; g * 8 + 8 <= sl.num_cols; ++g) {
+      bool fast = true;
+      for (int k = 0; k < 8; ++k) {
+        const DevSlabCol& sc = p->slab_cols[sl.first_col + g * 8 + k];
+        fast = fast && sc.transform == RECOM_XFORM_BUCKETIZE && sc.value_dtype == RECOM_F32 &&
+               sc.bnd_off >= 0 && sc.num_boundaries > 0;
+      }
+      if (fast) sl.fast8_mask |= 1u << g;
+    }
+  }
+  // shared memory layout: [staged tables | staged boundaries | DENSE contexts | warp scratch]
   int max_stage = 0, max_bnd = 0, max_cols = 1;
+  int dense_need = 0, sparse_need = 0, sparse_min = 0;
   for (const DevSlab& s : p->slabs) {
     max_stage = std::max(max_stage, s.stage_bytes);
     max_bnd = std::max(max_bnd, s.bnd_bytes);
-    if (s.cls != kSlabSparse) max_cols = std::max(max_cols, s.num_cols);
+    if (s.cls != kSlabSparse) {
+      max_cols = std::max(max_cols, s.num_cols);
+      dense_need = std::max(dense_need, s.num_cols * kIdPitch * 4);
+    } else {
+      const int base = s.num_cols * (int)sizeof(ColCtx) + (s.num_cols + 1) * 4 +
+                       s.num_cols * (s.tile_rows + 1) * 4;
+      sparse_need = std::max(sparse_need, base + s.num_cols * s.tile_rows * kSparseIdsPerRow * 4);
+      sparse_min = std::max(sparse_min, base + 128);
+    }
   }
   p->dev.smem_off_bnd = (int32_t)align_up((size_t)max_stage, 128);
-  p->dev.smem_off_ids = p->dev.smem_off_bnd + (int32_t)align_up((size_t)max_bnd, 128);
-  p->dev.smem_ids_cols = max_cols;
-  p->dev.smem_bytes = p->dev.smem_off_ids + 2 * max_cols * kIdPitch * 4;  // two ring slots
-  // a SPARSE tile stages its row_splits and ids in the same memory: room for 16 ids per row
-  for (const DevSlab& s : p->slabs)
-    if (s.cls == kSlabSparse) {
-      const int need = s.num_cols * (s.tile_rows + 1 + s.tile_rows * 16 + 4) * 4;
-      p->dev.smem_bytes = std::max(p->dev.smem_bytes, std::min(need, 48 << 10));
-    }
+  p->dev.smem_off_ctx = p->dev.smem_off_bnd + (int32_t)align_up((size_t)max_bnd, 128);
+  p->dev.smem_off_scratch =
+      p->dev.smem_off_ctx + (int32_t)align_up((size_t)max_cols * sizeof(ColCtx), 128);
+  {
+    const int fixed = p->dev.smem_off_scratch;
+    const int want = std::max(dense_need, std::min(sparse_need, std::max(sparse_min, kMaxWarpScratch)));
+    const int need = (int)align_up((size_t)want, 128);
+    const int min_need = (int)align_up((size_t)std::max(dense_need, sparse_min), 128);
+    // two CTAs per SM when the scratch can be made to fit (228 KB per SM, 1 KB reserved per CTA)
+    const int per2 = ((233472 / 2 - 1024 - 256 - fixed) / kWarps) & ~127;
+    const int per1 = ((232448 - 256 - fixed) / kWarps) & ~127;
+    int scratch = need;
+    if (scratch > per2) scratch = per2 >= min_need ? per2 : std::min(need, std::max(per1, 128));
+    p->dev.scratch_bytes = scratch;
+    p->dev.smem_bytes = fixed + kWarps * scratch;
+  }
 
   // relative cost of a slab's output byte: hashing a value costs far more issue slots than a
   // bucket search, so slabs of hashed columns get fewer rows per CTA
@@ -469,18 +520,18 @@ void build_layout(recom_plan* p) {
   for (auto& o : order2) p->slab_order.push_back(o.second);
 }
 
-// Schedule of a batch size.
-//   * SPARSE tiles go to a shared pool (heavy slabs first).
-//   * The CTAs are split into "sparse first" CTAs (a share proportional to the estimated
-//     cost of the SPARSE tiles) and dense CTAs. Every dense CTA owns ONE static macro tile:
-//     a run of consecutive rows of one slab, so the slab's staged tables and the column
-//     contexts are paid once per CTA. Dense CTAs are apportioned to the DENSE slabs by
-//     output bytes.
-//   * What the macro tiles leave over (about pool_frac of the rows) goes to a second shared
-//     pool of small tiles that evens out the finish.
-// Layout of `tiles`: [sparse pool | static tiles (CTA order) | dense pool].
+// Static schedule of a batch size (Sched in plan.h).
+//   * Every SPARSE slab is cut into warp tiles of slab.tile_rows rows, heavy slabs first; the
+//     sparse warps of the grid take them interleaved (tile t -> CTA t % grid).
+//   * The 16 warps of a CTA are split into dense and sparse warps in proportion to the
+//     estimated cost of the two kinds of work (a SPARSE warp tile chases several dependent
+//     DRAM round trips: sparse_weight DENSE tiles), never more sparse warps than tiles.
+//   * Every CTA owns ONE dense run: a row range of one slab, so the slab's staged tables and
+//     column contexts are paid once per CTA. CTAs are apportioned to the DENSE slabs by cost
+//     (output bytes, hashed columns weighted), rows split evenly in 32-row warp tiles. With
+//     more DENSE slabs than CTAs, whole slabs go to the least loaded CTA instead.
 std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
-  const int cap_ctas = p->num_sms * p->ctas_per_sm;
+  const int cap_ctas = std::max(1, p->num_sms * p->ctas_per_sm);
   auto tt = std::make_shared<TileTable>();
   auto make = [&](int s, int64_t b, int64_t rows) {
     Tile t{};
@@ -488,86 +539,85 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     t.row_begin = (int32_t)b;
     t.rows = (int32_t)rows;
     t.slab = p->slabs[s];
+    t.stage = t.slab.cls == kSlabDenseStaged && rows >= kMinStageRows;
     return t;
   };
-  // sparse pool
-  double sparse_cost = 0, dense_cost = 0;
+  std::vector<int> dense;
   for (int s : p->slab_order) {
     const DevSlab& sl = p->slabs[s];
-    if (sl.cls != kSlabSparse) continue;
-    for (int64_t b = 0; b < B; b += sl.tile_rows)
-      tt->tiles.push_back(make(s, b, std::min<int64_t>(sl.tile_rows, B - b)));
-    // guess: 5 ids per row, latency-bound gathers weigh 3x their bytes
-    sparse_cost += (double)B * sl.num_chunks * sl.vec_bytes * 5.0 * 3.0;
-  }
-  tt->num_sparse = (int)tt->tiles.size();
-  std::vector<int> dense;
-  auto slab_cost = [&](int s) { return (double)B * p->slabs[s].num_chunks * p->slabs[s].vec_bytes * p->slab_weight[s]; };
-  for (int s : p->slab_order)
-    if (p->slabs[s].cls != kSlabSparse) {
+    if (sl.cls != kSlabSparse) {
       dense.push_back(s);
-      dense_cost += slab_cost(s);
+      continue;
     }
-  // grid: never more CTAs than 32-row units of work
-  int64_t units = tt->num_sparse;
-  for (size_t i = 0; i < dense.size(); ++i) units += (B + 31) / 32;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cap_ctas, units));
-  tt->grid = grid;
-  int sparse_ctas = 0;
-  if (tt->num_sparse > 0 && !dense.empty()) {
-    sparse_ctas = (int)(grid * sparse_cost / (sparse_cost + dense_cost) + 0.5);
-    sparse_ctas = std::max(1, std::min({sparse_ctas, grid - 1, tt->num_sparse}));
-  } else if (tt->num_sparse > 0) {
-    sparse_ctas = grid;
+    for (int64_t b = 0; b < B; b += sl.tile_rows)
+      tt->sparse.push_back(make(s, b, std::min<int64_t>(sl.tile_rows, B - b)));
   }
-  tt->sparse_first = sparse_ctas;
-  const int dense_ctas = grid - sparse_ctas;
-  // apportion the dense CTAs to the dense slabs by cost (largest remainder)
-  std::vector<int> n_ctas(dense.size(), 0);
-  if (dense_ctas > 0 && !dense.empty()) {
+  const int64_t T = (B + kDenseTileRows - 1) / kDenseTileRows;  // DENSE warp tiles per slab
+  std::vector<double> cost(dense.size());
+  double dense_cost = 0;
+  for (size_t i = 0; i < dense.size(); ++i) {
+    const DevSlab& sl = p->slabs[dense[i]];
+    cost[i] = (double)T * p->slab_weight[dense[i]] *
+              std::max(0.25, sl.num_chunks * sl.vec_bytes / 512.0);
+    dense_cost += cost[i];
+  }
+  const double sparse_cost = (double)tt->sparse.size() * p->sparse_weight;
+  int S = 0;
+  if (tt->sparse.empty()) S = 0;
+  else if (dense.empty()) S = kWarps;
+  else S = std::max(1, std::min(kWarps - 1, (int)(kWarps * sparse_cost / (sparse_cost + dense_cost) + 0.5)));
+  int64_t units = 1;
+  if (S > 0) units = std::max<int64_t>(units, ((int64_t)tt->sparse.size() + S - 1) / S);
+  if (S < kWarps)
+    units = std::max<int64_t>(units, ((int64_t)dense.size() * T + (kWarps - S) - 1) / (kWarps - S));
+  const int grid = (int)std::min<int64_t>(cap_ctas, units);
+  if (S > 0 && !dense.empty()) {
+    const int s_need = (int)(((int64_t)tt->sparse.size() + grid - 1) / grid);
+    S = std::max(1, std::min({S, s_need, kWarps - 1}));
+  }
+  tt->grid = grid;
+  tt->sparse_warps = S;
+
+  std::vector<std::vector<Tile>> per_cta(grid);
+  if (!dense.empty() && (size_t)grid >= dense.size()) {
+    std::vector<int> n_ctas(dense.size(), 1);
+    int given = (int)dense.size();
     std::vector<std::pair<double, int>> rem;
-    int given = 0;
     for (size_t i = 0; i < dense.size(); ++i) {
-      const double share = dense_ctas * slab_cost(dense[i]) / dense_cost;
-      n_ctas[i] = (int)share;
-      given += n_ctas[i];
-      rem.push_back({-(share - n_ctas[i]), (int)i});
+      const double share = (grid - (double)dense.size()) * cost[i] / dense_cost;
+      n_ctas[i] += (int)share;
+      given += (int)share;
+      rem.push_back({-(share - (int)share), (int)i});
     }
     std::sort(rem.begin(), rem.end());
-    for (int k = 0; given < dense_ctas && k < (int)rem.size(); ++k, ++given) n_ctas[rem[k].second]++;
-  }
-  // static macro tiles, then the pool
-  std::vector<Tile> statics;
-  int pool_rows = kPoolTileRows;
-  {
-    // small batches: shrink pool tiles until every CTA can have one
-    int64_t est = 0;
-    for (size_t i = 0; i < dense.size(); ++i) est += (B + pool_rows - 1) / pool_rows;
-    while (pool_rows > 16 && est < grid) {
-      pool_rows /= 2;
-      est = 0;
-      for (size_t i = 0; i < dense.size(); ++i) est += (B + pool_rows - 1) / pool_rows;
-    }
-  }
-  for (size_t i = 0; i < dense.size(); ++i) {
-    int64_t static_rows = 0;
-    if (n_ctas[i] > 0) {
-      int64_t per = (int64_t)((1.0 - p->pool_frac) * (double)B / n_ctas[i]);
-      per = per / 32 * 32;
-      if (per >= 64) {
-        for (int c = 0; c < n_ctas[i]; ++c) statics.push_back(make(dense[i], c * per, per));
-        static_rows = per * n_ctas[i];
+    for (int k = 0; given < grid && k < (int)rem.size(); ++k, ++given) n_ctas[rem[k].second]++;
+    int c = 0;
+    for (size_t i = 0; i < dense.size(); ++i) {
+      const int64_t n = std::min<int64_t>(n_ctas[i], T);
+      for (int64_t j = 0; j < n; ++j) {
+        const int64_t t0 = j * T / n, t1 = (j + 1) * T / n;
+        const int64_t r0 = t0 * kDenseTileRows, r1 = std::min<int64_t>(B, t1 * kDenseTileRows);
+        if (r1 > r0) per_cta[c % grid].push_back(make(dense[i], r0, r1 - r0));
+        ++c;
       }
     }
-    for (int64_t b = static_rows; b < B; b += pool_rows)
-      tt->tiles.push_back(make(dense[i], b, std::min<int64_t>(pool_rows, B - b)));
+  } else if (!dense.empty()) {
+    std::vector<int> idx(dense.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<double> load(grid, 0.0);
+    for (int i : idx) {
+      const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      per_cta[c].push_back(make(dense[i], 0, B));
+      load[c] += cost[i];
+    }
   }
-  // CTA c >= sparse_ctas owns static tile (c - sparse_ctas), if there is one
-  Tile none{};
-  none.slab_id = -1;
-  tt->start.assign(grid, none);
-  for (int k = 0; k < (int)statics.size() && sparse_ctas + k < grid; ++k)
-    tt->start[sparse_ctas + k] = statics[k];
+  tt->cta.assign(grid, CtaWork{0, 0});
+  for (int c = 0; c < grid; ++c) {
+    tt->cta[c].first = (int32_t)tt->runs.size();
+    tt->cta[c].count = (int32_t)per_cta[c].size();
+    tt->runs.insert(tt->runs.end(), per_cta[c].begin(), per_cta[c].end());
+  }
   return tt;
 }
 
@@ -583,8 +633,7 @@ std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, recom_st
   if (p->tiles_by_batch.size() >= kMaxCachedTileTables) return nullptr;
   std::shared_ptr<TileTable> tt = build_tiles(p, B);
   std::vector<uint8_t> host(tt->bytes() + 64, 0);
-  memcpy(host.data(), tt->tiles.data(), tt->tiles_bytes());
-  memcpy(host.data() + tt->tiles_bytes(), tt->start.data(), tt->start.size() * sizeof(Tile));
+  tt->write(host.data());
   // first use of a batch size (warm-up): a blocking allocation + copy
   if (cudaMalloc(&tt->d_block, host.size()) != cudaSuccess ||
       cudaMemcpy(tt->d_block, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -729,8 +778,8 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
   // tuning knobs (the reference's counterpart: its RECOM_* env flags, fc_optimize_pass.cc:41-69)
   if (const char* e = getenv("RECOM_B200_STAGE_TABLES")) p->stage_tables = atoi(e) != 0;
   if (const char* e = getenv("RECOM_B200_HASH_WEIGHT")) p->hash_weight = atof(e);
-  if (const char* e = getenv("RECOM_B200_POOL_PCT"))
-    p->pool_frac = std::min(100, std::max(0, atoi(e))) / 100.0;
+  if (const char* e = getenv("RECOM_B200_SPARSE_WEIGHT")) p->sparse_weight = atof(e);
+  if (const char* e = getenv("RECOM_B200_CACHE_ARGS")) p->cache_args = atoi(e) != 0;
   build_layout(p);
   st = upload_plan(p);
   if (st == RECOM_OK) {
@@ -745,7 +794,7 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
     p->ctas_per_sm = cfg->max_ctas_per_sm > 0 ? std::min(cfg->max_ctas_per_sm, occ) : occ;
     if (const char* e = getenv("RECOM_B200_PROF_DUMP")) {
       p->prof_path = e;
-      if (cudaMalloc((void**)&p->d_prof, (size_t)p->num_sms * 16 * 16 * 8) != cudaSuccess) p->d_prof = nullptr;
+      if (cudaMalloc((void**)&p->d_prof, (size_t)p->num_sms * 4 * kWarps * 8 * 8) != cudaSuccess) p->d_prof = nullptr;
     }
     for (int i = 0; i < kRing && st == RECOM_OK; ++i) {
       cudaError_t e = cudaEventCreateWithFlags(&p->ring[i].done, cudaEventDisableTiming);
@@ -765,11 +814,11 @@ recom_status recom_plan_destroy(recom_plan* p) {
   if (!p) return RECOM_OK;
   if (p->d_prof && p->prof_grid > 0) {
     cudaDeviceSynchronize();
-    std::vector<uint64_t> h((size_t)p->prof_grid * 16);
+    std::vector<uint64_t> h((size_t)p->prof_grid * kWarps * 8);
     if (cudaMemcpy(h.data(), p->d_prof, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
       if (FILE* f = fopen(p->prof_path.c_str(), "w")) {
-        for (int c = 0; c < p->prof_grid; ++c) {
-          for (int i = 0; i < 16; ++i) fprintf(f, "%llu%c", (unsigned long long)h[(size_t)c * 16 + i], i == 15 ? '\n' : ' ');
+        for (size_t w = 0; w < (size_t)p->prof_grid * kWarps; ++w) {
+          for (int i = 0; i < 8; ++i) fprintf(f, "%llu%c", (unsigned long long)h[w * 8 + i], i == 7 ? '\n' : ' ');
         }
         fclose(f);
       }
@@ -783,6 +832,8 @@ recom_status recom_plan_destroy(recom_plan* p) {
     }
     if (p->ring[i].pinned) cudaFreeHost(p->ring[i].pinned);
   }
+  for (auto& e : p->arg_cache)
+    if (e->dev) cudaFree(e->dev);
   if (p->d_block) cudaFree(p->d_block);
   delete p;
   return RECOM_OK;
@@ -857,33 +908,30 @@ recom_status recom_plan_out_width(const recom_plan* p, int32_t* out) {
   return RECOM_OK;
 }
 
-// Bytes of the per-request argument block; `sched_bytes` > 0 only when the schedule is not
-// cached on the device and travels with the request.
-static size_t arg_block_bytes(const recom_plan* p, size_t sched_bytes) {
+// Bytes of a request's argument block (header + the arrays ReqParams points to).
+static size_t arg_block_bytes(const recom_plan* p) {
   size_t b = align_up(sizeof(ReqHeader), 16);
   b += align_up((size_t)p->cfg.num_slots * 8, 16);
   b += align_up((size_t)p->cfg.num_tables * 8, 16);
   b += align_up((p->descs.size() + 1) * 4, 16);
   b += align_up((p->sparse_cols.size() + 1) * 4, 16);
   b += align_up(p->coo_cols.size() * 4 + 4, 16);
-  b += sched_bytes + 64;
-  return b;
+  return align_up(b, 64);
 }
 
 static size_t max_sched_bytes(const recom_plan* p, int64_t batch) {
-  // only used when the schedule cache is full and the schedule travels with the request;
-  // smallest tile is 8 rows (HBM-resident multi-hot) resp. 16 rows (dense pool)
-  size_t tiles = 1;
+  // only used when the schedule cache is full and the schedule travels with the request
+  size_t tiles = p->slabs.size() + (size_t)p->num_sms * p->ctas_per_sm + 4;
   for (const DevSlab& s : p->slabs)
-    tiles += (size_t)((batch + (s.cls == kSlabSparse ? 7 : 15)) / (s.cls == kSlabSparse ? 8 : 16) + 1);
-  return (tiles + (size_t)p->num_sms * p->ctas_per_sm + 2) * sizeof(Tile);
+    if (s.cls == kSlabSparse) tiles += (size_t)((batch + s.tile_rows - 1) / s.tile_rows);
+  return tiles * sizeof(Tile) + (size_t)p->num_sms * p->ctas_per_sm * sizeof(CtaWork) + 64;
 }
 
 recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int64_t total_ids,
                                         size_t* out) {
   if (!p || !out || batch < 0 || total_ids < 0)
     return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
-  size_t b = align_up(arg_block_bytes(p, max_sched_bytes(p, batch)), 256);
+  size_t b = align_up(arg_block_bytes(p) + max_sched_bytes(p, batch), 256);
   b += align_up((size_t)total_ids * 4 + 16, 256);                            // ws_ids
   b += align_up(p->coo_cols.size() * (size_t)(batch + 1) * 4 + 16, 256);     // ws_row_splits
   *out = b;
@@ -901,9 +949,37 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   const int64_t B = req->batch;
   cudaStream_t stream = (cudaStream_t)req->stream;
 
+  std::shared_ptr<const TileTable> tt = cached_tiles(p, B, &st);
+  if (st != RECOM_OK) return st;
+  const bool sched_in_args = !tt;
+  if (sched_in_args) tt = build_tiles(p, B);
+  const int grid = tt->grid;
+
+  // the argument block: nothing in it differs between requests of the same shape
+  const size_t args_bytes = arg_block_bytes(p);
+  thread_local std::vector<uint8_t> block;
+  block.assign(args_bytes, 0);
+  uint8_t* h = block.data();
+  ReqHeader* hdr = (ReqHeader*)h;
+  hdr->batch = B;
+  hdr->num_coo = (int32_t)p->coo_cols.size();
+  size_t o = align_up(sizeof(ReqHeader), 16);
+  hdr->off_slot_offsets = (uint32_t)o;
+  memcpy(h + o, req->slot_offsets, (size_t)p->cfg.num_slots * 8);
+  o += align_up((size_t)p->cfg.num_slots * 8, 16);
+  hdr->off_tables = (uint32_t)o;
+  memcpy(h + o, req->tables, (size_t)p->cfg.num_tables * 8);
+  o += align_up((size_t)p->cfg.num_tables * 8, 16);
+  hdr->off_ids_base = (uint32_t)o;
+  int32_t* ids_base = (int32_t*)(h + o);
+  o += align_up(((size_t)n + 1) * 4, 16);
+  hdr->off_sparse_base = (uint32_t)o;
+  int32_t* sparse_base = (int32_t*)(h + o);
+  o += align_up((p->sparse_cols.size() + 1) * 4, 16);
+  hdr->off_coo_cols = (uint32_t)o;
+  if (!p->coo_cols.empty()) memcpy(h + o, p->coo_cols.data(), p->coo_cols.size() * 4);
+  hdr->total_bytes = (uint32_t)args_bytes;
   // per-column id counts
-  std::vector<int32_t> ids_base(n + 1, 0);
-  std::vector<int32_t> sparse_base(p->sparse_cols.size() + 1, 0);
   int64_t total = 0, sparse_total = 0, max_coo_nnz = 0;
   for (int i = 0; i < n; ++i) {
     const int64_t cnt = column_num_ids(p, i, req);
@@ -919,15 +995,8 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   ids_base[n] = (int32_t)total;
   sparse_base[p->sparse_cols.size()] = (int32_t)sparse_total;
 
-  std::shared_ptr<const TileTable> tt = cached_tiles(p, B, &st);
-  if (st != RECOM_OK) return st;
-  const bool sched_in_args = !tt;
-  if (sched_in_args) tt = build_tiles(p, B);
-  const int grid = tt->grid;
-
-  // workspace carve-up
-  const size_t args_bytes = arg_block_bytes(p, sched_in_args ? tt->bytes() : 0);
-  size_t off = align_up(args_bytes, 256);
+  // workspace carve-up: [argument block + schedule (upload path only) | ws_ids | ws_row_splits]
+  size_t off = align_up(args_bytes + max_sched_bytes(p, B), 256);
   const size_t off_ws_ids = off;
   off += align_up((size_t)sparse_total * 4 + 16, 256);
   const size_t off_rs = off;
@@ -937,28 +1006,65 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
                 req->workspace_bytes);
   uint8_t* ws = (uint8_t*)req->workspace;
 
-  // pinned staging slot
-  ArgSlot& slot = p->ring[p->ring_next.fetch_add(1) % kRing];
-  std::lock_guard<std::mutex> lock(slot.mu);
-  if (slot.in_flight) {
-    CUDA_TRY(cudaEventSynchronize(slot.done));
-    slot.in_flight = false;
+  // a device-resident copy of exactly this block?
+  const uint8_t* d_args = nullptr;
+  if (p->cache_args && !sched_in_args) {
+    std::lock_guard<std::mutex> lock(p->args_mu);
+    for (const auto& e : p->arg_cache)
+      if (e->host.size() == args_bytes && memcmp(e->host.data(), h, args_bytes) == 0) {
+        d_args = e->dev;
+        break;
+      }
+    if (!d_args) {
+      if (p->arg_cache.size() < (size_t)kArgCache && p->last_miss.size() == args_bytes &&
+          memcmp(p->last_miss.data(), h, args_bytes) == 0) {
+        // seen twice in a row: publish a device copy (a blocking allocation + copy, like the
+        // first use of a batch size)
+        std::unique_ptr<ArgEntry> e(new ArgEntry());
+        e->host.assign(h, h + args_bytes);
+        if (cudaMalloc((void**)&e->dev, args_bytes) == cudaSuccess &&
+            cudaMemcpy(e->dev, h, args_bytes, cudaMemcpyHostToDevice) == cudaSuccess) {
+          d_args = e->dev;
+          p->arg_cache.push_back(std::move(e));
+        } else {
+          if (e->dev) cudaFree(e->dev);
+          cudaGetLastError();
+        }
+      } else {
+        p->last_miss.assign(h, h + args_bytes);
+      }
+    }
   }
-  if (slot.cap < args_bytes) {
-    if (slot.pinned) cudaFreeHost(slot.pinned);
-    slot.pinned = nullptr;
-    slot.cap = 0;
-    const size_t cap = align_up(args_bytes * 2, 4096);
-    CUDA_TRY(cudaHostAlloc((void**)&slot.pinned, cap, cudaHostAllocDefault));
-    slot.cap = cap;
+
+  Sched sched = sched_in_args ? Sched{} : tt->sched(tt->d_block);
+  ArgSlot* slot = nullptr;
+  std::unique_lock<std::mutex> slot_lock;
+  if (!d_args) {
+    // upload path: pinned staging slot -> one cudaMemcpyAsync into the workspace
+    const size_t up_bytes = args_bytes + (sched_in_args ? tt->bytes() : 0);
+    slot = &p->ring[p->ring_next.fetch_add(1) % kRing];
+    slot_lock = std::unique_lock<std::mutex>(slot->mu);
+    if (slot->in_flight) {
+      CUDA_TRY(cudaEventSynchronize(slot->done));
+      slot->in_flight = false;
+    }
+    if (slot->cap < up_bytes) {
+      if (slot->pinned) cudaFreeHost(slot->pinned);
+      slot->pinned = nullptr;
+      slot->cap = 0;
+      const size_t cap = align_up(up_bytes * 2, 4096);
+      CUDA_TRY(cudaHostAlloc((void**)&slot->pinned, cap, cudaHostAllocDefault));
+      slot->cap = cap;
+    }
+    memcpy(slot->pinned, h, args_bytes);
+    if (sched_in_args) {
+      tt->write(slot->pinned + args_bytes);
+      sched = tt->sched(ws + args_bytes);
+    }
+    CUDA_TRY(cudaMemcpyAsync(ws, slot->pinned, up_bytes, cudaMemcpyHostToDevice, stream));
+    d_args = ws;
   }
-  uint8_t* h = slot.pinned;
-  ReqHeader* hdr = (ReqHeader*)h;
-  memset(hdr, 0, sizeof *hdr);
-  hdr->blob = (const uint8_t*)req->blob;
-  hdr->ws_row_splits = (int32_t*)(ws + off_rs);
-  hdr->batch = B;
-  hdr->num_coo = (int32_t)p->coo_cols.size();
+
   ReqParams A{};
   A.blob = (const uint8_t*)req->blob;
   A.out = (uint8_t*)req->out;
@@ -966,54 +1072,27 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   A.status = req->status_out;
   A.ws_ids = (int32_t*)(ws + off_ws_ids);
   A.ws_row_splits = (int32_t*)(ws + off_rs);
-  A.counters = (int32_t*)ws;  // ReqHeader::counters
+  A.slot_offsets = (const int64_t*)(d_args + hdr->off_slot_offsets);
+  A.tables = (const void* const*)(d_args + hdr->off_tables);
+  A.ids_base = (const int32_t*)(d_args + hdr->off_ids_base);
+  A.sparse_base = (const int32_t*)(d_args + hdr->off_sparse_base);
   A.prof = p->d_prof;
   if (p->d_prof) p->prof_grid = grid;
   A.batch = B;
   A.out_row_bytes = (int64_t)p->cfg.out_width * p->elem_bytes;
-  size_t o = align_up(sizeof(ReqHeader), 16);
-  hdr->off_slot_offsets = (uint32_t)o;
-  A.slot_offsets = (const int64_t*)(ws + o);
-  memcpy(h + o, req->slot_offsets, (size_t)p->cfg.num_slots * 8);
-  o += align_up((size_t)p->cfg.num_slots * 8, 16);
-  hdr->off_tables = (uint32_t)o;
-  A.tables = (const void* const*)(ws + o);
-  memcpy(h + o, req->tables, (size_t)p->cfg.num_tables * 8);
-  o += align_up((size_t)p->cfg.num_tables * 8, 16);
-  hdr->off_ids_base = (uint32_t)o;
-  A.ids_base = (const int32_t*)(ws + o);
-  memcpy(h + o, ids_base.data(), ids_base.size() * 4);
-  o += align_up(ids_base.size() * 4, 16);
-  hdr->off_sparse_base = (uint32_t)o;
-  A.sparse_base = (const int32_t*)(ws + o);
-  memcpy(h + o, sparse_base.data(), sparse_base.size() * 4);
-  o += align_up(sparse_base.size() * 4, 16);
-  hdr->off_coo_cols = (uint32_t)o;
-  if (!p->coo_cols.empty()) memcpy(h + o, p->coo_cols.data(), p->coo_cols.size() * 4);
-  o += align_up(p->coo_cols.size() * 4 + 4, 16);
-  Sched sched;
-  if (sched_in_args) {
-    o = align_up(o, 64);
-    memcpy(h + o, tt->tiles.data(), tt->tiles_bytes());
-    memcpy(h + o + tt->tiles_bytes(), tt->start.data(), tt->start.size() * sizeof(Tile));
-    sched = tt->sched(ws + o);
-    o += tt->bytes();
-  } else {
-    sched = tt->sched(tt->d_block);
-  }
-  hdr->total_bytes = (uint32_t)o;
 
-  CUDA_TRY(cudaMemcpyAsync(ws, h, o, cudaMemcpyHostToDevice, stream));
-  ReqHeader* d_req = (ReqHeader*)ws;
   if (!p->coo_cols.empty()) {
-    launch_coo_to_row_splits(p->dev, d_req, (int)p->coo_cols.size(), max_coo_nnz, stream);
+    launch_coo_to_row_splits(p->dev, (const ReqHeader*)d_args, A.blob, A.ws_row_splits,
+                             (int)p->coo_cols.size(), max_coo_nnz, stream);
     g_last_launches++;
   }
   launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream);
   g_last_launches++;
   cudaError_t e = cudaGetLastError();
-  cudaEventRecord(slot.done, stream);
-  slot.in_flight = true;
+  if (slot) {
+    cudaEventRecord(slot->done, stream);
+    slot->in_flight = true;
+  }
   if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return RECOM_OK;
 }

@@ -12,27 +12,24 @@
 //   * the TF-CPU ops the reference leaves upstream: StringToHashBucketFast and
 //     AsString.
 //
-// Work decomposition: a table of tiles (slab, row block) per batch size, cached on
-// the device. A slab is a run of columns whose output slices are adjacent in the
-// concat row and at most 32 16-byte chunks wide, so one warp store covers up to
-// 512 contiguous bytes of one output row. Persistent CTAs (256 threads, 3 per SM)
-// first drain a shared pool of multi-hot tiles, then walk a static run of dense
-// tiles of ONE slab (so what they staged in shared memory is reused), then drain
-// a shared pool of left-over dense tiles (load balance).
-//
-// Per tile:
-//   stage    (dense, on slab change) the slab's small tables and bucket boundaries
-//            are copied into shared memory with TMA bulk copies (cp.async.bulk,
-//            mbarrier completion), overlapping phase 1.
-//   phase 1  transform raw inputs to row ids (bucketize / hash / cast), one warp
-//            per column with lanes along the batch so input reads are coalesced;
-//            ids go to shared memory (DENSE) or to the workspace (multi-hot).
-//   phase 2  lane = chunk of the slab; per output row: read id(s), 128-bit gathers
-//            of the table row chunk (from shared memory when staged, else
-//            ld.global.nc), fp32 accumulation, combiner scaling, one 128-bit
-//            streaming store into the concat row.
-// One __syncthreads per dense tile (ids and the next tile index are double
-// buffered), so fast warps start the next tile's phase 1 while others still store.
+// Work decomposition (v4): a STATIC schedule per batch size, cached on the device. A slab is
+// a run of columns whose output slices are adjacent in the concat row and at most 32 16-byte
+// chunks wide, so one warp store covers up to 512 contiguous bytes of one output row.
+// Persistent CTAs (512 threads, 2 per SM); the warps of a CTA are split into
+//   dense warps   - the CTA owns one DENSE run (a row range of one slab; more when there are
+//                   more slabs than CTAs). The run's column contexts, bucket boundaries and
+//                   small tables are staged in shared memory once (TMA bulk copies, mbarrier
+//                   completion); then every warp walks its own 32-row tiles alone:
+//                     phase 1  lane = row: coalesced input loads of 8 columns in flight, 8
+//                              upper_bound searches in lock step (or hashing, 4 chains at a
+//                              time) -> row ids in the warp's shared-memory scratch;
+//                     phase 2  lane = 16-byte chunk: 128-bit gathers from the staged tables
+//                              (or ld.global.nc), 128-bit streaming stores into the concat row.
+//   sparse warps  - a static, interleaved share of the SPARSE (multi-hot) warp tiles: row_splits
+//                   and transformed ids of all the slab's columns in the warp's scratch, then
+//                   one pipelined gather stream per lane (fp32 accumulation, TF-CPU scaling).
+// No block-wide barrier after start-up, no atomics, no per-request upload: latency-bound
+// multi-hot gathers and bandwidth-bound dense stores overlap on every SM.
 //
 // The path is HBM / L2 bound integer+copy work: no tensor cores by design.
 #include <cuda_bf16.h>
@@ -286,41 +283,115 @@ __device__ __forceinline__ int32_t bucketize(const float* __restrict__ bnd, int3
   return o[0];
 }
 
-// Any transform, one element. `bnd` = this column's boundaries (shared or global).
-__device__ __forceinline__ int32_t column_id(const ColCtx& c, const float* __restrict__ bnd,
-                                             int64_t i) {
+// ---------------------------------------------------------------------------
+// raw value -> row id, N at a time
+// ---------------------------------------------------------------------------
+// Every id is the end of a chain of dependent memory round trips (value; for strings:
+// offsets -> bytes). ids_n runs N chains side by side: stage 1 loads the N raw values, stage 2
+// the words of the N strings, stage 3 computes. A warp never waits for one chain alone.
+
+// I32 / F32: the low 32 bits; I64 / F64: 64 bits; STR: begin offset | end offset << 32.
+__device__ __forceinline__ uint64_t load_raw(const ColCtx& c, int64_t i) {
   const uint8_t* vals = c.values;
+  switch (c.value_dtype) {
+    case RECOM_STR: {
+      const uint32_t* off = (const uint32_t*)vals;
+      const uint32_t o0 = __ldg(off + i), o1 = __ldg(off + i + 1);
+      return (uint64_t)o0 | ((uint64_t)o1 << 32);
+    }
+    case RECOM_I64:
+    case RECOM_F64: return (uint64_t)__ldg((const unsigned long long*)vals + i);
+    default: return (uint64_t)__ldg((const uint32_t*)vals + i);
+  }
+}
+
+// The (at most three) aligned 8-byte words that cover a string of 1..16 bytes. Every word
+// read holds at least one byte of the string (see fh::MemBytes on slot padding).
+struct StrWords {
+  uint64_t w0, w1, w2;
+};
+__device__ __forceinline__ StrWords load_short_words(const uint8_t* p, uint32_t len) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a & ~uintptr_t(7));
+  const uint32_t words = ((uint32_t)(a & 7) + len + 7) >> 3;
+  StrWords w;
+  w.w0 = __ldg(q);
+  w.w1 = words > 1 ? __ldg(q + 1) : 0ull;
+  w.w2 = words > 2 ? __ldg(q + 2) : 0ull;
+  return w;
+}
+__device__ __forceinline__ fh::RegBytes short_bytes(const StrWords& w, const uint8_t* p) {
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+  fh::RegBytes s;
+  if (sh == 0) {
+    s.w0 = w.w0;
+    s.w1 = w.w1;
+  } else {
+    s.w0 = (w.w0 >> sh) | (w.w1 << (64 - sh));
+    s.w1 = (w.w1 >> sh) | (w.w2 << (64 - sh));
+  }
+  s.w2 = 0;
+  return s;
+}
+
+// Stage 3. `bnd` = this column's boundaries (shared or global memory).
+__device__ __noinline__ int32_t finish_id(const ColCtx& c, const float* __restrict__ bnd,
+                                          uint64_t raw, const StrWords sw) {
   switch (c.transform) {
     case RECOM_XFORM_NONE:
-      if (c.value_dtype == RECOM_I32) return __ldg((const int32_t*)vals + i);
-      return (int32_t)__ldg((const long long*)vals + i);
+      return c.value_dtype == RECOM_I32 ? (int32_t)(uint32_t)raw : (int32_t)(long long)raw;
     case RECOM_XFORM_BUCKETIZE: {
       switch (c.value_dtype) {
-        case RECOM_F32: return bucketize<float>(bnd, c.num_boundaries, __ldg((const float*)vals + i));
-        case RECOM_I32: return bucketize<int32_t>(bnd, c.num_boundaries, __ldg((const int32_t*)vals + i));
-        case RECOM_I64:
-          return bucketize<long long>(bnd, c.num_boundaries, __ldg((const long long*)vals + i));
-        default: return bucketize<double>(bnd, c.num_boundaries, __ldg((const double*)vals + i));
+        case RECOM_F32: return bucketize<float>(bnd, c.num_boundaries, __uint_as_float((uint32_t)raw));
+        case RECOM_I32: return bucketize<int32_t>(bnd, c.num_boundaries, (int32_t)(uint32_t)raw);
+        case RECOM_I64: return bucketize<long long>(bnd, c.num_boundaries, (long long)raw);
+        default: return bucketize<double>(bnd, c.num_boundaries, __longlong_as_double((long long)raw));
       }
     }
     case RECOM_XFORM_HASH_STR: {
-      const int32_t* off = (const int32_t*)vals;
-      const int32_t o0 = __ldg(off + i), o1 = __ldg(off + i + 1);
-      const uint64_t h = fh::fingerprint64(c.bytes + o0, (uint32_t)(o1 - o0));
+      const uint32_t o0 = (uint32_t)raw, len = (uint32_t)(raw >> 32) - o0;
+      const uint8_t* p = c.bytes + o0;
+      uint64_t h;
+      if (len - 1u < 16u) h = fh::hash_len_0_16(short_bytes(sw, p), len);
+      else h = fh::fingerprint64(p, len);  // empty, or longer than 16 bytes
       return (int32_t)fh::mod_bucket(h, (uint64_t)c.num_buckets, c.bucket_magic);
     }
     default: {  // RECOM_XFORM_HASH_INT
       uint64_t h;
       if (c.value_dtype == RECOM_I32) {
-        const int32_t v = __ldg((const int32_t*)vals + i);
+        const int32_t v = (int32_t)(uint32_t)raw;
         h = (v >= 0 && v < 100000000) ? fh::fingerprint64_of_decimal_u32small((uint32_t)v)
                                       : fh::fingerprint64_of_decimal((int64_t)v);
       } else {
-        h = fh::fingerprint64_of_decimal((int64_t)__ldg((const long long*)vals + i));
+        h = fh::fingerprint64_of_decimal((int64_t)raw);
       }
       return (int32_t)fh::mod_bucket(h, (uint64_t)c.num_buckets, c.bucket_magic);
     }
   }
+}
+
+template <int N>
+__device__ __forceinline__ void ids_n(const ColCtx* const (&c)[N], const float* const (&bnd)[N],
+                                      const int64_t (&i)[N], const bool (&valid)[N],
+                                      int32_t (&id)[N]) {
+#ifdef RECOM_TEST_NOIDS
+  for (int k = 0; k < N; ++k) id[k] = (int32_t)i[k] + (valid[k] ? c[k]->col : 0) + (int32_t)bnd[k][0];
+  return;
+#endif
+  uint64_t raw[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) raw[k] = valid[k] ? load_raw(*c[k], i[k]) : 0ull;
+  StrWords sw[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    sw[k].w0 = sw[k].w1 = sw[k].w2 = 0ull;
+    if (valid[k] && c[k]->value_dtype == RECOM_STR) {
+      const uint32_t o0 = (uint32_t)raw[k], len = (uint32_t)(raw[k] >> 32) - o0;
+      if (len - 1u < 16u) sw[k] = load_short_words(c[k]->bytes + o0, len);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) id[k] = valid[k] ? finish_id(*c[k], bnd[k], raw[k], sw[k]) : 0;
 }
 
 __device__ __forceinline__ int32_t checked_id(int32_t id, int32_t rows, int32_t* status) {
@@ -336,188 +407,178 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.wait_all;" ::: "memory");
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// Static shared state of a CTA. The dynamic part holds, for a DENSE slab,
-// [staged tables | staged boundaries | ids of the tile]; a SPARSE tile reuses all of it for
-// the tile's row_splits and row ids.
-struct __align__(16) CtaShared {
-  Tile next[2];            // the tile two steps ahead (slab < 0: none), double buffered
-  uint64_t mbar_bnd;       // boundaries of the staged slab have landed
-  uint64_t mbar_tbl;       // tables of the staged slab have landed
-  uint64_t full[2];        // ids ring: slot filled by the producer warps
-  uint64_t empty[2];       // ids ring: slot released by the consumer warps
-  ColCtx ctx[kMaxChunks];  // the columns of the slab the CTA is working on
-  int32_t sp_cnt[kMaxChunks];  // SPARSE tile: ids of the tile per column, -1: not staged
-};
-
-// Request-wide values every tile needs, read once per CTA.
+// Request-wide values every tile needs.
 struct ReqRegs {
   uint8_t* out;
   int64_t out_row_bytes;
   int32_t* status;
+  int32_t* ids_out;
+  const int32_t* ids_base;
+  bool check;
 };
 
+// Resolve a column against the request (one thread per column): one read of the static
+// record plus one read each of the request's slot / table arrays.
+__device__ __forceinline__ void build_ctx(const ReqParams& A, const DevSlabCol& sc, bool stage_tbl,
+                                          bool stage_bnd, ColCtx& x) {
+  x.values = A.blob + A.slot_offsets[sc.value_slot];
+  x.bytes = sc.bytes_slot >= 0 ? A.blob + A.slot_offsets[sc.bytes_slot] : nullptr;
+  x.table = (const uint8_t*)A.tables[sc.table];
+  x.row_splits = nullptr;
+  if (sc.sparse_index >= 0)
+    x.row_splits = sc.coo_index >= 0 ? A.ws_row_splits + (int64_t)sc.coo_index * (A.batch + 1)
+                                     : (const int32_t*)(A.blob + A.slot_offsets[sc.seg_slot]);
+  x.bucket_magic = sc.bucket_magic;
+  x.num_buckets = sc.num_buckets;
+  x.table_rows = sc.table_rows;
+  x.row_bytes = sc.row_bytes;
+  x.transform = sc.transform;
+  x.value_dtype = sc.value_dtype;
+  x.num_boundaries = sc.num_boundaries;
+  x.bnd_off = stage_bnd ? sc.bnd_off : -1;
+  x.bnd_pool_off = sc.boundaries_offset;
+  x.stage_off = stage_tbl ? sc.stage_off : -1;
+  x.combiner = sc.combiner;
+  x.col = sc.col;
+  x.sparse_index = sc.sparse_index;
+}
+
 // ---------------------------------------------------------------------------
-// entering a slab: resolve its columns against the request (one thread per column), start
-// the TMA bulk copies of its small tables and bucket boundaries into shared memory
+// DENSE run: exactly one id per (column, row). The run's dense warps share the column
+// contexts, the bucket boundaries and (run.stage) the slab's small tables in shared memory;
+// everything else is private to a warp, which walks its 32-row tiles without any block-wide
+// synchronisation.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void enter_slab(const DevPlan& P, const ReqParams& A,
-                                           const DevSlab& slab, CtaShared& cs, uint8_t* s_tables,
-                                           float* s_bnd, bool keep_bnd) {
-  const int tid = threadIdx.x;
-  if (tid < slab.num_cols) {
-    const DevSlabCol sc = P.slab_cols[slab.first_col + tid];
-    ColCtx x;
-    x.values = A.blob + A.slot_offsets[sc.value_slot];
-    x.bytes = sc.bytes_slot >= 0 ? A.blob + A.slot_offsets[sc.bytes_slot] : nullptr;
-    x.table = (const uint8_t*)A.tables[sc.table];
-    x.row_splits = nullptr;
-    x.ws_ids = nullptr;
-    if (sc.sparse_index >= 0) {
-      x.row_splits = sc.coo_index >= 0
-                         ? A.ws_row_splits + (int64_t)sc.coo_index * (A.batch + 1)
-                         : (const int32_t*)(A.blob + A.slot_offsets[sc.seg_slot]);
-      x.ws_ids = A.ws_ids + A.sparse_base[sc.sparse_index];
+__device__ __forceinline__ void enter_run(const DevPlan& P, const ReqParams& A, const Tile& run,
+                                          ColCtx* ctx, uint8_t* s_tables, float* s_bnd,
+                                          bool keep_bnd, uint64_t* mbar_tbl, uint64_t* mbar_bnd,
+                                          int dense_warps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DevSlab& slab = run.slab;
+  const bool stage = run.stage != 0 && slab.stage_bytes > 0;
+  if (warp == 0) {
+    if (lane < slab.num_cols) {
+      const DevSlabCol sc = P.slab_cols[slab.first_col + lane];
+      ColCtx x;
+      build_ctx(A, sc, stage, true, x);
+      ctx[lane] = x;
+      if (stage && sc.stage_off >= 0 && sc.stage_copy) {
+        fence_proxy_async();  // the region was read through the generic proxy by the last run
+        bulk_g2s(s_tables + sc.stage_off, x.table, (uint32_t)sc.table_rows * (uint32_t)sc.row_bytes,
+                 mbar_tbl);
+      }
     }
-    x.ids_out = A.ids_out ? A.ids_out + A.ids_base[sc.col] : nullptr;
-    x.bucket_magic = sc.bucket_magic;
-    x.num_buckets = sc.num_buckets;
-    x.table_rows = sc.table_rows;
-    x.row_bytes = sc.row_bytes;
-    x.transform = sc.transform;
-    x.value_dtype = sc.value_dtype;
-    x.num_boundaries = sc.num_boundaries;
-    x.bnd_off = sc.bnd_off;
-    x.bnd_pool_off = sc.boundaries_offset;
-    x.stage_off = sc.stage_off;
-    x.combiner = sc.combiner;
-    cs.ctx[tid] = x;
-    if (sc.stage_off >= 0 && sc.stage_copy) {
-      fence_proxy_async();  // the region was read through the generic proxy by the last slab
-      bulk_g2s(s_tables + sc.stage_off, x.table, (uint32_t)sc.table_rows * (uint32_t)sc.row_bytes,
-               &cs.mbar_tbl);
-    }
-  } else if (!keep_bnd && tid >= 32 && tid - 32 < slab.num_bnds) {
-    const DevSlabBnd b = P.slab_bnds[slab.first_bnd + tid - 32];
-    fence_proxy_async();
-    bulk_g2s(s_bnd + b.smem_off, P.boundaries + b.pool_off, (uint32_t)b.floats * 4, &cs.mbar_bnd);
-  }
-  const int bnd_bytes = keep_bnd ? 0 : slab.bnd_bytes;
-  if (tid == 0 && slab.stage_bytes + bnd_bytes > 0) {
     // complete_tx of a copy issued above may precede this expect_tx: the phase cannot
     // complete before this (the only) arrival
-    mbar_expect_tx(&cs.mbar_bnd, (uint32_t)bnd_bytes);
-    mbar_expect_tx(&cs.mbar_tbl, (uint32_t)slab.stage_bytes);
+    if (lane == 0 && stage) mbar_expect_tx(mbar_tbl, (uint32_t)slab.stage_bytes);
+  }
+  if (warp == (dense_warps > 1 ? 1 : 0) && !keep_bnd && slab.bnd_bytes > 0) {
+    if (lane < slab.num_bnds) {
+      const DevSlabBnd b = P.slab_bnds[slab.first_bnd + lane];
+      fence_proxy_async();
+      bulk_g2s(s_bnd + b.smem_off, P.boundaries + b.pool_off, (uint32_t)b.floats * 4, mbar_bnd);
+    }
+    if (lane == 0) mbar_expect_tx(mbar_bnd, (uint32_t)slab.bnd_bytes);
   }
 }
 
-// ---------------------------------------------------------------------------
-// DENSE slab: exactly one id per (column, row)
-// ---------------------------------------------------------------------------
-// Is this column on the fast path: float32 input bucketized against boundaries staged in smem?
-__device__ __forceinline__ bool fast_bucketize(const ColCtx& c) {
-  return c.transform == RECOM_XFORM_BUCKETIZE && c.value_dtype == RECOM_F32 && c.bnd_off >= 0;
-}
-
-// 8 upper_bound searches in lock step over boundaries in shared memory; search k uses
-// boundary set k / 2 (see bucketize_n for why `half` serves both sides of a probe).
-__device__ __forceinline__ void search_smem8(const uint32_t (&bp)[4], const int32_t (&nb)[4],
+// 8 upper_bound searches in lock step, one per column, over boundaries in shared memory (see
+// bucketize_n for why `half` serves both sides of a probe).
+__device__ __forceinline__ void search_smem8(const uint32_t (&bp)[8], const int32_t (&nb)[8],
                                              const float (&v)[8], int32_t (&lo)[8]) {
+  int32_t nmax = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) lo[k] = 0;
-  for (int32_t n = max(max(nb[0], nb[1]), max(nb[2], nb[3])); n > 0; n >>= 1) {
+  for (int k = 0; k < 8; ++k) {
+    lo[k] = 0;
+    nmax = max(nmax, nb[k]);
+  }
+  for (int32_t n = nmax; n > 0; n >>= 1) {
     const int32_t half = n >> 1;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int32_t idx = lo[k] + half;
-      const float b = lds_f32(bp[k >> 1] + 4u * (uint32_t)min(idx, nb[k >> 1] - 1));
-      const bool right = idx < nb[k >> 1] && !(v[k] < b);
+      const float b = lds_f32(bp[k] + 4u * (uint32_t)min(idx, nb[k] - 1));
+      const bool right = idx < nb[k] && !(v[k] < b);
       lo[k] = right ? idx + 1 : lo[k];
     }
   }
 }
 
-// DENSE tiles are processed by two groups of warps that hand over 64-row sub-tiles through a
-// two-slot ring of row ids in shared memory (mbarrier full / empty per slot):
-//   producers (warps 0-3): inputs -> row ids (bucketize / hash), lanes along the batch;
-//   consumers (warps 4-7): lane = chunk; gather the table rows, store into the concat rows.
-// The stores, which bound this path, therefore never wait for id computation or input latency.
-//
-// Producer side of one sub-tile. A producer warp owns the columns pw, pw + 4, pw + 8, ... and
-// takes them four at a time: 8 coalesced loads in flight, then 8 searches in lock step. The
-// id slot receives the byte offset of the row inside the smem table region when the table is
-// staged, else the raw row id.
-template <bool CHECK>
-__device__ __forceinline__ void produce_ids(const DevPlan& P, const ReqRegs& Q, const CtaShared& cs,
-                                            int num_cols, int64_t b0, int rows, const float* s_bnd,
-                                            int32_t* s_ids, int pw, int lane) {
-  for (int cbase = pw; cbase < num_cols; cbase += 4 * kProducerWarps) {
-    const int nq = min(4, (num_cols - cbase + kProducerWarps - 1) / kProducerWarps);
-    bool fast = nq == 4;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q < nq) fast = fast && fast_bucketize(cs.ctx[cbase + q * kProducerWarps]);
-    if (fast) {
+// phase 1 of a DENSE warp tile: lane = row. The id slot receives the byte offset of the row
+// inside the smem table region when the table is staged, else the raw row id.
+__device__ __forceinline__ void dense_phase1(const DevPlan& P, const ReqRegs& Q, const ColCtx* ctx,
+                                             const DevSlab& slab, int64_t b0, int rows,
+                                             const float* s_bnd, int32_t* s_ids, int lane) {
+  const int nc = slab.num_cols;
+  const bool valid = lane < rows;
+  const int64_t i = b0 + lane;
+  auto put = [&](int cl, int32_t id) {
+    const ColCtx& c = ctx[cl];
+    if (Q.check) id = checked_id(id, c.table_rows, Q.status);
+    s_ids[cl * kIdPitch + lane] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
+    if (Q.ids_out) Q.ids_out[Q.ids_base[c.col] + i] = id;
+  };
+  for (int cbase = 0; cbase < nc;) {
+#ifndef RECOM_TEST_NOFAST
+    if ((cbase & 7) == 0 && ((slab.fast8_mask >> (cbase >> 3)) & 1u)) {
+      // 8 float32 bucketize columns: 8 coalesced loads in flight, 8 searches in lock step
       float v[8];
-      uint32_t bp[4];
-      int32_t nb[4];
+      uint32_t bp[8];
+      int32_t nb[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const ColCtx& c = cs.ctx[cbase + q * kProducerWarps];
-        const float* in = (const float*)c.values + b0;
-        v[2 * q] = lane < rows ? __ldg(in + lane) : 0.f;
-        v[2 * q + 1] = lane + 32 < rows ? __ldg(in + lane + 32) : 0.f;
-        bp[q] = smem_u32(s_bnd + c.bnd_off);
-        nb[q] = c.num_boundaries;
+      for (int k = 0; k < 8; ++k) {
+        const ColCtx& c = ctx[cbase + k];
+        v[k] = valid ? __ldg((const float*)c.values + i) : 0.f;
+        bp[k] = smem_u32(s_bnd + c.bnd_off);
+        nb[k] = c.num_boundaries;
       }
       int32_t lo[8];
       search_smem8(bp, nb, v, lo);
+      if (valid) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int cl = cbase + (k >> 1) * kProducerWarps;
-        const ColCtx& c = cs.ctx[cl];
-        const int r = lane + 32 * (k & 1);
-        if (r < rows) {
-          int32_t id = lo[k];
-          if (CHECK) id = checked_id(id, c.table_rows, Q.status);
-          s_ids[cl * kIdPitch + r] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
-          if (c.ids_out) c.ids_out[b0 + r] = id;
-        }
+        for (int k = 0; k < 8; ++k) put(cbase + k, lo[k]);
       }
+      cbase += 8;
       continue;
     }
-    for (int q = 0; q < nq; ++q) {
-      const int cl = cbase + q * kProducerWarps;
-      const ColCtx& c = cs.ctx[cl];
-      const float* bnd = c.bnd_off >= 0 ? s_bnd + c.bnd_off : P.boundaries + c.bnd_pool_off;
-      for (int r = lane; r < rows; r += 32) {
-        int32_t id = column_id(c, bnd, b0 + r);
-        if (CHECK) id = checked_id(id, c.table_rows, Q.status);
-        s_ids[cl * kIdPitch + r] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
-        if (c.ids_out) c.ids_out[b0 + r] = id;
-      }
+#endif
+    const int n4 = min(4, nc - cbase);
+    const ColCtx* c[4];
+    const float* bnd[4];
+    int64_t ii[4];
+    bool ok[4];
+    int32_t id[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      c[k] = ctx + cbase + (k < n4 ? k : 0);
+      bnd[k] = c[k]->bnd_off >= 0 ? s_bnd + c[k]->bnd_off : P.boundaries + c[k]->bnd_pool_off;
+      ii[k] = i;
+      ok[k] = valid && k < n4;
     }
+    ids_n<4>(c, bnd, ii, ok, id);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[k]) put(cbase + k, id[k]);
+    cbase += n4;
   }
 }
 
-// Consumer side of one sub-tile: lane = chunk; 32 / W rows per warp pass; UNROLL independent
-// rows in flight.
+// phase 2 of a DENSE warp tile: lane = chunk; 32 / W rows per pass; UNROLL independent rows in
+// flight; 128-bit gathers from the staged tables (or ld.global.nc), 128-bit streaming stores
+// straight into the concat rows.
 template <int VEC, bool STAGED>
-__device__ __forceinline__ void consume_ids(const ReqRegs& Q, const CtaShared& cs, int W,
-                                            const DevChunk& ch, int64_t b0, int rows,
-                                            const uint8_t* s_tables, const int32_t* s_ids, int cw,
-                                            int lane) {
-  const int rpp = 32 / W;  // rows handled by one warp per pass
+__device__ __forceinline__ void dense_phase2(const ReqRegs& Q, const ColCtx* ctx, int W,
+                                             const DevChunk& ch, int64_t b0, int rows,
+                                             const uint8_t* s_tables, const int32_t* s_ids,
+                                             int lane) {
+#ifdef RECOM_TEST_NODP2
+  return;
+#endif
+  const int rpp = 32 / W;  // rows handled per pass
   const int sub = lane / W;
   if (sub >= rpp) return;
   const uint8_t* tbl;
@@ -525,22 +586,24 @@ __device__ __forceinline__ void consume_ids(const ReqRegs& Q, const CtaShared& c
   if (STAGED) {
     tbl = s_tables + ch.table_byte;
   } else {
-    const ColCtx& c = cs.ctx[ch.col_local];
+    const ColCtx& c = ctx[ch.col_local];
     tbl = c.table + ch.table_byte;
     row_bytes = c.row_bytes;
   }
   const int32_t* ids = s_ids + ch.col_local * kIdPitch;
   const int64_t orb = Q.out_row_bytes;
-  const int step = kConsumerWarps * rpp;
-  int r = cw * rpp + sub;
+  int r = sub;
   uint8_t* outp = Q.out + (b0 + r) * orb + ch.out_byte;
-  const int64_t ostep = (int64_t)step * orb;
-  constexpr int UNROLL = 8;
-  for (; r + (UNROLL - 1) * step < rows; r += UNROLL * step) {
+  const int64_t ostep = (int64_t)rpp * orb;
+  #ifndef RECOM_DENSE_U
+#define RECOM_DENSE_U 8
+#endif
+  constexpr int UNROLL = RECOM_DENSE_U;
+  for (; r + (UNROLL - 1) * rpp < rows; r += UNROLL * rpp) {
     Chunk<VEC> v[UNROLL];
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k) {
-      const int32_t o = ids[r + k * step];
+      const int32_t o = ids[r + k * rpp];
       if (STAGED) v[k] = lds_chunk<VEC>(tbl + o);
       else v[k].load(tbl + (int64_t)o * row_bytes);
     }
@@ -550,7 +613,7 @@ __device__ __forceinline__ void consume_ids(const ReqRegs& Q, const CtaShared& c
       outp += ostep;
     }
   }
-  for (; r < rows; r += step) {
+  for (; r < rows; r += rpp) {
     const int32_t o = ids[r];
     Chunk<VEC> v;
     if (STAGED) v = lds_chunk<VEC>(tbl + o);
@@ -560,376 +623,314 @@ __device__ __forceinline__ void consume_ids(const ReqRegs& Q, const CtaShared& c
   }
 }
 
-// One DENSE tile (any number of rows), producers and consumers running concurrently.
-// `ring_it` counts the sub-tiles handed over since the kernel started (same value in every
-// thread); slot = ring_it & 1, and use u of a slot completes phase u of its barriers.
-template <int ELEM, bool CHECK>
-__device__ __forceinline__ void dense_tile(const DevPlan& P, const ReqRegs& Q, CtaShared& cs,
-                                           const DevSlab& slab, const DevChunk& ch, const Tile& tile,
-                                           const uint8_t* s_tables, const float* s_bnd,
-                                           int32_t* s_ids, int ids_slot, uint32_t stage_parity,
-                                           uint32_t& ring_it) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nsub = (tile.rows + kSubRows - 1) / kSubRows;
-  uint32_t it = ring_it;
-  if (warp < kProducerWarps) {
-    if (slab.bnd_bytes > 0) mbar_wait(&cs.mbar_bnd, stage_parity);
-    for (int j = 0; j < nsub; ++j, ++it) {
-      const int slot = it & 1;
-      if (it >= 2) mbar_wait(&cs.empty[slot], ((it >> 1) - 1) & 1);
-      const int rows = min(kSubRows, tile.rows - j * kSubRows);
-      produce_ids<CHECK>(P, Q, cs, slab.num_cols, (int64_t)tile.row_begin + j * kSubRows, rows, s_bnd,
-                         s_ids + slot * ids_slot, warp, lane);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&cs.full[slot]);
-    }
-  } else {
-    if (slab.cls == kSlabDenseStaged) mbar_wait(&cs.mbar_tbl, stage_parity);
-    const int cw = warp - kProducerWarps;
-    for (int j = 0; j < nsub; ++j, ++it) {
-      const int slot = it & 1;
-      mbar_wait(&cs.full[slot], (it >> 1) & 1);
-      const int rows = min(kSubRows, tile.rows - j * kSubRows);
-      const int64_t b0 = (int64_t)tile.row_begin + j * kSubRows;
-      const int32_t* ids = s_ids + slot * ids_slot;
-      if (slab.cls == kSlabDenseStaged) {
-        if (slab.vec_bytes == 16) consume_ids<16, true>(Q, cs, slab.num_chunks, ch, b0, rows, s_tables, ids, cw, lane);
-        else consume_ids<ELEM, true>(Q, cs, slab.num_chunks, ch, b0, rows, s_tables, ids, cw, lane);
-      } else {
-        if (slab.vec_bytes == 16) consume_ids<16, false>(Q, cs, slab.num_chunks, ch, b0, rows, s_tables, ids, cw, lane);
-        else consume_ids<ELEM, false>(Q, cs, slab.num_chunks, ch, b0, rows, s_tables, ids, cw, lane);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&cs.empty[slot]);
-    }
-  }
-  ring_it += (uint32_t)nsub;
-}
-
 // ---------------------------------------------------------------------------
-// SPARSE slab: row b owns ids [row_splits[b], row_splits[b+1])
+// SPARSE warp tile: row b owns ids [row_splits[b], row_splits[b+1]) of every column of the
+// slab. One warp, no block-wide synchronisation. Warp scratch (shared memory):
+//   [ColCtx x cols | prefix (cols + 1) | row_splits (cols x (tile_rows + 1)) | ids]
+// phase 1 flattens the ids of all columns of the tile into one index space, so that every lane
+// has work whatever the row lengths are, and transforms them four chains at a time;
+// phase 2 (lane = chunk) walks the ids of its rows as ONE stream with up to U independent
+// 128-bit row gathers in flight across row boundaries, fp32 accumulation, TF-CPU scaling, one
+// 128-bit store per row. A tile whose ids do not fit the scratch uses the workspace instead.
 // ---------------------------------------------------------------------------
-// The tile's row_splits and row ids are staged in shared memory (`sp`, `stride` ints per
-// column: rows + 1 splits, then the ids), so that phase 2's only global accesses are the
-// table rows. A column whose ids do not fit (very long rows) falls back to the workspace.
-//
-// phase 1: one warp per column, so the dependent chains (row_splits -> offsets -> bytes ->
-// hash) of different columns overlap.
-template <bool CHECK>
-__device__ __forceinline__ void sparse_phase1(const DevPlan& P, const ReqRegs& Q, CtaShared& cs,
-                                              int num_cols, const Tile& tile, int32_t* sp,
-                                              int stride) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows = tile.rows;
-  const int64_t b0 = tile.row_begin;
-  const int cap = stride - (rows + 1);
-  for (int cl = warp; cl < num_cols; cl += kWarps) {
-    const ColCtx& c = cs.ctx[cl];
-    int32_t* rs_s = sp + cl * stride;
-    int32_t* ids_s = rs_s + rows + 1;
-    for (int r = lane; r <= rows; r += 32) rs_s[r] = c.row_splits[b0 + r];
-    __syncwarp();
-    const int32_t e0 = rs_s[0], e1 = rs_s[rows];
-    const bool staged = e1 - e0 <= cap;
-    if (lane == 0) cs.sp_cnt[cl] = staged ? e1 - e0 : -1;
-    const bool xform = c.transform != RECOM_XFORM_NONE;
-    if (!staged && !xform && !c.ids_out && !CHECK) continue;
-    const float* bnd = P.boundaries + c.bnd_pool_off;
-    for (int32_t e = e0 + lane; e < e1; e += 32) {
-      int32_t id = column_id(c, bnd, e);
-      if (CHECK) id = checked_id(id, c.table_rows, Q.status);
-      if (staged) ids_s[e - e0] = id;
-      else if (xform || CHECK) c.ws_ids[e] = id;
-      if (c.ids_out) c.ids_out[e] = id;
-    }
-  }
-}
-
-template <int VEC, bool BF16, bool CHECK>
-__device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const CtaShared& cs, int W,
-                                              const DevChunk& ch, const Tile& tile,
-                                              const int32_t* sp, int stride) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows = tile.rows;
-  const int64_t b0 = tile.row_begin;
+template <int VEC, bool BF16>
+__device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const ColCtx& c, int W,
+                                              const DevChunk& ch, int64_t b0, int rows,
+                                              const int32_t* sp, const int32_t* ids, int lane) {
+#ifdef RECOM_TEST_NOSP2
+  return;
+#endif
   const int rpp = 32 / W;
   const int sub = lane / W;
   if (sub >= rpp) return;
-  const ColCtx& c = cs.ctx[ch.col_local];
+  const int rps = (rows + rpp - 1) / rpp;  // rows of this lane group
+  int r = sub * rps;
+  const int r_end = min(rows, r + rps);
+  if (r >= r_end) return;
   const uint8_t* tbl = c.table + ch.table_byte;
   const int64_t row_bytes = c.row_bytes;
-  const int32_t* rs = sp + ch.col_local * stride;
-  const bool staged = cs.sp_cnt[ch.col_local] >= 0;
-  // id source: smem (relative to the tile's first id), the workspace, or the raw input slot
-  const bool from_ws = (c.transform != RECOM_XFORM_NONE) || CHECK;
-  const int32_t* ids32 = staged ? rs + rows + 1 - rs[0]
-                                : (from_ws ? c.ws_ids : (const int32_t*)c.values);
-  const bool ids64 = !staged && !from_ws && c.value_dtype == RECOM_I64;
-  const long long* idsll = (const long long*)c.values;
-  uint8_t* outp = Q.out + b0 * Q.out_row_bytes + ch.out_byte;
+  const int64_t orb = Q.out_row_bytes;
   const int combiner = c.combiner;
-  auto id_at = [&](int32_t e) -> int64_t {
-    return ids64 ? (int64_t)idsll[e] : (int64_t)ids32[e];
-  };
-  constexpr int U = BF16 ? 4 : 8;  // independent row gathers in flight per lane
-
-  for (int r = warp * rpp + sub; r < rows; r += kWarps * rpp) {
-    const int32_t beg = rs[r], end = rs[r + 1];
-    Acc<VEC, BF16> acc;
-    acc.clear();
-    int32_t e = beg;
-    for (; e + U - 1 < end; e += U) {
-      Chunk<VEC> v[U];
-#pragma unroll
-      for (int k = 0; k < U; ++k) v[k].load(tbl + id_at(e + k) * row_bytes);
-#pragma unroll
-      for (int k = 0; k < U; ++k) acc.add(v[k]);
-    }
-    if (U == 8 && e + 3 < end) {
-      Chunk<VEC> v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k].load(tbl + id_at(e + k) * row_bytes);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc.add(v[k]);
-      e += 4;
-    }
-    {
-      // up to 3 left: issue them together as well (named registers: a conditionally indexed
-      // array would live in local memory)
-      const int left = end - e;
-      Chunk<VEC> v0, v1, v2;
-      v0.zero();
-      v1.zero();
-      v2.zero();
-      if (left > 0) v0.load(tbl + id_at(e) * row_bytes);
-      if (left > 1) v1.load(tbl + id_at(e + 1) * row_bytes);
-      if (left > 2) v2.load(tbl + id_at(e + 2) * row_bytes);
-      acc.add(v0);
-      acc.add(v1);
-      acc.add(v2);
-    }
-    const int32_t n = end - beg;
+  uint8_t* outp = Q.out + (b0 + r) * orb + ch.out_byte;
+  #ifndef RECOM_SPARSE_U
+#define RECOM_SPARSE_U 8
+#endif
+  constexpr int U = BF16 ? 4 : RECOM_SPARSE_U;
+  int32_t e = sp[r];
+  const int32_t e_end = sp[r_end];
+  int32_t row_beg = e, row_end = sp[r + 1];
+  Acc<VEC, BF16> acc;
+  acc.clear();
+  auto flush = [&]() {
+    const int32_t n = row_end - row_beg;
     if (n > 1 && combiner != RECOM_COMBINE_SUM) {
       // TF-CPU scaling (segment_reduction_ops_impl.h:619-629,765-770):
       // n < 10 multiplies by 1/m, n >= 10 divides by m; m = n or sqrt(n).
-      const float m = combiner == RECOM_COMBINE_MEAN ? (float)n
-                                                     : (float)__dsqrt_rn((double)n);
+      const float m = combiner == RECOM_COMBINE_MEAN ? (float)n : (float)__dsqrt_rn((double)n);
       if (n < 10) acc.mul(__fdiv_rn(1.0f, m));
       else acc.div(m);
     }
-    acc.pack().store(outp + (int64_t)r * Q.out_row_bytes);
+    acc.pack().store(outp);
+    outp += orb;
+  };
+  while (e < e_end) {
+    Chunk<VEC> v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (e + k < e_end) v[k].load(tbl + (int64_t)ids[e + k] * row_bytes);
+      else v[k].zero();
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (e + k < e_end) {
+        while (e + k >= row_end) {  // the stream enters the next (possibly empty) row
+          flush();
+          ++r;
+          row_beg = row_end;
+          row_end = sp[r + 1];
+          acc.clear();
+        }
+        acc.add(v[k]);
+      }
+    }
+    e += U;
   }
+  for (;;) {  // the row being accumulated, then the empty rows after the last id
+    flush();
+    if (++r >= r_end) break;
+    row_beg = row_end;
+    row_end = sp[r + 1];
+    acc.clear();
+  }
+}
+
+template <bool BF16>
+__device__ __forceinline__ void sparse_warp_tile(const DevPlan& P, const ReqParams& A,
+                                                 const ReqRegs& Q, const Tile& tile, bool new_slab,
+                                                 uint8_t* scratch, DevChunk& ch, int lane) {
+  constexpr int ELEM = BF16 ? 2 : 4;
+  const DevSlab& slab = tile.slab;
+  const int nc = slab.num_cols, rows = tile.rows;
+  const int pitch = slab.tile_rows + 1;
+  const int64_t b0 = tile.row_begin;
+  ColCtx* ctx = reinterpret_cast<ColCtx*>(scratch);
+  int32_t* prefix = reinterpret_cast<int32_t*>(scratch + nc * sizeof(ColCtx));
+  int32_t* splits = prefix + nc + 1;
+  int32_t* ids_s = splits + nc * pitch;
+  const int cap = (P.scratch_bytes - (int)(reinterpret_cast<uint8_t*>(ids_s) - scratch)) / 4;
+  if (new_slab) {
+    __syncwarp();
+    if (lane < nc) {
+      ColCtx x;
+      build_ctx(A, P.slab_cols[slab.first_col + lane], false, false, x);
+      ctx[lane] = x;
+    }
+    ch = P.chunks[slab.first_chunk + lane % slab.num_chunks];
+    __syncwarp();
+  }
+  // the tile's row_splits, every column at once
+  for (int idx = lane; idx < nc * (rows + 1); idx += 32) {
+    const int cl = idx / (rows + 1), r = idx - cl * (rows + 1);
+    splits[cl * pitch + r] = __ldg(ctx[cl].row_splits + b0 + r);
+  }
+  __syncwarp();
+  // ids per column -> exclusive prefix
+  int32_t incl = lane < nc ? splits[lane * pitch + rows] - splits[lane * pitch] : 0;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane < nc) prefix[lane + 1] = incl;
+  if (lane == 0) prefix[0] = 0;
+  const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  __syncwarp();
+  const bool in_smem = total <= cap;
+
+  // phase 1: flat index f -> (column, element), four chains per lane
+  for (int32_t f0 = 0; f0 < total; f0 += 128) {
+    const ColCtx* c[4];
+    const float* bnd[4];
+    int64_t ee[4];
+    bool ok[4];
+    int32_t id[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int32_t f = f0 + 32 * k + lane;
+      ok[k] = f < total;
+      int lo = 0, hi = nc;  // largest cl with prefix[cl] <= f
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= f) lo = mid;
+        else hi = mid;
+      }
+      const int cl = ok[k] ? lo : 0;
+      c[k] = ctx + cl;
+      bnd[k] = P.boundaries + c[k]->bnd_pool_off;
+      ee[k] = (int64_t)splits[cl * pitch] + (f - prefix[cl]);
+    }
+    ids_n<4>(c, bnd, ee, ok, id);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      int32_t v = id[k];
+      if (Q.check) v = checked_id(v, c[k]->table_rows, Q.status);
+      if (in_smem) ids_s[f0 + 32 * k + lane] = v;
+      else A.ws_ids[A.sparse_base[c[k]->sparse_index] + ee[k]] = v;
+      if (Q.ids_out) Q.ids_out[Q.ids_base[c[k]->col] + ee[k]] = v;
+    }
+  }
+  __syncwarp();
+
+  // phase 2
+  const int cl = ch.col_local;
+  const ColCtx& cc = ctx[cl];
+  const int32_t* sp = splits + cl * pitch;
+  // ids indexed by the absolute element number e
+  const int32_t* ids = in_smem ? ids_s + prefix[cl] - sp[0]
+                               : A.ws_ids + A.sparse_base[cc.sparse_index];
+  if (slab.vec_bytes == 16)
+    sparse_phase2<16, BF16>(Q, cc, slab.num_chunks, ch, b0, rows, sp, ids, lane);
+  else
+    sparse_phase2<ELEM, BF16>(Q, cc, slab.num_chunks, ch, b0, rows, sp, ids, lane);
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------
-// Tile sources of a CTA: ST = its own static DENSE macro tile (Sched::start), SP = the shared
-// pool of SPARSE tiles (long DRAM-latency chains), DP = the shared pool of small left-over
-// DENSE tiles (load balance). "Sparse first" CTAs walk SP, DP; the others ST, SP, DP, so that
-// latency-bound gathers and bandwidth-bound dense stores overlap on every SM.
-// Pool claims are issued one tile before they are looked at, so the atomic's latency is not
-// waited for (except when a pool runs dry). Lives in thread 0.
-struct TileCursor {
-  enum Kind : int { SP = 0, DP = 1, DONE = 2 };
-  struct Claim {
-    int kind;
-    int raw;  // the atomic's result, untouched until resolve()
-  };
-  int kind;
-  int num_sparse, num_tiles;
-
-  __device__ __forceinline__ void init(const Sched& S) {
-    kind = SP;
-    num_sparse = S.num_sparse_tiles;
-    num_tiles = S.num_tiles;
-  }
-  __device__ __forceinline__ Claim issue(const ReqParams& A) {
-    if (kind == SP) {
-      if (num_sparse > 0) return Claim{SP, atomicAdd(A.counters, 1)};
-      kind = DP;
-    }
-    if (kind == DP) {
-      if (num_sparse < num_tiles) return Claim{DP, atomicAdd(A.counters + 1, 1)};
-      kind = DONE;
-    }
-    return Claim{DONE, -1};
-  }
-  // -> tile index, or -1 when every source is exhausted
-  __device__ __forceinline__ int resolve(const ReqParams& A, Claim c) {
-    for (;;) {
-      if (c.kind == DONE) return -1;
-      if (c.kind == SP && c.raw < num_sparse) return c.raw;
-      if (c.kind == DP && num_sparse + c.raw < num_tiles) return num_sparse + c.raw;
-      if (kind == c.kind) ++kind;  // that pool is dry
-      c = issue(A);
-    }
-  }
-};
-
-// Optional per-CTA phase timing (thread 0's view), compiled in only with -DRECOM_PROFILE
-// (make prof): slots are summed over the CTA's tiles and written to R->prof.
+// Optional per-warp timing, compiled in only with -DRECOM_PROFILE (make prof): every warp
+// records [start, end] in globaltimer ns plus the cycles it spent per phase.
 #ifdef RECOM_PROFILE
 __device__ __forceinline__ uint64_t gtimer() {
   uint64_t t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// phase slots count SM cycles (clock64: cheap, exact); slots 14 / 15 hold the CTA's start /
-// end in globaltimer ns
-#define PROF_DECL                                                       \
-  uint32_t prof_acc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   \
-  const uint64_t prof_t0 = gtimer();                                    \
+#define PROF_DECL                                     \
+  uint32_t prof_acc[6] = {0, 0, 0, 0, 0, 0};          \
+  const uint64_t prof_t0 = gtimer();                  \
   uint32_t prof_last = (uint32_t)clock64();
-#define PROF_T(i)                                   \
-  if (threadIdx.x == 0) {                           \
-    const uint32_t now_ = (uint32_t)clock64();      \
-    prof_acc[i] += now_ - prof_last;                \
-    prof_last = now_;                               \
+#define PROF_T(i)                                     \
+  {                                                   \
+    const uint32_t now_ = (uint32_t)clock64();        \
+    prof_acc[i] += now_ - prof_last;                  \
+    prof_last = now_;                                 \
   }
-#define PROF_COUNT(i) if (threadIdx.x == 0) prof_acc[i] += 1;
-#define PROF_END                                                        \
-  if (threadIdx.x == 0 && A.prof) {                                     \
-    uint64_t* o_ = A.prof + blockIdx.x * 16;                            \
-    _Pragma("unroll") for (int i_ = 0; i_ < 14; ++i_) o_[i_] = prof_acc[i_]; \
-    o_[14] = prof_t0;                                                   \
-    o_[15] = gtimer();                                                  \
+#define PROF_END                                                                       \
+  if ((threadIdx.x & 31) == 0 && A.prof) {                                             \
+    uint64_t* o_ = A.prof + ((size_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * 8;    \
+    _Pragma("unroll") for (int i_ = 0; i_ < 6; ++i_) o_[i_] = prof_acc[i_];            \
+    o_[6] = prof_t0;                                                                   \
+    o_[7] = gtimer();                                                                  \
   }
 #else
 #define PROF_DECL
 #define PROF_T(i)
-#define PROF_COUNT(i)
 #define PROF_END
 #endif
 
-__device__ __forceinline__ void cp_async_tile(Tile* smem_dst, const Tile* gsrc) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    cp_async_16(reinterpret_cast<uint8_t*>(smem_dst) + 16 * i,
-                reinterpret_cast<const uint8_t*>(gsrc) + 16 * i);
-}
-
-template <bool BF16, bool CHECK>
-__global__ void __launch_bounds__(kThreads, 3)
+template <bool BF16>
+#ifndef RECOM_MIN_BLOCKS
+#define RECOM_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(kThreads, RECOM_MIN_BLOCKS)
 fused_columns_kernel(const DevPlan P, const Sched S, const ReqParams A) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ CtaShared cs;
+  __shared__ uint64_t mbar_tbl;  // tables of the staged slab have landed
+  __shared__ uint64_t mbar_bnd;  // boundaries of the staged slab have landed
   constexpr int ELEM = BF16 ? 2 : 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* s_tables = smem;
   float* s_bnd = reinterpret_cast<float*>(smem + P.smem_off_bnd);
-  int32_t* s_ids = reinterpret_cast<int32_t*>(smem + P.smem_off_ids);
+  ColCtx* s_ctx = reinterpret_cast<ColCtx*>(smem + P.smem_off_ctx);
+  uint8_t* scratch = smem + P.smem_off_scratch + warp * P.scratch_bytes;
   ReqRegs Q;
   Q.out = A.out;
   Q.out_row_bytes = A.out_row_bytes;
   Q.status = A.status;
-
+  Q.ids_out = A.ids_out;
+  Q.ids_base = A.ids_base;
+  Q.check = P.check_ids != 0;
   PROF_DECL
-  // The first tile: the CTA's static macro tile, read by every thread straight from the
-  // schedule (one global round trip, no hand-over), or a claim from the sparse pool.
-  Tile tile = S.start[blockIdx.x];
-  const bool sparse_first = (int)blockIdx.x < S.sparse_first_ctas || tile.slab_id < 0;
-  TileCursor cursor;
-  TileCursor::Claim pend{TileCursor::DONE, -1};
-  if (threadIdx.x == 0) {
-    mbar_init(&cs.mbar_bnd, 1);
-    mbar_init(&cs.mbar_tbl, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&cs.full[i], kProducerWarps);
-      mbar_init(&cs.empty[i], kConsumerWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    cursor.init(S);
-    if (sparse_first) {
-      const int i0 = cursor.resolve(A, cursor.issue(A));
-      if (i0 >= 0) cs.next[1] = S.tiles[i0];
-      else cs.next[1].slab_id = -1;
-    }
-    pend = cursor.issue(A);
-  }
-  __syncthreads();  // mbarriers initialised (and cs.next[1] written)
-  if (sparse_first) {
-    tile = cs.next[1];
-    __syncthreads();  // read before thread 0 reuses the slot
-  }
-  PROF_T(13)
 
-  int cur_slab = -1;
-  int staged_bnd = -1;        // pool offset of the single boundary set resident in smem, or -1
-  uint32_t stage_parity = 1;  // parity of the phase completed by the latest staging
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar_tbl, 1);
+    mbar_init(&mbar_bnd, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int D = kWarps - S.sparse_warps;  // dense warps
   DevChunk ch;
   ch.col = ch.col_local = ch.table_byte = ch.out_byte = 0;
-  int sp_stride = 0;
-  uint32_t ring_it = 0;
-  const int ids_slot = P.smem_ids_cols * kIdPitch;
 
-  for (int k = 0; tile.slab_id >= 0; ++k) {
-    const int buf = k & 1;
-    const DevSlab& slab = tile.slab;
-    PROF_T(0)
-    PROF_COUNT(11)
-    if (tile.slab_id != cur_slab) {
-      // (every warp has passed the barrier that ends the previous tile)
+  if (warp >= D) {
+    // ---- sparse warp: its static share of the SPARSE tiles, heavy slabs first ----
+    const int stride = (int)gridDim.x * S.sparse_warps;
+    int cur_slab = -1;
+    for (int t = (warp - D) * (int)gridDim.x + (int)blockIdx.x; t < S.num_sparse_tiles; t += stride) {
+      const Tile tile = S.sparse_tiles[t];
+      sparse_warp_tile<BF16>(P, A, Q, tile, tile.slab_id != cur_slab, scratch, ch, lane);
       cur_slab = tile.slab_id;
-      // a slab whose only boundary set is already resident keeps it (model E/F: one set for all)
-      const bool keep_bnd = slab.num_bnds == 1 && slab.first_bnd_pool == staged_bnd;
-      if (slab.cls == kSlabSparse) staged_bnd = -1;  // a sparse tile overwrites the whole region
-      else if (slab.num_bnds == 1) staged_bnd = slab.first_bnd_pool;
-      else if (slab.num_bnds > 1) staged_bnd = -1;
-      if (slab.stage_bytes + (keep_bnd ? 0 : slab.bnd_bytes) > 0) stage_parity ^= 1;
-      enter_slab(P, A, slab, cs, s_tables, s_bnd, keep_bnd);
-      {
-        const int lane = threadIdx.x & 31;
-        ch = P.chunks[slab.first_chunk + lane % slab.num_chunks];
-      }
-      if (slab.cls == kSlabSparse)
-        sp_stride = (P.smem_bytes / 4 / slab.num_cols) & ~3;
-      __syncthreads();  // the column contexts are visible
-      PROF_COUNT(12)
-    }
-    PROF_T(1)
-    // thread 0: look at the claim made one tile ago, start copying that tile's record into
-    // cs.next (read by everyone after the barrier that ends this tile), claim one more.
-    // Placed right after a barrier: a __syncthreads waits for outstanding atomics, so the
-    // claim must have the whole tile to come back.
-    if (threadIdx.x == 0) {
-      const int idx = cursor.resolve(A, pend);
-      PROF_T(2)
-      if (idx >= 0) {
-        cp_async_tile(&cs.next[buf], S.tiles + idx);
-        pend = cursor.issue(A);
-      } else {
-        cs.next[buf].slab_id = -1;
-        pend = TileCursor::Claim{TileCursor::DONE, -1};
-      }
       PROF_T(3)
     }
-    if (slab.cls == kSlabSparse) {
-      int32_t* sp = reinterpret_cast<int32_t*>(smem);
-      sparse_phase1<CHECK>(P, Q, cs, slab.num_cols, tile, sp, sp_stride);
-      PROF_T(8)
-      __syncthreads();  // staged splits / ids are visible
-      PROF_T(9)
-      if (slab.vec_bytes == 16)
-        sparse_phase2<16, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile, sp, sp_stride);
-      else
-        sparse_phase2<ELEM, BF16, CHECK>(Q, cs, slab.num_chunks, ch, tile, sp, sp_stride);
-      PROF_T(10)
-    } else {
-      dense_tile<ELEM, CHECK>(P, Q, cs, slab, ch, tile, s_tables, s_bnd, s_ids, ids_slot, stage_parity,
-                              ring_it);
-      PROF_T(6)
+    PROF_END
+    return;
+  }
+
+  // ---- dense warps: the CTA's runs, in order ----
+  const CtaWork cw = S.cta[blockIdx.x];
+  named_bar_sync(1, D * 32);  // the mbarriers are initialised (thread 0 is a dense thread)
+  uint32_t tbl_par = 0, bnd_par = 0;  // parity of the phase the next staging completes
+  int staged_bnd = -1;  // pool offset of the single boundary set resident in smem, or -1
+  int32_t* s_ids = reinterpret_cast<int32_t*>(scratch);
+  for (int ri = 0; ri < cw.count; ++ri) {
+    const Tile run = S.runs[cw.first + ri];
+    const DevSlab& slab = run.slab;
+    if (ri > 0) named_bar_sync(1, D * 32);  // every dense warp is done with the previous run
+    // a run whose only boundary set is already resident keeps it (model E/F: one set for all)
+    const bool keep_bnd = slab.num_bnds == 1 && slab.first_bnd_pool == staged_bnd;
+    if (slab.num_bnds == 1) staged_bnd = slab.first_bnd_pool;
+    else if (slab.num_bnds > 1) staged_bnd = -1;
+    const bool wait_bnd = !keep_bnd && slab.bnd_bytes > 0;
+    const bool staged = run.stage != 0 && slab.stage_bytes > 0;
+    enter_run(P, A, run, s_ctx, s_tables, s_bnd, keep_bnd, &mbar_tbl, &mbar_bnd, D);
+    ch = P.chunks[slab.first_chunk + lane % slab.num_chunks];
+    named_bar_sync(1, D * 32);  // the column contexts are visible
+    PROF_T(0)
+    if (wait_bnd) {
+      mbar_wait(&mbar_bnd, bnd_par);
+      bnd_par ^= 1;
     }
-    if (threadIdx.x == 0) cp_async_wait_all();
-    __syncthreads();  // end of tile: the ids ring / staged splits may be reused, cs.next is visible
-    PROF_T(7)
-    tile = cs.next[buf];
+    bool tbl_ready = !staged;
+    const int ntiles = (run.rows + kDenseTileRows - 1) / kDenseTileRows;
+    for (int t = warp; t < ntiles; t += D) {
+      const int64_t b0 = (int64_t)run.row_begin + (int64_t)t * kDenseTileRows;
+      const int rows = min(kDenseTileRows, run.rows - t * kDenseTileRows);
+      dense_phase1(P, Q, s_ctx, slab, b0, rows, s_bnd, s_ids, lane);
+      __syncwarp();
+      PROF_T(1)
+      if (!tbl_ready) {
+        mbar_wait(&mbar_tbl, tbl_par);
+        tbl_ready = true;
+      }
+      if (staged) {
+        if (slab.vec_bytes == 16) dense_phase2<16, true>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
+        else dense_phase2<ELEM, true>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
+      } else {
+        if (slab.vec_bytes == 16) dense_phase2<16, false>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
+        else dense_phase2<ELEM, false>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
+      }
+      __syncwarp();
+      PROF_T(2)
+    }
+    if (staged) tbl_par ^= 1;
   }
   PROF_END
 }
 
-template <bool BF16, bool CHECK>
+template <bool BF16>
 static int configure_one(int smem_bytes) {
-  auto fn = fused_columns_kernel<BF16, CHECK>;
+  auto fn = fused_columns_kernel<BF16>;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
       cudaSuccess)
     return -1;
@@ -940,22 +941,14 @@ static int configure_one(int smem_bytes) {
 }
 
 int fused_kernel_configure(bool bf16, int smem_bytes) {
-  const int a = bf16 ? configure_one<true, false>(smem_bytes) : configure_one<false, false>(smem_bytes);
-  const int b = bf16 ? configure_one<true, true>(smem_bytes) : configure_one<false, true>(smem_bytes);
-  return a < b ? a : b;
+  return bf16 ? configure_one<true>(smem_bytes) : configure_one<false>(smem_bytes);
 }
 
 void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqParams& req, int grid,
                           bool bf16, cudaStream_t stream) {
-  const bool check = plan.check_ids != 0;
   const size_t sm = (size_t)plan.smem_bytes;
-  if (bf16) {
-    if (check) fused_columns_kernel<true, true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
-    else fused_columns_kernel<true, false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
-  } else {
-    if (check) fused_columns_kernel<false, true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
-    else fused_columns_kernel<false, false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
-  }
+  if (bf16) fused_columns_kernel<true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+  else fused_columns_kernel<false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
 }
 
 // ---------------------------------------------------------------------------
@@ -973,26 +966,28 @@ __device__ __forceinline__ void fill_row_splits(const long long* __restrict__ co
 }
 
 __global__ void __launch_bounds__(256)
-coo_to_row_splits_kernel(const DevPlan P, const ReqHeader* __restrict__ R) {
+coo_to_row_splits_kernel(const DevPlan P, const ReqHeader* __restrict__ R,
+                         const uint8_t* __restrict__ blob, int32_t* __restrict__ ws_row_splits) {
   const int k = blockIdx.y;
   const int ci = req_coo_cols(R)[k];
   const DevColumn c = P.cols[ci];
   const int32_t* ids_base = req_ids_base(R);
   const int64_t nnz = ids_base[ci + 1] - ids_base[ci];
-  const long long* coo = (const long long*)(R->blob + req_slot_offsets(R)[c.seg_slot]);
-  int32_t* rs = R->ws_row_splits + (int64_t)k * (R->batch + 1);
+  const long long* coo = (const long long*)(blob + req_slot_offsets(R)[c.seg_slot]);
+  int32_t* rs = ws_row_splits + (int64_t)k * (R->batch + 1);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz;
        i += (int64_t)gridDim.x * blockDim.x)
     fill_row_splits(coo, nnz, c.seg_stride, R->batch, rs, i);
 }
 
-void launch_coo_to_row_splits(const DevPlan& plan, const ReqHeader* d_req, int num_coo,
-                              int64_t max_nnz, cudaStream_t stream) {
+void launch_coo_to_row_splits(const DevPlan& plan, const ReqHeader* d_req, const uint8_t* blob,
+                              int32_t* ws_row_splits, int num_coo, int64_t max_nnz,
+                              cudaStream_t stream) {
   int64_t bx = (max_nnz + 1 + 255) / 256;
   if (bx > 1024) bx = 1024;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)num_coo);
-  coo_to_row_splits_kernel<<<grid, 256, 0, stream>>>(plan, d_req);
+  coo_to_row_splits_kernel<<<grid, 256, 0, stream>>>(plan, d_req, blob, ws_row_splits);
 }
 
 __global__ void __launch_bounds__(256)

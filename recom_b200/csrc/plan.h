@@ -12,16 +12,15 @@
 
 namespace recom {
 
-constexpr int kThreads = 256;          // threads per CTA
+constexpr int kThreads = 512;          // threads per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxChunks = 32;         // a slab is at most one warp wide
-constexpr int kProducerWarps = 4;      // DENSE tiles: warps 0-3 turn inputs into row ids ...
-constexpr int kConsumerWarps = kWarps - kProducerWarps;  // ... warps 4-7 gather and store
-constexpr int kSubRows = 64;           // rows of one hand-over between them (ids ring slot)
-constexpr int kIdPitch = kSubRows + 1; // smem pitch of a column's ids (bank-conflict free)
-constexpr int kPoolTileRows = 64;      // rows of a DENSE tile in the load-balancing pool
-constexpr int kSparseTileRowsL2 = 16;  // rows per SPARSE tile, tables that fit in L2
-constexpr int kSparseTileRowsHbm = 8;  // rows per SPARSE tile, HBM-resident tables
+constexpr int kDenseTileRows = 32;     // rows of a DENSE warp tile (lane = row while ids are made)
+constexpr int kIdPitch = kDenseTileRows + 1;  // smem pitch of a column's ids (bank-conflict free)
+constexpr int kMinStageRows = 96;      // a DENSE run shorter than this gathers from global memory
+constexpr int kSparseRowsPerSub = 4;   // SPARSE warp tile: rows per lane group (32 / W groups)
+constexpr int kSparseIdsPerRow = 8;    // smem budget of a SPARSE warp tile, ids per (column, row)
+constexpr int kMaxWarpScratch = 6 << 10;
 constexpr int64_t kHbmTableBytes = 32ll << 20;  // a table beyond this is "HBM resident"
 // shared-memory staging limits (per CTA)
 constexpr int kStageTableRows = 256;       // only tables with few rows are staged
@@ -91,15 +90,13 @@ struct DevSlabCol {
   int32_t combiner;
 };
 
-// The same column resolved against one request; lives in shared memory while a CTA works
-// on the slab (built once per slab change, one thread per column).
+// The same column resolved against one request; lives in shared memory while a CTA (DENSE
+// run) or a warp (SPARSE tile) works on the slab.
 struct ColCtx {
   const uint8_t* values;      // blob + slot_offsets[value_slot]
   const uint8_t* bytes;       // STR payload, else null
   const uint8_t* table;       // request table pointer
   const int32_t* row_splits;  // non-DENSE only
-  int32_t* ws_ids;            // non-DENSE only: transformed ids of this column
-  int32_t* ids_out;           // parity hook: where this column's ids go, or null
   uint64_t bucket_magic;
   int32_t num_buckets;
   int32_t table_rows;
@@ -111,7 +108,10 @@ struct ColCtx {
   int32_t bnd_pool_off;
   int32_t stage_off;          // smem byte offset of the staged table, -1: global
   int32_t combiner;
+  int32_t col;                // global column index (ids_out hook)
+  int32_t sparse_index;       // rank among non-DENSE columns (workspace ids), -1 for DENSE
 };
+static_assert(sizeof(ColCtx) == 88, "ColCtx layout");
 
 // A distinct boundary set staged by a slab.
 struct DevSlabBnd {
@@ -130,13 +130,16 @@ struct DevSlab {
   int32_t num_cols;
   int32_t first_col;    // into the slab_cols array
   int32_t vec_bytes;    // 16, or the element size when unaligned
-  int32_t tile_rows;
+  int32_t tile_rows;    // rows of a warp tile
   int32_t stage_bytes;  // total bytes of staged tables
   int32_t first_bnd;    // into the slab_bnds array
   int32_t num_bnds;
   int32_t bnd_bytes;    // total bytes of staged boundaries
   int32_t first_bnd_pool;  // pool offset of the first staged boundary set (-1: none)
+  uint32_t fast8_mask;  // bit g: columns [8g, 8g+8) are float32 bucketize with staged boundaries
+  int32_t pad[3];
 };
+static_assert(sizeof(DevSlab) == 64, "DevSlab layout");
 
 struct DevPlan {
   const DevColumn* cols;
@@ -149,32 +152,43 @@ struct DevPlan {
   int32_t num_slabs;
   int32_t elem_bytes;   // 4 (fp32) or 2 (bf16): table and output element size
   int32_t check_ids;
-  // dynamic shared memory layout (bytes from the start)
+  // dynamic shared memory layout (bytes from the start):
+  // [staged tables | staged boundaries | DENSE column contexts | kWarps x warp scratch]
   int32_t smem_off_bnd;
-  int32_t smem_off_ids;
-  int32_t smem_ids_cols;  // columns per ids buffer (max columns of a DENSE slab)
+  int32_t smem_off_ctx;
+  int32_t smem_off_scratch;
+  int32_t scratch_bytes;  // per warp: ids of a DENSE warp tile, or ctx + splits + ids of a SPARSE one
   int32_t smem_bytes;
+  int32_t pad;
 };
 
-// A unit of work of a persistent CTA: a row block of a slab. The slab record travels with
-// the tile so that a CTA entering a new slab needs no further lookup.
+// A unit of work: a row range of a slab. For a DENSE run (a CTA's dense warps walk it in
+// 32-row warp tiles) and for a SPARSE warp tile alike. The slab record travels with it so
+// that no dependent lookup is needed.
 struct Tile {
   int32_t slab_id;      // -1: none
   int32_t row_begin;
   int32_t rows;
-  int32_t pad;
+  int32_t stage;        // DENSE run: 1 = stage the slab's small tables in shared memory
   DevSlab slab;
 };
-static_assert(sizeof(Tile) == 64, "Tile is copied with four 16-byte cp.async");
+static_assert(sizeof(Tile) == 80, "Tile layout");
 
-// The schedule of a batch size (cached on the device by the plan); a kernel parameter.
+// The DENSE runs of a CTA: runs[first, first + count), walked in order.
+struct CtaWork {
+  int32_t first;
+  int32_t count;
+};
+
+// The static schedule of a batch size (cached on the device by the plan); a kernel parameter.
+// Warps [0, kWarps - sparse_warps) of every CTA are dense warps, the others sparse warps.
+// Sparse warp s of CTA c takes the sparse tiles s * grid + c, + grid * sparse_warps, ...
 struct Sched {
-  const Tile* tiles;   // [num_tiles]: SPARSE pool, then DENSE pool
-  const Tile* start;   // [grid]: the static DENSE macro tile of each CTA (slab_id -1: none)
-  int32_t num_tiles;
-  int32_t num_sparse_tiles;   // tiles [0, num_sparse_tiles) are the SPARSE pool
-  int32_t sparse_first_ctas;  // CTAs below this index start with the SPARSE pool
-  int32_t pad;
+  const Tile* runs;          // DENSE runs, grouped by CTA
+  const CtaWork* cta;        // [grid]
+  const Tile* sparse_tiles;  // [num_sparse_tiles], heavy slabs first
+  int32_t num_sparse_tiles;
+  int32_t sparse_warps;
 };
 
 // Per-request values known on the host at launch; a kernel parameter (no dependent loads).
@@ -183,26 +197,24 @@ struct ReqParams {
   uint8_t* out;
   int32_t* ids_out;        // may be null
   int32_t* status;         // may be null
-  int32_t* ws_ids;         // workspace: transformed ids of non-DENSE columns
+  int32_t* ws_ids;         // workspace: transformed ids of non-DENSE columns (overflow only)
   int32_t* ws_row_splits;  // workspace: row_splits built from COO columns
-  // arrays inside the uploaded argument block (device addresses)
+  // arrays of the request's argument block (device addresses; plan-cached or in the workspace)
   const int64_t* slot_offsets;  // [num_slots]
   const void* const* tables;    // [num_tables]
   const int32_t* ids_base;      // [num_cols + 1] prefix of ids per column
   const int32_t* sparse_base;   // [num_sparse + 1] prefix of ids, non-DENSE only
-  int32_t* counters;            // [2]: SPARSE pool, DENSE pool claim counters (start at 0)
-  uint64_t* prof;               // profiling builds only: [grid, 16] phase timers, else null
+  uint64_t* prof;               // profiling builds only, else null
   int64_t batch;
   int64_t out_row_bytes;
 };
 
-// Per-request argument block: a header followed by the arrays ReqParams points to. Built on
-// the host in pinned memory, uploaded with one cudaMemcpyAsync into the workspace (replaces the
-// reference's KnlArgs + SymbolResults uploads, cuda_emitter.cc:2182-2232).
+// Per-request argument block: a header followed by the arrays ReqParams points to. It holds
+// nothing that differs between requests of the same shape (no blob / output / workspace
+// pointers), so the plan keeps device copies keyed by content and a steady stream of
+// same-shaped requests uploads nothing (replaces the reference's per-call KnlArgs +
+// SymbolResults uploads, cuda_emitter.cc:2182-2232).
 struct ReqHeader {
-  int32_t counters[4];        // claim counters, zero on upload
-  const uint8_t* blob;        // (kept for the COO -> row_splits pre-pass)
-  int32_t* ws_row_splits;
   int64_t batch;
   int32_t num_coo;            // number of COO columns
   int32_t pad0;
@@ -213,6 +225,7 @@ struct ReqHeader {
   uint32_t off_sparse_base;   // int32[num_sparse + 1]
   uint32_t off_coo_cols;      // int32[num_coo] column index of each COO column
   uint32_t total_bytes;
+  int64_t pad1;
 };
 
 __host__ __device__ inline const int64_t* req_slot_offsets(const ReqHeader* r) {
@@ -239,8 +252,9 @@ __host__ __device__ inline const int32_t* req_coo_cols(const ReqHeader* r) {
 // kernels.cu
 void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqParams& req, int grid,
                           bool bf16, cudaStream_t stream);
-void launch_coo_to_row_splits(const DevPlan& plan, const ReqHeader* d_req, int num_coo,
-                              int64_t max_nnz, cudaStream_t stream);
+void launch_coo_to_row_splits(const DevPlan& plan, const ReqHeader* d_req, const uint8_t* blob,
+                              int32_t* ws_row_splits, int num_coo, int64_t max_nnz,
+                              cudaStream_t stream);
 void launch_scatter_columns(const void* const* d_cols, const int32_t* d_dims,
                             const int32_t* d_offsets, int32_t num_cols, int64_t batch,
                             int32_t out_width, int32_t elem_bytes, void* out,

@@ -1,17 +1,31 @@
 #!/usr/bin/env python
-"""Summarise a phase-timer dump (make prof build; RECOM_B200_PROF_DUMP)."""
+"""Summarise a per-warp timer dump (make prof build; RECOM_B200_PROF_DUMP).
+
+Rows = warps (CTA-major, 16 per CTA); columns: cycles in [run entry, dense phase 1, dense
+phase 2, sparse tiles, -, -], then the warp's start / end in globaltimer ns."""
 import sys
 import numpy as np
 a = np.loadtxt(sys.argv[1], dtype=np.uint64).astype(np.float64)
-names = ["looptop", "enter+sync", "resolve", "cp+issue", "-", "-", "dense_tile", "end_sync",
-         "s_phase1", "s_barrier", "s_phase2", "tiles", "stagings", "prologue", "t_start", "t_end"]
+a = a[a[:, 6] > 0]
 CYC = 1.0 / 1.965  # ns per SM cycle at 1965 MHz
-t0 = a[:, 14].min()
-dur = a[:, 15] - a[:, 14]
-print(f"CTAs {a.shape[0]}  kernel span {(a[:,15].max()-t0)/1e3:.1f} us  start spread {(a[:,14].max()-t0)/1e3:.1f} us  "
-      f"CTA busy mean {dur.mean()/1e3:.1f} max {dur.max()/1e3:.1f} min {dur.min()/1e3:.1f} us")
-print(f"tiles/CTA mean {a[:,11].mean():.2f} max {a[:,11].max():.0f}; stagings/CTA mean {a[:,12].mean():.2f}")
-for i in list(range(11)) + [13]:
-    c = a[:, i] * CYC
-    print(f"  {names[i]:<12} mean/CTA {c.mean()/1e3:7.2f} us   per tile {c.sum()/max(a[:,11].sum(),1)/1e3:6.3f} us   max/CTA {c.max()/1e3:7.2f}")
-print(f"  sum of phases mean/CTA {(a[:, list(range(11)) + [13]].sum(axis=1) * CYC).mean()/1e3:.2f} us")
+t0 = a[:, 6].min()
+dur = (a[:, 7] - a[:, 6]) / 1e3
+print(f"warps {a.shape[0]}  kernel span {(a[:,7].max()-t0)/1e3:.1f} us  start spread {(a[:,6].max()-t0)/1e3:.1f} us")
+names = ["enter", "d_phase1", "d_phase2", "sparse"]
+dense = a[:, 1] + a[:, 2] > 0
+sparse = a[:, 3] > 0
+for nm, m in (("dense", dense), ("sparse", sparse)):
+    if not m.any():
+        continue
+    d = dur[m]
+    end = (a[m, 7] - t0) / 1e3
+    print(f"{nm}: warps {m.sum()}  busy mean {d.mean():.1f} p50 {np.median(d):.1f} p90 {np.percentile(d,90):.1f} max {d.max():.1f} us; "
+          f"end mean {end.mean():.1f} p90 {np.percentile(end,90):.1f} max {end.max():.1f} us")
+    for i, n in enumerate(names):
+        c = a[m, i] * CYC / 1e3
+        if c.sum() > 0:
+            print(f"   {n:<9} mean {c.mean():6.2f} p50 {np.median(c):6.2f} p90 {np.percentile(c,90):6.2f} max {c.max():6.2f} us")
+# the slowest dense warps
+idx = np.argsort(-(a[:, 7] - t0))[:8]
+for i in idx:
+    print(f"  late warp row {i} (cta {i//16} warp {i%16}): end {(a[i,7]-t0)/1e3:.1f} us, enter {a[i,0]*CYC/1e3:.1f} p1 {a[i,1]*CYC/1e3:.1f} p2 {a[i,2]*CYC/1e3:.1f} sp {a[i,3]*CYC/1e3:.1f}")
