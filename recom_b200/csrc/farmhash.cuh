@@ -76,16 +76,19 @@ struct RegBytes {
   }
 };
 
+// HashLen0to16 for 8 <= len <= 16; first = bytes [0, 8), last = bytes [len - 8, len).
+__device__ __forceinline__ uint64_t hash_len_8_16(uint64_t first, uint64_t last, uint32_t len) {
+  const uint64_t mul = kK2 + (uint64_t)len * 2;
+  const uint64_t a = first + kK2;
+  const uint64_t b = last;
+  const uint64_t c = rot(b, 37) * mul + a;
+  const uint64_t d = (rot(a, 25) + b) * mul;
+  return hash_len16(c, d, mul);
+}
+
 template <class B>
 __device__ __forceinline__ uint64_t hash_len_0_16(const B& s, uint32_t len) {
-  if (len >= 8) {
-    const uint64_t mul = kK2 + (uint64_t)len * 2;
-    const uint64_t a = s.fetch64(0) + kK2;
-    const uint64_t b = s.fetch64(len - 8);
-    const uint64_t c = rot(b, 37) * mul + a;
-    const uint64_t d = (rot(a, 25) + b) * mul;
-    return hash_len16(c, d, mul);
-  }
+  if (len >= 8) return hash_len_8_16(s.fetch64(0), s.fetch64(len - 8), len);
   if (len >= 4) {
     const uint64_t mul = kK2 + (uint64_t)len * 2;
     const uint64_t a = s.fetch32(0);

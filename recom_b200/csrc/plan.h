@@ -12,13 +12,19 @@
 
 namespace recom {
 
-constexpr int kThreads = 512;          // threads per CTA
+#ifndef RECOM_THREADS
+#define RECOM_THREADS 512
+#endif
+constexpr int kThreads = RECOM_THREADS;  // threads per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxChunks = 32;         // a slab is at most one warp wide
 constexpr int kDenseTileRows = 32;     // rows of a DENSE warp tile (lane = row while ids are made)
+constexpr int kFastTileRows = 16;      // ... of a slab of fast groups only: lane = (group parity, row)
+constexpr int kHashTileRows = 8;       // ... of a slab with hashed columns: lane = (column group, row)
 constexpr int kIdPitch = kDenseTileRows + 1;  // smem pitch of a column's ids (bank-conflict free)
 constexpr int kMinStageRows = 96;      // a DENSE run shorter than this gathers from global memory
 constexpr int kSparseRowsPerSub = 4;   // SPARSE warp tile: rows per lane group (32 / W groups)
+constexpr int kSparseRowsPerSubHash = 2;  // ... when the ids are hashed on the fly
 constexpr int kSparseIdsPerRow = 8;    // smem budget of a SPARSE warp tile, ids per (column, row)
 constexpr int kMaxWarpScratch = 6 << 10;
 constexpr int64_t kHbmTableBytes = 32ll << 20;  // a table beyond this is "HBM resident"
@@ -26,7 +32,7 @@ constexpr int64_t kHbmTableBytes = 32ll << 20;  // a table beyond this is "HBM r
 constexpr int kStageTableRows = 256;       // only tables with few rows are staged
 constexpr int kStageTableBytes = 16 << 10; // ... and at most this large
 constexpr int kStageSlabBytes = 56 << 10;  // staged tables of one slab
-constexpr int kStageBndFloats = 2048;      // staged bucket boundaries of one slab
+constexpr int kStageBndFloats = 4096;      // staged boundary sets (with their grids) of one slab
 
 enum SlabClass : int32_t {
   kSlabDenseStaged = 0,  // DENSE lookups, every table staged in shared memory
@@ -137,7 +143,13 @@ struct DevSlab {
   int32_t bnd_bytes;    // total bytes of staged boundaries
   int32_t first_bnd_pool;  // pool offset of the first staged boundary set (-1: none)
   uint32_t fast8_mask;  // bit g: columns [8g, 8g+8) are float32 bucketize with staged boundaries
-  int32_t pad[3];
+  uint32_t uni8_mask;   // ... and share one boundary set
+  int16_t all_fast;     // every column belongs to a fast group
+  int16_t pad;
+  // DENSE run only (filled per run by the scheduler)
+  int16_t run_tile_rows;  // rows of this run's warp tiles (<= tile_rows)
+  int16_t run_tiles;      // number of warp tiles of this run
+
 };
 static_assert(sizeof(DevSlab) == 64, "DevSlab layout");
 
@@ -182,11 +194,13 @@ struct CtaWork {
 
 // The static schedule of a batch size (cached on the device by the plan); a kernel parameter.
 // Warps [0, kWarps - sparse_warps) of every CTA are dense warps, the others sparse warps.
-// Sparse warp s of CTA c takes the sparse tiles s * grid + c, + grid * sparse_warps, ...
+// Sparse warp s of CTA c is sparse warp g = s * grid + c of the grid and takes the sparse tiles
+// [sparse_first[g], sparse_first[g + 1]) (assigned longest-first by estimated cost).
 struct Sched {
   const Tile* runs;          // DENSE runs, grouped by CTA
   const CtaWork* cta;        // [grid]
-  const Tile* sparse_tiles;  // [num_sparse_tiles], heavy slabs first
+  const Tile* sparse_tiles;  // [num_sparse_tiles], grouped by sparse warp
+  const int32_t* sparse_first;  // [grid * sparse_warps + 1]
   int32_t num_sparse_tiles;
   int32_t sparse_warps;
 };

@@ -11,9 +11,9 @@ CYC = 1.0 / 1.965  # ns per SM cycle at 1965 MHz
 t0 = a[:, 6].min()
 dur = (a[:, 7] - a[:, 6]) / 1e3
 print(f"warps {a.shape[0]}  kernel span {(a[:,7].max()-t0)/1e3:.1f} us  start spread {(a[:,6].max()-t0)/1e3:.1f} us")
-names = ["enter", "d_phase1", "d_phase2", "sparse"]
-dense = a[:, 1] + a[:, 2] > 0
-sparse = a[:, 3] > 0
+names = ["enter/tile", "d_phase1", "phase2", "s_ctx", "s_splits", "s_phase1"]
+dense = a[:, 1] > 0
+sparse = a[:, 3] + a[:, 4] + a[:, 5] > 0
 for nm, m in (("dense", dense), ("sparse", sparse)):
     if not m.any():
         continue
@@ -28,4 +28,4 @@ for nm, m in (("dense", dense), ("sparse", sparse)):
 # the slowest dense warps
 idx = np.argsort(-(a[:, 7] - t0))[:8]
 for i in idx:
-    print(f"  late warp row {i} (cta {i//16} warp {i%16}): end {(a[i,7]-t0)/1e3:.1f} us, enter {a[i,0]*CYC/1e3:.1f} p1 {a[i,1]*CYC/1e3:.1f} p2 {a[i,2]*CYC/1e3:.1f} sp {a[i,3]*CYC/1e3:.1f}")
+    print(f"  late warp row {i} (cta {i//16} warp {i%16}): end {(a[i,7]-t0)/1e3:.1f} us, start {(a[i,6]-t0)/1e3:.1f} phases " + " ".join(f"{a[i,j]*CYC/1e3:.1f}" for j in range(6)))
