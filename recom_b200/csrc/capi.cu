@@ -73,6 +73,7 @@ namespace {
 
 constexpr int kRing = 16;       // pinned staging slots of the upload path
 constexpr int kArgCache = 16;   // device-resident argument blocks kept per plan
+constexpr int kCounterSlots = 1024;
 
 struct ArgSlot {
   std::mutex mu;
@@ -104,39 +105,32 @@ int dtype_bytes(int32_t dt) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Static schedule of one batch size (see Sched in plan.h).
+// Schedule of one batch size (see Sched in plan.h).
 struct TileTable {
-  std::vector<Tile> runs;      // DENSE runs grouped by CTA
-  std::vector<Tile> sparse;    // SPARSE warp tiles, heavy slabs first
+  std::vector<Tile> runs;      // FAST runs grouped by CTA
+  std::vector<Tile> queue;     // queue of warp tiles, descending cost
   std::vector<CtaWork> cta;    // [grid]
-  std::vector<int32_t> sparse_first;  // [grid * sparse_warps + 1]: tiles of each sparse warp
   int grid = 1;
-  int sparse_warps = 0;
-  void* d_block = nullptr;  // device copy: runs, sparse, cta (cached tables only)
+  int queue_warps = 0;
+  void* d_block = nullptr;  // device copy: runs, queue, cta (cached tables only)
   ~TileTable() {
     if (d_block) cudaFree(d_block);
   }
   size_t runs_bytes() const { return align_up(runs.size() * sizeof(Tile), 16); }
-  size_t sparse_bytes() const { return align_up(sparse.size() * sizeof(Tile), 16); }
-  size_t cta_bytes() const { return align_up(cta.size() * sizeof(CtaWork), 16); }
-  size_t bytes() const {
-    return runs_bytes() + sparse_bytes() + cta_bytes() + sparse_first.size() * sizeof(int32_t);
-  }
+  size_t queue_bytes() const { return align_up(queue.size() * sizeof(Tile), 16); }
+  size_t bytes() const { return runs_bytes() + queue_bytes() + cta.size() * sizeof(CtaWork); }
   void write(uint8_t* dst) const {
     if (!runs.empty()) memcpy(dst, runs.data(), runs.size() * sizeof(Tile));
-    if (!sparse.empty()) memcpy(dst + runs_bytes(), sparse.data(), sparse.size() * sizeof(Tile));
-    memcpy(dst + runs_bytes() + sparse_bytes(), cta.data(), cta.size() * sizeof(CtaWork));
-    memcpy(dst + runs_bytes() + sparse_bytes() + cta_bytes(), sparse_first.data(),
-           sparse_first.size() * sizeof(int32_t));
+    if (!queue.empty()) memcpy(dst + runs_bytes(), queue.data(), queue.size() * sizeof(Tile));
+    memcpy(dst + runs_bytes() + queue_bytes(), cta.data(), cta.size() * sizeof(CtaWork));
   }
   Sched sched(const void* base) const {
     Sched s{};
     s.runs = (const Tile*)base;
-    s.sparse_tiles = (const Tile*)((const uint8_t*)base + runs_bytes());
-    s.cta = (const CtaWork*)((const uint8_t*)base + runs_bytes() + sparse_bytes());
-    s.sparse_first = (const int32_t*)((const uint8_t*)base + runs_bytes() + sparse_bytes() + cta_bytes());
-    s.num_sparse_tiles = (int32_t)sparse.size();
-    s.sparse_warps = sparse_warps;
+    s.queue = (const Tile*)((const uint8_t*)base + runs_bytes());
+    s.cta = (const CtaWork*)((const uint8_t*)base + runs_bytes() + queue_bytes());
+    s.num_queue = (int32_t)queue.size();
+    s.queue_warps = queue_warps;
     return s;
   }
 };
@@ -182,6 +176,10 @@ struct recom_plan {
   std::vector<std::unique_ptr<ArgEntry>> arg_cache;
   std::vector<uint64_t> seen;      // hashes of recent blocks: a block is cached at its second sight
   bool cache_args = true;
+  // queue claim counters: a ring of self-resetting slots in device memory, one per request in
+  // flight (a slot comes round again after kCounterSlots later requests of this plan)
+  int32_t* d_counters = nullptr;
+  std::atomic<uint32_t> counter_next{0};
   // pinned argument ring of the upload path (first sight of a block, COO inputs, full caches)
   ArgSlot ring[kRing];
   std::atomic<uint32_t> ring_next{0};
@@ -607,11 +605,13 @@ void build_layout(recom_plan* p) {
       const int ncg = 32 / sl.tile_rows;
       p1 = std::ceil(sl.num_cols / (4.0 * ncg)) * 4.0 * (xavg + 20.0);
     }
-    if (sl.tile_rows == kDenseTileRows && sl.num_cols >= 16 && sl.num_cols % 8 == 0 &&
+    if (sl.tile_rows == kDenseTileRows && sl.num_cols >= 8 && sl.num_cols % 8 == 0 &&
         sl.fast8_mask == (1u << (sl.num_cols / 8)) - 1u) {
-      sl.all_fast = 1;
-      sl.tile_rows = kFastTileRows;
-      p1 *= (double)kFastTileRows / kDenseTileRows;
+      sl.all_fast = 1;  // a FAST slab: scheduled statically, everything else goes to the queue
+      if (sl.num_cols >= 16) {
+        sl.tile_rows = kFastTileRows;
+        p1 *= (double)kFastTileRows / kDenseTileRows;
+      }
     }
     const int rpp = 32 / sl.num_chunks;
     p->tile_cost[si] = 120.0 + p1 + std::ceil((double)sl.tile_rows / rpp) * 8.0;
@@ -624,7 +624,10 @@ void build_layout(recom_plan* p) {
     max_bnd = std::max(max_bnd, s.bnd_bytes);
     if (s.cls != kSlabSparse) {
       max_cols = std::max(max_cols, s.num_cols);
-      dense_need = std::max(dense_need, s.num_cols * kIdPitch * 4);
+      // a FAST run keeps the contexts per CTA; a queue tile keeps them in the warp's scratch
+      const bool fast_run = s.all_fast && s.cls == kSlabDenseStaged;
+      dense_need = std::max(dense_need, s.num_cols * kIdPitch * 4 +
+                                            (fast_run ? 0 : (s.num_cols * (int)sizeof(ColCtx) + 15) / 16 * 16));
     } else {
       const int base = s.num_cols * (int)sizeof(ColCtx) + (s.num_cols + 1) * 4 +
                        s.num_cols * (s.tile_rows + 1) * 4;
@@ -671,16 +674,16 @@ void build_layout(recom_plan* p) {
   for (auto& o : order2) p->slab_order.push_back(o.second);
 }
 
-// Static schedule of a batch size (Sched in plan.h).
-//   * Every SPARSE slab is cut into warp tiles of slab.tile_rows rows, heavy slabs first; the
-//     sparse warps of the grid take them interleaved (tile t -> CTA t % grid).
-//   * The 16 warps of a CTA are split into dense and sparse warps in proportion to the
-//     estimated cost of the two kinds of work (a SPARSE warp tile chases several dependent
-//     DRAM round trips: sparse_weight DENSE tiles), never more sparse warps than tiles.
-//   * Every CTA owns ONE dense run: a row range of one slab, so the slab's staged tables and
-//     column contexts are paid once per CTA. CTAs are apportioned to the DENSE slabs by cost
-//     (output bytes, hashed columns weighted), rows split evenly in 32-row warp tiles. With
-//     more DENSE slabs than CTAs, whole slabs go to the least loaded CTA instead.
+// Schedule of a batch size (Sched in plan.h).
+//   * FAST slabs (fast bucketize groups only, tables staged in shared memory) are scheduled
+//     statically: the CTAs are apportioned to them by cost, each CTA owns ONE run (a row range
+//     of one slab, so the staged tables and column contexts are paid once per CTA), split
+//     evenly over the CTA's dense warps. With more FAST slabs than CTAs, whole slabs go to the
+//     least loaded CTA instead.
+//   * Every other slab is cut into warp tiles of slab.tile_rows rows; the tiles form one queue
+//     in descending order of estimated cost (same slab contiguous, so a warp seldom has to
+//     rebuild its column contexts). queue_warps warps of every CTA start on the queue at once,
+//     in proportion to the estimated cost of the two kinds of work.
 std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   const int cap_ctas = std::max(1, p->num_sms * p->ctas_per_sm);
   auto tt = std::make_shared<TileTable>();
@@ -693,7 +696,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     t.stage = t.slab.cls == kSlabDenseStaged && rows >= kMinStageRows;
     return t;
   };
-  // split a DENSE run evenly over the CTA's dense warps (see the kernel's tile loop)
+  // split a FAST run evenly over the CTA's dense warps (see the kernel's tile loop)
   auto tile_run = [&](Tile& t, int dense_warps) {
     const int64_t trmax = t.slab.tile_rows, dw = std::max(1, dense_warps);
     const int64_t k = std::max<int64_t>(1, (t.rows + dw * trmax - 1) / (dw * trmax));
@@ -702,51 +705,60 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     t.slab.run_tile_rows = (int16_t)rpt;
     t.slab.run_tiles = (int16_t)std::min<int64_t>(32767, (t.rows + rpt - 1) / rpt);
   };
-  std::vector<int> dense;
-  for (int s : p->slab_order) {
-    const DevSlab& sl = p->slabs[s];
-    if (sl.cls != kSlabSparse) {
-      dense.push_back(s);
-      continue;
-    }
-    for (int64_t b = 0; b < B; b += sl.tile_rows)
-      tt->sparse.push_back(make(s, b, std::min<int64_t>(sl.tile_rows, B - b)));
-  }
   auto tiles_of = [&](int s) { return (B + p->slabs[s].tile_rows - 1) / p->slabs[s].tile_rows; };
-  std::vector<double> cost(dense.size());
-  double dense_cost = 0;
-  int64_t dense_tiles = 0;
-  for (size_t i = 0; i < dense.size(); ++i) {
-    cost[i] = (double)tiles_of(dense[i]) * p->tile_cost[dense[i]];
-    dense_cost += cost[i];
-    dense_tiles += tiles_of(dense[i]);
+  std::vector<int> fast, other;
+  for (int s = 0; s < (int)p->slabs.size(); ++s) {
+    const DevSlab& sl = p->slabs[s];
+    if (sl.cls == kSlabDenseStaged && sl.all_fast) fast.push_back(s);
+    else other.push_back(s);
   }
-  double sparse_cost = 0;
-  for (const Tile& t : tt->sparse) sparse_cost += p->tile_cost[t.slab_id] * p->sparse_weight;
-  int S = 0;
-  if (tt->sparse.empty()) S = 0;
-  else if (dense.empty()) S = kWarps;
-  else S = std::max(1, std::min(kWarps - 1, (int)(kWarps * sparse_cost / (sparse_cost + dense_cost) + 0.5)));
+  // the queue: heaviest tiles first
+  std::stable_sort(other.begin(), other.end(),
+                   [&](int a, int b) { return p->tile_cost[a] > p->tile_cost[b]; });
+  double queue_cost = 0;
+  for (int s : other) {
+    const DevSlab& sl = p->slabs[s];
+    for (int64_t b = 0; b < B; b += sl.tile_rows) {
+      Tile t = make(s, b, std::min<int64_t>(sl.tile_rows, B - b));
+      t.stage = 0;
+      t.slab.fast8_mask = t.slab.uni8_mask = 0;  // queue tiles read boundaries from the pool
+      t.slab.all_fast = 0;
+      tt->queue.push_back(t);
+      queue_cost += p->tile_cost[s] * p->sparse_weight;
+    }
+  }
+  std::vector<double> cost(fast.size());
+  double fast_cost = 0;
+  int64_t fast_tiles = 0;
+  for (size_t i = 0; i < fast.size(); ++i) {
+    cost[i] = (double)tiles_of(fast[i]) * p->tile_cost[fast[i]];
+    fast_cost += cost[i];
+    fast_tiles += tiles_of(fast[i]);
+  }
+  int Q = 0;
+  if (tt->queue.empty()) Q = 0;
+  else if (fast.empty()) Q = kWarps;
+  else Q = std::max(1, std::min(kWarps - 1, (int)(kWarps * queue_cost / (queue_cost + fast_cost) + 0.5)));
   int64_t units = 1;
-  if (S > 0) units = std::max<int64_t>(units, ((int64_t)tt->sparse.size() + S - 1) / S);
-  if (S < kWarps) units = std::max<int64_t>(units, (dense_tiles + (kWarps - S) - 1) / (kWarps - S));
+  if (Q > 0) units = std::max<int64_t>(units, ((int64_t)tt->queue.size() + Q - 1) / Q);
+  if (Q < kWarps) units = std::max<int64_t>(units, (fast_tiles + (kWarps - Q) - 1) / (kWarps - Q));
   // whole waves: a grid between one and two CTAs per SM would leave some SMs with twice the work
   if (units > p->num_sms) units = (units + p->num_sms - 1) / p->num_sms * p->num_sms;
   const int grid = (int)std::min<int64_t>(cap_ctas, units);
-  if (S > 0 && !dense.empty()) {
-    const int s_need = (int)(((int64_t)tt->sparse.size() + grid - 1) / grid);
-    S = std::max(1, std::min({S, s_need, kWarps - 1}));
+  if (Q > 0 && !fast.empty()) {
+    const int q_need = (int)(((int64_t)tt->queue.size() + grid - 1) / grid);
+    Q = std::max(1, std::min({Q, q_need, kWarps - 1}));
   }
   tt->grid = grid;
-  tt->sparse_warps = S;
+  tt->queue_warps = Q;
 
   std::vector<std::vector<Tile>> per_cta(grid);
-  if (!dense.empty() && (size_t)grid >= dense.size()) {
-    std::vector<int> n_ctas(dense.size(), 1);
-    int given = (int)dense.size();
+  if (!fast.empty() && (size_t)grid >= fast.size()) {
+    std::vector<int> n_ctas(fast.size(), 1);
+    int given = (int)fast.size();
     std::vector<std::pair<double, int>> rem;
-    for (size_t i = 0; i < dense.size(); ++i) {
-      const double share = (grid - (double)dense.size()) * cost[i] / dense_cost;
+    for (size_t i = 0; i < fast.size(); ++i) {
+      const double share = (grid - (double)fast.size()) * cost[i] / fast_cost;
       n_ctas[i] += (int)share;
       given += (int)share;
       rem.push_back({-(share - (int)share), (int)i});
@@ -754,24 +766,24 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     std::sort(rem.begin(), rem.end());
     for (int k = 0; given < grid && k < (int)rem.size(); ++k, ++given) n_ctas[rem[k].second]++;
     int c = 0;
-    for (size_t i = 0; i < dense.size(); ++i) {
-      const int64_t T = tiles_of(dense[i]), TR = p->slabs[dense[i]].tile_rows;
+    for (size_t i = 0; i < fast.size(); ++i) {
+      const int64_t T = tiles_of(fast[i]), TR = p->slabs[fast[i]].tile_rows;
       const int64_t n = std::min<int64_t>(n_ctas[i], T);
       for (int64_t j = 0; j < n; ++j) {
         const int64_t t0 = j * T / n, t1 = (j + 1) * T / n;
         const int64_t r0 = t0 * TR, r1 = std::min<int64_t>(B, t1 * TR);
-        if (r1 > r0) per_cta[c % grid].push_back(make(dense[i], r0, r1 - r0));
+        if (r1 > r0) per_cta[c % grid].push_back(make(fast[i], r0, r1 - r0));
         ++c;
       }
     }
-  } else if (!dense.empty()) {
-    std::vector<int> idx(dense.size());
+  } else if (!fast.empty()) {
+    std::vector<int> idx(fast.size());
     for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     std::vector<double> load(grid, 0.0);
     for (int i : idx) {
       const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-      per_cta[c].push_back(make(dense[i], 0, B));
+      per_cta[c].push_back(make(fast[i], 0, B));
       load[c] += cost[i];
     }
   }
@@ -780,36 +792,9 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     tt->cta[c].first = (int32_t)tt->runs.size();
     tt->cta[c].count = (int32_t)per_cta[c].size();
     for (Tile& t : per_cta[c]) {
-      tile_run(t, kWarps - S);
+      tile_run(t, kWarps - Q);
       tt->runs.push_back(t);
     }
-  }
-  // SPARSE warp tiles: longest-processing-time-first over the grid's sparse warps (the tiles
-  // are in descending cost order already); warp g = s * grid + c of sparse warp s of CTA c
-  {
-    const int G = grid * S;
-    std::vector<std::vector<int>> mine(std::max(G, 1));
-    if (G > 0) {
-      typedef std::pair<double, int> Load;  // (load, warp)
-      std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pq;
-      for (int g = 0; g < G; ++g) pq.push({0.0, g});
-      for (size_t i = 0; i < tt->sparse.size(); ++i) {
-        Load l = pq.top();
-        pq.pop();
-        mine[l.second].push_back((int)i);
-        l.first += p->tile_cost[tt->sparse[i].slab_id];
-        pq.push(l);
-      }
-    }
-    std::vector<Tile> ordered;
-    ordered.reserve(tt->sparse.size());
-    tt->sparse_first.assign(G + 1, 0);
-    for (int g = 0; g < G; ++g) {
-      tt->sparse_first[g] = (int32_t)ordered.size();
-      for (int i : mine[g]) ordered.push_back(tt->sparse[i]);
-    }
-    tt->sparse_first[G] = (int32_t)ordered.size();
-    tt->sparse.swap(ordered);
   }
   return tt;
 }
@@ -998,6 +983,9 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
       p->prof_path = e;
       if (cudaMalloc((void**)&p->d_prof, (size_t)p->num_sms * 4 * kWarps * 8 * 8) != cudaSuccess) p->d_prof = nullptr;
     }
+    if (cudaMalloc((void**)&p->d_counters, (size_t)kCounterSlots * 8) != cudaSuccess ||
+        cudaMemset(p->d_counters, 0, (size_t)kCounterSlots * 8) != cudaSuccess)
+      st = fail(RECOM_ERR_CUDA, "counter ring allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     for (int i = 0; i < kRing && st == RECOM_OK; ++i) {
       cudaError_t e = cudaEventCreateWithFlags(&p->ring[i].done, cudaEventDisableTiming);
       if (e != cudaSuccess) st = fail(RECOM_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
@@ -1036,6 +1024,7 @@ recom_status recom_plan_destroy(recom_plan* p) {
   }
   for (auto& e : p->arg_cache)
     if (e->dev) cudaFree(e->dev);
+  if (p->d_counters) cudaFree(p->d_counters);
   if (p->d_block) cudaFree(p->d_block);
   delete p;
   return RECOM_OK;
@@ -1123,11 +1112,10 @@ static size_t arg_block_bytes(const recom_plan* p) {
 
 static size_t max_sched_bytes(const recom_plan* p, int64_t batch) {
   // only used when the schedule cache is full and the schedule travels with the request
-  size_t tiles = p->slabs.size() + (size_t)p->num_sms * p->ctas_per_sm + 4;
-  for (const DevSlab& s : p->slabs)
-    if (s.cls == kSlabSparse) tiles += (size_t)((batch + s.tile_rows - 1) / s.tile_rows);
   const size_t ctas = (size_t)p->num_sms * p->ctas_per_sm;
-  return tiles * sizeof(Tile) + ctas * sizeof(CtaWork) + (ctas * kWarps + 1) * 4 + 128;
+  size_t tiles = p->slabs.size() + ctas + 4;
+  for (const DevSlab& s : p->slabs) tiles += (size_t)((batch + s.tile_rows - 1) / s.tile_rows);
+  return tiles * sizeof(Tile) + ctas * sizeof(CtaWork) + 128;
 }
 
 recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int64_t total_ids,
@@ -1286,6 +1274,7 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   A.tables = (const void* const*)(d_args + hdr->off_tables);
   A.ids_base = (const int32_t*)(d_args + hdr->off_ids_base);
   A.sparse_base = (const int32_t*)(d_args + hdr->off_sparse_base);
+  A.counters = p->d_counters + 2 * (p->counter_next.fetch_add(1) % kCounterSlots);
   A.prof = p->d_prof;
   if (p->d_prof) p->prof_grid = grid;
   A.batch = B;

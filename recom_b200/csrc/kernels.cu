@@ -600,22 +600,24 @@ __device__ __forceinline__ void bucket_smem8_uniform(uint32_t bp, int32_t nb, co
 // whose ids cost hundreds of instructions each (four lane groups of 4 columns). lane = (column
 // group, row). The id slot receives the byte offset of the row inside the smem table region
 // when the table is staged, else the raw row id.
-__device__ __forceinline__ void dense_phase1(const DevPlan& P, const ReqRegs& Q, const ColCtx* ctx,
-                                             const DevSlab& slab, int64_t b0, int rows,
-                                             const float* s_bnd, int32_t* s_ids, int lane) {
+__device__ __forceinline__ void put_id(const ReqRegs& Q, const ColCtx& c, int32_t* s_ids, int cl,
+                                       int row, int64_t i, int32_t id) {
+  if (Q.check) id = checked_id(id, c.table_rows, Q.status);
+  s_ids[cl * kIdPitch + row] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
+  if (Q.ids_out) Q.ids_out[Q.ids_base[c.col] + i] = id;
+}
+
+// FAST run (every column belongs to a fast group): lane group cg takes the groups cg,
+// cg + ncg, ...; 8 coalesced loads in flight, 8 searches in lock step.
+__device__ __forceinline__ void dense_phase1_fast(const ReqRegs& Q, const ColCtx* ctx,
+                                                  const DevSlab& slab, int64_t b0, int rows,
+                                                  const float* s_bnd, int32_t* s_ids, int lane) {
   const int nc = slab.num_cols;
   const int TR = slab.tile_rows;
   const int row = lane & (TR - 1), cg = lane / TR, ncg = 32 / TR;
   const bool valid = row < rows;
   const int64_t i = b0 + row;
-  auto put = [&](int cl, int32_t id) {
-    const ColCtx& c = ctx[cl];
-    if (Q.check) id = checked_id(id, c.table_rows, Q.status);
-    s_ids[cl * kIdPitch + row] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
-    if (Q.ids_out) Q.ids_out[Q.ids_base[c.col] + i] = id;
-  };
-  // 8 float32 bucketize columns: 8 coalesced loads in flight, 8 searches in lock step
-  auto fast_group = [&](int cbase) {
+  for (int cbase = cg * 8; cbase < nc; cbase += ncg * 8) {
     float v[8];
     int32_t lo[8];
 #pragma unroll
@@ -637,32 +639,31 @@ __device__ __forceinline__ void dense_phase1(const DevPlan& P, const ReqRegs& Q,
     }
     if (valid) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) put(cbase + k, lo[k]);
+      for (int k = 0; k < 8; ++k) put_id(Q, ctx[cbase + k], s_ids, cbase + k, row, i, lo[k]);
     }
-  };
-  if (slab.all_fast) {
-    // every column belongs to a fast group: lane group cg takes the groups cg, cg + ncg, ...
-    for (int cbase = cg * 8; cbase < nc; cbase += ncg * 8) fast_group(cbase);
-    return;
   }
-  for (int cbase = 0; cbase < nc;) {
-    // (fast8_mask is zero unless TR == 32, where every lane walks every column)
-    if ((cbase & 7) == 0 && cbase + 8 <= nc && ((slab.fast8_mask >> (cbase >> 3)) & 1u)) {
-      fast_group(cbase);
-      cbase += 8;
-      continue;
-    }
-    // any transform, 4 chains per lane; the column groups take 4 columns each
+}
+
+// Queue tile, any transform: 4 chains per lane; the lane groups take 4 columns each.
+__device__ __forceinline__ void dense_phase1_generic(const DevPlan& P, const ReqRegs& Q,
+                                                     const ColCtx* ctx, const DevSlab& slab,
+                                                     int64_t b0, int rows, int32_t* s_ids,
+                                                     int lane) {
+  const int nc = slab.num_cols;
+  const int TR = slab.tile_rows;
+  const int row = lane & (TR - 1), cg = lane / TR, ncg = 32 / TR;
+  const bool valid = row < rows;
+  const int64_t i = b0 + row;
+  for (int cbase = 0; cbase < nc; cbase += 4 * ncg) {
     const int mine = cbase + cg * 4;
     uint32_t okmask = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) okmask |= (valid && mine + k < nc) ? (1u << k) : 0u;
     auto cx = [&](int k) { return ctx + (mine + k < nc ? mine + k : 0); };
-    const Ids4 r = ids4(cx(0), cx(1), cx(2), cx(3), s_bnd, P.boundaries, i, i, i, i, okmask);
+    const Ids4 r = ids4(cx(0), cx(1), cx(2), cx(3), nullptr, P.boundaries, i, i, i, i, okmask);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if ((okmask >> k) & 1u) put(mine + k, r.id[k]);
-    cbase += 4 * ncg;
+      if ((okmask >> k) & 1u) put_id(Q, ctx[mine + k], s_ids, mine + k, row, i, r.id[k]);
   }
 }
 
@@ -841,6 +842,38 @@ __device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const ColCtx& c,
   else sparse_phase2_cold<VEC, BF16>(Q, c, W, ch, b0, rows, sp, ids, lane);
 }
 
+// A DENSE tile from the queue (hashed or unstaged slab): like a SPARSE tile, one warp on its
+// own - column contexts and row ids in the warp's scratch, rows gathered with ld.global.nc.
+// (The tile's slab record has its fast-group masks cleared: boundaries are read from the pool.)
+template <bool BF16>
+__device__ __forceinline__ void generic_dense_tile(const DevPlan& P, const ReqParams& A,
+                                                   const ReqRegs& Q, const Tile& tile,
+                                                   bool new_slab, uint8_t* scratch, DevChunk& ch,
+                                                   int lane) {
+  constexpr int ELEM = BF16 ? 2 : 4;
+  const DevSlab& slab = tile.slab;
+  const int nc = slab.num_cols;
+  ColCtx* ctx = reinterpret_cast<ColCtx*>(scratch);
+  int32_t* s_ids = reinterpret_cast<int32_t*>(scratch + ((nc * (int)sizeof(ColCtx) + 15) & ~15));
+  if (new_slab) {
+    __syncwarp();
+    if (lane < nc) {
+      ColCtx x;
+      build_ctx(A, P.slab_cols[slab.first_col + lane], false, false, x);
+      ctx[lane] = x;
+    }
+    ch = P.chunks[slab.first_chunk + lane % slab.num_chunks];
+    __syncwarp();
+  }
+  dense_phase1_generic(P, Q, ctx, slab, tile.row_begin, tile.rows, s_ids, lane);
+  __syncwarp();
+  if (slab.vec_bytes == 16)
+    dense_phase2<16, false>(Q, ctx, slab.num_chunks, ch, tile.row_begin, tile.rows, nullptr, s_ids, lane);
+  else
+    dense_phase2<ELEM, false>(Q, ctx, slab.num_chunks, ch, tile.row_begin, tile.rows, nullptr, s_ids, lane);
+  __syncwarp();
+}
+
 // Optional per-warp timing, compiled in only with -DRECOM_PROFILE (make prof): every warp
 // records [start, end] in globaltimer ns plus the cycles it spent per phase.
 #ifdef RECOM_PROFILE
@@ -1009,83 +1042,108 @@ fused_columns_kernel(const DevPlan P, const Sched S, const ReqParams A) {
     mbar_init(&mbar_bnd, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const int D = kWarps - S.sparse_warps;  // dense warps
+  const int D = kWarps - S.queue_warps;  // dense warps
   DevChunk ch;
   ch.col = ch.col_local = ch.table_byte = ch.out_byte = 0;
 
-  if (warp >= D) {
-    // ---- sparse warp: its static share of the SPARSE tiles, heavy slabs first ----
-    const int g = (warp - D) * (int)gridDim.x + (int)blockIdx.x;
-    const int t_end = S.sparse_first[g + 1];
-    int cur_slab = -1;
-    for (int t = S.sparse_first[g]; t < t_end; ++t) {
-      const Tile tile = S.sparse_tiles[t];
-#ifdef RECOM_PROFILE
+  if (warp < D) {
+    // ---- dense warps: the CTA's FAST runs, in order ----
+    const CtaWork cw = S.cta[blockIdx.x];
+    named_bar_sync(1, D * 32);  // the mbarriers are initialised (thread 0 is a dense thread)
+    uint32_t tbl_par = 0, bnd_par = 0;  // parity of the phase the next staging completes
+    int staged_bnd = -1;  // pool offset of the single boundary set resident in smem, or -1
+    int32_t* s_ids = reinterpret_cast<int32_t*>(scratch);
+    for (int ri = 0; ri < cw.count; ++ri) {
+      const Tile run = S.runs[cw.first + ri];
+      const DevSlab& slab = run.slab;
+      if (ri > 0) named_bar_sync(1, D * 32);  // every dense warp is done with the previous run
+      // a run whose only boundary set is already resident keeps it (model E/F: one set for all)
+      const bool keep_bnd = slab.num_bnds == 1 && slab.first_bnd_pool == staged_bnd;
+      if (slab.num_bnds == 1) staged_bnd = slab.first_bnd_pool;
+      else if (slab.num_bnds > 1) staged_bnd = -1;
+      const bool wait_bnd = !keep_bnd && slab.bnd_bytes > 0;
+      const bool staged = run.stage != 0 && slab.stage_bytes > 0;
+      enter_run(P, A, run, s_ctx, s_tables, s_bnd, keep_bnd, &mbar_tbl, &mbar_bnd, D);
+      ch = P.chunks[slab.first_chunk + lane % slab.num_chunks];
+      named_bar_sync(1, D * 32);  // the column contexts are visible
       PROF_T(0)
-      sparse_warp_tile<BF16>(P, A, Q, tile, tile.slab_id != cur_slab, scratch, ch, lane, prof_acc, prof_last);
-      PROF_T(2)
+      if (wait_bnd) {
+        mbar_wait(&mbar_bnd, bnd_par);
+        bnd_par ^= 1;
+      }
+      bool tbl_ready = !staged;
+      // the run's rows are split evenly into run_tiles tiles of run_tile_rows (<= tile_rows)
+      // rows, so that every dense warp of the CTA gets the same number of (smaller) tiles
+      const int rpt = slab.run_tile_rows;
+      for (int t = warp; t < slab.run_tiles; t += D) {
+        const int64_t b0 = (int64_t)run.row_begin + (int64_t)t * rpt;
+        const int rows = min(rpt, run.rows - t * rpt);
+#ifdef RECOM_TEST_NOP1
+        for (int q = lane; q < slab.num_cols * kIdPitch; q += 32) s_ids[q] = (q & 63) * 32;
 #else
-      sparse_warp_tile<BF16>(P, A, Q, tile, tile.slab_id != cur_slab, scratch, ch, lane);
+        dense_phase1_fast(Q, s_ctx, slab, b0, rows, s_bnd, s_ids, lane);
 #endif
-      cur_slab = tile.slab_id;
+        __syncwarp();
+        PROF_T(1)
+        if (!tbl_ready) {
+          mbar_wait(&mbar_tbl, tbl_par);
+          tbl_ready = true;
+        }
+        if (staged) {
+          if (slab.vec_bytes == 16) dense_phase2<16, true>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
+          else dense_phase2<ELEM, true>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
+        } else {
+          if (slab.vec_bytes == 16) dense_phase2<16, false>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
+          else dense_phase2<ELEM, false>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
+        }
+        __syncwarp();
+        PROF_T(2)
+      }
+      if (staged) tbl_par ^= 1;
     }
-    PROF_END
-    return;
   }
 
-  // ---- dense warps: the CTA's runs, in order ----
-  const CtaWork cw = S.cta[blockIdx.x];
-  named_bar_sync(1, D * 32);  // the mbarriers are initialised (thread 0 is a dense thread)
-  uint32_t tbl_par = 0, bnd_par = 0;  // parity of the phase the next staging completes
-  int staged_bnd = -1;  // pool offset of the single boundary set resident in smem, or -1
-  int32_t* s_ids = reinterpret_cast<int32_t*>(scratch);
-  for (int ri = 0; ri < cw.count; ++ri) {
-    const Tile run = S.runs[cw.first + ri];
-    const DevSlab& slab = run.slab;
-    if (ri > 0) named_bar_sync(1, D * 32);  // every dense warp is done with the previous run
-    // a run whose only boundary set is already resident keeps it (model E/F: one set for all)
-    const bool keep_bnd = slab.num_bnds == 1 && slab.first_bnd_pool == staged_bnd;
-    if (slab.num_bnds == 1) staged_bnd = slab.first_bnd_pool;
-    else if (slab.num_bnds > 1) staged_bnd = -1;
-    const bool wait_bnd = !keep_bnd && slab.bnd_bytes > 0;
-    const bool staged = run.stage != 0 && slab.stage_bytes > 0;
-    enter_run(P, A, run, s_ctx, s_tables, s_bnd, keep_bnd, &mbar_tbl, &mbar_bnd, D);
-    ch = P.chunks[slab.first_chunk + lane % slab.num_chunks];
-    named_bar_sync(1, D * 32);  // the column contexts are visible
-    PROF_T(0)
-    if (wait_bnd) {
-      mbar_wait(&mbar_bnd, bnd_par);
-      bnd_par ^= 1;
+  // ---- every warp: the queue. Queue warps start with a static tile; a claim is always made
+  // one tile ahead, so its round trip is hidden behind the tile being processed. ----
+  {
+    const int nq = S.num_queue;
+    const int first_claim = (int)gridDim.x * S.queue_warps;  // tiles below it are static firsts
+    int t = warp >= D ? (warp - D) * (int)gridDim.x + (int)blockIdx.x : nq;
+    int ahead = nq;  // claimed, not yet looked at
+    if (nq > 0) {
+      if (lane == 0) ahead = first_claim + atomicAdd(A.counters, 1);
+      if (warp < D) {  // no static first tile: the claim is the first tile
+        t = __shfl_sync(0xffffffffu, ahead, 0);
+        if (t < nq && lane == 0) ahead = first_claim + atomicAdd(A.counters, 1);
+      }
     }
-    bool tbl_ready = !staged;
-    // the run's rows are split evenly into run_tiles tiles of run_tile_rows (<= tile_rows)
-    // rows, so that every dense warp of the CTA gets the same number of (smaller) tiles
-    const int rpt = slab.run_tile_rows;
-    for (int t = warp; t < slab.run_tiles; t += D) {
-      const int64_t b0 = (int64_t)run.row_begin + (int64_t)t * rpt;
-      const int rows = min(rpt, run.rows - t * rpt);
-#ifdef RECOM_TEST_NOP1
-      for (int q = lane; q < slab.num_cols * kIdPitch; q += 32) s_ids[q] = (q & 63) * 32;
+    int cur_slab = -1;
+    while (t < nq) {
+      const Tile tile = S.queue[t];
+      const bool new_slab = tile.slab_id != cur_slab;
+      cur_slab = tile.slab_id;
+      PROF_T(0)
+      if (tile.slab.cls == kSlabSparse) {
+#ifdef RECOM_PROFILE
+        sparse_warp_tile<BF16>(P, A, Q, tile, new_slab, scratch, ch, lane, prof_acc, prof_last);
 #else
-      dense_phase1(P, Q, s_ctx, slab, b0, rows, s_bnd, s_ids, lane);
+        sparse_warp_tile<BF16>(P, A, Q, tile, new_slab, scratch, ch, lane);
 #endif
-      __syncwarp();
-      PROF_T(1)
-      if (!tbl_ready) {
-        mbar_wait(&mbar_tbl, tbl_par);
-        tbl_ready = true;
-      }
-      if (staged) {
-        if (slab.vec_bytes == 16) dense_phase2<16, true>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
-        else dense_phase2<ELEM, true>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
       } else {
-        if (slab.vec_bytes == 16) dense_phase2<16, false>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
-        else dense_phase2<ELEM, false>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
+        generic_dense_tile<BF16>(P, A, Q, tile, new_slab, scratch, ch, lane);
       }
-      __syncwarp();
       PROF_T(2)
+      t = __shfl_sync(0xffffffffu, ahead, 0);
+      if (t < nq && lane == 0) ahead = first_claim + atomicAdd(A.counters, 1);
     }
-    if (staged) tbl_par ^= 1;
+    // the last warp of the grid to get here leaves the slot clean for the next launch
+    if (nq > 0 && lane == 0) {
+      const int done = atomicAdd(A.counters + 1, 1);
+      if (done == (int)gridDim.x * kWarps - 1) {
+        A.counters[0] = 0;
+        A.counters[1] = 0;
+      }
+    }
   }
   PROF_END
 }

@@ -13,7 +13,7 @@
 namespace recom {
 
 #ifndef RECOM_THREADS
-#define RECOM_THREADS 512
+#define RECOM_THREADS 384
 #endif
 constexpr int kThreads = RECOM_THREADS;  // threads per CTA
 constexpr int kWarps = kThreads / 32;
@@ -192,17 +192,19 @@ struct CtaWork {
   int32_t count;
 };
 
-// The static schedule of a batch size (cached on the device by the plan); a kernel parameter.
-// Warps [0, kWarps - sparse_warps) of every CTA are dense warps, the others sparse warps.
-// Sparse warp s of CTA c is sparse warp g = s * grid + c of the grid and takes the sparse tiles
-// [sparse_first[g], sparse_first[g + 1]) (assigned longest-first by estimated cost).
+// The schedule of a batch size (cached on the device by the plan); a kernel parameter.
+//   * FAST runs (slabs made of fast bucketize groups with staged tables) are static: every CTA
+//     owns the runs cta[c], walked by its dense warps [0, kWarps - queue_warps).
+//   * Everything else - multi-hot tiles, tiles of hashed / unstaged DENSE slabs - is a queue of
+//     warp tiles in descending cost order. The queue warps of every CTA start there at once
+//     (queue warp s of CTA c with tile s * grid + c, no claim needed), the dense warps join when
+//     their run is done; further tiles are claimed with one atomicAdd each, one tile ahead.
 struct Sched {
-  const Tile* runs;          // DENSE runs, grouped by CTA
+  const Tile* runs;          // FAST runs, grouped by CTA
   const CtaWork* cta;        // [grid]
-  const Tile* sparse_tiles;  // [num_sparse_tiles], grouped by sparse warp
-  const int32_t* sparse_first;  // [grid * sparse_warps + 1]
-  int32_t num_sparse_tiles;
-  int32_t sparse_warps;
+  const Tile* queue;         // [num_queue]
+  int32_t num_queue;
+  int32_t queue_warps;
 };
 
 // Per-request values known on the host at launch; a kernel parameter (no dependent loads).
@@ -218,6 +220,7 @@ struct ReqParams {
   const void* const* tables;    // [num_tables]
   const int32_t* ids_base;      // [num_cols + 1] prefix of ids per column
   const int32_t* sparse_base;   // [num_sparse + 1] prefix of ids, non-DENSE only
+  int32_t* counters;            // [2] plan-owned slot: queue claims, finished warps (self-resetting)
   uint64_t* prof;               // profiling builds only, else null
   int64_t batch;
   int64_t out_row_bytes;
