@@ -600,11 +600,15 @@ __device__ __forceinline__ void bucket_smem8_uniform(uint32_t bp, int32_t nb, co
 // whose ids cost hundreds of instructions each (four lane groups of 4 columns). lane = (column
 // group, row). The id slot receives the byte offset of the row inside the smem table region
 // when the table is staged, else the raw row id.
+// The id slot holds the raw row id; phase 2, whose lanes own one column each, turns it into an
+// address. Bounds check and the ids_out parity hook are off the fast path.
 __device__ __forceinline__ void put_id(const ReqRegs& Q, const ColCtx& c, int32_t* s_ids, int cl,
                                        int row, int64_t i, int32_t id) {
-  if (Q.check) id = checked_id(id, c.table_rows, Q.status);
-  s_ids[cl * kIdPitch + row] = c.stage_off >= 0 ? c.stage_off + id * c.row_bytes : id;
-  if (Q.ids_out) Q.ids_out[Q.ids_base[c.col] + i] = id;
+  if (Q.check | (Q.ids_out != nullptr)) {
+    if (Q.check) id = checked_id(id, c.table_rows, Q.status);
+    if (Q.ids_out) Q.ids_out[Q.ids_base[c.col] + i] = id;
+  }
+  s_ids[cl * kIdPitch + row] = id;
 }
 
 // FAST run (every column belongs to a fast group): lane group cg takes the groups cg,
@@ -681,15 +685,9 @@ __device__ __forceinline__ void dense_phase2_impl(const ReqRegs& Q, const ColCtx
   const int rpp = 32 / W;  // rows handled per pass
   const int sub = lane / W;
   if (sub >= rpp) return;
-  const uint8_t* tbl;
-  int64_t row_bytes = 0;
-  if (STAGED) {
-    tbl = s_tables + ch.table_byte;
-  } else {
-    const ColCtx& c = ctx[ch.col_local];
-    tbl = c.table + ch.table_byte;
-    row_bytes = c.row_bytes;
-  }
+  const ColCtx& c = ctx[ch.col_local];
+  const uint8_t* tbl = (STAGED ? s_tables + c.stage_off : c.table) + ch.table_byte;
+  const int32_t row_bytes = c.row_bytes;
   const int32_t* ids = s_ids + ch.col_local * kIdPitch;
   const int64_t orb = Q.out_row_bytes;
   int r = sub;
@@ -704,7 +702,7 @@ __device__ __forceinline__ void dense_phase2_impl(const ReqRegs& Q, const ColCtx
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k) {
       const int32_t o = ids[r + k * rpp];
-      if (STAGED) v[k] = lds_chunk<VEC>(tbl + o);
+      if (STAGED) v[k] = lds_chunk<VEC>(tbl + o * row_bytes);
       else v[k].load(tbl + (int64_t)o * row_bytes);
     }
 #pragma unroll
@@ -716,7 +714,7 @@ __device__ __forceinline__ void dense_phase2_impl(const ReqRegs& Q, const ColCtx
   for (; r < rows; r += rpp) {
     const int32_t o = ids[r];
     Chunk<VEC> v;
-    if (STAGED) v = lds_chunk<VEC>(tbl + o);
+    if (STAGED) v = lds_chunk<VEC>(tbl + o * row_bytes);
     else v.load(tbl + (int64_t)o * row_bytes);
     v.store(outp);
     outp += ostep;
