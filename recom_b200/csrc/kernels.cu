@@ -903,6 +903,15 @@ __device__ __forceinline__ uint64_t gtimer() {
 #define PROF_END
 #endif
 
+// Rare paths of a SPARSE tile's phase 1, out of line so that their loads are not hoisted into
+// the hot loop: ids of a tile that does not fit the scratch go to the workspace; the parity
+// hook receives every id.
+__device__ __noinline__ void spill_id(const ReqParams& A, const ReqRegs& Q, const ColCtx& c,
+                                      int64_t e, int32_t v, bool in_smem) {
+  if (!in_smem) A.ws_ids[A.sparse_base[c.sparse_index] + e] = v;
+  if (Q.ids_out) Q.ids_out[Q.ids_base[c.col] + e] = v;
+}
+
 template <bool BF16>
 __device__ __forceinline__ void sparse_warp_tile(const DevPlan& P, const ReqParams& A,
                                                  const ReqRegs& Q, const Tile& tile, bool new_slab,
@@ -987,8 +996,7 @@ __device__ __forceinline__ void sparse_warp_tile(const DevPlan& P, const ReqPara
       int32_t v = r.id[k];
       if (Q.check) v = checked_id(v, c[k]->table_rows, Q.status);
       if (in_smem) ids_s[f0 + 32 * k + lane] = v;
-      else A.ws_ids[A.sparse_base[c[k]->sparse_index] + ee[k]] = v;
-      if (Q.ids_out) Q.ids_out[Q.ids_base[c[k]->col] + ee[k]] = v;
+      if (!in_smem | (Q.ids_out != nullptr)) spill_id(A, Q, *c[k], ee[k], v, in_smem);
     }
   }
   __syncwarp();
