@@ -54,7 +54,9 @@ def parse_args():
     ap.add_argument("--workload", default="model_E",
                     choices=["model_E", "model_F", "micro100", "large_table",
                              # diagnostic slices of model E (not headline workloads)
-                             "model_E_dense", "model_E_bucketize", "model_E_sparse"])
+                             "model_E_dense", "model_E_bucketize", "model_E_sparse",
+                             # other BASELINE.json configurations (informational lines)
+                             "model_E_bf16", "mixed1000", "mixed1000_bf16", "production2000"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--sets", type=int, default=4, help="rotating request/output buffer sets")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -77,6 +79,16 @@ def build_model(workload: str, world: int = 1, rank: int = 0):
         return synth.dlrm_model(880, 0, 0, 0, 0, name="E_bucketize"), 2048
     if workload == "model_E_sparse":
         return synth.dlrm_model(0, 0, 0, 15, 5, name="E_sparse"), 2048
+    # informational lines (parity-tested configurations of BASELINE.json, not the headline)
+    from recom_b200 import _lib as L
+    if workload == "model_E_bf16":
+        return synth.model_E(out_dtype=L.BF16), 2048
+    if workload == "mixed1000":      # config 2 extension: dims 8-64, sum / mean / sqrtn
+        return synth.mixed_model(1000, seed=0), 2048
+    if workload == "mixed1000_bf16":
+        return synth.mixed_model(1000, seed=0, out_dtype=L.BF16), 2048
+    if workload == "production2000":  # config 5: shared tables, duplicated (input, transform) pairs
+        return synth.production_model(2000, share=4, seed=0), 2048
     raise ValueError(workload)
 
 
@@ -373,7 +385,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "p50_ms": float(np.percentile(lat, 50)),
         "p99_ms": float(np.percentile(lat, 99)), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16" if outs[0].element_size() == 2 else "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}_b{batch}", "columns": len(model.columns),
                    "batch": batch, "out_width": model.out_width,
                    "table_bytes": model.table_bytes(), "parallelism": f"replicas x{world}",

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -160,6 +161,7 @@ struct recom_plan {
   int num_sms = 148;
   int ctas_per_sm = 2;
   double sparse_weight = 1.0; // scales the estimated cost of SPARSE warp tiles (schedule balance)
+  int force_queue_warps = -1;  // >= 0: override the cost-proportional split (experiments)
   int hash_tile_rows = kHashTileRows;             // rows of a DENSE warp tile with hashed columns
   int sparse_rows_hash = kSparseRowsPerSubHash;   // SPARSE rows per lane group, hashed ids
   int sparse_rows = kSparseRowsPerSub;            // ... ids given
@@ -705,7 +707,31 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     t.slab.run_tile_rows = (int16_t)rpt;
     t.slab.run_tiles = (int16_t)std::min<int64_t>(32767, (t.rows + rpt - 1) / rpt);
   };
-  auto tiles_of = [&](int s) { return (B + p->slabs[s].tile_rows - 1) / p->slabs[s].tile_rows; };
+  // Small batches: with fewer tiles than resident warps the launch lasts as long as its longest
+  // tile, so the queue's tiles are cut finer (down to one row per lane group / 2 rows of a hashed
+  // slab) until there is about one tile per warp.
+  std::vector<int32_t> rows_of(p->slabs.size());
+  for (size_t s = 0; s < p->slabs.size(); ++s) rows_of[s] = p->slabs[s].tile_rows;
+  {
+    const int64_t warps = (int64_t)cap_ctas * kWarps;
+    for (int pass = 0; pass < 3; ++pass) {
+      int64_t tiles = 0;
+      for (size_t s = 0; s < p->slabs.size(); ++s) tiles += (B + rows_of[s] - 1) / rows_of[s];
+      if (tiles * 2 > warps) break;
+      bool changed = false;
+      for (size_t s = 0; s < p->slabs.size(); ++s) {
+        const DevSlab& sl = p->slabs[s];
+        if (sl.cls == kSlabDenseStaged && sl.all_fast) continue;  // FAST runs are split per CTA
+        const int min_rows = sl.cls == kSlabSparse ? std::max(1, 32 / sl.num_chunks) : 2;
+        if (rows_of[s] / 2 >= min_rows) {
+          rows_of[s] /= 2;
+          changed = true;
+        }
+      }
+      if (!changed) break;
+    }
+  }
+  auto tiles_of = [&](int s) { return (B + rows_of[s] - 1) / rows_of[s]; };
   std::vector<int> fast, other;
   for (int s = 0; s < (int)p->slabs.size(); ++s) {
     const DevSlab& sl = p->slabs[s];
@@ -717,14 +743,14 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
                    [&](int a, int b) { return p->tile_cost[a] > p->tile_cost[b]; });
   double queue_cost = 0;
   for (int s : other) {
-    const DevSlab& sl = p->slabs[s];
-    for (int64_t b = 0; b < B; b += sl.tile_rows) {
-      Tile t = make(s, b, std::min<int64_t>(sl.tile_rows, B - b));
+    for (int64_t b = 0; b < B; b += rows_of[s]) {
+      Tile t = make(s, b, std::min<int64_t>(rows_of[s], B - b));
+      t.slab.tile_rows = rows_of[s];
       t.stage = 0;
       t.slab.fast8_mask = t.slab.uni8_mask = 0;  // queue tiles read boundaries from the pool
       t.slab.all_fast = 0;
       tt->queue.push_back(t);
-      queue_cost += p->tile_cost[s] * p->sparse_weight;
+      queue_cost += p->tile_cost[s] * p->sparse_weight * rows_of[s] / p->slabs[s].tile_rows;
     }
   }
   std::vector<double> cost(fast.size());
@@ -742,6 +768,8 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   int64_t units = 1;
   if (Q > 0) units = std::max<int64_t>(units, ((int64_t)tt->queue.size() + Q - 1) / Q);
   if (Q < kWarps) units = std::max<int64_t>(units, (fast_tiles + (kWarps - Q) - 1) / (kWarps - Q));
+  // a FAST slab per CTA where possible: runs of one CTA are walked one after the other
+  units = std::max<int64_t>(units, (int64_t)fast.size());
   // whole waves: a grid between one and two CTAs per SM would leave some SMs with twice the work
   if (units > p->num_sms) units = (units + p->num_sms - 1) / p->num_sms * p->num_sms;
   const int grid = (int)std::min<int64_t>(cap_ctas, units);
@@ -749,6 +777,8 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     const int q_need = (int)(((int64_t)tt->queue.size() + grid - 1) / grid);
     Q = std::max(1, std::min({Q, q_need, kWarps - 1}));
   }
+  if (p->force_queue_warps >= 0 && !tt->queue.empty() && !fast.empty())
+    Q = std::min(kWarps - 1, p->force_queue_warps);
   tt->grid = grid;
   tt->queue_warps = Q;
 
@@ -963,6 +993,7 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
     while (r * 2 <= v && r * 2 <= hi) r *= 2;
     return r;
   };
+  if (const char* e = getenv("RECOM_B200_QUEUE_WARPS")) p->force_queue_warps = atoi(e);
   p->hash_tile_rows = pow2_env("RECOM_B200_HASH_TILE_ROWS", 4, 32, kHashTileRows);
   p->sparse_rows_hash = pow2_env("RECOM_B200_SPARSE_ROWS_HASH", 1, 8, kSparseRowsPerSubHash);
   p->sparse_rows = pow2_env("RECOM_B200_SPARSE_ROWS", 1, 8, kSparseRowsPerSub);
@@ -1113,8 +1144,10 @@ static size_t arg_block_bytes(const recom_plan* p) {
 static size_t max_sched_bytes(const recom_plan* p, int64_t batch) {
   // only used when the schedule cache is full and the schedule travels with the request
   const size_t ctas = (size_t)p->num_sms * p->ctas_per_sm;
-  size_t tiles = p->slabs.size() + ctas + 4;
+  size_t tiles = 0;
   for (const DevSlab& s : p->slabs) tiles += (size_t)((batch + s.tile_rows - 1) / s.tile_rows);
+  // (small batches are cut finer, but never into more than 2 tiles per resident warp)
+  tiles = std::max(tiles, 2 * ctas * kWarps + p->slabs.size()) + p->slabs.size() + ctas + 4;
   return tiles * sizeof(Tile) + ctas * sizeof(CtaWork) + 128;
 }
 
@@ -1129,8 +1162,33 @@ recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int6
   return RECOM_OK;
 }
 
+namespace {
+struct HostProf {
+  bool on = getenv("RECOM_B200_HOST_PROF") != nullptr;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  long calls = 0;
+  std::chrono::steady_clock::time_point last;
+  void start() { if (on) last = std::chrono::steady_clock::now(); }
+  void lap(int i) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    acc[i] += std::chrono::duration<double, std::micro>(now - last).count();
+    last = now;
+  }
+  ~HostProf() {
+    if (on && calls)
+      fprintf(stderr, "[recom_b200 host] %ld calls; us/call: validate %.2f, schedule %.2f, block %.2f, "
+              "cache %.2f, launch %.2f\n", calls, acc[0] / calls, acc[1] / calls, acc[2] / calls,
+              acc[3] / calls, acc[4] / calls);
+  }
+};
+HostProf g_host_prof;
+}  // namespace
+
 recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   g_last_launches = 0;
+  g_host_prof.start();
+  g_host_prof.calls++;
   if (!cp || !req) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
   recom_plan* p = const_cast<recom_plan*>(cp);  // only internally locked caches mutate
   recom_status st = validate_request(p, req);
@@ -1140,8 +1198,10 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   const int64_t B = req->batch;
   cudaStream_t stream = (cudaStream_t)req->stream;
 
+  g_host_prof.lap(0);
   std::shared_ptr<const TileTable> tt = cached_tiles(p, B, &st);
   if (st != RECOM_OK) return st;
+  g_host_prof.lap(1);
   const bool sched_in_args = !tt;
   if (sched_in_args) tt = build_tiles(p, B);
   const int grid = tt->grid;
@@ -1197,6 +1257,7 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
                 req->workspace_bytes);
   uint8_t* ws = (uint8_t*)req->workspace;
 
+  g_host_prof.lap(2);
   // a device-resident copy of exactly this block?
   const uint8_t* d_args = nullptr;
   if (p->cache_args && !sched_in_args) {
@@ -1234,6 +1295,7 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
     }
   }
 
+  g_host_prof.lap(3);
   Sched sched = sched_in_args ? Sched{} : tt->sched(tt->d_block);
   ArgSlot* slot = nullptr;
   std::unique_lock<std::mutex> slot_lock;
@@ -1292,6 +1354,7 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
     cudaEventRecord(slot->done, stream);
     slot->in_flight = true;
   }
+  g_host_prof.lap(4);
   if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return RECOM_OK;
 }
