@@ -897,7 +897,8 @@ int64_t column_num_ids(const recom_plan* p, int ci, const recom_request* req) {
   return d.value_dtype == RECOM_STR ? e - 1 : e;
 }
 
-recom_status validate_request(const recom_plan* p, const recom_request* req) {
+// O(1) checks, every call.
+recom_status validate_request_head(const recom_plan* p, const recom_request* req) {
   if (!req->slot_offsets || !req->slot_elems || !req->tables)
     return fail(RECOM_ERR_INVALID_ARGUMENT, "request host arrays must not be null");
   if (req->batch < 0 || req->batch > 0x7fffffffLL)
@@ -907,6 +908,13 @@ recom_status validate_request(const recom_plan* p, const recom_request* req) {
   if (((uintptr_t)req->blob & 15) || ((uintptr_t)req->out & 15) || ((uintptr_t)req->workspace & 255))
     return fail(RECOM_ERR_INVALID_ARGUMENT,
                 "blob/out must be 16-byte aligned and workspace 256-byte aligned");
+  return RECOM_OK;
+}
+
+// O(tables + columns) checks of the request's shape (slot offsets / element counts / table
+// pointers). Skipped when the request's argument block - which covers all of these - equals a
+// block that passed them before.
+recom_status validate_request(const recom_plan* p, const recom_request* req) {
   for (int t = 0; t < p->cfg.num_tables; ++t)
     if (!req->tables[t] || ((uintptr_t)req->tables[t] & 15))
       return fail(RECOM_ERR_INVALID_ARGUMENT, "table %d pointer is null or not 16-byte aligned", t);
@@ -1191,9 +1199,9 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   g_host_prof.calls++;
   if (!cp || !req) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
   recom_plan* p = const_cast<recom_plan*>(cp);  // only internally locked caches mutate
-  recom_status st = validate_request(p, req);
+  recom_status st = validate_request_head(p, req);
   if (st != RECOM_OK) return st;
-  if (req->batch == 0) return RECOM_OK;
+  if (req->batch == 0) return validate_request(p, req);
   const int n = (int)p->descs.size();
   const int64_t B = req->batch;
   cudaStream_t stream = (cudaStream_t)req->stream;
@@ -1245,6 +1253,11 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   }
   ids_base[n] = (int32_t)total;
   sparse_base[p->sparse_cols.size()] = (int32_t)sparse_total;
+  {
+    uint64_t eh = 1469598103934665603ull;  // the element counts are part of the block's identity
+    for (int i = 0; i < p->cfg.num_slots; ++i) eh = (eh ^ (uint64_t)req->slot_elems[i]) * 1099511628211ull;
+    hdr->pad1 = (int64_t)eh;
+  }
 
   // workspace carve-up: [argument block + schedule (upload path only) | ws_ids | ws_row_splits]
   size_t off = align_up(args_bytes + max_sched_bytes(p, B), 256);
@@ -1260,6 +1273,7 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   g_host_prof.lap(2);
   // a device-resident copy of exactly this block?
   const uint8_t* d_args = nullptr;
+  bool validated = false;
   if (p->cache_args && !sched_in_args) {
     std::lock_guard<std::mutex> lock(p->args_mu);
     for (const auto& e : p->arg_cache)
@@ -1268,6 +1282,9 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
         break;
       }
     if (!d_args) {
+      st = validate_request(p, req);  // a shape not seen (or not published) before
+      if (st != RECOM_OK) return st;
+      validated = true;
       uint64_t hash = 1469598103934665603ull;  // FNV-1a over 8-byte words
       for (size_t i = 0; i + 8 <= args_bytes; i += 8) {
         uint64_t w;
@@ -1295,6 +1312,10 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
     }
   }
 
+  if (!d_args && !validated) {
+    st = validate_request(p, req);
+    if (st != RECOM_OK) return st;
+  }
   g_host_prof.lap(3);
   Sched sched = sched_in_args ? Sched{} : tt->sched(tt->d_block);
   ArgSlot* slot = nullptr;
