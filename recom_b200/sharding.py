@@ -14,7 +14,9 @@ with exactly one exchange step at the end:
   Mode C  replicas: everything fits (models E, F): batch split, no collective.
 
 This module is host logic plus torch.distributed plumbing (one process per GPU). The
-exchange of Mode A is an NCCL all-gather of the padded slices followed by one
+exchange of Mode A is an NCCL all-to-all of row blocks (every rank keeps its B/G rows of the
+concat tensor: what a data-parallel consumer needs, and the exchanged bytes per rank shrink with
+G) or an all-gather of the padded slices (every rank gets all B rows), each followed by one
 concatenation copy; the kernel-side variant (stores straight into peer concat tensors over
 NVLink) is described in DESIGN.md.
 """
@@ -131,6 +133,39 @@ def all_gather_columns(local_out, shards: Sequence[ColumnShard], group=None):
     return torch.cat([gathered[g, :, :shards[g].width] for g in range(world)], dim=1)
 
 
+def batch_rows(batch: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of the batch that rank `rank` keeps after the all-to-all exchange."""
+    return batch * rank // world, batch * (rank + 1) // world
+
+
+def all_to_all_columns(local_out, shards: Sequence[ColumnShard], group=None):
+    """Exchange of Mode A when the consumer is data parallel (the dense layers of the model
+    split the batch over the same ranks): every rank ends with ITS rows of the full concat
+    tensor, [B_rank, sum D], instead of all B rows. One all-to-all of row blocks of the local
+    slice - a rank receives (B / G) * sum D elements instead of B * sum D, so the exchanged
+    bytes per rank shrink with the number of ranks - then one concatenation of the received
+    [B_rank, W_g] blocks. Works with nccl (GPU) and gloo (CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    B, w_me = local_out.shape
+    assert w_me == shards[rank].width
+    lo, hi = batch_rows(B, world, rank)
+    rows_me = hi - lo
+    send = local_out.contiguous().reshape(-1)
+    in_splits = [(batch_rows(B, world, d)[1] - batch_rows(B, world, d)[0]) * w_me for d in range(world)]
+    out_splits = [rows_me * shards[g].width for g in range(world)]
+    recv = torch.empty(sum(out_splits), dtype=local_out.dtype, device=local_out.device)
+    dist.all_to_all_single(recv, send, out_splits, in_splits, group=group)
+    blocks, o = [], 0
+    for g in range(world):
+        blocks.append(recv[o:o + out_splits[g]].view(rows_me, shards[g].width))
+        o += out_splits[g]
+    return torch.cat(blocks, dim=1)
+
+
 # ---------------------------------------------------------------------------------------
 # Mode B: table row-sharding
 # ---------------------------------------------------------------------------------------
@@ -230,10 +265,16 @@ def bench_large_table(args, world: int, rank: int, local: int):
     stream = torch.cuda.current_stream(local)
     alg = float(np.mean([algorithmic_bytes(sh.model, r) for r in reqs]))
 
+    exchange = getattr(args, "lt_exchange", None) or "all_to_all"
+
     def step(i):
         s = i % S
         plan.run(reqs[s], blobs[s], ptrs, outs[s], wss[s], stream=stream)
-        return all_gather_columns(outs[s], shards) if world > 1 else outs[s]
+        if world == 1:
+            return outs[s]
+        if exchange == "all_gather":
+            return all_gather_columns(outs[s], shards)
+        return all_to_all_columns(outs[s], shards)
 
     def barrier():
         torch.cuda.synchronize(local)
@@ -243,7 +284,9 @@ def bench_large_table(args, world: int, rank: int, local: int):
 
     for i in range(W):
         full = step(i)
-    assert full.shape == (batch, model.out_width)
+    want_rows = batch if (world == 1 or exchange == "all_gather") else (
+        batch_rows(batch, world, rank)[1] - batch_rows(batch, world, rank)[0])
+    assert full.shape == (want_rows, model.out_width)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -265,7 +308,9 @@ def bench_large_table(args, world: int, rank: int, local: int):
             "data": "synthetic",
             "config": {"workload": f"large_table_{n_cols}x{rows}x32_b{batch}", "columns": n_cols,
                        "batch": batch, "table_bytes": model.table_bytes(),
-                       "parallelism": f"column-group x{world}, NCCL all-gather of [B, W_g] slices",
+                       "parallelism": (f"column-group x{world}, NCCL all-gather of [B, W_g] slices" if exchange == "all_gather"
+                                       else f"column-group x{world}, NCCL all-to-all of [B/{world}, W_g] row blocks "
+                                            f"(every rank keeps its B/{world} rows of the concat tensor)"),
                        "l2": f"rotating {S} request/output sets"},
             "roofline": {"bound": "hbm", "achieved": float(alg_t[0]) / (ms * 1e-3) / 1e9,
                          "unit": "GB/s", "note": "aggregate algorithmic bytes over all ranks / step time"},

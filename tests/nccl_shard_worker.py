@@ -35,6 +35,10 @@ def main():
     torch.cuda.synchronize()
     ref, _ = run_oracle(m, pack_request(m, batch, feats), tables)
     np.testing.assert_allclose(full.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+    mine = sharding.all_to_all_columns(out, shards)
+    torch.cuda.synchronize()
+    lo, hi = sharding.batch_rows(batch, world, rank)
+    np.testing.assert_array_equal(mine.cpu().numpy(), full.cpu().numpy()[lo:hi])
     dist.barrier()
     if rank == 0:
         print("SHARD_OK")

@@ -103,7 +103,10 @@ def _gloo_worker(rank, world, port, q):
         local = _full(s.model, batch, sharding.shard_features(s, feats), [tables[t] for t in s.table_ids])
         full = sharding.all_gather_columns(torch.from_numpy(local), shards).numpy()
         ref = _full(m, batch, feats, tables)
-        q.put((rank, bool(np.array_equal(full, ref)), full.shape))
+        mine = sharding.all_to_all_columns(torch.from_numpy(local), shards).numpy()
+        lo, hi = sharding.batch_rows(batch, world, rank)
+        ok = bool(np.array_equal(full, ref)) and bool(np.array_equal(mine, ref[lo:hi]))
+        q.put((rank, ok, full.shape))
     finally:
         dist.destroy_process_group()
 
