@@ -61,8 +61,8 @@ def parse_args():
     ap.add_argument("--sets", type=int, default=4, help="rotating request/output buffer sets")
     ap.add_argument("--lt-columns", dest="lt_columns", type=int, default=0, help="large_table: columns")
     ap.add_argument("--lt-rows", dest="lt_rows", type=int, default=0, help="large_table: rows per table")
-    ap.add_argument("--lt-exchange", dest="lt_exchange", default="all_to_all",
-                    choices=["all_to_all", "all_gather"], help="large_table: exchange of the slices")
+    ap.add_argument("--lt-exchange", dest="lt_exchange", default="fused",
+                    choices=["fused", "all_to_all", "all_gather"], help="large_table: exchange of the slices")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()

@@ -183,6 +183,32 @@ RECOM_API recom_status recom_plan_workspace_bytes(const recom_plan *plan, int64_
 RECOM_API recom_status recom_plan_run(const recom_plan *plan, const recom_request *req);
 
 /* Number of kernels the last recom_plan_run on this thread launched. */
+/* Mode A with the exchange fused into the kernel (recom_b200/sharding.py):
+ * this plan computes the columns [col_offset, col_offset + out_width) of a global concat row
+ * of `global_width` elements; rows [g*rows_per_rank, (g+1)*rows_per_rank) of the batch are
+ * stored straight into peer_out[g], rank g's [rows_per_rank, global_width] tensor (peer-mapped
+ * device memory, e.g. opened with recom_ipc_open), from the kernel's phase 2 over NVLink. No
+ * collective and no concatenation copy follow; the caller only has to order the consumers after
+ * all ranks' launches (one barrier). req->out is not used. batch <= world * rows_per_rank,
+ * rows_per_rank >= 32, world <= 8. The reference has no counterpart (single GPU). */
+typedef struct recom_shard_out {
+  int32_t world;
+  int32_t col_offset;   /* elements */
+  int32_t global_width; /* elements */
+  int32_t reserved;
+  int64_t rows_per_rank;
+  void *const *peer_out; /* host [world] */
+} recom_shard_out;
+RECOM_API recom_status recom_plan_run_sharded(const recom_plan *plan, const recom_request *req,
+                                              const recom_shard_out *shard);
+
+/* Peer-visible device buffers for recom_plan_run_sharded: one cudaMalloc'ed buffer per rank,
+ * exported as a 64-byte CUDA IPC handle that the other ranks of the node open. */
+RECOM_API recom_status recom_ipc_alloc(size_t bytes, void **dev_ptr, uint8_t handle[64]);
+RECOM_API recom_status recom_ipc_open(const uint8_t handle[64], void **dev_ptr);
+RECOM_API recom_status recom_ipc_close(void *dev_ptr);
+RECOM_API recom_status recom_ipc_free(void *dev_ptr);
+
 RECOM_API int recom_last_launch_count(void);
 
 /* Algorithmic bytes of the request just described:

@@ -57,6 +57,13 @@ class Request(C.Structure):
     ]
 
 
+class ShardOut(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("col_offset", C.c_int32), ("global_width", C.c_int32),
+        ("reserved", C.c_int32), ("rows_per_rank", C.c_int64), ("peer_out", C.c_void_p),
+    ]
+
+
 class RecomError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"recom_b200 status {status}: {message}")
@@ -70,7 +77,8 @@ EXPORTS = [
     "recom_last_launch_count", "recom_plan_algorithmic_bytes", "recom_scatter_columns",
     "recom_segment_ids_to_row_splits", "recom_string_to_hash_bucket_fast", "recom_fingerprint64",
     "recom_concat_inputs", "recom_shape_construct_create", "recom_shape_construct_eval",
-    "recom_shape_construct_destroy",
+    "recom_shape_construct_destroy", "recom_plan_run_sharded", "recom_ipc_alloc", "recom_ipc_open",
+    "recom_ipc_close", "recom_ipc_free",
 ]
 
 
@@ -95,6 +103,11 @@ def _load() -> C.CDLL:
         "recom_plan_out_width": [vp, C.POINTER(i32)],
         "recom_plan_workspace_bytes": [vp, i64, i64, C.POINTER(sz)],
         "recom_plan_run": [vp, C.POINTER(Request)],
+        "recom_plan_run_sharded": [vp, C.POINTER(Request), C.POINTER(ShardOut)],
+        "recom_ipc_alloc": [sz, C.POINTER(vp), vp],
+        "recom_ipc_open": [vp, C.POINTER(vp)],
+        "recom_ipc_close": [vp],
+        "recom_ipc_free": [vp],
         "recom_plan_algorithmic_bytes": [vp, C.POINTER(Request), C.POINTER(i64)],
         "recom_scatter_columns": [vp, vp, vp, i32, i64, i32, i32, vp, vp],
         "recom_segment_ids_to_row_splits": [vp, i64, i32, i64, vp, vp],

@@ -1193,13 +1193,43 @@ struct HostProf {
 HostProf g_host_prof;
 }  // namespace
 
+static recom_status run_impl(const recom_plan* cp, const recom_request* req, const recom_shard_out* so);
+
 recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
+  return run_impl(cp, req, nullptr);
+}
+
+recom_status recom_plan_run_sharded(const recom_plan* cp, const recom_request* req,
+                                    const recom_shard_out* so) {
+  if (!so || !cp || !req) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  if (so->world < 1 || so->world > kMaxPeers || !so->peer_out)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "world must be 1..%d and peer_out non-null", kMaxPeers);
+  if (so->rows_per_rank < 32 || so->rows_per_rank > 0x7fffffffLL ||
+      req->batch > (int64_t)so->world * so->rows_per_rank)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "rows_per_rank must be >= 32 and cover the batch");
+  if (so->col_offset < 0 || (int64_t)so->col_offset + cp->cfg.out_width > so->global_width)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "slice [%d, +%d) outside the global row of %d",
+                so->col_offset, cp->cfg.out_width, so->global_width);
+  const int es = cp->elem_bytes;
+  // the plan's vector width was chosen for its own row pitch and offsets: the global row must
+  // keep 16-byte alignment where the plan uses 128-bit chunks
+  if (((int64_t)so->global_width * es) % 16 || ((int64_t)so->col_offset * es) % 16)
+    return fail(RECOM_ERR_UNSUPPORTED, "global row pitch and slice offset must be 16-byte multiples");
+  for (int g = 0; g < so->world; ++g)
+    if (!so->peer_out[g] || ((uintptr_t)so->peer_out[g] & 15))
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "peer_out[%d] is null or not 16-byte aligned", g);
+  return run_impl(cp, req, so);
+}
+
+static recom_status run_impl(const recom_plan* cp, const recom_request* req, const recom_shard_out* so) {
   g_last_launches = 0;
   g_host_prof.start();
   g_host_prof.calls++;
   if (!cp || !req) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
   recom_plan* p = const_cast<recom_plan*>(cp);  // only internally locked caches mutate
-  recom_status st = validate_request_head(p, req);
+  recom_request head = *req;
+  if (so) head.out = so->peer_out[0];
+  recom_status st = validate_request_head(p, &head);
   if (st != RECOM_OK) return st;
   if (req->batch == 0) return validate_request(p, req);
   const int n = (int)p->descs.size();
@@ -1362,6 +1392,16 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   if (p->d_prof) p->prof_grid = grid;
   A.batch = B;
   A.out_row_bytes = (int64_t)p->cfg.out_width * p->elem_bytes;
+  A.world = 0;  // 0: plain output (A.out); >= 1: sharded output through peer_out
+  A.rows_per_rank = 0x7fffffff;
+  if (so) {
+    A.world = so->world;
+    A.rows_per_rank = so->rows_per_rank;
+    A.out_row_bytes = (int64_t)so->global_width * p->elem_bytes;
+    A.col_off_bytes = so->col_offset * p->elem_bytes;
+    for (int g = 0; g < so->world; ++g) A.peer_out[g] = (uint8_t*)so->peer_out[g];
+    A.out = (uint8_t*)so->peer_out[0];
+  }
 
   if (!p->coo_cols.empty()) {
     launch_coo_to_row_splits(p->dev, (const ReqHeader*)d_args, A.blob, A.ws_row_splits,
@@ -1377,6 +1417,39 @@ recom_status recom_plan_run(const recom_plan* cp, const recom_request* req) {
   }
   g_host_prof.lap(4);
   if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return RECOM_OK;
+}
+
+recom_status recom_ipc_alloc(size_t bytes, void** dev_ptr, uint8_t handle[64]) {
+  if (!dev_ptr || !handle || bytes == 0) return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaMalloc(dev_ptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*dev_ptr);
+    *dev_ptr = nullptr;
+    return fail(RECOM_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle, &h, 64);
+  return RECOM_OK;
+}
+
+recom_status recom_ipc_open(const uint8_t handle[64], void** dev_ptr) {
+  if (!dev_ptr || !handle) return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RECOM_OK;
+}
+
+recom_status recom_ipc_close(void* dev_ptr) {
+  if (dev_ptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return RECOM_OK;
+}
+
+recom_status recom_ipc_free(void* dev_ptr) {
+  if (dev_ptr) CUDA_TRY(cudaFree(dev_ptr));
   return RECOM_OK;
 }
 

@@ -459,6 +459,72 @@ struct ReqRegs {
   bool check;
 };
 
+template <bool SH>
+struct ReqRegsT;
+template <>
+struct ReqRegsT<false> : ReqRegs {
+  static constexpr bool kSharded = false;
+  __device__ __forceinline__ void bind(const ReqParams&) {}
+};
+template <>
+struct ReqRegsT<true> : ReqRegs {
+  static constexpr bool kSharded = true;
+  const ReqParams* A;
+  __device__ __forceinline__ void bind(const ReqParams& a) { A = &a; }
+};
+
+// Where the rows a lane stores go: a cursor over the output rows b0 + r0, + step_rows, ...
+// Single GPU: one pointer bumped by a constant. Sharded output (Mode A, fused exchange): the
+// rows of a tile (at most 32, never more than rows_per_rank) belong to at most two ranks; the
+// cursor runs in the first owner's address space (base pre-biased by the owner's first row) and
+// rows at or past the boundary are displaced by the distance between the two owners' bases.
+template <bool SH>
+struct RowCursor;
+template <>
+struct RowCursor<false> {
+  uint8_t* p;
+  int64_t step;
+  __device__ __forceinline__ RowCursor(const ReqRegs& Q, int64_t b0, int r0, int step_rows,
+                                       int32_t out_byte) {
+    p = Q.out + (b0 + r0) * Q.out_row_bytes + out_byte;
+    step = (int64_t)step_rows * Q.out_row_bytes;
+  }
+  __device__ __forceinline__ uint8_t* next() {
+    uint8_t* q = p;
+    p += step;
+    return q;
+  }
+};
+template <>
+struct RowCursor<true> {
+  uint8_t* p;
+  int64_t step;
+  int64_t delta;   // second owner's biased base - first owner's
+  int32_t left;    // rows until the boundary (<= 0: past it)
+  int32_t step_rows;
+  __device__ __forceinline__ RowCursor(const ReqRegsT<true>& Q, int64_t b0, int r0,
+                                       int step_rows_, int32_t out_byte) {
+    const ReqParams& A = *Q.A;
+    const int32_t rpr = (int32_t)A.rows_per_rank;
+    const int32_t g = (int32_t)b0 / rpr;
+    const int32_t g1 = min(g + 1, A.world - 1);
+    const int64_t orb = Q.out_row_bytes;
+    uint8_t* base0 = A.peer_out[g] - (int64_t)g * rpr * orb;
+    uint8_t* base1 = A.peer_out[g1] - (int64_t)g1 * rpr * orb;
+    delta = base1 - base0;
+    left = (g + 1) * rpr - ((int32_t)b0 + r0);
+    step_rows = step_rows_;
+    p = base0 + (b0 + r0) * orb + A.col_off_bytes + out_byte;
+    step = (int64_t)step_rows * orb;
+  }
+  __device__ __forceinline__ uint8_t* next() {
+    uint8_t* q = left > 0 ? p : p + delta;
+    p += step;
+    left -= step_rows;
+    return q;
+  }
+};
+
 // Resolve a column against the request (one thread per column): one read of the static
 // record plus one read each of the request's slot / table arrays.
 __device__ __forceinline__ void build_ctx(const ReqParams& A, const DevSlabCol& sc, bool stage_tbl,
@@ -674,8 +740,8 @@ __device__ __forceinline__ void dense_phase1_generic(const DevPlan& P, const Req
 // phase 2 of a DENSE warp tile: lane = chunk; 32 / W rows per pass; UNROLL independent rows in
 // flight; 128-bit gathers from the staged tables (or ld.global.nc), 128-bit streaming stores
 // straight into the concat rows.
-template <int VEC, bool STAGED>
-__device__ __forceinline__ void dense_phase2_impl(const ReqRegs& Q, const ColCtx* ctx, int W,
+template <int VEC, bool STAGED, class QT>
+__device__ __forceinline__ void dense_phase2_impl(const QT& Q, const ColCtx* ctx, int W,
                                              const DevChunk& ch, int64_t b0, int rows,
                                              const uint8_t* s_tables, const int32_t* s_ids,
                                              int lane) {
@@ -689,10 +755,8 @@ __device__ __forceinline__ void dense_phase2_impl(const ReqRegs& Q, const ColCtx
   const uint8_t* tbl = (STAGED ? s_tables + c.stage_off : c.table) + ch.table_byte;
   const int32_t row_bytes = c.row_bytes;
   const int32_t* ids = s_ids + ch.col_local * kIdPitch;
-  const int64_t orb = Q.out_row_bytes;
   int r = sub;
-  uint8_t* outp = Q.out + (b0 + r) * orb + ch.out_byte;
-  const int64_t ostep = (int64_t)rpp * orb;
+  RowCursor<QT::kSharded> outp(Q, b0, r, rpp, ch.out_byte);
   #ifndef RECOM_DENSE_U
 #define RECOM_DENSE_U 8
 #endif
@@ -707,8 +771,7 @@ __device__ __forceinline__ void dense_phase2_impl(const ReqRegs& Q, const ColCtx
     }
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k) {
-      v[k].store(outp);
-      outp += ostep;
+      v[k].store(outp.next());
     }
   }
   for (; r < rows; r += rpp) {
@@ -716,22 +779,21 @@ __device__ __forceinline__ void dense_phase2_impl(const ReqRegs& Q, const ColCtx
     Chunk<VEC> v;
     if (STAGED) v = lds_chunk<VEC>(tbl + o * row_bytes);
     else v.load(tbl + (int64_t)o * row_bytes);
-    v.store(outp);
-    outp += ostep;
+    v.store(outp.next());
   }
 }
 
 // The 16-byte variants are the hot ones and inlined; element-wise slabs (unaligned slices) are
 // rare and kept out of line to keep the hot code small.
-template <int VEC, bool STAGED>
-__device__ __noinline__ void dense_phase2_cold(const ReqRegs& Q, const ColCtx* ctx, int W,
+template <int VEC, bool STAGED, class QT>
+__device__ __noinline__ void dense_phase2_cold(const QT& Q, const ColCtx* ctx, int W,
                                                const DevChunk& ch, int64_t b0, int rows,
                                                const uint8_t* s_tables, const int32_t* s_ids,
                                                int lane) {
   dense_phase2_impl<VEC, STAGED>(Q, ctx, W, ch, b0, rows, s_tables, s_ids, lane);
 }
-template <int VEC, bool STAGED>
-__device__ __forceinline__ void dense_phase2(const ReqRegs& Q, const ColCtx* ctx, int W,
+template <int VEC, bool STAGED, class QT>
+__device__ __forceinline__ void dense_phase2(const QT& Q, const ColCtx* ctx, int W,
                                              const DevChunk& ch, int64_t b0, int rows,
                                              const uint8_t* s_tables, const int32_t* s_ids,
                                              int lane) {
@@ -763,8 +825,8 @@ __device__ __noinline__ void flush_row(Acc<VEC, BF16> acc, int32_t n, int combin
   acc.pack().store(outp);
 }
 
-template <int VEC, bool BF16>
-__device__ __forceinline__ void sparse_phase2_impl(const ReqRegs& Q, const ColCtx& c, int W,
+template <int VEC, bool BF16, class QT>
+__device__ __forceinline__ void sparse_phase2_impl(const QT& Q, const ColCtx& c, int W,
                                               const DevChunk& ch, int64_t b0, int rows,
                                               const int32_t* sp, const int32_t* ids, int lane) {
 #ifdef RECOM_TEST_NOSP2
@@ -779,9 +841,8 @@ __device__ __forceinline__ void sparse_phase2_impl(const ReqRegs& Q, const ColCt
   if (r >= r_end) return;
   const uint8_t* tbl = c.table + ch.table_byte;
   const int64_t row_bytes = c.row_bytes;
-  const int64_t orb = Q.out_row_bytes;
   const int combiner = c.combiner;
-  uint8_t* outp = Q.out + (b0 + r) * orb + ch.out_byte;
+  RowCursor<QT::kSharded> outp(Q, b0, r, 1, ch.out_byte);
   #ifndef RECOM_SPARSE_U
 #define RECOM_SPARSE_U 8
 #endif
@@ -792,8 +853,7 @@ __device__ __forceinline__ void sparse_phase2_impl(const ReqRegs& Q, const ColCt
   Acc<VEC, BF16> acc;
   acc.clear();
   auto flush = [&]() {
-    flush_row<VEC, BF16>(acc, row_end - row_beg, combiner, outp);
-    outp += orb;
+    flush_row<VEC, BF16>(acc, row_end - row_beg, combiner, outp.next());
   };
   while (e < e_end) {
     Chunk<VEC> v[U];
@@ -826,14 +886,14 @@ __device__ __forceinline__ void sparse_phase2_impl(const ReqRegs& Q, const ColCt
   }
 }
 
-template <int VEC, bool BF16>
-__device__ __noinline__ void sparse_phase2_cold(const ReqRegs& Q, const ColCtx& c, int W,
+template <int VEC, bool BF16, class QT>
+__device__ __noinline__ void sparse_phase2_cold(const QT& Q, const ColCtx& c, int W,
                                                 const DevChunk& ch, int64_t b0, int rows,
                                                 const int32_t* sp, const int32_t* ids, int lane) {
   sparse_phase2_impl<VEC, BF16>(Q, c, W, ch, b0, rows, sp, ids, lane);
 }
-template <int VEC, bool BF16>
-__device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const ColCtx& c, int W,
+template <int VEC, bool BF16, class QT>
+__device__ __forceinline__ void sparse_phase2(const QT& Q, const ColCtx& c, int W,
                                               const DevChunk& ch, int64_t b0, int rows,
                                               const int32_t* sp, const int32_t* ids, int lane) {
   if (VEC == 16) sparse_phase2_impl<VEC, BF16>(Q, c, W, ch, b0, rows, sp, ids, lane);
@@ -843,9 +903,9 @@ __device__ __forceinline__ void sparse_phase2(const ReqRegs& Q, const ColCtx& c,
 // A DENSE tile from the queue (hashed or unstaged slab): like a SPARSE tile, one warp on its
 // own - column contexts and row ids in the warp's scratch, rows gathered with ld.global.nc.
 // (The tile's slab record has its fast-group masks cleared: boundaries are read from the pool.)
-template <bool BF16>
+template <bool BF16, class QT>
 __device__ __forceinline__ void generic_dense_tile(const DevPlan& P, const ReqParams& A,
-                                                   const ReqRegs& Q, const Tile& tile,
+                                                   const QT& Q, const Tile& tile,
                                                    bool new_slab, uint8_t* scratch, DevChunk& ch,
                                                    int lane) {
   constexpr int ELEM = BF16 ? 2 : 4;
@@ -912,9 +972,9 @@ __device__ __noinline__ void spill_id(const ReqParams& A, const ReqRegs& Q, cons
   if (Q.ids_out) Q.ids_out[Q.ids_base[c.col] + e] = v;
 }
 
-template <bool BF16>
+template <bool BF16, class QT>
 __device__ __forceinline__ void sparse_warp_tile(const DevPlan& P, const ReqParams& A,
-                                                 const ReqRegs& Q, const Tile& tile, bool new_slab,
+                                                 const QT& Q, const Tile& tile, bool new_slab,
                                                  uint8_t* scratch, DevChunk& ch, int lane
 #ifdef RECOM_PROFILE
                                                  , uint32_t (&prof_acc)[6], uint32_t& prof_last
@@ -1019,12 +1079,13 @@ __device__ __forceinline__ void sparse_warp_tile(const DevPlan& P, const ReqPara
 // ---------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------
-template <bool BF16>
+template <bool BF16, bool SH>
 #ifndef RECOM_MIN_BLOCKS
 #define RECOM_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(kThreads, RECOM_MIN_BLOCKS)
-fused_columns_kernel(const DevPlan P, const Sched S, const ReqParams A) {
+fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ Sched S,
+                     const __grid_constant__ ReqParams A) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t mbar_tbl;  // tables of the staged slab have landed
   __shared__ uint64_t mbar_bnd;  // boundaries of the staged slab have landed
@@ -1034,8 +1095,9 @@ fused_columns_kernel(const DevPlan P, const Sched S, const ReqParams A) {
   float* s_bnd = reinterpret_cast<float*>(smem + P.smem_off_bnd);
   ColCtx* s_ctx = reinterpret_cast<ColCtx*>(smem + P.smem_off_ctx);
   uint8_t* scratch = smem + P.smem_off_scratch + warp * P.scratch_bytes;
-  ReqRegs Q;
+  ReqRegsT<SH> Q;
   Q.out = A.out;
+  Q.bind(A);
   Q.out_row_bytes = A.out_row_bytes;
   Q.status = A.status;
   Q.ids_out = A.ids_out;
@@ -1156,9 +1218,11 @@ fused_columns_kernel(const DevPlan P, const Sched S, const ReqParams A) {
 
 template <bool BF16>
 static int configure_one(int smem_bytes) {
-  auto fn = fused_columns_kernel<BF16>;
+  auto fn = fused_columns_kernel<BF16, false>;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
-      cudaSuccess)
+          cudaSuccess ||
+      cudaFuncSetAttribute(fused_columns_kernel<BF16, true>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
     return -1;
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kThreads, smem_bytes) != cudaSuccess)
@@ -1177,8 +1241,14 @@ void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqPara
   (void)sm; (void)sched; (void)req; (void)grid; (void)stream; (void)bf16;
   return;
 #endif
-  if (bf16) fused_columns_kernel<true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
-  else fused_columns_kernel<false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+  const bool sh = req.world > 0;  // sharded output: rows stored into their owners' tensors
+  if (bf16) {
+    if (sh) fused_columns_kernel<true, true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+    else fused_columns_kernel<true, false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+  } else {
+    if (sh) fused_columns_kernel<false, true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+    else fused_columns_kernel<false, false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+  }
 }
 
 // ---------------------------------------------------------------------------

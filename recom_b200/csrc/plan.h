@@ -18,6 +18,7 @@ namespace recom {
 constexpr int kThreads = RECOM_THREADS;  // threads per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxChunks = 32;         // a slab is at most one warp wide
+constexpr int kMaxPeers = 8;           // ranks of a fused Mode-A exchange (one NVSwitch box)
 constexpr int kDenseTileRows = 32;     // rows of a DENSE warp tile (lane = row while ids are made)
 constexpr int kFastTileRows = 16;      // ... of a slab of fast groups only: lane = (group parity, row)
 constexpr int kHashTileRows = 8;       // ... of a slab with hashed columns: lane = (column group, row)
@@ -221,6 +222,13 @@ struct ReqParams {
   const int32_t* ids_base;      // [num_cols + 1] prefix of ids per column
   const int32_t* sparse_base;   // [num_sparse + 1] prefix of ids, non-DENSE only
   int32_t* counters;            // [2] plan-owned slot: queue claims, finished warps (self-resetting)
+  // Sharded output (Mode A, fused exchange): rows [g * rows_per_rank, (g + 1) * rows_per_rank)
+  // are stored into peer_out[g] (rank g's [rows_per_rank, global width] tensor, peer mapped);
+  // world == 0: everything goes to `out`.
+  uint8_t* peer_out[kMaxPeers];
+  int64_t rows_per_rank;
+  int32_t world;
+  int32_t col_off_bytes;        // byte offset of this plan's slice inside a global row
   uint64_t* prof;               // profiling builds only, else null
   int64_t batch;
   int64_t out_row_bytes;

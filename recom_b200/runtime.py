@@ -92,6 +92,14 @@ class Plan:
         r = self._request(req, blob_dev, tables_ptrs, out, workspace, ids_out, status_out, stream)
         L.check(L.lib.recom_plan_run(self._h, C.byref(r)))
 
+    def run_sharded(self, req: PackedRequest, blob_dev: torch.Tensor, tables_ptrs: np.ndarray,
+                    workspace: torch.Tensor, shard_out: "L.ShardOut", stream=None) -> None:
+        """Mode A with the exchange fused into the kernel: rows are stored straight into the
+        owning ranks' concat tensors (see sharding.PeerOutputs)."""
+        r = self._request(req, blob_dev, tables_ptrs, workspace, workspace, None, None, stream)
+        r.out = None
+        L.check(L.lib.recom_plan_run_sharded(self._h, C.byref(r), C.byref(shard_out)))
+
     def algorithmic_bytes(self, req: PackedRequest, blob_dev, tables_ptrs, out, workspace) -> int:
         r = self._request(req, blob_dev, tables_ptrs, out, workspace, None, None, None)
         n = C.c_int64()

@@ -166,6 +166,70 @@ def all_to_all_columns(local_out, shards: Sequence[ColumnShard], group=None):
     return torch.cat(blocks, dim=1)
 
 
+class PeerOutputs:
+    """The concat tensors of a fused Mode-A exchange: every rank owns [rows_per_rank, sum D]
+    (its rows of the batch) in a cudaMalloc'ed buffer that all ranks of the node map through
+    CUDA IPC, so that the kernel of every rank stores its column slice of every row straight
+    into the row's owner over NVLink (recom_plan_run_sharded). One process per GPU."""
+
+    def __init__(self, shards: Sequence[ColumnShard], batch: int, out_width: int, elem_bytes: int,
+                 group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows_per_rank = (batch + self.world - 1) // self.world
+        self.out_width, self.elem_bytes = out_width, elem_bytes
+        self.nbytes = self.rows_per_rank * out_width * elem_bytes
+        local = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        L.check(L.lib.recom_ipc_alloc(self.nbytes, C.byref(local), handle))
+        self.local_ptr = local.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._opened = []
+        self.ptrs = np.zeros(self.world, dtype=np.uint64)
+        for g in range(self.world):
+            if g == self.rank:
+                self.ptrs[g] = self.local_ptr
+                continue
+            buf = (C.c_uint8 * 64).from_buffer_copy(handles[g])
+            p = C.c_void_p()
+            L.check(L.lib.recom_ipc_open(buf, C.byref(p)))
+            self._opened.append(p.value)
+            self.ptrs[g] = p.value
+        sh = shards[self.rank]
+        self.shard_out = L.ShardOut(world=self.world, col_offset=sh.out_begin, global_width=out_width,
+                                    reserved=0, rows_per_rank=self.rows_per_rank,
+                                    peer_out=self.ptrs.ctypes.data)
+
+    def local_tensor(self, dtype):
+        """This rank's [rows_per_rank, sum D] tensor as a torch view of the IPC buffer."""
+        import torch
+
+        class _Arr:
+            pass
+
+        a = _Arr()
+        typestr = {torch.float32: "<f4", torch.bfloat16: "<u2"}[dtype]
+        a.__cuda_array_interface__ = {"shape": (self.rows_per_rank, self.out_width), "typestr": typestr,
+                                      "data": (self.local_ptr, False), "version": 2}
+        t = torch.as_tensor(a, device=f"cuda:{torch.cuda.current_device()}")
+        return t.view(torch.bfloat16) if dtype == torch.bfloat16 else t
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        for p in self._opened:
+            L.lib.recom_ipc_close(p)
+        self._opened = []
+        if self.local_ptr:
+            L.lib.recom_ipc_free(self.local_ptr)
+            self.local_ptr = None
+
+
 # ---------------------------------------------------------------------------------------
 # Mode B: table row-sharding
 # ---------------------------------------------------------------------------------------
@@ -265,10 +329,22 @@ def bench_large_table(args, world: int, rank: int, local: int):
     stream = torch.cuda.current_stream(local)
     alg = float(np.mean([algorithmic_bytes(sh.model, r) for r in reqs]))
 
-    exchange = getattr(args, "lt_exchange", None) or "all_to_all"
+    exchange = getattr(args, "lt_exchange", None) or "fused"
+    if world == 1:
+        exchange = "none"
+    peers, flag = None, None
+    if exchange == "fused":
+        # rows go straight into their owners' concat tensors from the kernel; one tiny NCCL
+        # all-reduce per step orders the consumers after every rank's launch
+        peers = [PeerOutputs(shards, batch, model.out_width, 4) for _ in range(S)]
+        flag = torch.zeros(1, device=f"cuda:{local}")
 
     def step(i):
         s = i % S
+        if exchange == "fused":
+            plan.run_sharded(reqs[s], blobs[s], ptrs, wss[s], peers[s].shard_out, stream=stream)
+            dist.all_reduce(flag)
+            return peers[s].local_tensor(torch.float32)
         plan.run(reqs[s], blobs[s], ptrs, outs[s], wss[s], stream=stream)
         if world == 1:
             return outs[s]
@@ -284,8 +360,11 @@ def bench_large_table(args, world: int, rank: int, local: int):
 
     for i in range(W):
         full = step(i)
-    want_rows = batch if (world == 1 or exchange == "all_gather") else (
-        batch_rows(batch, world, rank)[1] - batch_rows(batch, world, rank)[0])
+    if exchange == "fused":
+        want_rows = peers[0].rows_per_rank
+    else:
+        want_rows = batch if (world == 1 or exchange == "all_gather") else (
+            batch_rows(batch, world, rank)[1] - batch_rows(batch, world, rank)[0])
     assert full.shape == (want_rows, model.out_width)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -308,7 +387,10 @@ def bench_large_table(args, world: int, rank: int, local: int):
             "data": "synthetic",
             "config": {"workload": f"large_table_{n_cols}x{rows}x32_b{batch}", "columns": n_cols,
                        "batch": batch, "table_bytes": model.table_bytes(),
-                       "parallelism": (f"column-group x{world}, NCCL all-gather of [B, W_g] slices" if exchange == "all_gather"
+                       "parallelism": (f"column-group x{world}, exchange fused into the kernel: rows stored straight into the "
+                                       f"owners' [B/{world}, sum D] tensors over NVLink (IPC peer memory), one 4-byte "
+                                       f"all-reduce per step as the barrier" if exchange == "fused" else
+                                       f"column-group x{world}, NCCL all-gather of [B, W_g] slices" if exchange == "all_gather"
                                        else f"column-group x{world}, NCCL all-to-all of [B/{world}, W_g] row blocks "
                                             f"(every rank keeps its B/{world} rows of the concat tensor)"),
                        "l2": f"rotating {S} request/output sets"},

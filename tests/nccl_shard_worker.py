@@ -39,6 +39,19 @@ def main():
     torch.cuda.synchronize()
     lo, hi = sharding.batch_rows(batch, world, rank)
     np.testing.assert_array_equal(mine.cpu().numpy(), full.cpu().numpy()[lo:hi])
+    # exchange fused into the kernel: rows stored straight into their owners over NVLink
+    peers = sharding.PeerOutputs(shards, batch, m.out_width, 4)
+    mine_t = peers.local_tensor(torch.float32)
+    mine_t.fill_(float("nan"))
+    torch.cuda.synchronize()
+    dist.barrier()
+    plan.run_sharded(req, R.upload_blob(req, local), R.table_pointers(dev_tables), ws, peers.shard_out)
+    torch.cuda.synchronize()
+    dist.barrier()
+    rpr = peers.rows_per_rank
+    lo, hi = rank * rpr, min((rank + 1) * rpr, batch)
+    np.testing.assert_array_equal(mine_t.cpu().numpy()[: hi - lo], full.cpu().numpy()[lo:hi])
+    peers.close()
     dist.barrier()
     if rank == 0:
         print("SHARD_OK")

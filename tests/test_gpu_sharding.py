@@ -28,6 +28,67 @@ def test_column_shards_on_one_gpu_reassemble(world):
     np.testing.assert_array_equal(sharding.assemble_host(shards, outs), full)
 
 
+@pytest.mark.parametrize("world,batch,bf16", [(2, 130, False), (4, 257, False), (8, 256, False), (3, 100, True)])
+def test_fused_exchange_addressing_on_one_gpu(world, batch, bf16):
+    """recom_plan_run_sharded with every rank's concat tensor on this device: each shard's
+    kernel stores its column slice of every row into the row's owner; the owners' tensors,
+    stacked, are bit-identical to the single-plan result."""
+    import ctypes as C
+
+    import torch
+    from recom_b200 import _lib as L
+    from recom_b200 import runtime as R
+
+    m = synth.mixed_model(96, seed=17, large_rows=1 << 14, out_dtype=L.BF16) if bf16 else \
+        synth.mixed_model(96, seed=17, large_rows=1 << 14)
+    feats = synth.make_features(m, batch, seed=5, empty_frac=0.1)
+    tables = synth.make_tables_np(m)
+    full, _, status, _ = run_gpu(m, pack_request(m, batch, feats), tables)
+    assert status == 0
+    shards = sharding.partition_columns(m, world)
+    rpr = max(32, (batch + world - 1) // world)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    owners = [torch.full((rpr, m.out_width), float("nan"), dtype=dt, device="cuda:0") for _ in range(world)]
+    ptrs = np.array([o.data_ptr() for o in owners], dtype=np.uint64)
+    for s in shards:
+        plan = R.Plan(s.model, device=0)
+        dev_tables = R.tables_from_numpy(s.model, [tables[t] for t in s.table_ids], 0)
+        req = pack_request(s.model, batch, sharding.shard_features(s, feats))
+        ws = plan.alloc_workspace(batch, req.sparse_ids)
+        so = L.ShardOut(world=world, col_offset=s.out_begin, global_width=m.out_width, reserved=0,
+                        rows_per_rank=rpr, peer_out=ptrs.ctypes.data)
+        plan.run_sharded(req, R.upload_blob(req, 0), R.table_pointers(dev_tables), ws, so)
+        torch.cuda.synchronize()
+        plan.close()
+    got = torch.cat(owners, dim=0)[:batch].float().cpu().numpy()
+    np.testing.assert_array_equal(got, full)
+
+
+def test_fused_exchange_rejects_bad_arguments():
+    import torch
+    from recom_b200 import _lib as L
+    from recom_b200 import runtime as R
+
+    m = synth.mixed_model(16, seed=3, large_rows=1 << 12)
+    batch = 64
+    feats = synth.make_features(m, batch, seed=1)
+    req = pack_request(m, batch, feats)
+    plan = R.Plan(m, device=0)
+    dev_tables = R.tables_from_numpy(m, synth.make_tables_np(m), 0)
+    ws = plan.alloc_workspace(batch, req.sparse_ids)
+    out = torch.zeros((64, m.out_width), device="cuda:0")
+    ptrs = np.array([out.data_ptr()], dtype=np.uint64)
+    blob = R.upload_blob(req, 0)
+    for kw in (dict(world=0), dict(world=9), dict(rows_per_rank=16), dict(rows_per_rank=32),
+               dict(col_offset=4), dict(global_width=m.out_width - 4)):
+        a = dict(world=1, col_offset=0, global_width=m.out_width, reserved=0, rows_per_rank=64,
+                 peer_out=ptrs.ctypes.data)
+        a.update(kw)
+        with pytest.raises(L.RecomError):
+            plan.run_sharded(req, blob, R.table_pointers(dev_tables), ws, L.ShardOut(**a))
+    plan.close()
+
+
 def test_nccl_all_gather_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:
