@@ -182,25 +182,43 @@ RECOM_API recom_status recom_plan_workspace_bytes(const recom_plan *plan, int64_
 /* Enqueue the whole fused stage on req->stream. Re-entrant per plan. */
 RECOM_API recom_status recom_plan_run(const recom_plan *plan, const recom_request *req);
 
-/* Number of kernels the last recom_plan_run on this thread launched. */
 /* Mode A with the exchange fused into the kernel (recom_b200/sharding.py):
  * this plan computes the columns [col_offset, col_offset + out_width) of a global concat row
  * of `global_width` elements; rows [g*rows_per_rank, (g+1)*rows_per_rank) of the batch are
  * stored straight into peer_out[g], rank g's [rows_per_rank, global_width] tensor (peer-mapped
  * device memory, e.g. opened with recom_ipc_open), from the kernel's phase 2 over NVLink. No
  * collective and no concatenation copy follow; the caller only has to order the consumers after
- * all ranks' launches (one barrier). req->out is not used. batch <= world * rows_per_rank,
- * rows_per_rank >= 32, world <= 8. The reference has no counterpart (single GPU). */
+ * all ranks' kernels. req->out is not used. batch <= world * rows_per_rank,
+ * rows_per_rank >= 32, world <= 8. The reference has no counterpart (single GPU).
+ *
+ * Completion signal (optional, peer_flags != NULL): peer_flags[g] is rank g's array of
+ * RECOM_SHARD_FLAG_WORDS uint32 words (peer mapped, zeroed before the first step). When the
+ * last warp of this rank's kernel has finished, and after a system-scope fence, the kernel
+ * stores `epoch` into word `rank` of every peer's array (release, system scope). A consumer on
+ * rank g enqueues recom_shard_wait(peer_flags[g], world, epoch, stream) ahead of its readers: a
+ * one-warp kernel that spins until words [0, world) have all reached `epoch`. The exchange then
+ * needs no host barrier and no collective at all. Epochs of one flag array must increase by
+ * one per step (wrap-around is handled); with the output tensors rotated over >= 2 sets, a
+ * rank that has passed the wait of step j-1 may overwrite the set of step j - 2 or older. */
+#define RECOM_SHARD_FLAG_WORDS 16
 typedef struct recom_shard_out {
   int32_t world;
   int32_t col_offset;   /* elements */
   int32_t global_width; /* elements */
-  int32_t reserved;
+  int32_t rank;         /* this plan's rank: the flag word it signals */
   int64_t rows_per_rank;
-  void *const *peer_out; /* host [world] */
+  void *const *peer_out;   /* host [world] */
+  void *const *peer_flags; /* host [world], or NULL: no completion signal */
+  uint32_t epoch;
+  uint32_t reserved;
 } recom_shard_out;
 RECOM_API recom_status recom_plan_run_sharded(const recom_plan *plan, const recom_request *req,
                                               const recom_shard_out *shard);
+/* Stream-ordered wait for the completion signals of all `world` ranks (see above). If a signal
+ * has not arrived after timeout_ms (0: 10 s) the kernel stores 1 into word
+ * RECOM_SHARD_FLAG_WORDS - 1 of local_flags and returns; the host may inspect that word. */
+RECOM_API recom_status recom_shard_wait(void *local_flags, int32_t world, uint32_t epoch,
+                                        uint32_t timeout_ms, void *stream);
 
 /* Peer-visible device buffers for recom_plan_run_sharded: one cudaMalloc'ed buffer per rank,
  * exported as a 64-byte CUDA IPC handle that the other ranks of the node open. */
@@ -209,6 +227,7 @@ RECOM_API recom_status recom_ipc_open(const uint8_t handle[64], void **dev_ptr);
 RECOM_API recom_status recom_ipc_close(void *dev_ptr);
 RECOM_API recom_status recom_ipc_free(void *dev_ptr);
 
+/* Number of kernels the last recom_plan_run on this thread launched. */
 RECOM_API int recom_last_launch_count(void);
 
 /* Algorithmic bytes of the request just described:

@@ -60,8 +60,12 @@ class Request(C.Structure):
 class ShardOut(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("col_offset", C.c_int32), ("global_width", C.c_int32),
-        ("reserved", C.c_int32), ("rows_per_rank", C.c_int64), ("peer_out", C.c_void_p),
+        ("rank", C.c_int32), ("rows_per_rank", C.c_int64), ("peer_out", C.c_void_p),
+        ("peer_flags", C.c_void_p), ("epoch", C.c_uint32), ("reserved", C.c_uint32),
     ]
+
+
+SHARD_FLAG_WORDS = 16
 
 
 class RecomError(RuntimeError):
@@ -78,7 +82,7 @@ EXPORTS = [
     "recom_segment_ids_to_row_splits", "recom_string_to_hash_bucket_fast", "recom_fingerprint64",
     "recom_concat_inputs", "recom_shape_construct_create", "recom_shape_construct_eval",
     "recom_shape_construct_destroy", "recom_plan_run_sharded", "recom_ipc_alloc", "recom_ipc_open",
-    "recom_ipc_close", "recom_ipc_free",
+    "recom_ipc_close", "recom_ipc_free", "recom_shard_wait",
 ]
 
 
@@ -104,6 +108,7 @@ def _load() -> C.CDLL:
         "recom_plan_workspace_bytes": [vp, i64, i64, C.POINTER(sz)],
         "recom_plan_run": [vp, C.POINTER(Request)],
         "recom_plan_run_sharded": [vp, C.POINTER(Request), C.POINTER(ShardOut)],
+        "recom_shard_wait": [vp, i32, C.c_uint32, C.c_uint32, vp],
         "recom_ipc_alloc": [sz, C.POINTER(vp), vp],
         "recom_ipc_open": [vp, C.POINTER(vp)],
         "recom_ipc_close": [vp],

@@ -1218,6 +1218,12 @@ recom_status recom_plan_run_sharded(const recom_plan* cp, const recom_request* r
   for (int g = 0; g < so->world; ++g)
     if (!so->peer_out[g] || ((uintptr_t)so->peer_out[g] & 15))
       return fail(RECOM_ERR_INVALID_ARGUMENT, "peer_out[%d] is null or not 16-byte aligned", g);
+  if (so->rank < 0 || so->rank >= so->world)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "rank %d outside [0, %d)", so->rank, so->world);
+  if (so->peer_flags)
+    for (int g = 0; g < so->world; ++g)
+      if (!so->peer_flags[g] || ((uintptr_t)so->peer_flags[g] & 3))
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "peer_flags[%d] is null or misaligned", g);
   return run_impl(cp, req, so);
 }
 
@@ -1400,6 +1406,10 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     A.out_row_bytes = (int64_t)so->global_width * p->elem_bytes;
     A.col_off_bytes = so->col_offset * p->elem_bytes;
     for (int g = 0; g < so->world; ++g) A.peer_out[g] = (uint8_t*)so->peer_out[g];
+    for (int g = 0; g < kMaxPeers; ++g)
+      A.peer_flags[g] = so->peer_flags && g < so->world ? (uint32_t*)so->peer_flags[g] : nullptr;
+    A.epoch = so->epoch;
+    A.rank = so->rank;
     A.out = (uint8_t*)so->peer_out[0];
   }
 
@@ -1417,6 +1427,17 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   }
   g_host_prof.lap(4);
   if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return RECOM_OK;
+}
+
+recom_status recom_shard_wait(void* local_flags, int32_t world, uint32_t epoch,
+                              uint32_t timeout_ms, void* stream) {
+  if (!local_flags || world < 1 || world > kMaxPeers)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "local_flags null or world outside 1..%d", kMaxPeers);
+  launch_shard_wait((uint32_t*)local_flags, world, epoch, timeout_ms ? timeout_ms : 10000u,
+                    (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "shard wait launch: %s", cudaGetErrorString(e));
   return RECOM_OK;
 }
 

@@ -1204,12 +1204,25 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
       t = __shfl_sync(0xffffffffu, ahead, 0);
       if (t < nq && lane == 0) ahead = first_claim + atomicAdd(A.counters, 1);
     }
-    // the last warp of the grid to get here leaves the slot clean for the next launch
-    if (nq > 0 && lane == 0) {
+    // the last warp of the grid to get here leaves the slot clean for the next launch and,
+    // with a sharded output, tells every peer that this rank's slices of its rows are in place
+    const bool signal = SH && A.peer_flags[0] != nullptr;
+    if (signal) {
+      __syncwarp();  // the lanes' row stores are ordered before lane 0's fence
+      if (lane == 0) __threadfence_system();
+    }
+    if ((nq > 0 || signal) && lane == 0) {
       const int done = atomicAdd(A.counters + 1, 1);
       if (done == (int)gridDim.x * kWarps - 1) {
         A.counters[0] = 0;
         A.counters[1] = 0;
+        if (signal) {
+          __threadfence_system();
+          for (int g = 0; g < A.world; ++g)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peer_flags[g] + A.rank),
+                         "r"(A.epoch)
+                         : "memory");
+        }
       }
     }
   }
@@ -1249,6 +1262,32 @@ void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqPara
     if (sh) fused_columns_kernel<false, true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
     else fused_columns_kernel<false, false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
   }
+}
+
+// Stream-side end of the fused exchange: lane g waits for rank g's completion signal.
+__global__ void __launch_bounds__(32)
+shard_wait_kernel(uint32_t* flags, int world, uint32_t epoch, uint32_t timeout_ms) {
+  const int g = threadIdx.x;
+  if (g >= world) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + g) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > (uint64_t)timeout_ms * 1000000ull) {
+      flags[RECOM_SHARD_FLAG_WORDS - 1] = 1;
+      break;
+    }
+    __nanosleep(100);
+  }
+}
+
+void launch_shard_wait(uint32_t* local_flags, int world, uint32_t epoch, uint32_t timeout_ms,
+                       cudaStream_t stream) {
+  shard_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, epoch, timeout_ms);
 }
 
 // ---------------------------------------------------------------------------

@@ -226,6 +226,9 @@ struct ReqParams {
   // are stored into peer_out[g] (rank g's [rows_per_rank, global width] tensor, peer mapped);
   // world == 0: everything goes to `out`.
   uint8_t* peer_out[kMaxPeers];
+  uint32_t* peer_flags[kMaxPeers];  // completion flags of every rank (null: no signal)
+  uint32_t epoch;               // value stored into word `rank` of every peer's flags
+  int32_t rank;
   int64_t rows_per_rank;
   int32_t world;
   int32_t col_off_bytes;        // byte offset of this plan's slice inside a global row
@@ -277,6 +280,8 @@ __host__ __device__ inline const int32_t* req_coo_cols(const ReqHeader* r) {
 // kernels.cu
 void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqParams& req, int grid,
                           bool bf16, cudaStream_t stream);
+void launch_shard_wait(uint32_t* local_flags, int world, uint32_t epoch, uint32_t timeout_ms,
+                       cudaStream_t stream);
 void launch_coo_to_row_splits(const DevPlan& plan, const ReqHeader* d_req, const uint8_t* blob,
                               int32_t* ws_row_splits, int num_coo, int64_t max_nnz,
                               cudaStream_t stream);

@@ -183,10 +183,16 @@ class PeerOutputs:
         self.rows_per_rank = (batch + self.world - 1) // self.world
         self.out_width, self.elem_bytes = out_width, elem_bytes
         self.nbytes = self.rows_per_rank * out_width * elem_bytes
+        # the completion flags (recom_b200.h, RECOM_SHARD_FLAG_WORDS) follow the tensor
+        self.flags_off = (self.nbytes + 255) // 256 * 256
         local = C.c_void_p()
         handle = (C.c_uint8 * 64)()
-        L.check(L.lib.recom_ipc_alloc(self.nbytes, C.byref(local), handle))
+        L.check(L.lib.recom_ipc_alloc(self.flags_off + 4 * L.SHARD_FLAG_WORDS, C.byref(local), handle))
         self.local_ptr = local.value
+        self.epoch = 0
+        self._flags_view().zero_()
+        import torch
+        torch.cuda.synchronize()
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle), group=group)
         self._opened = []
@@ -201,9 +207,39 @@ class PeerOutputs:
             self._opened.append(p.value)
             self.ptrs[g] = p.value
         sh = shards[self.rank]
+        self.flag_ptrs = self.ptrs + np.uint64(self.flags_off)
         self.shard_out = L.ShardOut(world=self.world, col_offset=sh.out_begin, global_width=out_width,
-                                    reserved=0, rows_per_rank=self.rows_per_rank,
-                                    peer_out=self.ptrs.ctypes.data)
+                                    rank=self.rank, rows_per_rank=self.rows_per_rank,
+                                    peer_out=self.ptrs.ctypes.data,
+                                    peer_flags=self.flag_ptrs.ctypes.data, epoch=0, reserved=0)
+        dist.barrier(group=group)  # every rank's flags are zeroed before anyone signals
+
+    def _flags_view(self):
+        import torch
+
+        class _Arr:
+            pass
+
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (L.SHARD_FLAG_WORDS,), "typestr": "<i4",
+                                      "data": (self.local_ptr + self.flags_off, False), "version": 2}
+        return torch.as_tensor(a, device=f"cuda:{torch.cuda.current_device()}")
+
+    def next_step(self) -> "L.ShardOut":
+        """The argument of this step's recom_plan_run_sharded: the epoch moves on by one."""
+        self.epoch = (self.epoch + 1) & 0xFFFFFFFF
+        self.shard_out.epoch = self.epoch
+        return self.shard_out
+
+    def wait(self, stream=None, timeout_ms: int = 0) -> None:
+        """Order `stream` after the kernels of this step on all ranks (recom_shard_wait)."""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream()
+        L.check(L.lib.recom_shard_wait(self.local_ptr + self.flags_off, self.world, self.epoch,
+                                       timeout_ms, s.cuda_stream))
+
+    def timed_out(self) -> bool:
+        return bool(self._flags_view()[L.SHARD_FLAG_WORDS - 1].item())
 
     def local_tensor(self, dtype):
         """This rank's [rows_per_rank, sum D] tensor as a torch view of the IPC buffer."""
@@ -334,16 +370,16 @@ def bench_large_table(args, world: int, rank: int, local: int):
         exchange = "none"
     peers, flag = None, None
     if exchange == "fused":
-        # rows go straight into their owners' concat tensors from the kernel; one tiny NCCL
-        # all-reduce per step orders the consumers after every rank's launch
+        # rows go straight into their owners' concat tensors from the kernel; the last warp of
+        # every rank's kernel signals all peers, and a one-warp wait orders the consumers
+        assert S >= 2, "the fused exchange needs two rotating output sets"
         peers = [PeerOutputs(shards, batch, model.out_width, 4) for _ in range(S)]
-        flag = torch.zeros(1, device=f"cuda:{local}")
 
     def step(i):
         s = i % S
         if exchange == "fused":
-            plan.run_sharded(reqs[s], blobs[s], ptrs, wss[s], peers[s].shard_out, stream=stream)
-            dist.all_reduce(flag)
+            plan.run_sharded(reqs[s], blobs[s], ptrs, wss[s], peers[s].next_step(), stream=stream)
+            peers[s].wait(stream)
             return peers[s].local_tensor(torch.float32)
         plan.run(reqs[s], blobs[s], ptrs, outs[s], wss[s], stream=stream)
         if world == 1:
@@ -367,12 +403,22 @@ def bench_large_table(args, world: int, rank: int, local: int):
             batch_rows(batch, world, rank)[1] - batch_rows(batch, world, rank)[0])
     assert full.shape == (want_rows, model.out_width)
     barrier()
+    if exchange == "fused":
+        # the fused exchange leaves exactly what the NCCL all-to-all of the local slices leaves
+        plan.run(reqs[0], blobs[0], ptrs, outs[0], wss[0], stream=stream)
+        ref = all_to_all_columns(outs[0], shards)
+        got = step(0)
+        barrier()
+        assert torch.equal(got[: ref.shape[0]], ref), "fused exchange differs from the NCCL all-to-all"
+        barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(K):
         step(i)
     e1.record(stream)
     barrier()
+    if exchange == "fused":
+        assert not any(p.timed_out() for p in peers), "a completion signal never arrived"
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
     alg_t = torch.tensor([alg], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
@@ -388,15 +434,20 @@ def bench_large_table(args, world: int, rank: int, local: int):
             "config": {"workload": f"large_table_{n_cols}x{rows}x32_b{batch}", "columns": n_cols,
                        "batch": batch, "table_bytes": model.table_bytes(),
                        "parallelism": (f"column-group x{world}, exchange fused into the kernel: rows stored straight into the "
-                                       f"owners' [B/{world}, sum D] tensors over NVLink (IPC peer memory), one 4-byte "
-                                       f"all-reduce per step as the barrier" if exchange == "fused" else
+                                       f"owners' [B/{world}, sum D] tensors over NVLink (IPC peer memory); completion "
+                                       f"flags stored to every peer by the kernel's last warp, one-warp wait kernel "
+                                       f"(no NCCL call in the step)" if exchange == "fused" else
                                        f"column-group x{world}, NCCL all-gather of [B, W_g] slices" if exchange == "all_gather"
                                        else f"column-group x{world}, NCCL all-to-all of [B/{world}, W_g] row blocks "
                                             f"(every rank keeps its B/{world} rows of the concat tensor)"),
                        "l2": f"rotating {S} request/output sets"},
             "roofline": {"bound": "hbm", "achieved": float(alg_t[0]) / (ms * 1e-3) / 1e9,
                          "unit": "GB/s", "note": "aggregate algorithmic bytes over all ranks / step time"},
-            "gpu_launches": plan.last_launch_count() * K,
+            "gpu_launches": (plan.last_launch_count() + (1 if exchange == "fused" else 0)) * K,
         }), flush=True)
+    if peers:
+        barrier()
+        for p in peers:
+            p.close()
     if world > 1:
         dist.destroy_process_group()

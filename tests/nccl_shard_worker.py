@@ -45,12 +45,16 @@ def main():
     mine_t.fill_(float("nan"))
     torch.cuda.synchronize()
     dist.barrier()
-    plan.run_sharded(req, R.upload_blob(req, local), R.table_pointers(dev_tables), ws, peers.shard_out)
+    # two steps: no host barrier or collective between launch and read, only the flag wait
+    for _ in range(2):
+        plan.run_sharded(req, R.upload_blob(req, local), R.table_pointers(dev_tables), ws, peers.next_step())
+        peers.wait()
+        got = mine_t.clone()
     torch.cuda.synchronize()
-    dist.barrier()
+    assert not peers.timed_out()
     rpr = peers.rows_per_rank
     lo, hi = rank * rpr, min((rank + 1) * rpr, batch)
-    np.testing.assert_array_equal(mine_t.cpu().numpy()[: hi - lo], full.cpu().numpy()[lo:hi])
+    np.testing.assert_array_equal(got.cpu().numpy()[: hi - lo], full.cpu().numpy()[lo:hi])
     peers.close()
     dist.barrier()
     if rank == 0:

@@ -50,18 +50,32 @@ def test_fused_exchange_addressing_on_one_gpu(world, batch, bf16):
     dt = torch.bfloat16 if bf16 else torch.float32
     owners = [torch.full((rpr, m.out_width), float("nan"), dtype=dt, device="cuda:0") for _ in range(world)]
     ptrs = np.array([o.data_ptr() for o in owners], dtype=np.uint64)
+    flags = [torch.zeros(L.SHARD_FLAG_WORDS, dtype=torch.int32, device="cuda:0") for _ in range(world)]
+    fptrs = np.array([f.data_ptr() for f in flags], dtype=np.uint64)
     for s in shards:
         plan = R.Plan(s.model, device=0)
         dev_tables = R.tables_from_numpy(s.model, [tables[t] for t in s.table_ids], 0)
         req = pack_request(s.model, batch, sharding.shard_features(s, feats))
         ws = plan.alloc_workspace(batch, req.sparse_ids)
-        so = L.ShardOut(world=world, col_offset=s.out_begin, global_width=m.out_width, reserved=0,
-                        rows_per_rank=rpr, peer_out=ptrs.ctypes.data)
+        so = L.ShardOut(world=world, col_offset=s.out_begin, global_width=m.out_width, rank=s.rank,
+                        rows_per_rank=rpr, peer_out=ptrs.ctypes.data, peer_flags=fptrs.ctypes.data,
+                        epoch=7, reserved=0)
         plan.run_sharded(req, R.upload_blob(req, 0), R.table_pointers(dev_tables), ws, so)
         torch.cuda.synchronize()
         plan.close()
+    # every rank's kernel signalled every owner; the stream-side wait returns at once
+    for f in flags:
+        L.check(L.lib.recom_shard_wait(f.data_ptr(), world, 7, 2000, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    for f in flags:
+        v = f.cpu().numpy()
+        assert (v[:world] == 7).all() and (v[world:] == 0).all()
     got = torch.cat(owners, dim=0)[:batch].float().cpu().numpy()
     np.testing.assert_array_equal(got, full)
+    # a signal that never comes: the wait gives up and says so
+    L.check(L.lib.recom_shard_wait(flags[0].data_ptr(), world, 8, 20, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(flags[0][L.SHARD_FLAG_WORDS - 1].item()) == 1
 
 
 def test_fused_exchange_rejects_bad_arguments():
@@ -79,10 +93,10 @@ def test_fused_exchange_rejects_bad_arguments():
     out = torch.zeros((64, m.out_width), device="cuda:0")
     ptrs = np.array([out.data_ptr()], dtype=np.uint64)
     blob = R.upload_blob(req, 0)
-    for kw in (dict(world=0), dict(world=9), dict(rows_per_rank=16), dict(rows_per_rank=32),
+    for kw in (dict(world=0), dict(world=9), dict(rank=1), dict(rank=-1), dict(rows_per_rank=16), dict(rows_per_rank=32),
                dict(col_offset=4), dict(global_width=m.out_width - 4)):
-        a = dict(world=1, col_offset=0, global_width=m.out_width, reserved=0, rows_per_rank=64,
-                 peer_out=ptrs.ctypes.data)
+        a = dict(world=1, col_offset=0, global_width=m.out_width, rank=0, rows_per_rank=64,
+                 peer_out=ptrs.ctypes.data, peer_flags=None, epoch=0, reserved=0)
         a.update(kw)
         with pytest.raises(L.RecomError):
             plan.run_sharded(req, blob, R.table_pointers(dev_tables), ws, L.ShardOut(**a))

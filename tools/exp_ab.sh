@@ -5,7 +5,7 @@ for rep in 1 2; do
 for v in "$@"; do
   lib=$PWD/recom_b200/librecom_b200${v:+_$v}.so
   for w in $wl; do
-    RECOM_B200_LIB=$lib python bench.py --steps 200 --warmup 10 --no-cpu-baseline --workload $w 2>/dev/null | python -c "
+    RECOM_B200_LIB=$lib python bench.py --steps 200 --warmup 10 --no-cpu-baseline --workload $w 2>>gpurun_out/ab.err | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
