@@ -374,12 +374,33 @@ def bench_large_table(args, world: int, rank: int, local: int):
         # every rank's kernel signals all peers, and a one-warp wait orders the consumers
         assert S >= 2, "the fused exchange needs two rotating output sets"
         peers = [PeerOutputs(shards, batch, model.out_width, 4) for _ in range(S)]
+    # The consumers' stream: the wait for step i (and whatever reads the concat rows) runs here
+    # while the launch stream already computes step i + 1; a launch only waits for the
+    # consumers of `lag` steps back, so the ranks are not forced into lock step by every wait
+    # (a rank that has passed the wait of step j - lag may overwrite the set of step j - 2 lag
+    # or older: S >= 2 lag). lag 0: wait on the launch stream itself.
+    lag = min(int(getattr(args, "lt_lag", 0)), S // 2) if exchange == "fused" else 0
+    cstream = torch.cuda.Stream(local) if lag > 0 else None
+    ev_k = [torch.cuda.Event() for _ in range(S)]
+    ev_c = [torch.cuda.Event() for _ in range(S)]
+    n_steps = [0]
 
     def step(i):
         s = i % S
         if exchange == "fused":
+            j = n_steps[0]
+            n_steps[0] += 1
+            s = j % S  # the sets rotate in launch order
+            if lag > 0 and j >= lag:
+                stream.wait_event(ev_c[(j - lag) % S])
             plan.run_sharded(reqs[s], blobs[s], ptrs, wss[s], peers[s].next_step(), stream=stream)
-            peers[s].wait(stream)
+            if lag == 0:
+                peers[s].wait(stream)
+            else:
+                ev_k[j % S].record(stream)
+                cstream.wait_event(ev_k[j % S])
+                peers[s].wait(cstream)
+                ev_c[j % S].record(cstream)  # (a real pipeline records it after its readers)
             return peers[s].local_tensor(torch.float32)
         plan.run(reqs[s], blobs[s], ptrs, outs[s], wss[s], stream=stream)
         if world == 1:
@@ -405,8 +426,9 @@ def bench_large_table(args, world: int, rank: int, local: int):
     barrier()
     if exchange == "fused":
         # the fused exchange leaves exactly what the NCCL all-to-all of the local slices leaves
-        plan.run(reqs[0], blobs[0], ptrs, outs[0], wss[0], stream=stream)
-        ref = all_to_all_columns(outs[0], shards)
+        s0 = n_steps[0] % S
+        plan.run(reqs[s0], blobs[s0], ptrs, outs[s0], wss[s0], stream=stream)
+        ref = all_to_all_columns(outs[s0], shards)
         got = step(0)
         barrier()
         assert torch.equal(got[: ref.shape[0]], ref), "fused exchange differs from the NCCL all-to-all"
@@ -415,6 +437,8 @@ def bench_large_table(args, world: int, rank: int, local: int):
     e0.record(stream)
     for i in range(K):
         step(i)
+    if cstream is not None:
+        stream.wait_event(ev_c[(n_steps[0] - 1) % S])  # the last step's wait is inside the timed region
     e1.record(stream)
     barrier()
     if exchange == "fused":
@@ -436,7 +460,7 @@ def bench_large_table(args, world: int, rank: int, local: int):
                        "parallelism": (f"column-group x{world}, exchange fused into the kernel: rows stored straight into the "
                                        f"owners' [B/{world}, sum D] tensors over NVLink (IPC peer memory); completion "
                                        f"flags stored to every peer by the kernel's last warp, one-warp wait kernel "
-                                       f"(no NCCL call in the step)" if exchange == "fused" else
+                                       f"{'on the launch stream' if lag == 0 else f'on a second stream, launches run {lag} step(s) ahead'} (no NCCL call in the step)" if exchange == "fused" else
                                        f"column-group x{world}, NCCL all-gather of [B, W_g] slices" if exchange == "all_gather"
                                        else f"column-group x{world}, NCCL all-to-all of [B/{world}, W_g] row blocks "
                                             f"(every rank keeps its B/{world} rows of the concat tensor)"),
