@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument("--lt-rows", dest="lt_rows", type=int, default=0, help="large_table: rows per table")
     ap.add_argument("--lt-exchange", dest="lt_exchange", default="fused",
                     choices=["fused", "all_to_all", "all_gather"], help="large_table: exchange of the slices")
+    ap.add_argument("--lt-wait", dest="lt_wait", default="kernel", choices=["kernel", "stream"],
+                    help="large_table, fused exchange: barrier inside the kernel, or a one-warp wait kernel")
     ap.add_argument("--lt-lag", dest="lt_lag", type=int, default=0,
                     help="large_table, fused exchange: steps the launch stream may run ahead of the waits")
     ap.add_argument("--no-cpu-baseline", action="store_true")

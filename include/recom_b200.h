@@ -199,8 +199,15 @@ RECOM_API recom_status recom_plan_run(const recom_plan *plan, const recom_reques
  * one-warp kernel that spins until words [0, world) have all reached `epoch`. The exchange then
  * needs no host barrier and no collective at all. Epochs of one flag array must increase by
  * one per step (wrap-around is handled); with the output tensors rotated over >= 2 sets, a
- * rank that has passed the wait of step j-1 may overwrite the set of step j - 2 or older. */
+ * rank that has passed the wait of step j-1 may overwrite the set of step j - 2 or older.
+ *
+ * RECOM_SHARD_WAIT_IN_KERNEL: the kernel's last warp, after it has signalled, itself waits for
+ * the signals of all ranks (10 s time-out, reported like recom_shard_wait's): the launch then ends
+ * only when every rank's slices of THIS rank's rows have landed, i.e. compute, exchange and
+ * barrier are one kernel and anything enqueued behind it on the stream may read the rows. Every
+ * rank must launch the step without waiting for another rank's launch of the same step. */
 #define RECOM_SHARD_FLAG_WORDS 16
+#define RECOM_SHARD_WAIT_IN_KERNEL 1u
 typedef struct recom_shard_out {
   int32_t world;
   int32_t col_offset;   /* elements */
@@ -210,7 +217,7 @@ typedef struct recom_shard_out {
   void *const *peer_out;   /* host [world] */
   void *const *peer_flags; /* host [world], or NULL: no completion signal */
   uint32_t epoch;
-  uint32_t reserved;
+  uint32_t flags; /* RECOM_SHARD_WAIT_IN_KERNEL or 0 */
 } recom_shard_out;
 RECOM_API recom_status recom_plan_run_sharded(const recom_plan *plan, const recom_request *req,
                                               const recom_shard_out *shard);

@@ -61,11 +61,12 @@ class ShardOut(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("col_offset", C.c_int32), ("global_width", C.c_int32),
         ("rank", C.c_int32), ("rows_per_rank", C.c_int64), ("peer_out", C.c_void_p),
-        ("peer_flags", C.c_void_p), ("epoch", C.c_uint32), ("reserved", C.c_uint32),
+        ("peer_flags", C.c_void_p), ("epoch", C.c_uint32), ("flags", C.c_uint32),
     ]
 
 
 SHARD_FLAG_WORDS = 16
+SHARD_WAIT_IN_KERNEL = 1
 
 
 class RecomError(RuntimeError):

@@ -113,6 +113,7 @@ struct TileTable {
   std::vector<CtaWork> cta;    // [grid]
   int grid = 1;
   int queue_warps = 0;
+  int claim_ahead = 0;
   void* d_block = nullptr;  // device copy: runs, queue, cta (cached tables only)
   ~TileTable() {
     if (d_block) cudaFree(d_block);
@@ -132,6 +133,7 @@ struct TileTable {
     s.cta = (const CtaWork*)((const uint8_t*)base + runs_bytes() + queue_bytes());
     s.num_queue = (int32_t)queue.size();
     s.queue_warps = queue_warps;
+    s.claim_ahead = claim_ahead;
     return s;
   }
 };
@@ -162,6 +164,7 @@ struct recom_plan {
   int ctas_per_sm = 2;
   double sparse_weight = 1.0; // scales the estimated cost of SPARSE warp tiles (schedule balance)
   int force_queue_warps = -1;  // >= 0: override the cost-proportional split (experiments)
+  int claim_ahead = 0;         // queue claims: 0 when a warp is free (measured best), 1 always one tile ahead, 2 ahead except near the end
   int hash_tile_rows = kHashTileRows;             // rows of a DENSE warp tile with hashed columns
   int sparse_rows_hash = kSparseRowsPerSubHash;   // SPARSE rows per lane group, hashed ids
   int sparse_rows = kSparseRowsPerSub;            // ... ids given
@@ -781,6 +784,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     Q = std::min(kWarps - 1, p->force_queue_warps);
   tt->grid = grid;
   tt->queue_warps = Q;
+  tt->claim_ahead = p->claim_ahead;
 
   std::vector<std::vector<Tile>> per_cta(grid);
   if (!fast.empty() && (size_t)grid >= fast.size()) {
@@ -1002,6 +1006,7 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
     return r;
   };
   if (const char* e = getenv("RECOM_B200_QUEUE_WARPS")) p->force_queue_warps = atoi(e);
+  if (const char* e = getenv("RECOM_B200_CLAIM_AHEAD")) p->claim_ahead = atoi(e);
   p->hash_tile_rows = pow2_env("RECOM_B200_HASH_TILE_ROWS", 4, 32, kHashTileRows);
   p->sparse_rows_hash = pow2_env("RECOM_B200_SPARSE_ROWS_HASH", 1, 8, kSparseRowsPerSubHash);
   p->sparse_rows = pow2_env("RECOM_B200_SPARSE_ROWS", 1, 8, kSparseRowsPerSub);
@@ -1410,6 +1415,8 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
       A.peer_flags[g] = so->peer_flags && g < so->world ? (uint32_t*)so->peer_flags[g] : nullptr;
     A.epoch = so->epoch;
     A.rank = so->rank;
+    A.wait_in_kernel = (so->flags & RECOM_SHARD_WAIT_IN_KERNEL) && so->peer_flags ? 1u : 0u;
+    A.wait_timeout_ms = 10000u;
     A.out = (uint8_t*)so->peer_out[0];
   }
 

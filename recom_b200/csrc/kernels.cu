@@ -449,6 +449,26 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Spin until word g of a completion-flag array has reached `epoch` (wrap-around safe); after
+// timeout_ms the last word of the array is set to 1 and the wait gives up.
+__device__ __forceinline__ void wait_flag(uint32_t* flags, int g, uint32_t epoch,
+                                          uint32_t timeout_ms) {
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + g) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > (uint64_t)timeout_ms * 1000000ull) {
+      flags[RECOM_SHARD_FLAG_WORDS - 1] = 1;
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
 // Request-wide values every tile needs.
 struct ReqRegs {
   uint8_t* out;
@@ -1176,17 +1196,24 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
   {
     const int nq = S.num_queue;
     const int first_claim = (int)gridDim.x * S.queue_warps;  // tiles below it are static firsts
+    // Queue claims (Sched::claim_ahead). 0, the default: a warp claims its next tile when it is
+    // free, so the warps that finish early take what is left (the exposed atomic round trip,
+    // ~1 us per tile, costs less than the imbalance: model E 48.5 -> 41.8 us, model F 47.9 ->
+    // 40.4). 1: always one tile ahead (round trip hidden behind the tile, but every warp holds a
+    // tile in reserve that nobody else can take). 2: ahead except within the last grid * warps
+    // tiles of the queue.
+    const int horizon = S.claim_ahead == 1 ? 0x7fffffff
+                        : S.claim_ahead == 0 ? 0 : nq - (int)gridDim.x * kWarps;
     int t = warp >= D ? (warp - D) * (int)gridDim.x + (int)blockIdx.x : nq;
-    int ahead = nq;  // claimed, not yet looked at
-    if (nq > 0) {
+    int ahead = nq;
+    if (nq > 0 && warp < D) {  // no static first tile: the claim is the first tile
       if (lane == 0) ahead = first_claim + atomicAdd(A.counters, 1);
-      if (warp < D) {  // no static first tile: the claim is the first tile
-        t = __shfl_sync(0xffffffffu, ahead, 0);
-        if (t < nq && lane == 0) ahead = first_claim + atomicAdd(A.counters, 1);
-      }
+      t = __shfl_sync(0xffffffffu, ahead, 0);
     }
     int cur_slab = -1;
     while (t < nq) {
+      const bool pre = t < horizon;
+      if (pre && lane == 0) ahead = first_claim + atomicAdd(A.counters, 1);
       const Tile tile = S.queue[t];
       const bool new_slab = tile.slab_id != cur_slab;
       cur_slab = tile.slab_id;
@@ -1201,8 +1228,8 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
         generic_dense_tile<BF16>(P, A, Q, tile, new_slab, scratch, ch, lane);
       }
       PROF_T(2)
+      if (!pre && lane == 0) ahead = first_claim + atomicAdd(A.counters, 1);
       t = __shfl_sync(0xffffffffu, ahead, 0);
-      if (t < nq && lane == 0) ahead = first_claim + atomicAdd(A.counters, 1);
     }
     // the last warp of the grid to get here leaves the slot clean for the next launch and,
     // with a sharded output, tells every peer that this rank's slices of its rows are in place
@@ -1211,18 +1238,25 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
       __syncwarp();  // the lanes' row stores are ordered before lane 0's fence
       if (lane == 0) __threadfence_system();
     }
-    if ((nq > 0 || signal) && lane == 0) {
-      const int done = atomicAdd(A.counters + 1, 1);
-      if (done == (int)gridDim.x * kWarps - 1) {
-        A.counters[0] = 0;
-        A.counters[1] = 0;
-        if (signal) {
-          __threadfence_system();
-          for (int g = 0; g < A.world; ++g)
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peer_flags[g] + A.rank),
-                         "r"(A.epoch)
-                         : "memory");
+    if (nq > 0 || signal) {
+      bool last = false;
+      if (lane == 0) {
+        last = atomicAdd(A.counters + 1, 1) == (int)gridDim.x * kWarps - 1;
+        if (last) {
+          A.counters[0] = 0;
+          A.counters[1] = 0;
         }
+      }
+      if (signal && __shfl_sync(0xffffffffu, (int)last, 0)) {
+        __threadfence_system();
+        if (lane < A.world)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peer_flags[lane] + A.rank),
+                       "r"(A.epoch)
+                       : "memory");
+        // the barrier inside the kernel: this launch ends when every rank's slices of this
+        // rank's rows have landed (lane g watches rank g's word of the local flag array)
+        if (A.wait_in_kernel && lane < A.world)
+          wait_flag(A.peer_flags[A.rank], lane, A.epoch, A.wait_timeout_ms);
       }
     }
   }
@@ -1268,21 +1302,7 @@ void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqPara
 __global__ void __launch_bounds__(32)
 shard_wait_kernel(uint32_t* flags, int world, uint32_t epoch, uint32_t timeout_ms) {
   const int g = threadIdx.x;
-  if (g >= world) return;
-  uint64_t t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + g) : "memory");
-    if ((int32_t)(v - epoch) >= 0) break;
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if (t - t0 > (uint64_t)timeout_ms * 1000000ull) {
-      flags[RECOM_SHARD_FLAG_WORDS - 1] = 1;
-      break;
-    }
-    __nanosleep(100);
-  }
+  if (g < world) wait_flag(flags, g, epoch, timeout_ms);
 }
 
 void launch_shard_wait(uint32_t* local_flags, int world, uint32_t epoch, uint32_t timeout_ms,

@@ -206,6 +206,7 @@ struct Sched {
   const Tile* queue;         // [num_queue]
   int32_t num_queue;
   int32_t queue_warps;
+  int32_t claim_ahead;       // 0: claim when free, 1: always one tile ahead, 2: ahead except near the end
 };
 
 // Per-request values known on the host at launch; a kernel parameter (no dependent loads).
@@ -229,6 +230,8 @@ struct ReqParams {
   uint32_t* peer_flags[kMaxPeers];  // completion flags of every rank (null: no signal)
   uint32_t epoch;               // value stored into word `rank` of every peer's flags
   int32_t rank;
+  uint32_t wait_in_kernel;      // the last warp also waits for all ranks' flags of this epoch
+  uint32_t wait_timeout_ms;
   int64_t rows_per_rank;
   int32_t world;
   int32_t col_off_bytes;        // byte offset of this plan's slice inside a global row

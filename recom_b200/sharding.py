@@ -211,7 +211,7 @@ class PeerOutputs:
         self.shard_out = L.ShardOut(world=self.world, col_offset=sh.out_begin, global_width=out_width,
                                     rank=self.rank, rows_per_rank=self.rows_per_rank,
                                     peer_out=self.ptrs.ctypes.data,
-                                    peer_flags=self.flag_ptrs.ctypes.data, epoch=0, reserved=0)
+                                    peer_flags=self.flag_ptrs.ctypes.data, epoch=0, flags=0)
         dist.barrier(group=group)  # every rank's flags are zeroed before anyone signals
 
     def _flags_view(self):
@@ -225,10 +225,13 @@ class PeerOutputs:
                                       "data": (self.local_ptr + self.flags_off, False), "version": 2}
         return torch.as_tensor(a, device=f"cuda:{torch.cuda.current_device()}")
 
-    def next_step(self) -> "L.ShardOut":
-        """The argument of this step's recom_plan_run_sharded: the epoch moves on by one."""
+    def next_step(self, wait_in_kernel: bool = False) -> "L.ShardOut":
+        """The argument of this step's recom_plan_run_sharded: the epoch moves on by one.
+        wait_in_kernel: the launch itself ends only when all ranks' slices of this rank's rows
+        have landed (RECOM_SHARD_WAIT_IN_KERNEL), no wait() needed."""
         self.epoch = (self.epoch + 1) & 0xFFFFFFFF
         self.shard_out.epoch = self.epoch
+        self.shard_out.flags = L.SHARD_WAIT_IN_KERNEL if wait_in_kernel else 0
         return self.shard_out
 
     def wait(self, stream=None, timeout_ms: int = 0) -> None:
@@ -380,6 +383,9 @@ def bench_large_table(args, world: int, rank: int, local: int):
     # (a rank that has passed the wait of step j - lag may overwrite the set of step j - 2 lag
     # or older: S >= 2 lag). lag 0: wait on the launch stream itself.
     lag = min(int(getattr(args, "lt_lag", 0)), S // 2) if exchange == "fused" else 0
+    wait_mode = getattr(args, "lt_wait", None) or "kernel"  # barrier inside the kernel, or a wait kernel
+    if wait_mode == "kernel":
+        lag = 0
     cstream = torch.cuda.Stream(local) if lag > 0 else None
     ev_k = [torch.cuda.Event() for _ in range(S)]
     ev_c = [torch.cuda.Event() for _ in range(S)]
@@ -393,8 +399,11 @@ def bench_large_table(args, world: int, rank: int, local: int):
             s = j % S  # the sets rotate in launch order
             if lag > 0 and j >= lag:
                 stream.wait_event(ev_c[(j - lag) % S])
-            plan.run_sharded(reqs[s], blobs[s], ptrs, wss[s], peers[s].next_step(), stream=stream)
-            if lag == 0:
+            plan.run_sharded(reqs[s], blobs[s], ptrs, wss[s], peers[s].next_step(wait_mode == "kernel"),
+                             stream=stream)
+            if wait_mode == "kernel":
+                pass
+            elif lag == 0:
                 peers[s].wait(stream)
             else:
                 ev_k[j % S].record(stream)
@@ -459,15 +468,18 @@ def bench_large_table(args, world: int, rank: int, local: int):
                        "batch": batch, "table_bytes": model.table_bytes(),
                        "parallelism": (f"column-group x{world}, exchange fused into the kernel: rows stored straight into the "
                                        f"owners' [B/{world}, sum D] tensors over NVLink (IPC peer memory); completion "
-                                       f"flags stored to every peer by the kernel's last warp, one-warp wait kernel "
-                                       f"{'on the launch stream' if lag == 0 else f'on a second stream, launches run {lag} step(s) ahead'} (no NCCL call in the step)" if exchange == "fused" else
+                                       f"flags stored to every peer by the kernel's last warp, " +
+                                       ("which also waits for all ranks' flags: compute, exchange and barrier in one kernel"
+                                        if wait_mode == "kernel" else
+                                        f"one-warp wait kernel {'on the launch stream' if lag == 0 else f'on a second stream, launches run {lag} step(s) ahead'}") +
+                                       " (no NCCL call in the step)" if exchange == "fused" else
                                        f"column-group x{world}, NCCL all-gather of [B, W_g] slices" if exchange == "all_gather"
                                        else f"column-group x{world}, NCCL all-to-all of [B/{world}, W_g] row blocks "
                                             f"(every rank keeps its B/{world} rows of the concat tensor)"),
                        "l2": f"rotating {S} request/output sets"},
             "roofline": {"bound": "hbm", "achieved": float(alg_t[0]) / (ms * 1e-3) / 1e9,
                          "unit": "GB/s", "note": "aggregate algorithmic bytes over all ranks / step time"},
-            "gpu_launches": (plan.last_launch_count() + (1 if exchange == "fused" else 0)) * K,
+            "gpu_launches": (plan.last_launch_count() + (1 if exchange == "fused" and wait_mode != "kernel" else 0)) * K,
         }), flush=True)
     if peers:
         barrier()

@@ -52,6 +52,16 @@ def main():
         got = mine_t.clone()
     torch.cuda.synchronize()
     assert not peers.timed_out()
+    # the barrier inside the kernel: no wait at all behind the launch
+    dist.barrier()
+    mine_t.fill_(float("nan"))
+    torch.cuda.synchronize()
+    dist.barrier()
+    plan.run_sharded(req, R.upload_blob(req, local), R.table_pointers(dev_tables), ws, peers.next_step(True))
+    got2 = mine_t.clone()
+    torch.cuda.synchronize()
+    assert not peers.timed_out()
+    assert torch.equal(got2[: got.shape[0]].nan_to_num(), got.nan_to_num())
     rpr = peers.rows_per_rank
     lo, hi = rank * rpr, min((rank + 1) * rpr, batch)
     np.testing.assert_array_equal(got.cpu().numpy()[: hi - lo], full.cpu().numpy()[lo:hi])

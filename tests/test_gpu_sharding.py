@@ -59,7 +59,7 @@ def test_fused_exchange_addressing_on_one_gpu(world, batch, bf16):
         ws = plan.alloc_workspace(batch, req.sparse_ids)
         so = L.ShardOut(world=world, col_offset=s.out_begin, global_width=m.out_width, rank=s.rank,
                         rows_per_rank=rpr, peer_out=ptrs.ctypes.data, peer_flags=fptrs.ctypes.data,
-                        epoch=7, reserved=0)
+                        epoch=7, flags=0)
         plan.run_sharded(req, R.upload_blob(req, 0), R.table_pointers(dev_tables), ws, so)
         torch.cuda.synchronize()
         plan.close()
@@ -76,6 +76,39 @@ def test_fused_exchange_addressing_on_one_gpu(world, batch, bf16):
     L.check(L.lib.recom_shard_wait(flags[0].data_ptr(), world, 8, 20, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert int(flags[0][L.SHARD_FLAG_WORDS - 1].item()) == 1
+
+
+def test_fused_exchange_world1_waits_in_kernel():
+    """World 1 with RECOM_SHARD_WAIT_IN_KERNEL: the launch signals itself, sees its own flag and
+    ends (the multi-rank case needs concurrent kernels: tests/nccl_shard_worker.py)."""
+    import torch
+    from recom_b200 import _lib as L
+    from recom_b200 import runtime as R
+
+    m = synth.mixed_model(40, seed=5, large_rows=1 << 12)
+    batch = 77
+    feats = synth.make_features(m, batch, seed=2, empty_frac=0.2)
+    tables = synth.make_tables_np(m)
+    req = pack_request(m, batch, feats)
+    full, _, status, _ = run_gpu(m, req, tables)
+    plan = R.Plan(m, device=0)
+    dev_tables = R.tables_from_numpy(m, tables, 0)
+    ws = plan.alloc_workspace(batch, req.sparse_ids)
+    out = torch.full((80, m.out_width), float("nan"), device="cuda:0")
+    flags = torch.zeros(L.SHARD_FLAG_WORDS, dtype=torch.int32, device="cuda:0")
+    ptrs = np.array([out.data_ptr()], dtype=np.uint64)
+    fptrs = np.array([flags.data_ptr()], dtype=np.uint64)
+    blob = R.upload_blob(req, 0)
+    for epoch in (1, 2, 3):
+        so = L.ShardOut(world=1, col_offset=0, global_width=m.out_width, rank=0, rows_per_rank=80,
+                        peer_out=ptrs.ctypes.data, peer_flags=fptrs.ctypes.data, epoch=epoch,
+                        flags=L.SHARD_WAIT_IN_KERNEL)
+        plan.run_sharded(req, blob, R.table_pointers(dev_tables), ws, so)
+    torch.cuda.synchronize()
+    v = flags.cpu().numpy()
+    assert v[0] == 3 and v[L.SHARD_FLAG_WORDS - 1] == 0
+    np.testing.assert_array_equal(out[:batch].cpu().numpy(), full)
+    plan.close()
 
 
 def test_fused_exchange_rejects_bad_arguments():
@@ -96,7 +129,7 @@ def test_fused_exchange_rejects_bad_arguments():
     for kw in (dict(world=0), dict(world=9), dict(rank=1), dict(rank=-1), dict(rows_per_rank=16), dict(rows_per_rank=32),
                dict(col_offset=4), dict(global_width=m.out_width - 4)):
         a = dict(world=1, col_offset=0, global_width=m.out_width, rank=0, rows_per_rank=64,
-                 peer_out=ptrs.ctypes.data, peer_flags=None, epoch=0, reserved=0)
+                 peer_out=ptrs.ctypes.data, peer_flags=None, epoch=0, flags=0)
         a.update(kw)
         with pytest.raises(L.RecomError):
             plan.run_sharded(req, blob, R.table_pointers(dev_tables), ws, L.ShardOut(**a))
