@@ -310,6 +310,9 @@ def run_ours(args):
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    # cudaProfilerStart/Stop bracket the timed region: `ncu --profile-from-start off` lists
+    # exactly the launches of the K timed steps (profiles/*_launches.csv)
+    torch.cuda.profiler.start()
     e0.record(stream)
     for i in range(K):
         st = run(h, refs[i % S])
@@ -317,6 +320,7 @@ def run_ours(args):
             L.check(st)
     e1.record(stream)
     barrier()
+    torch.cuda.profiler.stop()
     total_ms = e0.elapsed_time(e1)
 
     # per-step latency distribution (event pair per step)
