@@ -164,6 +164,7 @@ struct recom_plan {
   int ctas_per_sm = 2;
   double sparse_weight = 1.0; // scales the estimated cost of SPARSE warp tiles (schedule balance)
   int force_queue_warps = -1;  // >= 0: override the cost-proportional split (experiments)
+  double tail_split = 0.0;     // fraction of the resident warps' worth of final queue tiles cut in half
   int claim_ahead = 0;         // queue claims: 0 when a warp is free (measured best), 1 always one tile ahead, 2 ahead except near the end
   int hash_tile_rows = kHashTileRows;             // rows of a DENSE warp tile with hashed columns
   int sparse_rows_hash = kSparseRowsPerSubHash;   // SPARSE rows per lane group, hashed ids
@@ -756,6 +757,32 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
       queue_cost += p->tile_cost[s] * p->sparse_weight * rows_of[s] / p->slabs[s].tile_rows;
     }
   }
+  // The launch ends one tile after the queue runs dry: the last tiles of the queue (as many as
+  // tail_split x the resident warps) are cut once more, so that the tail is half a tile.
+  if (p->tail_split > 0 && !tt->queue.empty()) {
+    const int64_t warps = (int64_t)cap_ctas * kWarps;
+    const size_t n_tail = (size_t)std::min<double>((double)tt->queue.size(), p->tail_split * (double)warps);
+    std::vector<Tile> tail;
+    for (size_t i = tt->queue.size() - n_tail; i < tt->queue.size(); ++i) {
+      const Tile& t = tt->queue[i];
+      const DevSlab& sl = p->slabs[t.slab_id];
+      const int min_rows = sl.cls == kSlabSparse ? std::max(1, 32 / sl.num_chunks) : 2;
+      const int half = t.slab.tile_rows / 2;
+      if (half < min_rows || t.rows <= half) {
+        tail.push_back(t);
+        continue;
+      }
+      Tile a = t, b = t;
+      a.rows = half;
+      b.row_begin = t.row_begin + half;
+      b.rows = t.rows - half;
+      a.slab.tile_rows = b.slab.tile_rows = half;
+      tail.push_back(a);
+      tail.push_back(b);
+    }
+    tt->queue.resize(tt->queue.size() - n_tail);
+    tt->queue.insert(tt->queue.end(), tail.begin(), tail.end());
+  }
   std::vector<double> cost(fast.size());
   double fast_cost = 0;
   int64_t fast_tiles = 0;
@@ -1007,6 +1034,7 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
   };
   if (const char* e = getenv("RECOM_B200_QUEUE_WARPS")) p->force_queue_warps = atoi(e);
   if (const char* e = getenv("RECOM_B200_CLAIM_AHEAD")) p->claim_ahead = atoi(e);
+  if (const char* e = getenv("RECOM_B200_TAIL_SPLIT")) p->tail_split = atof(e);
   p->hash_tile_rows = pow2_env("RECOM_B200_HASH_TILE_ROWS", 4, 32, kHashTileRows);
   p->sparse_rows_hash = pow2_env("RECOM_B200_SPARSE_ROWS_HASH", 1, 8, kSparseRowsPerSubHash);
   p->sparse_rows = pow2_env("RECOM_B200_SPARSE_ROWS", 1, 8, kSparseRowsPerSub);
