@@ -189,7 +189,13 @@ def time_oracle(model, batch, n_sets, seconds, warmup, steps=None):
     reqs = [pack_request(model, batch, synth.make_features(model, batch, seed=100 + s))
             for s in range(n_sets)]
     out = np.zeros((batch, model.out_width), np.float32)
-    threads = O.num_threads()
+    # all the host cores this process may use; torchrun exports OMP_NUM_THREADS=1 to its
+    # workers, which must not shrink the CPU arm (only rank 0 runs it)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or O.num_threads()
+    threads = max(threads, O.num_threads())
 
     def one(r):
         rc = O.lib.oracle_run_model(descs.ctypes.data, len(descs), bnd.ctypes.data if bnd.size else None,
