@@ -283,6 +283,32 @@ __device__ __forceinline__ int32_t bucketize(const float* __restrict__ bnd, int3
   return o[0];
 }
 
+// One upper_bound through the set's grid (append_grid in capi.cu; the layout bucket_smem8 reads
+// from shared memory): header and cell word narrow the search to the candidates of the value's
+// cell - usually one boundary - so a queue tile pays three dependent loads per id instead of
+// log2(n) + 1. Exact for every float (the cells were built over the whole key space); NaN
+// compares false with everything: the last bucket.
+__device__ __forceinline__ int32_t bucketize_grid(const float* __restrict__ bnd, int32_t nb,
+                                                  float v) {
+  if (nb <= 0) return 0;  // no boundaries, no set in the pool
+  const float* hdr = bnd + ((nb + 3) & ~3);
+  const float b0 = hdr[0], inv = hdr[1];
+  const int32_t cells = __float_as_int(hdr[2]);
+  int32_t cell = __float2int_rz((v - b0) * inv);
+  cell = min(max(cell, 0), cells - 1);
+  const uint32_t w = __float_as_uint(hdr[4 + cell]);
+  if (v != v) return nb;
+  int32_t lo = (int32_t)(w & 0xffffu);
+  const int32_t hi = (int32_t)(w >> 16);
+  for (int32_t n = hi - lo; n > 0; n >>= 1) {
+    const int32_t idx = lo + (n >> 1);
+    const float b = bnd[min(idx, nb - 1)];
+    const bool right = idx < hi && !(v < b);
+    lo = right ? idx + 1 : lo;
+  }
+  return lo;
+}
+
 // ---------------------------------------------------------------------------
 // raw value -> row id, N at a time
 // ---------------------------------------------------------------------------
@@ -342,9 +368,17 @@ __device__ __noinline__ int32_t finish_id(const ColCtx& c, const float* __restri
       return c.value_dtype == RECOM_I32 ? (int32_t)(uint32_t)raw : (int32_t)(long long)raw;
     case RECOM_XFORM_BUCKETIZE: {
       switch (c.value_dtype) {
+#ifndef RECOM_NO_GRID_BUCKETIZE
+        // integers compare as floats (`value < boundary` converts the integer, like TF's
+        // upper_bound over float boundaries does): the same search on the converted value
+        case RECOM_F32: return bucketize_grid(bnd, c.num_boundaries, __uint_as_float((uint32_t)raw));
+        case RECOM_I32: return bucketize_grid(bnd, c.num_boundaries, (float)(int32_t)(uint32_t)raw);
+        case RECOM_I64: return bucketize_grid(bnd, c.num_boundaries, (float)(long long)raw);
+#else
         case RECOM_F32: return bucketize<float>(bnd, c.num_boundaries, __uint_as_float((uint32_t)raw));
         case RECOM_I32: return bucketize<int32_t>(bnd, c.num_boundaries, (int32_t)(uint32_t)raw);
         case RECOM_I64: return bucketize<long long>(bnd, c.num_boundaries, (long long)raw);
+#endif
         default: return bucketize<double>(bnd, c.num_boundaries, __longlong_as_double((long long)raw));
       }
     }

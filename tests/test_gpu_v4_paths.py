@@ -69,6 +69,47 @@ def test_bucketize_grid_is_exact_on_edge_values(batch):
     np.testing.assert_array_equal(got, ref)
 
 
+@pytest.mark.parametrize("batch", [61, 600])
+def test_bucketize_grid_on_queue_tiles_all_value_dtypes(batch):
+    """Bucketize columns that do NOT form fast groups (mixed value dtypes, dims and a hashed
+    neighbour) go through the queue's generic tiles, whose search reads the set's grid from the
+    global pool (bucketize_grid): float32, int32 and int64 values (integers compare as floats,
+    like TF's upper_bound over float boundaries), multi-hot bucketize, every edge set."""
+    sets = _boundary_sets()
+    names = sorted(sets)
+    cols, tables, feats = [], [], {}
+    rng = np.random.default_rng(batch)
+    big = [0, 1, -1, 2**24, 2**24 + 1, -(2**24) - 1, 2**31 - 1, -(2**31), 16777217, 33554433]
+    for i in range(3 * len(names)):
+        b = sets[names[i % len(names)]]
+        dt = (L.F32, L.I32, L.I64)[i // len(names)]
+        dim = (8, 16, 32)[i % 3]
+        cols.append(Column(f"c{i}", L.LOOKUP_DENSE, L.XFORM_BUCKETIZE, dt, i, len(b) + 1, dim, boundaries=b))
+        tables.append((len(b) + 1, dim))
+        v = _edge_values(b, batch, rng)
+        if dt == L.F32:
+            vals = v
+        else:
+            with np.errstate(invalid="ignore"):
+                iv = np.nan_to_num(v, nan=0.0, posinf=2e9, neginf=-2e9).clip(-2e9, 2e9)
+            wide = np.int64 if dt == L.I64 else np.int32
+            vals = np.rint(iv).astype(np.int64)
+            vals[: len(big)] = big
+            if dt == L.I64:
+                vals[len(big): len(big) + 4] = [2**40 + 1, -(2**40) - 1, 2**62, -(2**62)]
+            else:
+                vals = vals.clip(-(2**31), 2**31 - 1)
+            vals = vals.astype(wide)
+        feats[cols[-1].key] = Feature(np.resize(vals, batch))
+    n = len(cols)
+    cols.append(Column("h", L.LOOKUP_DENSE, L.XFORM_HASH_INT, L.I32, n, 97, 8, num_buckets=97))
+    tables.append((97, 8))
+    feats[cols[-1].key] = Feature(rng.integers(0, 1000, batch).astype(np.int32))
+    m = Model(cols, tables).finalize()
+    req, got, ref = assert_parity(m, batch, feats, synth.make_tables_np(m))
+    np.testing.assert_array_equal(got, ref)
+
+
 def test_same_plan_many_requests_resets_its_queue_counters():
     """The queue's claim counters live in plan-owned slots that the last warp of a launch
     resets; results must not depend on how many launches (or which batch sizes) came before."""
