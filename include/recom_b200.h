@@ -29,6 +29,11 @@
  *       scattered into their concat slices.
  *   recom_segment_ids_to_row_splits
  *       replaces experiment::ComputeSegmentOffsets (cuda_emitter.cc:768-818).
+ *   recom_plan_run_sharded, recom_shard_wait, recom_ipc_alloc/open/close/free
+ *       no counterpart in the reference (one GPU + CPU spill, tf_cpu_gpu_pass):
+ *       column groups on several GPUs of one NVSwitch box, every row's slice
+ *       stored straight into the concat tensor of the GPU that owns the row,
+ *       exchange and barrier inside the same kernel.
  *
  * No C++ types, no torch types: plain pointers and sizes only. Every function
  * returns a recom_status; recom_last_error() gives a thread-local message. The
