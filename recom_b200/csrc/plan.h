@@ -13,7 +13,7 @@
 namespace recom {
 
 #ifndef RECOM_THREADS
-#define RECOM_THREADS 384
+#define RECOM_THREADS 320
 #endif
 constexpr int kThreads = RECOM_THREADS;  // threads per CTA
 constexpr int kWarps = kThreads / 32;
