@@ -256,6 +256,13 @@ def run_reference(args):
 def run_ours(args):
     import ctypes as C
 
+    if args.workload == "large_table" and not os.environ.get("RECOM_B200_LIB"):
+        # multi-hot columns over large tables: the 12-warps-per-CTA flavour of the library
+        # (recom_b200/_lib.py); must be chosen before the package loads its library
+        w12 = os.path.join(ROOT, "recom_b200", "librecom_b200_w12.so")
+        if os.path.exists(w12):
+            os.environ["RECOM_B200_LIB"] = w12
+
     import torch
     import torch.distributed as dist
 

@@ -22,6 +22,8 @@ NVLink) is described in DESIGN.md.
 """
 from __future__ import annotations
 
+import os
+
 import copy
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -476,7 +478,8 @@ def bench_large_table(args, world: int, rank: int, local: int):
                                        f"column-group x{world}, NCCL all-gather of [B, W_g] slices" if exchange == "all_gather"
                                        else f"column-group x{world}, NCCL all-to-all of [B/{world}, W_g] row blocks "
                                             f"(every rank keeps its B/{world} rows of the concat tensor)"),
-                       "l2": f"rotating {S} request/output sets"},
+                       "l2": f"rotating {S} request/output sets",
+                       "library": os.path.basename(L.LIB_PATH)},
             "roofline": {"bound": "hbm", "achieved": float(alg_t[0]) / (ms * 1e-3) / 1e9,
                          "unit": "GB/s", "note": "aggregate algorithmic bytes over all ranks / step time"},
             "gpu_launches": (plan.last_launch_count() + (1 if exchange == "fused" and wait_mode != "kernel" else 0)) * K,
