@@ -10,7 +10,7 @@ import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
     except Exception: continue
-    print('rep$rep %-10s %-20s us/step %7.2f p50 %7.2f' % ('${v:-base}', d['config']['workload'], d['ms_per_step']*1e3, d['p50_ms']*1e3))
+    print('rep$rep %-10s %-20s us/step %7.2f p50 %7.2f' % ('${v:-default}', d['config']['workload'], d['ms_per_step']*1e3, d['p50_ms']*1e3))
 "
   done
 done
