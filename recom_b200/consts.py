@@ -1,0 +1,36 @@
+"""Enums and record layouts of include/recom_b200.h as plain Python (no native code).
+
+Split from `_lib` so that the workload generators (`schema`, `synth`) can be used by the CPU
+reference arm of bench.py without mapping librecom_b200.so into that process. The product
+package itself (`import recom_b200`) always loads the library and fails loudly without it.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# enums (include/recom_b200.h)
+OK = 0
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WORKSPACE_TOO_SMALL = 1, 2, 3
+ERR_UNSUPPORTED, ERR_OUT_OF_MEMORY, ERR_ID_OUT_OF_RANGE = 4, 5, 6
+F32, BF16, I32, I64, STR, F64 = 0, 1, 2, 3, 4, 5
+LOOKUP_DENSE, LOOKUP_GATHER_SCATTER, LOOKUP_SEGMENT = 0, 1, 2
+COMBINE_SUM, COMBINE_MEAN, COMBINE_SQRTN = 0, 1, 2
+XFORM_NONE, XFORM_BUCKETIZE, XFORM_HASH_STR, XFORM_HASH_INT = 0, 1, 2, 3
+SEG_NONE, SEG_ROW_SPLITS_I32, SEG_COO_I64 = 0, 1, 2
+
+DTYPE_BYTES = {F32: 4, BF16: 2, I32: 4, I64: 8, STR: 4, F64: 8}
+
+# numpy mirror of struct recom_column_desc (natural C alignment)
+COLUMN_DESC = np.dtype(
+    [
+        ("lookup", "<i4"), ("combiner", "<i4"), ("transform", "<i4"), ("value_dtype", "<i4"),
+        ("table", "<i4"), ("table_dtype", "<i4"), ("table_rows", "<i8"),
+        ("dim", "<i4"), ("out_offset", "<i4"), ("value_slot", "<i4"), ("bytes_slot", "<i4"),
+        ("seg_slot", "<i4"), ("seg_format", "<i4"), ("seg_stride", "<i4"),
+        ("num_boundaries", "<i4"), ("boundaries_offset", "<i8"), ("num_buckets", "<i8"),
+    ],
+    align=True,
+)
+assert COLUMN_DESC.itemsize == 80
+
+

@@ -186,6 +186,11 @@ struct recom_plan {
   // flight (a slot comes round again after kCounterSlots later requests of this plan)
   int32_t* d_counters = nullptr;
   std::atomic<uint32_t> counter_next{0};
+  // Blocking uploads of the caches (first use of a batch size / second sight of an argument
+  // block) go through this stream and are complete when the device pointer is published: a
+  // plain cudaMemcpy from pageable memory is ordered on the legacy stream only, which does not
+  // order it before kernels on the caller's non-blocking streams.
+  cudaStream_t up_stream = nullptr;
   // pinned argument ring of the upload path (first sight of a block, COO inputs, full caches)
   ArgSlot ring[kRing];
   std::atomic<uint32_t> ring_next{0};
@@ -228,18 +233,29 @@ recom_status validate_columns(const recom_column_desc* cols, int32_t n, const re
         if (c.num_boundaries < 0 || c.boundaries_offset < 0 ||
             c.boundaries_offset + c.num_boundaries > num_boundaries)
           return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: boundaries out of range", i);
+        // ids are 0..num_boundaries (bucketize_op.cc:42-44): they must index the table
+        if ((int64_t)c.num_boundaries + 1 > c.table_rows)
+          return fail(RECOM_ERR_INVALID_ARGUMENT,
+                      "column %d: %d boundaries give ids up to %d, table has %lld rows", i,
+                      c.num_boundaries, c.num_boundaries, (long long)c.table_rows);
         break;
       case RECOM_XFORM_HASH_STR:
         if (c.value_dtype != RECOM_STR || c.bytes_slot < 0 || c.bytes_slot >= cfg.num_slots)
           return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: HASH_STR needs STR values + bytes_slot", i);
         if (c.num_buckets <= 0 || c.num_buckets > 0x7fffffffLL)
           return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: num_buckets unsupported", i);
+        if (c.num_buckets > c.table_rows)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: num_buckets %lld exceeds table_rows %lld",
+                      i, (long long)c.num_buckets, (long long)c.table_rows);
         break;
       case RECOM_XFORM_HASH_INT:
         if (c.value_dtype != RECOM_I32 && c.value_dtype != RECOM_I64)
           return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: HASH_INT needs I32/I64 values", i);
         if (c.num_buckets <= 0 || c.num_buckets > 0x7fffffffLL)
           return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: num_buckets unsupported", i);
+        if (c.num_buckets > c.table_rows)
+          return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: num_buckets %lld exceeds table_rows %lld",
+                      i, (long long)c.num_buckets, (long long)c.table_rows);
         break;
       default:
         return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: unknown transform %d", i, c.transform);
@@ -260,6 +276,21 @@ recom_status validate_columns(const recom_column_desc* cols, int32_t n, const re
         return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: unknown combiner", i);
     } else {
       return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: unknown lookup kind", i);
+    }
+  }
+  // columns that share a table must describe the same table
+  {
+    std::vector<int32_t> first(cfg.num_tables, -1);
+    for (int32_t i = 0; i < n; ++i) {
+      const int32_t f = first[cols[i].table];
+      if (f < 0) {
+        first[cols[i].table] = i;
+      } else if (cols[f].table_rows != cols[i].table_rows || cols[f].dim != cols[i].dim ||
+                 cols[f].table_dtype != cols[i].table_dtype) {
+        return fail(RECOM_ERR_INVALID_ARGUMENT,
+                    "columns %d and %d share table %d but declare different shapes", f, i,
+                    cols[i].table);
+      }
     }
   }
   // output slices must not overlap
@@ -307,7 +338,16 @@ void append_grid(std::vector<float>& pool, const std::vector<float>& b) {
   const int nb = (int)b.size();
   int G = 1;
   float b0 = 0.f, inv = 0.f;
-  bool ok = nb >= 8 && nb <= 65535;
+  if (nb > 65535) {
+    // lo | hi << 16 cannot describe such a set: header with cells = 0, the kernel falls back to
+    // the plain upper_bound over the whole set (bucketize_grid in kernels.cu)
+    pool.push_back(0.f);
+    pool.push_back(0.f);
+    pool.push_back(0.f);
+    pool.push_back(0.f);
+    return;
+  }
+  bool ok = nb >= 8;
   if (ok) {
     for (float x : b) ok = ok && std::isfinite(x);
     ok = ok && b[nb - 1] > b[0];
@@ -709,7 +749,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     int64_t rpt = (t.rows + dw * k - 1) / (dw * k);
     rpt = std::min<int64_t>(trmax, std::max<int64_t>(rpt, std::min<int64_t>(8, trmax)));
     t.slab.run_tile_rows = (int16_t)rpt;
-    t.slab.run_tiles = (int16_t)std::min<int64_t>(32767, (t.rows + rpt - 1) / rpt);
+    t.slab.run_tiles = (int32_t)((t.rows + rpt - 1) / rpt);
   };
   // Small batches: with fewer tiles than resident warps the launch lasts as long as its longest
   // tile, so the queue's tiles are cut finer (down to one row per lane group / 2 rows of a hashed
@@ -862,6 +902,14 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
 
 constexpr size_t kMaxCachedTileTables = 512;
 
+// Host -> device copy that has fully landed when this returns, whatever stream the caller will
+// launch on (see recom_plan::up_stream).
+cudaError_t blocking_upload(recom_plan* p, void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, p->up_stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(p->up_stream);
+}
+
 // Cached (device resident) schedule of a batch size, or nullptr when the cache is full:
 // the caller then ships the schedule inside the request's argument block.
 std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, recom_status* st) {
@@ -875,7 +923,7 @@ std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, recom_st
   tt->write(host.data());
   // first use of a batch size (warm-up): a blocking allocation + copy
   if (cudaMalloc(&tt->d_block, host.size()) != cudaSuccess ||
-      cudaMemcpy(tt->d_block, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      blocking_upload(p, tt->d_block, host.data(), host.size()) != cudaSuccess) {
     *st = fail(RECOM_ERR_CUDA, "tile table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     return nullptr;
   }
@@ -1055,6 +1103,8 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
       p->prof_path = e;
       if (cudaMalloc((void**)&p->d_prof, (size_t)p->num_sms * 4 * kWarps * 8 * 8) != cudaSuccess) p->d_prof = nullptr;
     }
+    if (cudaStreamCreateWithFlags(&p->up_stream, cudaStreamNonBlocking) != cudaSuccess)
+      st = fail(RECOM_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (cudaMalloc((void**)&p->d_counters, (size_t)kCounterSlots * 8) != cudaSuccess ||
         cudaMemset(p->d_counters, 0, (size_t)kCounterSlots * 8) != cudaSuccess)
       st = fail(RECOM_ERR_CUDA, "counter ring allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1098,6 +1148,7 @@ recom_status recom_plan_destroy(recom_plan* p) {
     if (e->dev) cudaFree(e->dev);
   if (p->d_counters) cudaFree(p->d_counters);
   if (p->d_block) cudaFree(p->d_block);
+  if (p->up_stream) cudaStreamDestroy(p->up_stream);
   delete p;
   return RECOM_OK;
 }
@@ -1260,12 +1311,32 @@ recom_status recom_plan_run_sharded(const recom_plan* cp, const recom_request* r
   return run_impl(cp, req, so);
 }
 
+namespace {
+// The plan's allocations, cached uploads and launches belong to cfg.device; the caller's current
+// device may be another one (multi-GPU hosts). Switch for the duration of the call only.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess || prev == device) return e;
+    switched = true;
+    return cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+
 static recom_status run_impl(const recom_plan* cp, const recom_request* req, const recom_shard_out* so) {
   g_last_launches = 0;
   g_host_prof.start();
   g_host_prof.calls++;
   if (!cp || !req) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
   recom_plan* p = const_cast<recom_plan*>(cp);  // only internally locked caches mutate
+  DeviceGuard guard;
+  CUDA_TRY(guard.enter(p->cfg.device));
   recom_request head = *req;
   if (so) head.out = so->peer_out[0];
   recom_status st = validate_request_head(p, &head);
@@ -1367,7 +1438,7 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
         std::unique_ptr<ArgEntry> e(new ArgEntry());
         e->host.assign(h, h + args_bytes);
         if (cudaMalloc((void**)&e->dev, args_bytes) == cudaSuccess &&
-            cudaMemcpy(e->dev, h, args_bytes, cudaMemcpyHostToDevice) == cudaSuccess) {
+            blocking_upload(p, e->dev, h, args_bytes) == cudaSuccess) {
           d_args = e->dev;
           p->arg_cache.push_back(std::move(e));
         } else {

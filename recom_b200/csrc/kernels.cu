@@ -294,6 +294,7 @@ __device__ __forceinline__ int32_t bucketize_grid(const float* __restrict__ bnd,
   const float* hdr = bnd + ((nb + 3) & ~3);
   const float b0 = hdr[0], inv = hdr[1];
   const int32_t cells = __float_as_int(hdr[2]);
+  if (cells == 0) return bucketize<float>(bnd, nb, v);  // more than 65535 boundaries: no grid
   int32_t cell = __float2int_rz((v - b0) * inv);
   cell = min(max(cell, 0), cells - 1);
   const uint32_t w = __float_as_uint(hdr[4 + cell]);

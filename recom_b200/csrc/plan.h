@@ -146,10 +146,9 @@ struct DevSlab {
   uint32_t fast8_mask;  // bit g: columns [8g, 8g+8) are float32 bucketize with staged boundaries
   uint32_t uni8_mask;   // ... and share one boundary set
   int16_t all_fast;     // every column belongs to a fast group
-  int16_t pad;
   // DENSE run only (filled per run by the scheduler)
   int16_t run_tile_rows;  // rows of this run's warp tiles (<= tile_rows)
-  int16_t run_tiles;      // number of warp tiles of this run
+  int32_t run_tiles;      // number of warp tiles of this run
 
 };
 static_assert(sizeof(DevSlab) == 64, "DevSlab layout");

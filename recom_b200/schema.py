@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
-from . import _lib as L
+from . import consts as L
 
 NP_OF = {L.F32: np.float32, L.I32: np.int32, L.I64: np.int64, L.F64: np.float64}
 

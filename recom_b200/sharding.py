@@ -67,6 +67,9 @@ def partition_columns(model: Model, world: int, max_table_bytes: Optional[int] =
     optionally bounded by table bytes per rank. Deterministic: every rank computes the same
     partition from the same model."""
     assert world >= 1
+    if world > len(model.columns):
+        raise ValueError(f"{len(model.columns)} columns cannot be split over {world} ranks "
+                         "(every rank needs at least one column)")
     es = 2 if model.out_dtype == L.BF16 else 4
     order = sorted(range(len(model.columns)), key=lambda i: model.columns[i].out_offset)
     assert order == list(range(len(model.columns))), "model columns must be in concat order"
@@ -76,7 +79,8 @@ def partition_columns(model: Model, world: int, max_table_bytes: Optional[int] =
     for g in range(1, world):
         target = cum[-1] * g / world
         k = int(np.searchsorted(cum, target, side="left"))
-        k = min(max(k, cuts[-1] + (1 if len(model.columns) - cuts[-1] > world - g else 0)), len(model.columns))
+        # at least one column for this rank and for each of the ranks still to come
+        k = min(max(k, cuts[-1] + 1), len(model.columns) - (world - g))
         cuts.append(k)
     cuts.append(len(model.columns))
     shards = []
@@ -135,9 +139,16 @@ def all_gather_columns(local_out, shards: Sequence[ColumnShard], group=None):
     return torch.cat([gathered[g, :, :shards[g].width] for g in range(world)], dim=1)
 
 
+def rows_per_rank(batch: int, world: int) -> int:
+    """Row ownership of every Mode-A exchange (all-to-all and the fused peer stores alike):
+    blocks of ceil(batch / world) rows, the last ranks may own fewer (or none)."""
+    return (batch + world - 1) // world
+
+
 def batch_rows(batch: int, world: int, rank: int) -> Tuple[int, int]:
-    """Rows [lo, hi) of the batch that rank `rank` keeps after the all-to-all exchange."""
-    return batch * rank // world, batch * (rank + 1) // world
+    """Rows [lo, hi) of the batch that rank `rank` owns after the exchange."""
+    rpr = rows_per_rank(batch, world)
+    return min(batch, rank * rpr), min(batch, (rank + 1) * rpr)
 
 
 def all_to_all_columns(local_out, shards: Sequence[ColumnShard], group=None):
@@ -182,7 +193,12 @@ class PeerOutputs:
 
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.rows_per_rank = (batch + self.world - 1) // self.world
+        self.rows_per_rank = rows_per_rank(batch, self.world)
+        if self.rows_per_rank < 32:
+            raise ValueError(f"fused exchange needs >= 32 rows per rank (batch {batch} over "
+                             f"{self.world} ranks gives {self.rows_per_rank}): use all_to_all_columns")
+        if len(shards) != self.world or any(s.last_col <= s.first_col for s in shards):
+            raise ValueError("every rank needs a non-empty column shard")
         self.out_width, self.elem_bytes = out_width, elem_bytes
         self.nbytes = self.rows_per_rank * out_width * elem_bytes
         # the completion flags (recom_b200.h, RECOM_SHARD_FLAG_WORDS) follow the tensor

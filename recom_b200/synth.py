@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from . import _lib as L
+from . import consts as L
 from .schema import Column, Feature, Model, Strings
 
 ALPHABET = np.frombuffer(
