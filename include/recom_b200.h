@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define RECOM_B200_ABI_VERSION 1
+#define RECOM_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RECOM_API __attribute__((visibility("default")))
@@ -158,6 +158,11 @@ typedef struct recom_request {
                          column order: the row id every gather used (parity hook) */
   int32_t *status_out; /* optional device int32: set !=0 on id-range violation */
   recom_stream_t stream;
+  int64_t args_offset; /* byte offset inside `blob` of the argument trailer that
+                          recom_concat_inputs_with_args appended (the slot offsets and element
+                          counts, device readable): recom_plan_run then uploads nothing per
+                          request. -1: the blob has no trailer; the two host arrays are staged
+                          through pinned memory into the workspace (one small H2D copy). */
 } recom_request;
 
 RECOM_API const char *recom_last_error(void);
@@ -282,6 +287,18 @@ RECOM_API recom_status recom_fingerprint64(const uint8_t *bytes, const int32_t *
 RECOM_API recom_status recom_concat_inputs(const void *const *inputs, const int64_t *nbytes,
                                  int32_t num_inputs, void *blob, size_t blob_bytes,
                                  int64_t *offsets, size_t *needed);
+
+/* The same, followed by the request's argument trailer: {magic, num_inputs, offsets[num_inputs],
+ * elems[num_inputs]} (int64 each) at byte *args_offset of the blob (16-byte aligned, past the last
+ * slot). `elems` are the element counts of the inputs (the products of the `shapes` the
+ * reference op outputs). A request whose blob carries the trailer (recom_request.args_offset)
+ * makes recom_plan_run upload nothing: the one H2D copy of the blob brings the arguments along
+ * (the reference uploads KnlArgs and SymbolResults on every call, cuda_emitter.cc:2182-2232). */
+RECOM_API recom_status recom_concat_inputs_with_args(const void *const *inputs,
+                                           const int64_t *nbytes, const int64_t *elems,
+                                           int32_t num_inputs, void *blob, size_t blob_bytes,
+                                           int64_t *offsets, int64_t *args_offset,
+                                           size_t *needed);
 
 /* Addons>ShapeConstruct (tensorflow_addons/custom_ops/shape_construct/shape_construct_ops.cc:34-153):
  * run-time evaluation of size expressions over named symbols (num_segments, reshape

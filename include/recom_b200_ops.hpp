@@ -138,6 +138,7 @@ class FeatureColumnProcess {
     r.workspace_bytes = buffer_bytes;
     r.status_out = status_out;
     r.stream = stream;
+    r.args_offset = -1;
     check(recom_plan_run(plan_, &r));
   }
 

@@ -35,7 +35,7 @@ class Request(C.Structure):
         ("batch", C.c_int64), ("blob", C.c_void_p), ("slot_offsets", C.c_void_p),
         ("slot_elems", C.c_void_p), ("tables", C.c_void_p), ("out", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("ids_out", C.c_void_p),
-        ("status_out", C.c_void_p), ("stream", C.c_void_p),
+        ("status_out", C.c_void_p), ("stream", C.c_void_p), ("args_offset", C.c_int64),
     ]
 
 
@@ -63,7 +63,7 @@ EXPORTS = [
     "recom_plan_out_width", "recom_plan_workspace_bytes", "recom_plan_run",
     "recom_last_launch_count", "recom_plan_algorithmic_bytes", "recom_scatter_columns",
     "recom_segment_ids_to_row_splits", "recom_string_to_hash_bucket_fast", "recom_fingerprint64",
-    "recom_concat_inputs", "recom_shape_construct_create", "recom_shape_construct_eval",
+    "recom_concat_inputs", "recom_concat_inputs_with_args", "recom_shape_construct_create", "recom_shape_construct_eval",
     "recom_shape_construct_destroy", "recom_plan_run_sharded", "recom_ipc_alloc", "recom_ipc_open",
     "recom_ipc_close", "recom_ipc_free", "recom_shard_wait",
 ]
@@ -102,6 +102,7 @@ def _load() -> C.CDLL:
         "recom_string_to_hash_bucket_fast": [vp, vp, i64, i64, vp, vp],
         "recom_fingerprint64": [vp, vp, i64, vp, vp],
         "recom_concat_inputs": [vp, vp, i32, vp, sz, vp, C.POINTER(sz)],
+        "recom_concat_inputs_with_args": [vp, vp, vp, i32, vp, sz, vp, C.POINTER(i64), C.POINTER(sz)],
         "recom_shape_construct_create": [vp, i32, vp, i32, C.POINTER(vp)],
         "recom_shape_construct_eval": [vp, vp, i32, vp, i32],
         "recom_shape_construct_destroy": [vp],

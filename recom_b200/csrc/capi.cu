@@ -73,8 +73,9 @@ namespace {
   } while (0)
 
 constexpr int kRing = 16;       // pinned staging slots of the upload path
-constexpr int kArgCache = 16;   // device-resident argument blocks kept per plan
-constexpr int kCounterSlots = 1024;
+constexpr int kTableSets = 8;   // device-resident table pointer arrays kept per plan
+constexpr int kCounterSlots = 64;  // requests of one plan in flight at once (more: the call waits)
+constexpr int kCounterInts = 4; // per slot: queue claims, finished warps, transform tasks done, -
 
 struct ArgSlot {
   std::mutex mu;
@@ -84,12 +85,13 @@ struct ArgSlot {
   bool in_flight = false;
 };
 
-// A device-resident copy of a request's argument block, keyed by content. Entries are
+// A device-resident copy of a request's table pointer array, keyed by content. Entries are
 // immutable once published and live until the plan dies, so kernels in flight on any stream
-// may read them without further synchronisation.
-struct ArgEntry {
-  std::vector<uint8_t> host;
-  uint8_t* dev = nullptr;
+// may read them without further synchronisation. (Tables are the graph's variables: a serving
+// process passes the same addresses on every call.)
+struct TableSet {
+  std::vector<const void*> host;
+  const void** dev = nullptr;
 };
 
 int dtype_bytes(int32_t dt) {
@@ -108,32 +110,29 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Schedule of one batch size (see Sched in plan.h).
 struct TileTable {
-  std::vector<Tile> runs;      // FAST runs grouped by CTA
-  std::vector<Tile> queue;     // queue of warp tiles, descending cost
-  std::vector<CtaWork> cta;    // [grid]
+  std::vector<Tile> runs;        // FAST runs grouped by CTA
+  std::vector<ColItem> queue;    // column tiles
+  std::vector<CtaWork> cta;      // [grid]
   int grid = 1;
-  int queue_warps = 0;
-  int claim_ahead = 0;
   void* d_block = nullptr;  // device copy: runs, queue, cta (cached tables only)
   ~TileTable() {
     if (d_block) cudaFree(d_block);
   }
   size_t runs_bytes() const { return align_up(runs.size() * sizeof(Tile), 16); }
-  size_t queue_bytes() const { return align_up(queue.size() * sizeof(Tile), 16); }
+  size_t queue_bytes() const { return align_up(queue.size() * sizeof(ColItem), 16); }
   size_t bytes() const { return runs_bytes() + queue_bytes() + cta.size() * sizeof(CtaWork); }
   void write(uint8_t* dst) const {
     if (!runs.empty()) memcpy(dst, runs.data(), runs.size() * sizeof(Tile));
-    if (!queue.empty()) memcpy(dst + runs_bytes(), queue.data(), queue.size() * sizeof(Tile));
+    if (!queue.empty()) memcpy(dst + runs_bytes(), queue.data(), queue.size() * sizeof(ColItem));
     memcpy(dst + runs_bytes() + queue_bytes(), cta.data(), cta.size() * sizeof(CtaWork));
   }
   Sched sched(const void* base) const {
     Sched s{};
-    s.runs = (const Tile*)base;
-    s.queue = (const Tile*)((const uint8_t*)base + runs_bytes());
-    s.cta = (const CtaWork*)((const uint8_t*)base + runs_bytes() + queue_bytes());
+    const uint8_t* b = (const uint8_t*)base;
+    s.runs = (const Tile*)b;
+    s.queue = (const ColItem*)(b + runs_bytes());
+    s.cta = (const CtaWork*)(b + runs_bytes() + queue_bytes());
     s.num_queue = (int32_t)queue.size();
-    s.queue_warps = queue_warps;
-    s.claim_ahead = claim_ahead;
     return s;
   }
 };
@@ -153,8 +152,10 @@ struct recom_plan {
   std::vector<float> boundary_pool;
   std::map<int32_t, int32_t> set_words;  // pool offset of a boundary set -> its words incl. grid
   std::vector<int32_t> sparse_cols;  // column index of each non-DENSE column
-  std::vector<int32_t> coo_cols;     // column index of each COO column
-  std::vector<int32_t> slab_order;   // slabs sorted for scheduling (heavy first)
+  std::vector<ColItem> units;        // queue units: distinct (input, transform, segments) triples
+  std::vector<ColUser> users;        // the columns reading each unit (ColItem::first_user)
+  std::vector<double> unit_cost;     // estimated cost of a full tile of a unit
+  std::vector<DevCoo> coos;          // distinct COO inputs
   std::vector<double> tile_cost;     // estimated warp instructions of one warp tile of a slab
   // device
   void* d_block = nullptr;
@@ -162,13 +163,8 @@ struct recom_plan {
   int elem_bytes = 4;
   int num_sms = 148;
   int ctas_per_sm = 2;
-  double sparse_weight = 1.0; // scales the estimated cost of SPARSE warp tiles (schedule balance)
-  int force_queue_warps = -1;  // >= 0: override the cost-proportional split (experiments)
-  double tail_split = 0.0;     // fraction of the resident warps' worth of final queue tiles cut in half
-  int claim_ahead = 0;         // queue claims: 0 when a warp is free (measured best), 1 always one tile ahead, 2 ahead except near the end
-  int hash_tile_rows = kHashTileRows;             // rows of a DENSE warp tile with hashed columns
-  int sparse_rows_hash = kSparseRowsPerSubHash;   // SPARSE rows per lane group, hashed ids
-  int sparse_rows = kSparseRowsPerSub;            // ... ids given
+  int col_rows_dense = kColTileRowsDense;    // rows of a column tile, one id per row (<= 128)
+  int col_rows_sparse = kColTileRowsSparse;  // rows of a multi-hot column tile (<= 32)
   // tile tables depend only on the batch size: cached (read-mostly)
   std::mutex tiles_mu;
   std::map<int64_t, std::shared_ptr<const TileTable>> tiles_by_batch;
@@ -177,14 +173,15 @@ struct recom_plan {
   uint64_t* d_prof = nullptr;
   int prof_grid = 0;
   std::string prof_path;
-  // device-resident argument blocks, keyed by content (steady state: no upload at all)
-  std::mutex args_mu;
-  std::vector<std::unique_ptr<ArgEntry>> arg_cache;
-  std::vector<uint64_t> seen;      // hashes of recent blocks: a block is cached at its second sight
-  bool cache_args = true;
-  // queue claim counters: a ring of self-resetting slots in device memory, one per request in
-  // flight (a slot comes round again after kCounterSlots later requests of this plan)
+  // device-resident table pointer arrays, keyed by content
+  std::mutex tables_mu;
+  std::vector<std::unique_ptr<TableSet>> table_sets;
+  // queue counters: a ring of slots in device memory, one per request in flight. The kernel's
+  // last warp resets the slot and stores the request's sequence number into the slot's word of
+  // `done_seq` (host-mapped): a slot is handed out again only when its previous user is done.
   int32_t* d_counters = nullptr;
+  uint32_t* h_done_seq = nullptr;  // pinned, mapped
+  uint32_t* d_done_seq = nullptr;  // device address of the same words
   std::atomic<uint32_t> counter_next{0};
   // Blocking uploads of the caches (first use of a batch size / second sight of an argument
   // block) go through this stream and are complete when the device pointer is published: a
@@ -441,8 +438,11 @@ void build_layout(recom_plan* p) {
       c.sparse_index = (int32_t)p->sparse_cols.size();
       p->sparse_cols.push_back(i);
       if (d.seg_format == RECOM_SEG_COO_I64) {
-        c.coo_index = (int32_t)p->coo_cols.size();
-        p->coo_cols.push_back(i);
+        int32_t k = 0;
+        for (; k < (int32_t)p->coos.size(); ++k)
+          if (p->coos[k].seg_slot == d.seg_slot && p->coos[k].seg_stride == d.seg_stride) break;
+        if (k == (int32_t)p->coos.size()) p->coos.push_back(DevCoo{d.seg_slot, d.seg_stride});
+        c.coo_index = k;
       }
     }
     if (d.transform == RECOM_XFORM_BUCKETIZE) {
@@ -587,149 +587,173 @@ void build_layout(recom_plan* p) {
     }
     prev_end = d.out_offset + d.dim;
   }
-  // per-slab derived fields: rows of a warp tile, fast groups, and the tile's cost in
-  // (roughly) warp instructions - the kernel is issue bound as much as store bound, so the
-  // static schedule balances instruction counts
-  auto xform_cost = [](const DevSlabCol& sc) {
-    switch (sc.transform) {
-      case RECOM_XFORM_HASH_STR: return 260.0;
-      case RECOM_XFORM_HASH_INT: return 220.0;
-      case RECOM_XFORM_BUCKETIZE: return 90.0;
-      default: return 15.0;
-    }
-  };
-  p->tile_cost.assign(p->slabs.size(), 1.0);
+  // per-slab derived fields: rows of a warp tile, fast groups
   for (size_t si = 0; si < p->slabs.size(); ++si) {
     DevSlab& sl = p->slabs[si];
-    bool hashed = false;
-    double xsum = 0;
-    for (int k = 0; k < sl.num_cols; ++k) {
-      const DevSlabCol& sc = p->slab_cols[sl.first_col + k];
-      hashed = hashed || sc.transform == RECOM_XFORM_HASH_STR || sc.transform == RECOM_XFORM_HASH_INT;
-      xsum += xform_cost(sc);
-    }
-    const double xavg = xsum / std::max(1, sl.num_cols);
     if (sl.cls == kSlabSparse) {
-      const int rpp = 32 / sl.num_chunks;
-      sl.tile_rows = std::min(32, rpp * (hashed ? p->sparse_rows_hash : p->sparse_rows));
-      bool hbm = false;
-      for (int k = 0; k < sl.num_cols; ++k) {
-        const recom_column_desc& d = p->descs[p->slab_cols[sl.first_col + k].col];
-        hbm = hbm || d.table_rows * d.dim * es > kHbmTableBytes;
-      }
-      const double ids = sl.num_cols * sl.tile_rows * 5.0;  // guess: 5 ids per (column, row)
-      const double chains = std::ceil(ids / 32.0);
-      const double rows_per_lane = std::ceil((double)sl.tile_rows / rpp);
-      p->tile_cost[si] = 250.0 + 6.0 * sl.num_cols + chains * (xavg + 40.0) +
-                         rows_per_lane * (hbm ? 400.0 : 120.0);
+      sl.tile_rows = kColTileRowsSparse;
       continue;
     }
-    sl.tile_rows = hashed ? p->hash_tile_rows : kDenseTileRows;
-    double p1 = 0;
-    if (sl.tile_rows == kDenseTileRows) {
-      for (int g = 0; g * 8 + 8 <= sl.num_cols; ++g) {
-        bool fast = true;
-        for (int k = 0; k < 8; ++k) {
-          const DevSlabCol& sc = p->slab_cols[sl.first_col + g * 8 + k];
-          fast = fast && sc.transform == RECOM_XFORM_BUCKETIZE && sc.value_dtype == RECOM_F32 &&
-                 sc.bnd_off >= 0 && sc.num_boundaries > 0;
-        }
-        if (fast) {
-          sl.fast8_mask |= 1u << g;
-          bool uni = true;
-          for (int k = 1; k < 8; ++k)
-            uni = uni && p->slab_cols[sl.first_col + g * 8 + k].bnd_off ==
-                             p->slab_cols[sl.first_col + g * 8].bnd_off &&
-                  p->slab_cols[sl.first_col + g * 8 + k].num_boundaries ==
-                      p->slab_cols[sl.first_col + g * 8].num_boundaries;
-          if (uni) sl.uni8_mask |= 1u << g;
-        }
+    sl.tile_rows = kDenseTileRows;
+    for (int g = 0; g * 8 + 8 <= sl.num_cols; ++g) {
+      bool fast = true;
+      for (int k = 0; k < 8; ++k) {
+        const DevSlabCol& sc = p->slab_cols[sl.first_col + g * 8 + k];
+        fast = fast && sc.transform == RECOM_XFORM_BUCKETIZE && sc.value_dtype == RECOM_F32 &&
+               sc.bnd_off >= 0 && sc.num_boundaries > 0;
       }
-      for (int k = 0; k < sl.num_cols; ++k)
-        p1 += ((sl.fast8_mask >> (k / 8)) & 1u) ? 32.0 : xform_cost(p->slab_cols[sl.first_col + k]) + 20.0;
-    } else {
-      const int ncg = 32 / sl.tile_rows;
-      p1 = std::ceil(sl.num_cols / (4.0 * ncg)) * 4.0 * (xavg + 20.0);
+      if (fast) {
+        sl.fast8_mask |= 1u << g;
+        bool uni = true;
+        for (int k = 1; k < 8; ++k)
+          uni = uni && p->slab_cols[sl.first_col + g * 8 + k].bnd_off ==
+                           p->slab_cols[sl.first_col + g * 8].bnd_off &&
+                p->slab_cols[sl.first_col + g * 8 + k].num_boundaries ==
+                    p->slab_cols[sl.first_col + g * 8].num_boundaries;
+        if (uni) sl.uni8_mask |= 1u << g;
+      }
     }
-    if (sl.tile_rows == kDenseTileRows && sl.num_cols >= 8 && sl.num_cols % 8 == 0 &&
-        sl.fast8_mask == (1u << (sl.num_cols / 8)) - 1u) {
+    if (sl.cls == kSlabDenseStaged && sl.num_cols >= 8 && sl.num_cols % 8 == 0 &&
+        sl.fast8_mask == (uint32_t)((1ull << (sl.num_cols / 8)) - 1ull)) {
       sl.all_fast = 1;  // a FAST slab: scheduled statically, everything else goes to the queue
-      if (sl.num_cols >= 16) {
-        sl.tile_rows = kFastTileRows;
-        p1 *= (double)kFastTileRows / kDenseTileRows;
+      if (sl.num_cols >= 16) sl.tile_rows = kFastTileRows;
+    } else {
+      sl.tile_rows = kDenseTileRows;
+    }
+  }
+
+  // units of the queue: every distinct (input, transform, segments) triple outside the FAST slabs
+  // is one unit - transformed once per tile, whatever number of columns (`users`) read it.
+  {
+    struct Key {
+      int32_t v[11];
+      bool operator<(const Key& o) const { return memcmp(v, o.v, sizeof v) < 0; }
+    };
+    std::map<Key, int32_t> index;
+    std::vector<std::vector<ColUser>> unit_users;
+    for (const DevSlab& sl : p->slabs) {
+      if (sl.all_fast && sl.cls == kSlabDenseStaged) continue;
+      for (int k = 0; k < sl.num_cols; ++k) {
+        const DevSlabCol& sc = p->slab_cols[sl.first_col + k];
+        const recom_column_desc& d = p->descs[sc.col];
+        const DevColumn& c = p->cols[sc.col];
+        const bool sparse = d.lookup != RECOM_LOOKUP_DENSE;
+        const bool bkt = d.transform == RECOM_XFORM_BUCKETIZE;
+        const bool hashed = d.transform == RECOM_XFORM_HASH_STR || d.transform == RECOM_XFORM_HASH_INT;
+        Key key{};
+        key.v[0] = d.value_slot;
+        key.v[1] = d.value_dtype == RECOM_STR ? d.bytes_slot : -1;
+        key.v[2] = d.transform;
+        key.v[3] = d.value_dtype;
+        key.v[4] = hashed ? (int32_t)d.num_buckets : 0;
+        key.v[5] = bkt ? c.boundaries_offset : -1;
+        key.v[6] = bkt ? d.num_boundaries : 0;
+        key.v[7] = sparse ? 1 : 0;
+        key.v[8] = sparse ? d.seg_slot : -1;
+        key.v[9] = sparse ? c.coo_index : -1;
+        key.v[10] = 0;
+        auto it = index.find(key);
+        if (it == index.end()) {
+          ColItem u{};
+          u.bucket_magic = c.bucket_magic;
+          u.num_buckets = (int32_t)d.num_buckets;
+          u.transform = d.transform;
+          u.value_dtype = d.value_dtype;
+          u.value_slot = d.value_slot;
+          u.bytes_slot = d.value_dtype == RECOM_STR ? d.bytes_slot : -1;
+          u.seg_slot = sparse ? d.seg_slot : -1;
+          u.coo_index = sparse ? c.coo_index : -1;
+          u.boundaries_offset = c.boundaries_offset;
+          u.num_boundaries = c.num_boundaries;
+          it = index.emplace(key, (int32_t)p->units.size()).first;
+          p->units.push_back(u);
+          unit_users.emplace_back();
+        }
+        ColUser cu{};
+        cu.table = d.table;
+        cu.row_bytes = d.dim * es;
+        cu.table_rows = (int32_t)d.table_rows;
+        cu.out_byte = d.out_offset * es;
+        cu.combiner = d.combiner;
+        cu.col = sc.col;
+        cu.vec_bytes = sl.vec_bytes;
+        unit_users[it->second].push_back(cu);
       }
     }
-    const int rpp = 32 / sl.num_chunks;
-    p->tile_cost[si] = 120.0 + p1 + std::ceil((double)sl.tile_rows / rpp) * 8.0;
+    p->unit_cost.assign(p->units.size(), 0.0);
+    for (size_t ui = 0; ui < p->units.size(); ++ui) {
+      ColItem& u = p->units[ui];
+      u.first_user = (int32_t)p->users.size();
+      u.num_users = (int32_t)unit_users[ui].size();
+      // estimated cost of a full tile (arbitrary units): the transform plus the gathers of every user
+      double xf;
+      switch (u.transform) {
+        case RECOM_XFORM_HASH_STR: xf = 3.0; break;
+        case RECOM_XFORM_HASH_INT: xf = 2.5; break;
+        case RECOM_XFORM_BUCKETIZE: xf = 1.5; break;
+        default: xf = 0.5; break;
+      }
+      double g = 0;
+      for (const ColUser& cu : unit_users[ui]) {
+        const bool hbm = (int64_t)cu.table_rows * cu.row_bytes > kHbmTableBytes;
+        g += (hbm ? 2.0 : 1.0) * (1.0 + cu.row_bytes / 64.0);
+        p->users.push_back(cu);
+      }
+      p->unit_cost[ui] = (u.seg_slot >= 0 ? 1.6 : 1.0) * (xf + g);
+    }
   }
-  // shared memory layout: [staged tables | staged boundaries | DENSE contexts | warp scratch]
-  int max_stage = 0, max_bnd = 0, max_cols = 1;
-  int dense_need = 0, sparse_need = 0, sparse_min = 0;
-  for (const DevSlab& s : p->slabs) {
-    max_stage = std::max(max_stage, s.stage_bytes);
-    max_bnd = std::max(max_bnd, s.bnd_bytes);
-    if (s.cls != kSlabSparse) {
-      max_cols = std::max(max_cols, s.num_cols);
-      // a FAST run keeps the contexts per CTA; a queue tile keeps them in the warp's scratch
-      const bool fast_run = s.all_fast && s.cls == kSlabDenseStaged;
-      dense_need = std::max(dense_need, s.num_cols * kIdPitch * 4 +
-                                            (fast_run ? 0 : (s.num_cols * (int)sizeof(ColCtx) + 15) / 16 * 16));
+
+  // cost of one warp item, in (roughly) warp instructions: the kernel is issue and latency bound
+  // as much as store bound, so the static schedule balances instruction counts. ~100 units
+  // are a microsecond of a warp on a busy SM.
+  p->tile_cost.assign(p->slabs.size(), 1.0);
+  for (size_t si = 0; si < p->slabs.size(); ++si) {
+    const DevSlab& sl = p->slabs[si];
+    const int rpp = 32 / sl.num_chunks;
+    bool hbm = false;
+    for (int k = 0; k < sl.num_cols; ++k) {
+      const recom_column_desc& d = p->descs[p->slab_cols[sl.first_col + k].col];
+      hbm = hbm || d.table_rows * d.dim * es > kHbmTableBytes;
+    }
+    if (sl.cls == kSlabSparse) {
+      const double rows_per_lane = std::ceil((double)sl.tile_rows / rpp);
+      p->tile_cost[si] = 200.0 + 4.0 * sl.num_cols + rows_per_lane * (hbm ? 220.0 : 110.0);
+    } else if (sl.all_fast && sl.cls == kSlabDenseStaged) {
+      p->tile_cost[si] = 120.0 + sl.num_cols * 32.0 * sl.tile_rows / kDenseTileRows +
+                         std::ceil((double)sl.tile_rows / rpp) * 8.0;
     } else {
-      const int base = s.num_cols * (int)sizeof(ColCtx) + (s.num_cols + 1) * 4 +
-                       s.num_cols * (s.tile_rows + 1) * 4;
-      sparse_need = std::max(sparse_need, base + s.num_cols * s.tile_rows * kSparseIdsPerRow * 4);
-      sparse_min = std::max(sparse_min, base + 128);
+      p->tile_cost[si] = 150.0 + std::ceil((double)sl.tile_rows / rpp) * (hbm ? 30.0 : 14.0);
+    }
+  }
+  // shared memory layout: [staged tables | staged boundaries | FAST contexts | warp scratch]
+  // Only FAST runs stage tables and boundaries; a FAST tile keeps its row ids in the warp's
+  // scratch, a column tile its row_splits and row ids.
+  int max_stage = 0, max_bnd = 0, max_cols = 1, need = kWarpScratchBytes;
+  for (const DevSlab& sl : p->slabs) {
+    if (sl.all_fast && sl.cls == kSlabDenseStaged) {
+      max_stage = std::max(max_stage, sl.stage_bytes);
+      max_bnd = std::max(max_bnd, sl.bnd_bytes);
+      max_cols = std::max(max_cols, sl.num_cols);
+      need = std::max(need, sl.num_cols * kIdPitch * 4);
     }
   }
   p->dev.smem_off_bnd = (int32_t)align_up((size_t)max_stage, 128);
   p->dev.smem_off_ctx = p->dev.smem_off_bnd + (int32_t)align_up((size_t)max_bnd, 128);
   p->dev.smem_off_scratch =
       p->dev.smem_off_ctx + (int32_t)align_up((size_t)max_cols * sizeof(ColCtx), 128);
-  {
-    const int fixed = p->dev.smem_off_scratch;
-    const int want = std::max(dense_need, std::min(sparse_need, std::max(sparse_min, kMaxWarpScratch)));
-    const int need = (int)align_up((size_t)want, 128);
-    const int min_need = (int)align_up((size_t)std::max(dense_need, sparse_min), 128);
-    // two CTAs per SM when the scratch can be made to fit (228 KB per SM, 1 KB reserved per CTA)
-    const int per2 = ((233472 / 2 - 1024 - 256 - fixed) / kWarps) & ~127;
-    const int per1 = ((232448 - 256 - fixed) / kWarps) & ~127;
-    int scratch = need;
-    if (scratch > per2) scratch = per2 >= min_need ? per2 : std::min(need, std::max(per1, 128));
-    p->dev.scratch_bytes = scratch;
-    p->dev.smem_bytes = fixed + kWarps * scratch;
-  }
-
-  // scheduling order: multi-hot slabs first (their tiles chase several dependent DRAM
-  // round trips), widest rows first; then the dense slabs in concat order.
-  std::vector<std::pair<double, int>> order2;
-  for (int s = 0; s < (int)p->slabs.size(); ++s) {
-    const DevSlab& sl = p->slabs[s];
-    double cost = 0;
-    if (sl.cls == kSlabSparse) {
-      for (int k = 0; k < sl.num_chunks; ++k) {
-        const recom_column_desc& d = p->descs[p->chunks[sl.first_chunk + k].col];
-        cost += (double)sl.vec_bytes * (d.table_rows * d.dim * es > kHbmTableBytes ? 64.0 : 1.0);
-      }
-      cost += 1e9;
-    } else {
-      cost = -(double)s;
-    }
-    order2.push_back({-cost, s});
-  }
-  std::sort(order2.begin(), order2.end());
-  for (auto& o : order2) p->slab_order.push_back(o.second);
+  p->dev.scratch_bytes = (int32_t)align_up((size_t)need, 128);
+  p->dev.smem_bytes = p->dev.smem_off_scratch + kWarps * p->dev.scratch_bytes;
 }
 
-// Schedule of a batch size (Sched in plan.h).
-//   * FAST slabs (fast bucketize groups only, tables staged in shared memory) are scheduled
-//     statically: the CTAs are apportioned to them by cost, each CTA owns ONE run (a row range
-//     of one slab, so the staged tables and column contexts are paid once per CTA), split
-//     evenly over the CTA's dense warps. With more FAST slabs than CTAs, whole slabs go to the
-//     least loaded CTA instead.
-//   * Every other slab is cut into warp tiles of slab.tile_rows rows; the tiles form one queue
-//     in descending order of estimated cost (same slab contiguous, so a warp seldom has to
-//     rebuild its column contexts). queue_warps warps of every CTA start on the queue at once,
-//     in proportion to the estimated cost of the two kinds of work.
+// Schedule of a batch size (Sched in plan.h): fully static.
+//   * FAST slabs (fast bucketize groups only, tables staged in shared memory): the CTAs are
+//     apportioned to them by cost, each CTA owns ONE run (a row range of one slab, so the staged
+//     tables and column contexts are paid once per CTA); with more FAST slabs than CTAs, whole
+//     slabs go to the least loaded CTA instead. Inside a run the warps take 16-row tiles from a
+//     shared-memory counter.
+//   * Everything else is cut into column tiles (one unit = one id stream, kColTileRowsDense /
+//     kColTileRowsSparse rows; fewer for small batches, until there is about one tile per
+//     resident warp), sorted by descending cost and dealt to the global warps round robin.
 std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   const int cap_ctas = std::max(1, p->num_sms * p->ctas_per_sm);
   auto tt = std::make_shared<TileTable>();
@@ -740,89 +764,58 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     t.rows = (int32_t)rows;
     t.slab = p->slabs[s];
     t.stage = t.slab.cls == kSlabDenseStaged && rows >= kMinStageRows;
+    t.slab.run_tile_rows = (int16_t)t.slab.tile_rows;
+    t.slab.run_tiles = (int32_t)((rows + t.slab.tile_rows - 1) / t.slab.tile_rows);
     return t;
   };
-  // split a FAST run evenly over the CTA's dense warps (see the kernel's tile loop)
-  auto tile_run = [&](Tile& t, int dense_warps) {
-    const int64_t trmax = t.slab.tile_rows, dw = std::max(1, dense_warps);
-    const int64_t k = std::max<int64_t>(1, (t.rows + dw * trmax - 1) / (dw * trmax));
-    int64_t rpt = (t.rows + dw * k - 1) / (dw * k);
-    rpt = std::min<int64_t>(trmax, std::max<int64_t>(rpt, std::min<int64_t>(8, trmax)));
-    t.slab.run_tile_rows = (int16_t)rpt;
-    t.slab.run_tiles = (int32_t)((t.rows + rpt - 1) / rpt);
-  };
-  // Small batches: with fewer tiles than resident warps the launch lasts as long as its longest
-  // tile, so the queue's tiles are cut finer (down to one row per lane group / 2 rows of a hashed
-  // slab) until there is about one tile per warp.
-  std::vector<int32_t> rows_of(p->slabs.size());
-  for (size_t s = 0; s < p->slabs.size(); ++s) rows_of[s] = p->slabs[s].tile_rows;
-  {
-    const int64_t warps = (int64_t)cap_ctas * kWarps;
-    for (int pass = 0; pass < 3; ++pass) {
-      int64_t tiles = 0;
-      for (size_t s = 0; s < p->slabs.size(); ++s) tiles += (B + rows_of[s] - 1) / rows_of[s];
-      if (tiles * 2 > warps) break;
-      bool changed = false;
-      for (size_t s = 0; s < p->slabs.size(); ++s) {
-        const DevSlab& sl = p->slabs[s];
-        if (sl.cls == kSlabDenseStaged && sl.all_fast) continue;  // FAST runs are split per CTA
-        const int min_rows = sl.cls == kSlabSparse ? std::max(1, 32 / sl.num_chunks) : 2;
-        if (rows_of[s] / 2 >= min_rows) {
-          rows_of[s] /= 2;
-          changed = true;
-        }
-      }
-      if (!changed) break;
-    }
-  }
-  auto tiles_of = [&](int s) { return (B + rows_of[s] - 1) / rows_of[s]; };
-  std::vector<int> fast, other;
+  std::vector<int> fast;
   for (int s = 0; s < (int)p->slabs.size(); ++s) {
     const DevSlab& sl = p->slabs[s];
     if (sl.cls == kSlabDenseStaged && sl.all_fast) fast.push_back(s);
-    else other.push_back(s);
   }
-  // the queue: heaviest tiles first
-  std::stable_sort(other.begin(), other.end(),
-                   [&](int a, int b) { return p->tile_cost[a] > p->tile_cost[b]; });
+  auto tiles_of = [&](int s) { return (B + p->slabs[s].tile_rows - 1) / p->slabs[s].tile_rows; };
+
+  // ---- column tiles ----
+  // rows per tile: the fewer tiles than warps, the finer (a launch lasts as long as its longest
+  // chain of dependent loads, and a tile's chain does not get shorter with fewer rows - but the
+  // transform and gather passes behind it do)
+  const int64_t warps = (int64_t)cap_ctas * kWarps;
+  int rows_dense = std::min(kColTileRowsDense, p->col_rows_dense);
+  int rows_sparse = std::min(kColTileRowsSparse, p->col_rows_sparse);
+  {
+    auto count = [&](int rd, int rs) {
+      int64_t n = 0;
+      for (const ColItem& u : p->units) n += u.seg_slot >= 0 ? (B + rs - 1) / rs : (B + rd - 1) / rd;
+      return n;
+    };
+    while (count(rows_dense, rows_sparse) * 2 <= warps && (rows_dense > 32 || rows_sparse > 4)) {
+      if (rows_dense > 32) rows_dense /= 2;
+      if (rows_sparse > 4) rows_sparse /= 2;
+    }
+  }
+  struct Costed {
+    double cost;
+    ColItem it;
+  };
+  std::vector<Costed> qs;
   double queue_cost = 0;
-  for (int s : other) {
-    for (int64_t b = 0; b < B; b += rows_of[s]) {
-      Tile t = make(s, b, std::min<int64_t>(rows_of[s], B - b));
-      t.slab.tile_rows = rows_of[s];
-      t.stage = 0;
-      t.slab.fast8_mask = t.slab.uni8_mask = 0;  // queue tiles read boundaries from the pool
-      t.slab.all_fast = 0;
-      tt->queue.push_back(t);
-      queue_cost += p->tile_cost[s] * p->sparse_weight * rows_of[s] / p->slabs[s].tile_rows;
+  for (size_t ui = 0; ui < p->units.size(); ++ui) {
+    const ColItem& u = p->units[ui];
+    const int64_t step = u.seg_slot >= 0 ? rows_sparse : rows_dense;
+    const int64_t full = u.seg_slot >= 0 ? kColTileRowsSparse : kColTileRowsDense;
+    for (int64_t b = 0; b < B; b += step) {
+      ColItem it = u;
+      it.begin = (int32_t)b;
+      it.count = (int32_t)std::min<int64_t>(step, B - b);
+      const double c = p->unit_cost[ui] * (0.5 + 0.5 * (double)it.count / (double)full);
+      qs.push_back({c, it});
+      queue_cost += c;
     }
   }
-  // The launch ends one tile after the queue runs dry: the last tiles of the queue (as many as
-  // tail_split x the resident warps) are cut once more, so that the tail is half a tile.
-  if (p->tail_split > 0 && !tt->queue.empty()) {
-    const int64_t warps = (int64_t)cap_ctas * kWarps;
-    const size_t n_tail = (size_t)std::min<double>((double)tt->queue.size(), p->tail_split * (double)warps);
-    std::vector<Tile> tail;
-    for (size_t i = tt->queue.size() - n_tail; i < tt->queue.size(); ++i) {
-      const Tile& t = tt->queue[i];
-      const DevSlab& sl = p->slabs[t.slab_id];
-      const int min_rows = sl.cls == kSlabSparse ? std::max(1, 32 / sl.num_chunks) : 2;
-      const int half = t.slab.tile_rows / 2;
-      if (half < min_rows || t.rows <= half) {
-        tail.push_back(t);
-        continue;
-      }
-      Tile a = t, b = t;
-      a.rows = half;
-      b.row_begin = t.row_begin + half;
-      b.rows = t.rows - half;
-      a.slab.tile_rows = b.slab.tile_rows = half;
-      tail.push_back(a);
-      tail.push_back(b);
-    }
-    tt->queue.resize(tt->queue.size() - n_tail);
-    tt->queue.insert(tt->queue.end(), tail.begin(), tail.end());
-  }
+  std::stable_sort(qs.begin(), qs.end(), [](const Costed& a, const Costed& b) { return a.cost > b.cost; });
+  for (const Costed& c : qs) tt->queue.push_back(c.it);
+
+  // ---- FAST runs ----
   std::vector<double> cost(fast.size());
   double fast_cost = 0;
   int64_t fast_tiles = 0;
@@ -831,27 +824,12 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     fast_cost += cost[i];
     fast_tiles += tiles_of(fast[i]);
   }
-  int Q = 0;
-  if (tt->queue.empty()) Q = 0;
-  else if (fast.empty()) Q = kWarps;
-  else Q = std::max(1, std::min(kWarps - 1, (int)(kWarps * queue_cost / (queue_cost + fast_cost) + 0.5)));
-  int64_t units = 1;
-  if (Q > 0) units = std::max<int64_t>(units, ((int64_t)tt->queue.size() + Q - 1) / Q);
-  if (Q < kWarps) units = std::max<int64_t>(units, (fast_tiles + (kWarps - Q) - 1) / (kWarps - Q));
-  // a FAST slab per CTA where possible: runs of one CTA are walked one after the other
-  units = std::max<int64_t>(units, (int64_t)fast.size());
-  // whole waves: a grid between one and two CTAs per SM would leave some SMs with twice the work
+  // grid: enough CTAs for one warp per item, in whole waves of the SMs
+  int64_t units = std::max<int64_t>(1, ((int64_t)tt->queue.size() + fast_tiles + kWarps - 1) / kWarps);
+  units = std::max<int64_t>(units, std::min<int64_t>((int64_t)fast.size(), cap_ctas));
   if (units > p->num_sms) units = (units + p->num_sms - 1) / p->num_sms * p->num_sms;
   const int grid = (int)std::min<int64_t>(cap_ctas, units);
-  if (Q > 0 && !fast.empty()) {
-    const int q_need = (int)(((int64_t)tt->queue.size() + grid - 1) / grid);
-    Q = std::max(1, std::min({Q, q_need, kWarps - 1}));
-  }
-  if (p->force_queue_warps >= 0 && !tt->queue.empty() && !fast.empty())
-    Q = std::min(kWarps - 1, p->force_queue_warps);
   tt->grid = grid;
-  tt->queue_warps = Q;
-  tt->claim_ahead = p->claim_ahead;
 
   std::vector<std::vector<Tile>> per_cta(grid);
   if (!fast.empty() && (size_t)grid >= fast.size()) {
@@ -892,10 +870,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   for (int c = 0; c < grid; ++c) {
     tt->cta[c].first = (int32_t)tt->runs.size();
     tt->cta[c].count = (int32_t)per_cta[c].size();
-    for (Tile& t : per_cta[c]) {
-      tile_run(t, kWarps - Q);
-      tt->runs.push_back(t);
-    }
+    for (Tile& t : per_cta[c]) tt->runs.push_back(t);
   }
   return tt;
 }
@@ -937,13 +912,15 @@ recom_status upload_plan(recom_plan* p) {
     size_t bytes;
     size_t off;
   };
-  Part parts[6] = {
+  Part parts[8] = {
       {p->cols.data(), p->cols.size() * sizeof(DevColumn), 0},
       {p->slabs.data(), p->slabs.size() * sizeof(DevSlab), 0},
       {p->chunks.data(), p->chunks.size() * sizeof(DevChunk), 0},
       {p->slab_cols.data(), p->slab_cols.size() * sizeof(DevSlabCol), 0},
       {p->slab_bnds.data(), p->slab_bnds.size() * sizeof(DevSlabBnd), 0},
       {p->boundary_pool.data(), p->boundary_pool.size() * sizeof(float), 0},
+      {p->users.data(), p->users.size() * sizeof(ColUser), 0},
+      {p->coos.data(), p->coos.size() * sizeof(DevCoo), 0},
   };
   size_t total = 0;
   for (Part& pt : parts) {
@@ -962,11 +939,31 @@ recom_status upload_plan(recom_plan* p) {
   p->dev.slab_cols = (const DevSlabCol*)(base + parts[3].off);
   p->dev.slab_bnds = (const DevSlabBnd*)(base + parts[4].off);
   p->dev.boundaries = (const float*)(base + parts[5].off);
+  p->dev.users = (const ColUser*)(base + parts[6].off);
+  p->dev.coos = (const DevCoo*)(base + parts[7].off);
+  p->dev.num_coo = (int32_t)p->coos.size();
   p->dev.num_cols = (int32_t)p->cols.size();
   p->dev.num_slabs = (int32_t)p->slabs.size();
   p->dev.elem_bytes = p->elem_bytes;
   p->dev.check_ids = p->cfg.check_ids;
   return RECOM_OK;
+}
+
+// Bytes of the blob the plan's columns reach (slots are 16-byte padded): what the kernel may
+// prefetch into L2.
+int64_t blob_extent(const recom_plan* p, const recom_request* req) {
+  int64_t end = 0;
+  for (const recom_column_desc& d : p->descs) {
+    end = std::max(end, req->slot_offsets[d.value_slot] +
+                            req->slot_elems[d.value_slot] * dtype_bytes(d.value_dtype));
+    if (d.value_dtype == RECOM_STR && d.bytes_slot >= 0)
+      end = std::max(end, req->slot_offsets[d.bytes_slot] + req->slot_elems[d.bytes_slot]);
+    if (d.lookup != RECOM_LOOKUP_DENSE && d.seg_slot >= 0)
+      end = std::max(end, req->slot_offsets[d.seg_slot] +
+                              req->slot_elems[d.seg_slot] *
+                                  (d.seg_format == RECOM_SEG_COO_I64 ? 8 : 4));
+  }
+  return end;
 }
 
 int64_t column_num_ids(const recom_plan* p, int ci, const recom_request* req) {
@@ -990,13 +987,9 @@ recom_status validate_request_head(const recom_plan* p, const recom_request* req
   return RECOM_OK;
 }
 
-// O(tables + columns) checks of the request's shape (slot offsets / element counts / table
-// pointers). Skipped when the request's argument block - which covers all of these - equals a
-// block that passed them before.
+// O(columns) checks of the request's shape (slot offsets / element counts). The table pointers
+// are checked when a table set is first seen (device_tables).
 recom_status validate_request(const recom_plan* p, const recom_request* req) {
-  for (int t = 0; t < p->cfg.num_tables; ++t)
-    if (!req->tables[t] || ((uintptr_t)req->tables[t] & 15))
-      return fail(RECOM_ERR_INVALID_ARGUMENT, "table %d pointer is null or not 16-byte aligned", t);
   const int n = (int)p->descs.size();
   for (int i = 0; i < n; ++i) {
     const recom_column_desc& d = p->descs[i];
@@ -1072,7 +1065,6 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
   p->elem_bytes = cfg->out_dtype == RECOM_BF16 ? 2 : 4;
   // tuning knobs (the reference's counterpart: its RECOM_* env flags, fc_optimize_pass.cc:41-69)
   if (const char* e = getenv("RECOM_B200_STAGE_TABLES")) p->stage_tables = atoi(e) != 0;
-  if (const char* e = getenv("RECOM_B200_SPARSE_WEIGHT")) p->sparse_weight = atof(e);
   auto pow2_env = [](const char* name, int lo, int hi, int dflt) {
     const char* e = getenv(name);
     if (!e) return dflt;
@@ -1080,13 +1072,8 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
     while (r * 2 <= v && r * 2 <= hi) r *= 2;
     return r;
   };
-  if (const char* e = getenv("RECOM_B200_QUEUE_WARPS")) p->force_queue_warps = atoi(e);
-  if (const char* e = getenv("RECOM_B200_CLAIM_AHEAD")) p->claim_ahead = atoi(e);
-  if (const char* e = getenv("RECOM_B200_TAIL_SPLIT")) p->tail_split = atof(e);
-  p->hash_tile_rows = pow2_env("RECOM_B200_HASH_TILE_ROWS", 4, 32, kHashTileRows);
-  p->sparse_rows_hash = pow2_env("RECOM_B200_SPARSE_ROWS_HASH", 1, 8, kSparseRowsPerSubHash);
-  p->sparse_rows = pow2_env("RECOM_B200_SPARSE_ROWS", 1, 8, kSparseRowsPerSub);
-  if (const char* e = getenv("RECOM_B200_CACHE_ARGS")) p->cache_args = atoi(e) != 0;
+  p->col_rows_dense = pow2_env("RECOM_B200_COL_ROWS_DENSE", 32, kColTileRowsDense, kColTileRowsDense);
+  p->col_rows_sparse = pow2_env("RECOM_B200_COL_ROWS_SPARSE", 4, kColTileRowsSparse, kColTileRowsSparse);
   build_layout(p);
   st = upload_plan(p);
   if (st == RECOM_OK) {
@@ -1105,9 +1092,14 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
     }
     if (cudaStreamCreateWithFlags(&p->up_stream, cudaStreamNonBlocking) != cudaSuccess)
       st = fail(RECOM_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (cudaMalloc((void**)&p->d_counters, (size_t)kCounterSlots * 8) != cudaSuccess ||
-        cudaMemset(p->d_counters, 0, (size_t)kCounterSlots * 8) != cudaSuccess)
+    const size_t cbytes = (size_t)kCounterSlots * kCounterInts * sizeof(int32_t);
+    if (cudaMalloc((void**)&p->d_counters, cbytes) != cudaSuccess ||
+        cudaMemset(p->d_counters, 0, cbytes) != cudaSuccess ||
+        cudaHostAlloc((void**)&p->h_done_seq, kCounterSlots * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&p->d_done_seq, p->h_done_seq, 0) != cudaSuccess)
       st = fail(RECOM_ERR_CUDA, "counter ring allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    else
+      for (int i = 0; i < kCounterSlots; ++i) p->h_done_seq[i] = (uint32_t)(i - kCounterSlots);
     for (int i = 0; i < kRing && st == RECOM_OK; ++i) {
       cudaError_t e = cudaEventCreateWithFlags(&p->ring[i].done, cudaEventDisableTiming);
       if (e != cudaSuccess) st = fail(RECOM_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
@@ -1144,9 +1136,10 @@ recom_status recom_plan_destroy(recom_plan* p) {
     }
     if (p->ring[i].pinned) cudaFreeHost(p->ring[i].pinned);
   }
-  for (auto& e : p->arg_cache)
-    if (e->dev) cudaFree(e->dev);
+  for (auto& e : p->table_sets)
+    if (e->dev) cudaFree((void*)e->dev);
   if (p->d_counters) cudaFree(p->d_counters);
+  if (p->h_done_seq) cudaFreeHost(p->h_done_seq);
   if (p->d_block) cudaFree(p->d_block);
   if (p->up_stream) cudaStreamDestroy(p->up_stream);
   delete p;
@@ -1222,34 +1215,33 @@ recom_status recom_plan_out_width(const recom_plan* p, int32_t* out) {
   return RECOM_OK;
 }
 
-// Bytes of a request's argument block (header + the arrays ReqParams points to).
+// Bytes of the argument data staged per request when it does not travel inside the blob:
+// slot offsets, slot element counts, (ids_out hook only) the per-column id prefix, and the table
+// pointers when the plan's table-set cache is full.
 static size_t arg_block_bytes(const recom_plan* p) {
-  size_t b = align_up(sizeof(ReqHeader), 16);
-  b += align_up((size_t)p->cfg.num_slots * 8, 16);
-  b += align_up((size_t)p->cfg.num_tables * 8, 16);
+  size_t b = 2 * align_up((size_t)p->cfg.num_slots * 8, 16);
   b += align_up((p->descs.size() + 1) * 4, 16);
-  b += align_up((p->sparse_cols.size() + 1) * 4, 16);
-  b += align_up(p->coo_cols.size() * 4 + 4, 16);
+  b += align_up((size_t)p->cfg.num_tables * 8, 16);
   return align_up(b, 64);
 }
 
 static size_t max_sched_bytes(const recom_plan* p, int64_t batch) {
   // only used when the schedule cache is full and the schedule travels with the request
   const size_t ctas = (size_t)p->num_sms * p->ctas_per_sm;
-  size_t tiles = 0;
-  for (const DevSlab& s : p->slabs) tiles += (size_t)((batch + s.tile_rows - 1) / s.tile_rows);
-  // (small batches are cut finer, but never into more than 2 tiles per resident warp)
-  tiles = std::max(tiles, 2 * ctas * kWarps + p->slabs.size()) + p->slabs.size() + ctas + 4;
-  return tiles * sizeof(Tile) + ctas * sizeof(CtaWork) + 128;
+  // column tiles: at least 4 rows (multi-hot) / 32 rows each, and never cut finer than that
+  size_t items = 0;
+  for (const ColItem& u : p->units) items += (size_t)(batch / (u.seg_slot >= 0 ? 4 : 32)) + 1;
+  return items * sizeof(ColItem) + (ctas + p->slabs.size() + 4) * sizeof(Tile) +
+         ctas * sizeof(CtaWork) + 256;
 }
 
 recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int64_t total_ids,
                                         size_t* out) {
   if (!p || !out || batch < 0 || total_ids < 0)
     return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  // [argument block + schedule (upload path only) | row_splits built from COO inputs]
   size_t b = align_up(arg_block_bytes(p) + max_sched_bytes(p, batch), 256);
-  b += align_up((size_t)total_ids * 4 + 16, 256);                            // ws_ids
-  b += align_up(p->coo_cols.size() * (size_t)(batch + 1) * 4 + 16, 256);     // ws_row_splits
+  b += align_up(p->coos.size() * (size_t)(batch + 1) * 4 + 16, 256);
   *out = b;
   return RECOM_OK;
 }
@@ -1269,12 +1261,57 @@ struct HostProf {
   }
   ~HostProf() {
     if (on && calls)
-      fprintf(stderr, "[recom_b200 host] %ld calls; us/call: validate %.2f, schedule %.2f, block %.2f, "
-              "cache %.2f, launch %.2f\n", calls, acc[0] / calls, acc[1] / calls, acc[2] / calls,
+      fprintf(stderr, "[recom_b200 host] %ld calls; us/call: head %.2f, schedule %.2f, validate %.2f, "
+              "tables+args %.2f, launch %.2f\n", calls, acc[0] / calls, acc[1] / calls, acc[2] / calls,
               acc[3] / calls, acc[4] / calls);
   }
 };
 HostProf g_host_prof;
+
+// The plan's allocations, cached uploads and launches belong to cfg.device; the caller's current
+// device may be another one (multi-GPU hosts). Switch for the duration of the call only.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess || prev == device) return e;
+    switched = true;
+    return cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+// Device copy of the request's table pointer array: the plan's cached copy when this very set
+// of addresses was seen before (every request of a serving process), a new published copy
+// otherwise; nullptr when the cache is full (the pointers then travel with the argument block).
+const void* const* device_tables(recom_plan* p, const recom_request* req, recom_status* st) {
+  *st = RECOM_OK;
+  const size_t n = (size_t)p->cfg.num_tables;
+  std::lock_guard<std::mutex> lock(p->tables_mu);
+  for (const auto& e : p->table_sets)
+    if (memcmp(e->host.data(), req->tables, n * sizeof(void*)) == 0) return e->dev;
+  for (size_t t = 0; t < n; ++t)
+    if (!req->tables[t] || ((uintptr_t)req->tables[t] & 15)) {
+      *st = fail(RECOM_ERR_INVALID_ARGUMENT, "table %zu pointer is null or not 16-byte aligned", t);
+      return nullptr;
+    }
+  if (p->table_sets.size() >= (size_t)kTableSets) return nullptr;
+  std::unique_ptr<TableSet> e(new TableSet());
+  e->host.assign(req->tables, req->tables + n);
+  // first sight of a table set (warm-up): a blocking allocation + copy
+  if (cudaMalloc((void**)&e->dev, std::max<size_t>(n, 1) * sizeof(void*)) != cudaSuccess ||
+      blocking_upload(p, (void*)e->dev, e->host.data(), n * sizeof(void*)) != cudaSuccess) {
+    if (e->dev) cudaFree((void*)e->dev);
+    *st = fail(RECOM_ERR_CUDA, "table pointer upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  const void* const* dev = e->dev;
+  p->table_sets.push_back(std::move(e));
+  return dev;
+}
 }  // namespace
 
 static recom_status run_impl(const recom_plan* cp, const recom_request* req, const recom_shard_out* so);
@@ -1311,24 +1348,6 @@ recom_status recom_plan_run_sharded(const recom_plan* cp, const recom_request* r
   return run_impl(cp, req, so);
 }
 
-namespace {
-// The plan's allocations, cached uploads and launches belong to cfg.device; the caller's current
-// device may be another one (multi-GPU hosts). Switch for the duration of the call only.
-struct DeviceGuard {
-  int prev = -1;
-  bool switched = false;
-  cudaError_t enter(int device) {
-    cudaError_t e = cudaGetDevice(&prev);
-    if (e != cudaSuccess || prev == device) return e;
-    switched = true;
-    return cudaSetDevice(device);
-  }
-  ~DeviceGuard() {
-    if (switched) cudaSetDevice(prev);
-  }
-};
-}  // namespace
-
 static recom_status run_impl(const recom_plan* cp, const recom_request* req, const recom_shard_out* so) {
   g_last_launches = 0;
   g_host_prof.start();
@@ -1344,6 +1363,7 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   if (req->batch == 0) return validate_request(p, req);
   const int n = (int)p->descs.size();
   const int64_t B = req->batch;
+  const int num_slots = p->cfg.num_slots;
   cudaStream_t stream = (cudaStream_t)req->stream;
 
   g_host_prof.lap(0);
@@ -1354,114 +1374,48 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   if (sched_in_args) tt = build_tiles(p, B);
   const int grid = tt->grid;
 
-  // the argument block: nothing in it differs between requests of the same shape
-  const size_t args_bytes = arg_block_bytes(p);
-  thread_local std::vector<uint8_t> block;
-  block.assign(args_bytes, 0);
-  uint8_t* h = block.data();
-  ReqHeader* hdr = (ReqHeader*)h;
-  hdr->batch = B;
-  hdr->num_coo = (int32_t)p->coo_cols.size();
-  size_t o = align_up(sizeof(ReqHeader), 16);
-  hdr->off_slot_offsets = (uint32_t)o;
-  memcpy(h + o, req->slot_offsets, (size_t)p->cfg.num_slots * 8);
-  o += align_up((size_t)p->cfg.num_slots * 8, 16);
-  hdr->off_tables = (uint32_t)o;
-  memcpy(h + o, req->tables, (size_t)p->cfg.num_tables * 8);
-  o += align_up((size_t)p->cfg.num_tables * 8, 16);
-  hdr->off_ids_base = (uint32_t)o;
-  int32_t* ids_base = (int32_t*)(h + o);
-  o += align_up(((size_t)n + 1) * 4, 16);
-  hdr->off_sparse_base = (uint32_t)o;
-  int32_t* sparse_base = (int32_t*)(h + o);
-  o += align_up((p->sparse_cols.size() + 1) * 4, 16);
-  hdr->off_coo_cols = (uint32_t)o;
-  if (!p->coo_cols.empty()) memcpy(h + o, p->coo_cols.data(), p->coo_cols.size() * 4);
-  hdr->total_bytes = (uint32_t)args_bytes;
-  // per-column id counts
-  int64_t total = 0, sparse_total = 0, max_coo_nnz = 0;
-  for (int i = 0; i < n; ++i) {
-    const int64_t cnt = column_num_ids(p, i, req);
-    ids_base[i] = (int32_t)total;
-    total += cnt;
-    if (p->cols[i].sparse_index >= 0) {
-      sparse_base[p->cols[i].sparse_index] = (int32_t)sparse_total;
-      sparse_total += cnt;
-      if (p->cols[i].coo_index >= 0) max_coo_nnz = std::max(max_coo_nnz, cnt);
-    }
-    if (total > 0x7fffffffLL) return fail(RECOM_ERR_INVALID_ARGUMENT, "too many ids in one request");
-  }
-  ids_base[n] = (int32_t)total;
-  sparse_base[p->sparse_cols.size()] = (int32_t)sparse_total;
-  {
-    uint64_t eh = 1469598103934665603ull;  // the element counts are part of the block's identity
-    for (int i = 0; i < p->cfg.num_slots; ++i) eh = (eh ^ (uint64_t)req->slot_elems[i]) * 1099511628211ull;
-    hdr->pad1 = (int64_t)eh;
-  }
+  st = validate_request(p, req);
+  if (st != RECOM_OK) return st;
+  // longest COO input (grid of the helper kernel)
+  int64_t max_coo_nnz = 0;
+  for (const DevCoo& c : p->coos)
+    max_coo_nnz = std::max<int64_t>(max_coo_nnz, req->slot_elems[c.seg_slot] / c.seg_stride);
+  g_host_prof.lap(2);
 
-  // workspace carve-up: [argument block + schedule (upload path only) | ws_ids | ws_row_splits]
-  size_t off = align_up(args_bytes + max_sched_bytes(p, B), 256);
-  const size_t off_ws_ids = off;
-  off += align_up((size_t)sparse_total * 4 + 16, 256);
+  // workspace: [argument block + schedule (upload path only) | ws_row_splits]
+  size_t off = align_up(arg_block_bytes(p) + max_sched_bytes(p, B), 256);
   const size_t off_rs = off;
-  off += align_up(p->coo_cols.size() * (size_t)(B + 1) * 4 + 16, 256);
+  off += align_up(p->coos.size() * (size_t)(B + 1) * 4 + 16, 256);
   if (!req->workspace || req->workspace_bytes < off)
     return fail(RECOM_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes, got %zu", off,
                 req->workspace_bytes);
   uint8_t* ws = (uint8_t*)req->workspace;
 
-  g_host_prof.lap(2);
-  // a device-resident copy of exactly this block?
-  const uint8_t* d_args = nullptr;
-  bool validated = false;
-  if (p->cache_args && !sched_in_args) {
-    std::lock_guard<std::mutex> lock(p->args_mu);
-    for (const auto& e : p->arg_cache)
-      if (e->host.size() == args_bytes && memcmp(e->host.data(), h, args_bytes) == 0) {
-        d_args = e->dev;
-        break;
-      }
-    if (!d_args) {
-      st = validate_request(p, req);  // a shape not seen (or not published) before
-      if (st != RECOM_OK) return st;
-      validated = true;
-      uint64_t hash = 1469598103934665603ull;  // FNV-1a over 8-byte words
-      for (size_t i = 0; i + 8 <= args_bytes; i += 8) {
-        uint64_t w;
-        memcpy(&w, h + i, 8);
-        hash = (hash ^ w) * 1099511628211ull;
-      }
-      const bool again = std::find(p->seen.begin(), p->seen.end(), hash) != p->seen.end();
-      if (again && p->arg_cache.size() < (size_t)kArgCache) {
-        // second sight: publish a device copy (a blocking allocation + copy, like the first use
-        // of a batch size); requests that never repeat stay on the upload path
-        std::unique_ptr<ArgEntry> e(new ArgEntry());
-        e->host.assign(h, h + args_bytes);
-        if (cudaMalloc((void**)&e->dev, args_bytes) == cudaSuccess &&
-            blocking_upload(p, e->dev, h, args_bytes) == cudaSuccess) {
-          d_args = e->dev;
-          p->arg_cache.push_back(std::move(e));
-        } else {
-          if (e->dev) cudaFree(e->dev);
-          cudaGetLastError();
-        }
-      } else if (!again) {
-        if (p->seen.size() >= 64) p->seen.erase(p->seen.begin());
-        p->seen.push_back(hash);
-      }
-    }
-  }
+  const void* const* d_tables = device_tables(p, req, &st);
+  if (st != RECOM_OK) return st;
 
-  if (!d_args && !validated) {
-    st = validate_request(p, req);
-    if (st != RECOM_OK) return st;
+  // Argument data. With the trailer recom_concat_inputs appends to the blob nothing is uploaded
+  // here; otherwise (or for the ids_out hook, a full table cache, an uncached schedule) one
+  // pinned staging slot -> one cudaMemcpyAsync into the workspace.
+  const int64_t* d_slot_offsets = nullptr;
+  const int64_t* d_slot_elems = nullptr;
+  const int32_t* d_ids_base = nullptr;
+  const bool trailer = req->args_offset >= 0;
+  if (trailer) {
+    if (req->args_offset % 16)
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "args_offset must be a multiple of 16");
+    const uint8_t* t = (const uint8_t*)req->blob + req->args_offset;
+    d_slot_offsets = (const int64_t*)(t + 16);
+    d_slot_elems = d_slot_offsets + num_slots;
   }
-  g_host_prof.lap(3);
   Sched sched = sched_in_args ? Sched{} : tt->sched(tt->d_block);
   ArgSlot* slot = nullptr;
   std::unique_lock<std::mutex> slot_lock;
-  if (!d_args) {
-    // upload path: pinned staging slot -> one cudaMemcpyAsync into the workspace
+  if (!trailer || req->ids_out || !d_tables || sched_in_args) {
+    const size_t slots_bytes = align_up((size_t)num_slots * 8, 16);
+    const size_t o_elems = slots_bytes, o_ids = 2 * slots_bytes;
+    const size_t o_tables = o_ids + align_up(((size_t)n + 1) * 4, 16);
+    const size_t args_bytes = arg_block_bytes(p);
     const size_t up_bytes = args_bytes + (sched_in_args ? tt->bytes() : 0);
     slot = &p->ring[p->ring_next.fetch_add(1) % kRing];
     slot_lock = std::unique_lock<std::mutex>(slot->mu);
@@ -1477,13 +1431,47 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
       CUDA_TRY(cudaHostAlloc((void**)&slot->pinned, cap, cudaHostAllocDefault));
       slot->cap = cap;
     }
-    memcpy(slot->pinned, h, args_bytes);
+    uint8_t* h = slot->pinned;
+    memcpy(h, req->slot_offsets, (size_t)num_slots * 8);
+    memcpy(h + o_elems, req->slot_elems, (size_t)num_slots * 8);
+    int32_t* ids_base = (int32_t*)(h + o_ids);
+    int64_t total = 0;
+    for (int i = 0; i < n; ++i) {
+      ids_base[i] = (int32_t)total;
+      total += column_num_ids(p, i, req);
+      if (total > 0x7fffffffLL) return fail(RECOM_ERR_INVALID_ARGUMENT, "too many ids in one request");
+    }
+    ids_base[n] = (int32_t)total;
+    memcpy(h + o_tables, req->tables, (size_t)p->cfg.num_tables * 8);
     if (sched_in_args) {
-      tt->write(slot->pinned + args_bytes);
+      tt->write(h + args_bytes);
       sched = tt->sched(ws + args_bytes);
     }
-    CUDA_TRY(cudaMemcpyAsync(ws, slot->pinned, up_bytes, cudaMemcpyHostToDevice, stream));
-    d_args = ws;
+    CUDA_TRY(cudaMemcpyAsync(ws, h, up_bytes, cudaMemcpyHostToDevice, stream));
+    if (!trailer) {
+      d_slot_offsets = (const int64_t*)ws;
+      d_slot_elems = (const int64_t*)(ws + o_elems);
+    }
+    d_ids_base = (const int32_t*)(ws + o_ids);
+    if (!d_tables) d_tables = (const void* const*)(ws + o_tables);
+  }
+  g_host_prof.lap(3);
+
+  // Sharded output only: a counter slot (finished warps -> the last one signals the peers) whose
+  // previous user, kCounterSlots requests ago, has finished
+  uint32_t seq = 0, cslot = 0;
+  const bool need_slot = so && so->peer_flags;
+  if (need_slot) {
+    seq = p->counter_next.fetch_add(1);
+    cslot = seq % kCounterSlots;
+    if (*(volatile uint32_t*)(p->h_done_seq + cslot) != seq - (uint32_t)kCounterSlots) {
+      const auto t0 = std::chrono::steady_clock::now();
+      while (*(volatile uint32_t*)(p->h_done_seq + cslot) != seq - (uint32_t)kCounterSlots) {
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10))
+          return fail(RECOM_ERR_CUDA, "no free request slot: %d sharded requests of this plan in flight for 10 s",
+                      kCounterSlots);
+      }
+    }
   }
 
   ReqParams A{};
@@ -1491,13 +1479,19 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   A.out = (uint8_t*)req->out;
   A.ids_out = req->ids_out;
   A.status = req->status_out;
-  A.ws_ids = (int32_t*)(ws + off_ws_ids);
   A.ws_row_splits = (int32_t*)(ws + off_rs);
-  A.slot_offsets = (const int64_t*)(d_args + hdr->off_slot_offsets);
-  A.tables = (const void* const*)(d_args + hdr->off_tables);
-  A.ids_base = (const int32_t*)(d_args + hdr->off_ids_base);
-  A.sparse_base = (const int32_t*)(d_args + hdr->off_sparse_base);
-  A.counters = p->d_counters + 2 * (p->counter_next.fetch_add(1) % kCounterSlots);
+  A.slot_offsets = d_slot_offsets;
+  A.slot_elems = d_slot_elems;
+  A.tables = d_tables;
+  A.ids_base = d_ids_base;
+  A.counters = need_slot ? p->d_counters + (size_t)kCounterInts * cslot : nullptr;
+  A.done_seq = need_slot ? p->d_done_seq + cslot : nullptr;
+  A.seq = seq;
+  {
+    static const bool pf = getenv("RECOM_B200_NO_PREFETCH") == nullptr;
+    A.blob_bytes = !pf ? 0 : req->args_offset >= 0
+                       ? req->args_offset + 16 + 16 * (int64_t)num_slots : blob_extent(p, req);
+  }
   A.prof = p->d_prof;
   if (p->d_prof) p->prof_grid = grid;
   A.batch = B;
@@ -1519,9 +1513,8 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     A.out = (uint8_t*)so->peer_out[0];
   }
 
-  if (!p->coo_cols.empty()) {
-    launch_coo_to_row_splits(p->dev, (const ReqHeader*)d_args, A.blob, A.ws_row_splits,
-                             (int)p->coo_cols.size(), max_coo_nnz, stream);
+  if (!p->coos.empty()) {
+    launch_coo_to_row_splits(p->dev, A, max_coo_nnz, stream);
     g_last_launches++;
   }
   launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream);
@@ -1532,7 +1525,10 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     slot->in_flight = true;
   }
   g_host_prof.lap(4);
-  if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    if (need_slot) *(volatile uint32_t*)(p->h_done_seq + cslot) = seq;  // the slot was not used
+    return fail(RECOM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  }
   return RECOM_OK;
 }
 

@@ -259,8 +259,11 @@ recom_status recom_shape_construct_destroy(recom_shape_construct* sc) {
 // ---------------------------------------------------------------------------------------
 // ConcatInputs
 // ---------------------------------------------------------------------------------------
-recom_status recom_concat_inputs(const void* const* inputs, const int64_t* nbytes, int32_t num_inputs,
-                                 void* blob, size_t blob_bytes, int64_t* offsets, size_t* needed) {
+namespace {
+// Shared body of the two packers. `elems` == nullptr: no argument trailer.
+recom_status concat_impl(const void* const* inputs, const int64_t* nbytes, const int64_t* elems,
+                         int32_t num_inputs, void* blob, size_t blob_bytes, int64_t* offsets,
+                         int64_t* args_offset, size_t* needed) {
   if (num_inputs < 0 || !needed || (num_inputs > 0 && (!nbytes || !offsets)))
     return set_error(RECOM_ERR_INVALID_ARGUMENT, "null argument");
   size_t off = 0;
@@ -269,8 +272,12 @@ recom_status recom_concat_inputs(const void* const* inputs, const int64_t* nbyte
     offsets[i] = (int64_t)off;
     off = (off + (size_t)nbytes[i] + 15) / 16 * 16;  // slots are 16-byte aligned and padded
   }
-  const size_t total = std::max<size_t>((off + 15) / 16 * 16, 16);
+  const size_t data_end = std::max<size_t>((off + 15) / 16 * 16, 16);
+  // trailer: {magic, num_slots, offsets[num_slots], elems[num_slots]}, 16-byte aligned
+  const size_t trailer = elems ? (16 + 2 * (size_t)num_inputs * 8 + 15) / 16 * 16 : 0;
+  const size_t total = data_end + trailer;
   *needed = total;
+  if (args_offset) *args_offset = elems ? (int64_t)data_end : -1;
   if (!blob) return RECOM_OK;  // size query
   if (blob_bytes < total)
     return set_error(RECOM_ERR_WORKSPACE_TOO_SMALL, "blob needs %zu bytes, got %zu", total, blob_bytes);
@@ -280,7 +287,7 @@ recom_status recom_concat_inputs(const void* const* inputs, const int64_t* nbyte
       uint8_t* dst = (uint8_t*)blob + offsets[i];
       if (nbytes[i]) memcpy(dst, inputs[i], (size_t)nbytes[i]);
       const size_t end = (size_t)offsets[i] + (size_t)nbytes[i];
-      const size_t pad_to = i + 1 < num_inputs ? (size_t)offsets[i + 1] : total;
+      const size_t pad_to = i + 1 < num_inputs ? (size_t)offsets[i + 1] : data_end;
       if (pad_to > end) memset((uint8_t*)blob + end, 0, pad_to - end);
     }
   };
@@ -296,7 +303,35 @@ recom_status recom_concat_inputs(const void* const* inputs, const int64_t* nbyte
                       (int32_t)((int64_t)num_inputs * (t + 1) / nthreads));
     for (auto& x : th) x.join();
   }
+  if (elems) {
+    uint8_t* t = (uint8_t*)blob + data_end;
+    memset(t, 0, trailer);
+    const uint64_t magic = 0x5247524132304252ull;  // kArgsMagic (csrc/plan.h)
+    const int64_t n = num_inputs;
+    memcpy(t, &magic, 8);
+    memcpy(t + 8, &n, 8);
+    if (num_inputs) {
+      memcpy(t + 16, offsets, (size_t)num_inputs * 8);
+      memcpy(t + 16 + (size_t)num_inputs * 8, elems, (size_t)num_inputs * 8);
+    }
+  }
   return RECOM_OK;
+}
+}  // namespace
+
+recom_status recom_concat_inputs(const void* const* inputs, const int64_t* nbytes, int32_t num_inputs,
+                                 void* blob, size_t blob_bytes, int64_t* offsets, size_t* needed) {
+  return concat_impl(inputs, nbytes, nullptr, num_inputs, blob, blob_bytes, offsets, nullptr, needed);
+}
+
+recom_status recom_concat_inputs_with_args(const void* const* inputs, const int64_t* nbytes,
+                                           const int64_t* elems, int32_t num_inputs, void* blob,
+                                           size_t blob_bytes, int64_t* offsets, int64_t* args_offset,
+                                           size_t* needed) {
+  if (num_inputs > 0 && !elems) return set_error(RECOM_ERR_INVALID_ARGUMENT, "null elems");
+  static const int64_t kNone = 0;
+  return concat_impl(inputs, nbytes, elems ? elems : &kNone, num_inputs, blob, blob_bytes, offsets,
+                     args_offset, needed);
 }
 
 }  // extern "C"

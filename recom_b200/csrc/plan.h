@@ -27,7 +27,9 @@ constexpr int kMinStageRows = 96;      // a DENSE run shorter than this gathers 
 constexpr int kSparseRowsPerSub = 4;   // SPARSE warp tile: rows per lane group (32 / W groups)
 constexpr int kSparseRowsPerSubHash = 2;  // ... when the ids are hashed on the fly
 constexpr int kSparseIdsPerRow = 8;    // smem budget of a SPARSE warp tile, ids per (column, row)
-constexpr int kMaxWarpScratch = 6 << 10;
+constexpr int kWarpScratchBytes = 4 << 10;  // per warp: row_splits + row ids of a column tile
+constexpr int kColTileRowsDense = 128;     // rows of a column tile with one id per row
+constexpr int kColTileRowsSparse = 32;     // rows of a multi-hot column tile
 constexpr int64_t kHbmTableBytes = 32ll << 20;  // a table beyond this is "HBM resident"
 // shared-memory staging limits (per CTA)
 constexpr int kStageTableRows = 256;       // only tables with few rows are staged
@@ -95,6 +97,52 @@ struct DevSlabCol {
   int32_t coo_index;    // rank among COO columns, -1 otherwise
   int32_t sparse_index; // rank among non-DENSE columns, -1 for DENSE
   int32_t combiner;
+  int32_t pad0, pad1;
+};
+
+// A column tile of the queue: rows [begin, begin + count) of ONE id stream - a distinct (input,
+// transform) pair - worked on by one warp: raw values -> row ids (hash / bucketize / none; every
+// lane runs the same transform on consecutive ids: coalesced, no divergence) -> for every column
+// that reads the stream (`users`: duplicates of an (input, transform) pair cost one transform,
+// pre_lookup_optimizer.cc:596-654 removes the same redundancy on the graph): 128-bit row
+// gathers, combine, concat row. The record is self-contained (the stream's static description
+// travels with it): one load, then one read of the request's slot offsets.
+struct ColItem {
+  uint64_t bucket_magic;      // floor(2^64 / num_buckets)
+  int32_t num_buckets;
+  int32_t transform;
+  int32_t value_dtype;
+  int32_t value_slot;
+  int32_t bytes_slot;         // STR payload, else -1
+  int32_t seg_slot;           // row_splits / COO slot; -1: DENSE (one id per row)
+  int32_t coo_index;          // rank among COO inputs (row_splits built in the workspace), -1
+  int32_t boundaries_offset;  // float offset in the boundary pool
+  int32_t num_boundaries;
+  int32_t begin;              // first row
+  int32_t count;              // rows
+  int32_t first_user;         // into the ColUser array
+  int32_t num_users;
+  int32_t pad;
+};
+static_assert(sizeof(ColItem) == 64, "ColItem layout");
+
+// A column reading an id stream.
+struct ColUser {
+  int32_t table;       // index into the request's table pointer array
+  int32_t row_bytes;
+  int32_t table_rows;
+  int32_t out_byte;    // byte offset of the column's slice inside an output row
+  int32_t combiner;
+  int32_t col;         // global column index (ids_out hook)
+  int32_t vec_bytes;   // 16, or the element size when the slice is not 16-byte aligned
+  int32_t pad;
+};
+static_assert(sizeof(ColUser) == 32, "ColUser layout");
+
+// A COO input (SparseTensor.indices) whose row ids are turned into row_splits in the workspace.
+struct DevCoo {
+  int32_t seg_slot;
+  int32_t seg_stride;
 };
 
 // The same column resolved against one request; lives in shared memory while a CTA (DENSE
@@ -116,7 +164,7 @@ struct ColCtx {
   int32_t stage_off;          // smem byte offset of the staged table, -1: global
   int32_t combiner;
   int32_t col;                // global column index (ids_out hook)
-  int32_t sparse_index;       // rank among non-DENSE columns (workspace ids), -1 for DENSE
+  int32_t pad;
 };
 static_assert(sizeof(ColCtx) == 88, "ColCtx layout");
 
@@ -160,18 +208,20 @@ struct DevPlan {
   const DevSlabCol* slab_cols;
   const DevSlabBnd* slab_bnds;
   const float* boundaries;
+  const ColUser* users;
+  const DevCoo* coos;
+  int32_t num_coo;
   int32_t num_cols;
   int32_t num_slabs;
   int32_t elem_bytes;   // 4 (fp32) or 2 (bf16): table and output element size
   int32_t check_ids;
   // dynamic shared memory layout (bytes from the start):
-  // [staged tables | staged boundaries | DENSE column contexts | kWarps x warp scratch]
+  // [staged tables | staged boundaries | FAST column contexts | kWarps x warp scratch]
   int32_t smem_off_bnd;
   int32_t smem_off_ctx;
   int32_t smem_off_scratch;
-  int32_t scratch_bytes;  // per warp: ids of a DENSE warp tile, or ctx + splits + ids of a SPARSE one
+  int32_t scratch_bytes;  // per warp: row ids of a FAST tile, or row_splits + row ids of a column tile
   int32_t smem_bytes;
-  int32_t pad;
 };
 
 // A unit of work: a row range of a slab. For a DENSE run (a CTA's dense warps walk it in
@@ -192,20 +242,24 @@ struct CtaWork {
   int32_t count;
 };
 
-// The schedule of a batch size (cached on the device by the plan); a kernel parameter.
-//   * FAST runs (slabs made of fast bucketize groups with staged tables) are static: every CTA
-//     owns the runs cta[c], walked by its dense warps [0, kWarps - queue_warps).
-//   * Everything else - multi-hot tiles, tiles of hashed / unstaged DENSE slabs - is a queue of
-//     warp tiles in descending cost order. The queue warps of every CTA start there at once
-//     (queue warp s of CTA c with tile s * grid + c, no claim needed), the dense warps join when
-//     their run is done; further tiles are claimed with one atomicAdd each, one tile ahead.
+// The schedule of a batch size (cached on the device by the plan); a kernel parameter. Fully
+// static: no claim counters, no atomics, no fences inside a launch (measured: an atomic claim
+// costs a warp 1-2 us, a gpu-scope release 2-6 us under load - as much as the work of a tile).
+//   * Column tiles (the queue): everything that is not a FAST slab - hashed, multi-hot, unstaged.
+//     Tile t belongs to global warp t mod (grid * kWarps), global warp = blockIdx.x + grid *
+//     warp, so the tiles of the (cost-sorted) queue are dealt CTA by CTA. A warp works on its
+//     column tiles first: they are chains of dependent loads, and start while the CTA's FAST
+//     staging is in flight.
+//   * FAST runs (slabs made of fast bucketize groups, tables staged in shared memory by TMA): every
+//     CTA owns the runs cta[c] (usually one: a row range of one slab); all warps of the CTA
+//     take its 16-row tiles from a counter in shared memory as they become free, so a warp
+//     with a long column tile simply takes fewer of them.
 struct Sched {
   const Tile* runs;          // FAST runs, grouped by CTA
   const CtaWork* cta;        // [grid]
-  const Tile* queue;         // [num_queue]
+  const ColItem* queue;      // [num_queue] column tiles
   int32_t num_queue;
-  int32_t queue_warps;
-  int32_t claim_ahead;       // 0: claim when free, 1: always one tile ahead, 2: ahead except near the end
+  int32_t pad;
 };
 
 // Per-request values known on the host at launch; a kernel parameter (no dependent loads).
@@ -214,14 +268,18 @@ struct ReqParams {
   uint8_t* out;
   int32_t* ids_out;        // may be null
   int32_t* status;         // may be null
-  int32_t* ws_ids;         // workspace: transformed ids of non-DENSE columns (overflow only)
-  int32_t* ws_row_splits;  // workspace: row_splits built from COO columns
-  // arrays of the request's argument block (device addresses; plan-cached or in the workspace)
+  int32_t* ws_row_splits;  // workspace: row_splits built from COO inputs, [num_coo][batch + 1]
+  // arrays of the request's argument block (device addresses)
   const int64_t* slot_offsets;  // [num_slots]
+  const int64_t* slot_elems;    // [num_slots]
   const void* const* tables;    // [num_tables]
-  const int32_t* ids_base;      // [num_cols + 1] prefix of ids per column
-  const int32_t* sparse_base;   // [num_sparse + 1] prefix of ids, non-DENSE only
-  int32_t* counters;            // [2] plan-owned slot: queue claims, finished warps (self-resetting)
+  const int32_t* ids_base;      // [num_cols + 1] prefix of ids per column (ids_out hook only)
+  int32_t* counters;            // sharded output only: [1] plan-owned slot counting finished warps
+                                // (the last one signals the peers and resets it)
+  uint32_t* done_seq;           // host-mapped word of this slot: receives `seq` when the launch ends
+  uint32_t seq;
+  int32_t pad0;
+  int64_t blob_bytes;           // extent of the blob (L2 prefetch at kernel entry), 0: unknown
   // Sharded output (Mode A, fused exchange): rows [g * rows_per_rank, (g + 1) * rows_per_rank)
   // are stored into peer_out[g] (rank g's [rows_per_rank, global width] tensor, peer mapped);
   // world == 0: everything goes to `out`.
@@ -239,53 +297,22 @@ struct ReqParams {
   int64_t out_row_bytes;
 };
 
-// Per-request argument block: a header followed by the arrays ReqParams points to. It holds
-// nothing that differs between requests of the same shape (no blob / output / workspace
-// pointers), so the plan keeps device copies keyed by content and a steady stream of
-// same-shaped requests uploads nothing (replaces the reference's per-call KnlArgs +
-// SymbolResults uploads, cuda_emitter.cc:2182-2232).
-struct ReqHeader {
-  int64_t batch;
-  int32_t num_coo;            // number of COO columns
-  int32_t pad0;
-  // byte offsets from the start of this block
-  uint32_t off_slot_offsets;  // int64[num_slots]
-  uint32_t off_tables;        // const void*[num_tables]
-  uint32_t off_ids_base;      // int32[num_cols + 1]
-  uint32_t off_sparse_base;   // int32[num_sparse + 1]
-  uint32_t off_coo_cols;      // int32[num_coo] column index of each COO column
-  uint32_t total_bytes;
-  int64_t pad1;
-};
-
-__host__ __device__ inline const int64_t* req_slot_offsets(const ReqHeader* r) {
-  return reinterpret_cast<const int64_t*>(reinterpret_cast<const uint8_t*>(r) +
-                                          r->off_slot_offsets);
-}
-__host__ __device__ inline const void* const* req_tables(const ReqHeader* r) {
-  return reinterpret_cast<const void* const*>(reinterpret_cast<const uint8_t*>(r) +
-                                              r->off_tables);
-}
-__host__ __device__ inline const int32_t* req_ids_base(const ReqHeader* r) {
-  return reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(r) +
-                                          r->off_ids_base);
-}
-__host__ __device__ inline const int32_t* req_sparse_base(const ReqHeader* r) {
-  return reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(r) +
-                                          r->off_sparse_base);
-}
-__host__ __device__ inline const int32_t* req_coo_cols(const ReqHeader* r) {
-  return reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(r) +
-                                          r->off_coo_cols);
-}
+// Per-request argument data on the device: int64 slot_offsets[num_slots] then int64
+// slot_elems[num_slots] (what Addons>ConcatInputs outputs as `offsets` / `shapes`,
+// concat_inputs_ops.cc:42-77). It either travels inside the blob - recom_concat_inputs appends it
+// as a trailer, so the one H2D copy of the blob brings it along and recom_plan_run uploads
+// nothing (the reference uploads KnlArgs + SymbolResults on every call,
+// cuda_emitter.cc:2182-2232) - or, for blobs packed by someone else, is staged through the
+// plan's pinned ring into the caller's workspace. The table pointer array lives in a plan-owned
+// device copy keyed by content (tables are graph variables: their addresses do not change).
+constexpr uint64_t kArgsMagic = 0x5247524132304252ull;  // trailer: {magic, num_slots, offsets[], elems[]}
 
 // kernels.cu
 void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqParams& req, int grid,
                           bool bf16, cudaStream_t stream);
 void launch_shard_wait(uint32_t* local_flags, int world, uint32_t epoch, uint32_t timeout_ms,
                        cudaStream_t stream);
-void launch_coo_to_row_splits(const DevPlan& plan, const ReqHeader* d_req, const uint8_t* blob,
-                              int32_t* ws_row_splits, int num_coo, int64_t max_nnz,
+void launch_coo_to_row_splits(const DevPlan& plan, const ReqParams& req, int64_t max_nnz,
                               cudaStream_t stream);
 void launch_scatter_columns(const void* const* d_cols, const int32_t* d_dims,
                             const int32_t* d_offsets, int32_t num_cols, int64_t batch,

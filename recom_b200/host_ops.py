@@ -17,20 +17,35 @@ import numpy as np
 from . import _lib as L
 
 
-def concat_inputs(inputs: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+def concat_inputs(inputs: Sequence[np.ndarray], with_args: bool = False):
     """-> (blob uint8, offsets int64[n], shapes int32[sum of ranks]) like the reference op's three
-    outputs (its offsets are int32; ours int64 and every slot is 16-byte aligned)."""
+    outputs (its offsets are int32; every slot here is 16-byte aligned). with_args: the blob also
+    carries the argument trailer (recom_concat_inputs_with_args) and its byte offset is returned
+    as a fourth value."""
     arrs = [np.ascontiguousarray(a) for a in inputs]
     n = len(arrs)
     ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
     nbytes = np.array([a.nbytes for a in arrs], np.int64)
+    elems = np.array([a.size for a in arrs], np.int64)
     offsets = np.zeros(max(n, 1), np.int64)
     need = C.c_size_t()
-    L.check(L.lib.recom_concat_inputs(ptrs, nbytes.ctypes.data, n, None, 0, offsets.ctypes.data, C.byref(need)))
+    args_off = C.c_int64(-1)
+
+    def call(blob_ptr, blob_bytes):
+        if with_args:
+            L.check(L.lib.recom_concat_inputs_with_args(ptrs, nbytes.ctypes.data, elems.ctypes.data, n,
+                                                        blob_ptr, blob_bytes, offsets.ctypes.data,
+                                                        C.byref(args_off), C.byref(need)))
+        else:
+            L.check(L.lib.recom_concat_inputs(ptrs, nbytes.ctypes.data, n, blob_ptr, blob_bytes,
+                                              offsets.ctypes.data, C.byref(need)))
+
+    call(None, 0)
     blob = np.empty(need.value, np.uint8)
-    L.check(L.lib.recom_concat_inputs(ptrs, nbytes.ctypes.data, n, blob.ctypes.data, blob.nbytes,
-                                      offsets.ctypes.data, C.byref(need)))
+    call(blob.ctypes.data, blob.nbytes)
     shapes = np.array([d for a in arrs for d in a.shape], np.int32)
+    if with_args:
+        return blob, offsets[:n], shapes, int(args_off.value)
     return blob, offsets[:n], shapes
 
 

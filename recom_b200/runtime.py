@@ -83,6 +83,7 @@ class Plan:
         r.status_out = status_out.data_ptr() if status_out is not None else None
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         r.stream = s.cuda_stream
+        r.args_offset = req.args_offset
         return r
 
     def run(self, req: PackedRequest, blob_dev: torch.Tensor, tables_ptrs: np.ndarray,

@@ -173,15 +173,22 @@ class PackedRequest:
     total_ids: int  # ids over all columns (ids_out length)
     sparse_ids: int  # ids over non-DENSE columns (workspace sizing)
     ids_base: np.ndarray  # int64[num_cols+1]
+    args_offset: int = -1  # byte offset of the argument trailer inside the blob, -1: none
 
 
 def _align(n: int, a: int = 16) -> int:
     return (n + a - 1) // a * a
 
 
+ARGS_MAGIC = 0x5247524132304252  # kArgsMagic (csrc/plan.h)
+
+
 def pack_request(model: Model, batch: int, features: Dict[str, Feature],
-                 pinned_blob: Optional[np.ndarray] = None) -> PackedRequest:
-    """numpy mirror of Addons>ConcatInputs (the C++ one lives in csrc/host_ops.cu)."""
+                 pinned_blob: Optional[np.ndarray] = None, trailer: bool = True) -> PackedRequest:
+    """numpy mirror of Addons>ConcatInputs (the C++ one: recom_concat_inputs_with_args in
+    csrc/host_ops.cc). trailer: append {magic, num_slots, slot_offsets[], slot_elems[]} (int64)
+    behind the last slot, so that the blob's one H2D copy carries the request's argument data
+    and recom_plan_run uploads nothing."""
     slot_arrays: List[Optional[np.ndarray]] = [None] * model.num_slots
     done = set()
     for c in model.columns:
@@ -210,7 +217,8 @@ def pack_request(model: Model, batch: int, features: Dict[str, Feature],
         offsets[s] = off
         elems[s] = a.size
         off = _align(off + a.nbytes)
-    total = _align(max(off, 16))
+    data_end = _align(max(off, 16))
+    total = data_end + (_align(16 + 16 * model.num_slots) if trailer else 0)
     if pinned_blob is not None:
         assert pinned_blob.nbytes >= total
         blob = pinned_blob[:total]
@@ -218,6 +226,9 @@ def pack_request(model: Model, batch: int, features: Dict[str, Feature],
         blob = np.zeros(total, np.uint8)
     for s, a in enumerate(slot_arrays):
         blob[offsets[s]:offsets[s] + a.nbytes] = a.view(np.uint8).reshape(-1)
+    if trailer:
+        t = np.concatenate([np.array([ARGS_MAGIC, model.num_slots], np.int64), offsets, elems])
+        blob[data_end:data_end + t.nbytes] = t.view(np.uint8)
     ids_base = np.zeros(len(model.columns) + 1, np.int64)
     sparse = 0
     for i, c in enumerate(model.columns):
@@ -227,7 +238,8 @@ def pack_request(model: Model, batch: int, features: Dict[str, Feature],
             n = int(elems[c.value_slot]) - (1 if c.value_dtype == L.STR else 0)
             sparse += n
         ids_base[i + 1] = ids_base[i] + n
-    return PackedRequest(batch, blob, offsets, elems, int(ids_base[-1]), sparse, ids_base)
+    return PackedRequest(batch, blob, offsets, elems, int(ids_base[-1]), sparse, ids_base,
+                         data_end if trailer else -1)
 
 
 def algorithmic_bytes(model: Model, req: PackedRequest) -> int:

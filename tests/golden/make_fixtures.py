@@ -41,7 +41,9 @@ def build_case(name):
 
 def digest(req, tables):
     h = hashlib.sha256()
-    h.update(req.blob.tobytes())
+    # the slots only: the argument trailer behind them repeats slot_offsets / slot_elems
+    data = req.blob if req.args_offset < 0 else req.blob[:req.args_offset]
+    h.update(data.tobytes())
     h.update(req.slot_offsets.tobytes())
     for t in tables:
         h.update(np.ascontiguousarray(t).tobytes())

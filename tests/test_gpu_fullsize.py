@@ -83,7 +83,7 @@ class Rig:
         assert torch.equal(out.view(torch.uint8), out2.view(torch.uint8))
         return out.float().cpu().numpy(), ids.cpu().numpy()[: req.total_ids]
 
-    def check(self, batches, seed0=0, **feat_kw):
+    def check(self, batches, seed0=0, plain=True, **feat_kw):
         m = self.model
         bf16 = m.out_dtype == L.BF16
         rtol = 1e-2 if bf16 else 1e-5
@@ -100,7 +100,9 @@ class Rig:
                     np.testing.assert_array_equal(got[:, sl], ref[:, sl], err_msg=c.name)
             atol = 1e-5 if bf16 else 1e-6
             bad = ~np.isclose(got, ref, rtol=rtol, atol=atol)
-            assert not bad.any(), f"B={B}: {bad.sum()} elements outside rtol={rtol} atol={atol}"
+            # (not for rows of thousands of ids: the rounding error of a long fp32 sum taken in
+            # another order is bounded by the summed magnitudes, not by the result)
+            assert not (plain and bad.any()), f"B={B}: {bad.sum()} elements outside rtol={rtol} atol={atol}"
             cases.append((req, got, ref))
         # forward bound against the summed magnitudes (the oracle re-run on |table|)
         if self.abs_tables is None:
@@ -152,7 +154,7 @@ def test_dynamic_shape_b8192_vs_oracle(dist):
     """BASELINE config 3: per-request segment counts, long tails and empty rows at the top of
     the batch sweep."""
     rig = Rig(synth.dlrm_model(40, 5, 5, 15, 5, large_rows=1 << 20, name="dyn"))
-    rig.check([8192, 33], seed0=11, dist=dist, empty_frac=0.2)
+    rig.check([8192, 33], seed0=11, plain=dist != "zipf", dist=dist, empty_frac=0.2)
     rig.close()
 
 

@@ -35,9 +35,18 @@ def test_concat_inputs_matches_python_packer():
             slot_arrays[c.value_slot] = f.values
         if c.seg_slot >= 0:
             slot_arrays[c.seg_slot] = f.row_splits
-    blob, off, _ = host_ops.concat_inputs(slot_arrays)
+    blob, off, _, args_off = host_ops.concat_inputs(slot_arrays, with_args=True)
     np.testing.assert_array_equal(off, req.slot_offsets)
-    np.testing.assert_array_equal(blob, req.blob)
+    assert args_off == req.args_offset and args_off % 16 == 0
+    np.testing.assert_array_equal(blob, req.blob)  # slots and the argument trailer alike
+    t = blob[args_off:].view(np.int64)
+    assert t[1] == m.num_slots
+    np.testing.assert_array_equal(t[2:2 + m.num_slots], req.slot_offsets)
+    np.testing.assert_array_equal(t[2 + m.num_slots:2 + 2 * m.num_slots], req.slot_elems)
+    plain = pack_request(m, 33, feats, trailer=False)
+    blob2, off2, _ = host_ops.concat_inputs(slot_arrays)
+    np.testing.assert_array_equal(blob2, plain.blob)
+    assert plain.args_offset == -1
 
 
 def test_concat_inputs_large_uses_threads_and_is_exact():

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Summarise a per-warp timer dump (make prof build; RECOM_B200_PROF_DUMP).
 
-Rows = warps (CTA-major, 16 per CTA); columns: cycles in [run entry, dense phase 1, dense
-phase 2, sparse tiles, -, -], then the warp's start / end in globaltimer ns."""
+Rows = warps (CTA-major); columns: cycles in [claims + run entry, FAST phase 1, FAST phase 2,
+wait for the transform tasks, gather tiles, transform tasks], then the warp's start / end in
+globaltimer ns."""
 import sys
 import numpy as np
 a = np.loadtxt(sys.argv[1], dtype=np.uint64).astype(np.float64)
@@ -11,10 +12,10 @@ CYC = 1.0 / 1.965  # ns per SM cycle at 1965 MHz
 t0 = a[:, 6].min()
 dur = (a[:, 7] - a[:, 6]) / 1e3
 print(f"warps {a.shape[0]}  kernel span {(a[:,7].max()-t0)/1e3:.1f} us  start spread {(a[:,6].max()-t0)/1e3:.1f} us")
-names = ["enter/tile", "d_phase1", "phase2", "s_ctx", "s_splits", "s_phase1"]
+names = ["claim/enter", "fast_p1", "fast_p2", "xform_wait", "gather", "xform"]
 dense = a[:, 1] > 0
-sparse = a[:, 3] + a[:, 4] + a[:, 5] > 0
-for nm, m in (("dense", dense), ("sparse", sparse)):
+sparse = a[:, 1] == 0
+for nm, m in (("fast", dense), ("queue", sparse)):
     if not m.any():
         continue
     d = dur[m]
