@@ -114,6 +114,8 @@ struct TileTable {
   std::vector<ColItem> queue;    // column tiles
   std::vector<CtaWork> cta;      // [grid]
   int grid = 1;
+  int fast_warps = 0;
+  int fast_ctas = -1;
   void* d_block = nullptr;  // device copy: runs, queue, cta (cached tables only)
   ~TileTable() {
     if (d_block) cudaFree(d_block);
@@ -133,6 +135,8 @@ struct TileTable {
     s.queue = (const ColItem*)(b + runs_bytes());
     s.cta = (const CtaWork*)(b + runs_bytes() + queue_bytes());
     s.num_queue = (int32_t)queue.size();
+    s.fast_warps = fast_warps;
+    s.fast_ctas = fast_ctas;
     return s;
   }
 };
@@ -154,15 +158,18 @@ struct recom_plan {
   std::vector<int32_t> sparse_cols;  // column index of each non-DENSE column
   std::vector<ColItem> units;        // queue units: distinct (input, transform, segments) triples
   std::vector<ColUser> users;        // the columns reading each unit (ColItem::first_user)
-  std::vector<double> unit_cost;     // estimated cost of a full tile of a unit
+  std::vector<double> unit_cost;     // estimated cost of a full tile of a unit (a FAST tile = 2)
+  std::vector<char> unit_hbm;        // a user's table is HBM resident: smaller tiles
   std::vector<DevCoo> coos;          // distinct COO inputs
-  std::vector<double> tile_cost;     // estimated warp instructions of one warp tile of a slab
   // device
   void* d_block = nullptr;
   DevPlan dev{};
   int elem_bytes = 4;
   int num_sms = 148;
   int ctas_per_sm = 2;
+  bool exclusive = false;      // FAST runs and column tiles on disjoint CTAs
+  double col_weight = 1.0;     // scales the column tiles' cost in that split
+  int force_fast_warps = -1;  // >= 0: override the cost-proportional split (experiments)
   int col_rows_dense = kColTileRowsDense;    // rows of a column tile, one id per row (<= 128)
   int col_rows_sparse = kColTileRowsSparse;  // rows of a multi-hot column tile (<= 32)
   // tile tables depend only on the batch size: cached (read-mostly)
@@ -677,10 +684,12 @@ void build_layout(recom_plan* p) {
         cu.combiner = d.combiner;
         cu.col = sc.col;
         cu.vec_bytes = sl.vec_bytes;
+        cu.hbm = d.table_rows * (int64_t)d.dim * es > kHbmTableBytes ? 1 : 0;
         unit_users[it->second].push_back(cu);
       }
     }
     p->unit_cost.assign(p->units.size(), 0.0);
+    p->unit_hbm.assign(p->units.size(), 0);
     for (size_t ui = 0; ui < p->units.size(); ++ui) {
       ColItem& u = p->units[ui];
       u.first_user = (int32_t)p->users.size();
@@ -695,36 +704,14 @@ void build_layout(recom_plan* p) {
       }
       double g = 0;
       for (const ColUser& cu : unit_users[ui]) {
-        const bool hbm = (int64_t)cu.table_rows * cu.row_bytes > kHbmTableBytes;
-        g += (hbm ? 2.0 : 1.0) * (1.0 + cu.row_bytes / 64.0);
+        g += (cu.hbm ? 2.0 : 1.0) * (1.0 + cu.row_bytes / 64.0);
+        p->unit_hbm[ui] = p->unit_hbm[ui] || cu.hbm;
         p->users.push_back(cu);
       }
       p->unit_cost[ui] = (u.seg_slot >= 0 ? 1.6 : 1.0) * (xf + g);
     }
   }
 
-  // cost of one warp item, in (roughly) warp instructions: the kernel is issue and latency bound
-  // as much as store bound, so the static schedule balances instruction counts. ~100 units
-  // are a microsecond of a warp on a busy SM.
-  p->tile_cost.assign(p->slabs.size(), 1.0);
-  for (size_t si = 0; si < p->slabs.size(); ++si) {
-    const DevSlab& sl = p->slabs[si];
-    const int rpp = 32 / sl.num_chunks;
-    bool hbm = false;
-    for (int k = 0; k < sl.num_cols; ++k) {
-      const recom_column_desc& d = p->descs[p->slab_cols[sl.first_col + k].col];
-      hbm = hbm || d.table_rows * d.dim * es > kHbmTableBytes;
-    }
-    if (sl.cls == kSlabSparse) {
-      const double rows_per_lane = std::ceil((double)sl.tile_rows / rpp);
-      p->tile_cost[si] = 200.0 + 4.0 * sl.num_cols + rows_per_lane * (hbm ? 220.0 : 110.0);
-    } else if (sl.all_fast && sl.cls == kSlabDenseStaged) {
-      p->tile_cost[si] = 120.0 + sl.num_cols * 32.0 * sl.tile_rows / kDenseTileRows +
-                         std::ceil((double)sl.tile_rows / rpp) * 8.0;
-    } else {
-      p->tile_cost[si] = 150.0 + std::ceil((double)sl.tile_rows / rpp) * (hbm ? 30.0 : 14.0);
-    }
-  }
   // shared memory layout: [staged tables | staged boundaries | FAST contexts | warp scratch]
   // Only FAST runs stage tables and boundaries; a FAST tile keeps its row ids in the warp's
   // scratch, a column tile its row_splits and row ids.
@@ -734,7 +721,8 @@ void build_layout(recom_plan* p) {
       max_stage = std::max(max_stage, sl.stage_bytes);
       max_bnd = std::max(max_bnd, sl.bnd_bytes);
       max_cols = std::max(max_cols, sl.num_cols);
-      need = std::max(need, sl.num_cols * kIdPitch * 4);
+      // row ids of a tile + two buffers of its raw values (the next tile's are copied ahead)
+      need = std::max(need, sl.num_cols * kIdPitch * 4 + 2 * sl.num_cols * sl.tile_rows * 4);
     }
   }
   p->dev.smem_off_bnd = (int32_t)align_up((size_t)max_stage, 128);
@@ -801,8 +789,10 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   double queue_cost = 0;
   for (size_t ui = 0; ui < p->units.size(); ++ui) {
     const ColItem& u = p->units[ui];
-    const int64_t step = u.seg_slot >= 0 ? rows_sparse : rows_dense;
     const int64_t full = u.seg_slot >= 0 ? kColTileRowsSparse : kColTileRowsDense;
+    int64_t step = u.seg_slot >= 0 ? rows_sparse : rows_dense;
+    // rows gathered from HBM-resident tables: a quarter of the rows, four times the tiles in flight
+    if (p->unit_hbm[ui]) step = std::max<int64_t>(u.seg_slot >= 0 ? 4 : 32, step / 4);
     for (int64_t b = 0; b < B; b += step) {
       ColItem it = u;
       it.begin = (int32_t)b;
@@ -813,37 +803,46 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     }
   }
   std::stable_sort(qs.begin(), qs.end(), [](const Costed& a, const Costed& b) { return a.cost > b.cost; });
-  for (const Costed& c : qs) tt->queue.push_back(c.it);
 
   // ---- FAST runs ----
   std::vector<double> cost(fast.size());
   double fast_cost = 0;
   int64_t fast_tiles = 0;
   for (size_t i = 0; i < fast.size(); ++i) {
-    cost[i] = (double)tiles_of(fast[i]) * p->tile_cost[fast[i]];
+    // a FAST tile costs 2 units per 8 KB it stores (16 rows x 512 bytes)
+    const DevSlab& sl = p->slabs[fast[i]];
+    cost[i] = (double)tiles_of(fast[i]) * 2.0 * (sl.tile_rows * sl.num_chunks * sl.vec_bytes) / 8192.0;
     fast_cost += cost[i];
     fast_tiles += tiles_of(fast[i]);
   }
   // grid: enough CTAs for one warp per item, in whole waves of the SMs
-  int64_t units = std::max<int64_t>(1, ((int64_t)tt->queue.size() + fast_tiles + kWarps - 1) / kWarps);
+  int64_t units = std::max<int64_t>(1, ((int64_t)qs.size() + fast_tiles + kWarps - 1) / kWarps);
   units = std::max<int64_t>(units, std::min<int64_t>((int64_t)fast.size(), cap_ctas));
   if (units > p->num_sms) units = (units + p->num_sms - 1) / p->num_sms * p->num_sms;
   const int grid = (int)std::min<int64_t>(cap_ctas, units);
   tt->grid = grid;
 
+  // Exclusive roles (RECOM_B200_EXCLUSIVE): the FAST runs go to the first `nf` CTAs only, the
+  // column tiles to the others, in proportion to the estimated cost of the two kinds of work.
+  int nf = grid;
+  if (p->exclusive && !fast.empty() && !qs.empty() && grid >= 4) {
+    nf = (int)(grid * fast_cost / (fast_cost + queue_cost * p->col_weight) + 0.5);
+    nf = std::max(1, std::min(grid - 1, nf));
+    tt->fast_ctas = nf;
+  }
   std::vector<std::vector<Tile>> per_cta(grid);
-  if (!fast.empty() && (size_t)grid >= fast.size()) {
+  if (!fast.empty() && (size_t)nf >= fast.size()) {
     std::vector<int> n_ctas(fast.size(), 1);
     int given = (int)fast.size();
     std::vector<std::pair<double, int>> rem;
     for (size_t i = 0; i < fast.size(); ++i) {
-      const double share = (grid - (double)fast.size()) * cost[i] / fast_cost;
+      const double share = (nf - (double)fast.size()) * cost[i] / fast_cost;
       n_ctas[i] += (int)share;
       given += (int)share;
       rem.push_back({-(share - (int)share), (int)i});
     }
     std::sort(rem.begin(), rem.end());
-    for (int k = 0; given < grid && k < (int)rem.size(); ++k, ++given) n_ctas[rem[k].second]++;
+    for (int k = 0; given < nf && k < (int)rem.size(); ++k, ++given) n_ctas[rem[k].second]++;
     int c = 0;
     for (size_t i = 0; i < fast.size(); ++i) {
       const int64_t T = tiles_of(fast[i]), TR = p->slabs[fast[i]].tile_rows;
@@ -851,7 +850,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
       for (int64_t j = 0; j < n; ++j) {
         const int64_t t0 = j * T / n, t1 = (j + 1) * T / n;
         const int64_t r0 = t0 * TR, r1 = std::min<int64_t>(B, t1 * TR);
-        if (r1 > r0) per_cta[c % grid].push_back(make(fast[i], r0, r1 - r0));
+        if (r1 > r0) per_cta[c % nf].push_back(make(fast[i], r0, r1 - r0));
         ++c;
       }
     }
@@ -859,19 +858,33 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     std::vector<int> idx(fast.size());
     for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-    std::vector<double> load(grid, 0.0);
+    std::vector<double> load(nf, 0.0);
     for (int i : idx) {
       const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
       per_cta[c].push_back(make(fast[i], 0, B));
       load[c] += cost[i];
     }
   }
-  tt->cta.assign(grid, CtaWork{0, 0});
+  tt->cta.assign(grid, CtaWork{0, 0, 0, 0});
   for (int c = 0; c < grid; ++c) {
     tt->cta[c].first = (int32_t)tt->runs.size();
     tt->cta[c].count = (int32_t)per_cta[c].size();
     for (Tile& t : per_cta[c]) tt->runs.push_back(t);
+    // the cost-sorted column tiles, dealt round robin over the CTAs that hold column tiles
+    // (all of them, or those behind the FAST CTAs): the cc-th of them gets tiles cc, cc + gc, ...
+    tt->cta[c].q_first = (int32_t)tt->queue.size();
+    const int first_c = tt->fast_ctas >= 0 ? tt->fast_ctas : 0, gc = grid - first_c;
+    if (c >= first_c)
+      for (size_t i = (size_t)(c - first_c); i < qs.size(); i += (size_t)gc) tt->queue.push_back(qs[i].it);
+    tt->cta[c].q_count = (int32_t)tt->queue.size() - tt->cta[c].q_first;
   }
+  // warps that start with the FAST tiles: in proportion to the estimated cost of the two kinds
+  if (fast.empty()) tt->fast_warps = 0;
+  else if (qs.empty()) tt->fast_warps = kWarps;
+  else
+    tt->fast_warps = std::max(1, std::min(kWarps - 1, (int)(kWarps * fast_cost / (fast_cost + queue_cost) + 0.5)));
+  if (p->force_fast_warps >= 0 && !fast.empty() && !qs.empty())
+    tt->fast_warps = std::max(1, std::min(kWarps - 1, p->force_fast_warps));
   return tt;
 }
 
@@ -1072,6 +1085,9 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
     while (r * 2 <= v && r * 2 <= hi) r *= 2;
     return r;
   };
+  if (const char* e = getenv("RECOM_B200_FAST_WARPS")) p->force_fast_warps = atoi(e);
+  if (const char* e = getenv("RECOM_B200_EXCLUSIVE")) p->exclusive = atoi(e) != 0;
+  if (const char* e = getenv("RECOM_B200_COL_WEIGHT")) p->col_weight = atof(e);
   p->col_rows_dense = pow2_env("RECOM_B200_COL_ROWS_DENSE", 32, kColTileRowsDense, kColTileRowsDense);
   p->col_rows_sparse = pow2_env("RECOM_B200_COL_ROWS_SPARSE", 4, kColTileRowsSparse, kColTileRowsSparse);
   build_layout(p);

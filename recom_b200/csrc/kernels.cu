@@ -43,7 +43,6 @@
 
 namespace recom {
 
-// Level timers of the transform path (-DRECOM_PROFILE_X, with -DRECOM_PROFILE): a clock read that
 
 // ---------------------------------------------------------------------------
 // small load/store helpers
@@ -817,176 +816,184 @@ __device__ __forceinline__ void bucket_smem8_uniform(uint32_t bp, int32_t nb, co
   }
 }
 
-// phase 1 of a FAST run's warp tile. A tile has at most slab.tile_rows rows: 32, or 16 for slabs
-// of at least 16 columns (two lane groups take alternate groups of 8 columns, so a 16-column
-// slab needs one pass and its stores start after half the time). lane = (column group, row).
-// The id slot holds the raw row id; phase 2, whose lanes own one column each, turns it into an
-// address. Bounds check and the ids_out parity hook are off the fast path.
-__device__ __forceinline__ void put_id(const ReqRegs& Q, const ColCtx& c, int32_t* s_ids, int cl,
-                                       int row, int64_t i, int32_t id) {
-  if (Q.check | (Q.ids_out != nullptr)) {
-    if (Q.check) id = checked_id(id, c.table_rows, Q.status);
-    if (Q.ids_out) Q.ids_out[Q.ids_base[c.col] + i] = id;
-  }
-  s_ids[cl * kIdPitch + row] = id;
+// ---------------------------------------------------------------------------
+// FAST tiles. Everything a warp touches between its global loads (the raw values, prefetched one
+// tile ahead) and its global stores lives in shared memory and is addressed with 32-bit shared
+// addresses.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+#define CTX_OFF(field) ((uint32_t)offsetof(ColCtx, field))
+
+// Bounds check and the ids_out parity hook of a FAST tile, off the fast path.
+__device__ __noinline__ int32_t fast_note_id(const ReqRegs Q, uint32_t ctx, int64_t i, int32_t id) {
+  if (Q.check) id = checked_id(id, (int32_t)lds_u32(ctx + CTX_OFF(table_rows)), Q.status);
+  if (Q.ids_out) Q.ids_out[Q.ids_base[lds_u32(ctx + CTX_OFF(col))] + i] = id;
+  return id;
 }
 
-// The raw values of one fast group (8 columns) for the lane's row: 8 coalesced loads in flight.
-__device__ __forceinline__ void fast_load(const ColCtx* ctx, int cbase, int64_t i, bool valid,
-                                          float (&v)[8]) {
+// The raw values of a tile, requested one tile ahead: asynchronous 4-byte copies (LDGSTS)
+// straight into the warp's value buffer in shared memory, slot (column, row) - no registers
+// are held while the previous tile is worked on, and nothing waits before phase 1 does. Every
+// lane copies (and later reads) the values of its own (column groups, row).
+__device__ __forceinline__ void fast_prefetch(uint32_t s_ctx, const DevSlab& slab, int64_t b0,
+                                              int rows, uint32_t s_val, int lane) {
+  const int nc = slab.num_cols;
+  const int TR = slab.tile_rows;
+  const int row = lane & (TR - 1), cg = lane / TR, ncg = 32 / TR;
+  if (row < rows) {
+    for (int cbase = cg * 8; cbase < nc; cbase += ncg * 8) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = valid ? __ldg((const float*)ctx[cbase + k].values + i) : 0.f;
+      for (int k = 0; k < 8; ++k) {
+        const float* p = reinterpret_cast<const float*>(
+            lds_u64(s_ctx + (uint32_t)(cbase + k) * (uint32_t)sizeof(ColCtx) + CTX_OFF(values)));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_val + 4u * (uint32_t)((cbase + k) * TR + row)),
+                     "l"(p + b0 + row)
+                     : "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// FAST run (every column belongs to a fast group): lane group cg takes the groups cg,
-// cg + ncg, ...; 8 searches in lock step. `v0` holds the values of the lane's first group,
-// requested while the warp's previous tile was still being worked on.
-__device__ __forceinline__ void dense_phase1_fast(const ReqRegs& Q, const ColCtx* ctx,
-                                                  const DevSlab& slab, int64_t b0, int rows,
-                                                  const float* s_bnd, int32_t* s_ids, int lane,
-                                                  const float (&v0)[8]) {
+// phase 1: lane = (column group of 8, row): 8 upper_bound searches in lock step through the
+// boundary set's grid; the id slot of (column, row) receives the byte offset of the table row
+// inside the staged table region (STAGED) or the raw row id. The values come from the warp's
+// value buffer (fast_prefetch). Lane group cg takes the groups cg, cg + ncg, ...
+template <bool STAGED>
+__device__ __forceinline__ void fast_phase1(const ReqRegs& Q, uint32_t s_ctx, const DevSlab& slab,
+                                            int64_t b0, int rows, uint32_t s_bnd, uint32_t s_ids,
+                                            uint32_t s_val, int lane) {
   const int nc = slab.num_cols;
   const int TR = slab.tile_rows;
   const int row = lane & (TR - 1), cg = lane / TR, ncg = 32 / TR;
   const bool valid = row < rows;
   const int64_t i = b0 + row;
+  const bool hook = Q.check | (Q.ids_out != nullptr);
   for (int cbase = cg * 8; cbase < nc; cbase += ncg * 8) {
+    const uint32_t ctx = s_ctx + (uint32_t)cbase * (uint32_t)sizeof(ColCtx);
     float v[8];
     int32_t lo[8];
-    if (cbase == cg * 8) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = v0[k];
-    } else {
-      fast_load(ctx, cbase, i, valid, v);
-    }
+    for (int k = 0; k < 8; ++k)
+      v[k] = valid ? lds_f32(s_val + 4u * (uint32_t)((cbase + k) * TR + row)) : 0.f;
     if ((slab.uni8_mask >> (cbase >> 3)) & 1u) {
-      const ColCtx& c0 = ctx[cbase];
-      bucket_smem8_uniform(smem_u32(s_bnd + c0.bnd_off), c0.num_boundaries, v, lo);
+      bucket_smem8_uniform(s_bnd + 4u * lds_u32(ctx + CTX_OFF(bnd_off)),
+                           (int32_t)lds_u32(ctx + CTX_OFF(num_boundaries)), v, lo);
     } else {
       uint32_t bp[8];
       int32_t nb[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const ColCtx& c = ctx[cbase + k];
-        bp[k] = smem_u32(s_bnd + c.bnd_off);
-        nb[k] = c.num_boundaries;
+        const uint32_t c = ctx + k * (uint32_t)sizeof(ColCtx);
+        bp[k] = s_bnd + 4u * lds_u32(c + CTX_OFF(bnd_off));
+        nb[k] = (int32_t)lds_u32(c + CTX_OFF(num_boundaries));
       }
       bucket_smem8(bp, nb, v, lo);
     }
     if (valid) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) put_id(Q, ctx[cbase + k], s_ids, cbase + k, row, i, lo[k]);
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t c = ctx + k * (uint32_t)sizeof(ColCtx);
+        int32_t id = lo[k];
+        if (hook) id = fast_note_id(Q, c, i, id);
+        if (STAGED) id = (int32_t)lds_u32(c + CTX_OFF(stage_off)) + id * (int32_t)lds_u32(c + CTX_OFF(row_bytes));
+        sts_i32(s_ids + 4u * (uint32_t)((cbase + k) * kIdPitch + row), id);
+      }
     }
   }
 }
 
-// phase 2 of a DENSE warp tile: lane = chunk; 32 / W rows per pass; UNROLL independent rows in
-// flight; 128-bit gathers from the staged tables (or ld.global.nc), 128-bit streaming stores
+// phase 2: lane = chunk of the slab's span; 32 / W rows per pass; U independent rows in
+// flight; 128-bit loads from the staged tables (or ld.global.nc), 128-bit streaming stores
 // straight into the concat rows.
-
-// phase 2 of a FAST tile: lane = chunk of the slab's span; 32 / W rows per pass; U independent
-// rows in flight; 128-bit gathers from the staged tables (or ld.global.nc), 128-bit streaming
-// stores straight into the concat rows.
 template <int VEC, bool STAGED, class QT>
-__device__ __forceinline__ void dense_phase2_impl(const QT& Q, const ColCtx* ctx, int W,
-                                             const DevChunk& ch, int64_t b0, int rows,
-                                             const uint8_t* s_tables, const int32_t* s_ids,
-                                             int lane) {
+__device__ __forceinline__ void fast_phase2_impl(const QT& Q, uint32_t s_ctx, int W,
+                                                 const DevChunk& ch, int64_t b0, int rows,
+                                                 uint32_t s_tables, uint32_t s_ids, int lane) {
 #ifdef RECOM_TEST_NODP2
   return;
 #endif
   const int rpp = 32 / W;  // rows handled per pass
   const int sub = lane / W;
   if (sub >= rpp) return;
-  const ColCtx& c = ctx[ch.col_local];
-  const int32_t row_bytes = c.row_bytes;
-  const uint32_t ids = smem_u32(s_ids + ch.col_local * kIdPitch);
+  const uint32_t ids = s_ids + 4u * (uint32_t)(ch.col_local * kIdPitch);
   RowCursor<QT::kSharded> outp(Q, b0, sub, rpp, ch.out_byte);
   constexpr int U = 8;
-  if (STAGED) {
-    const uint32_t tbl = smem_u32(s_tables + c.stage_off + ch.table_byte);
-    for (int r = sub; r < rows; r += U * rpp) {
-      Chunk<VEC> v[U];
+  const uint32_t ctx = s_ctx + (uint32_t)ch.col_local * (uint32_t)sizeof(ColCtx);
+  const uint32_t tbl_s = s_tables + (uint32_t)ch.table_byte;
+  const uint8_t* tbl_g = nullptr;
+  int32_t row_bytes = 0;
+  if (!STAGED) {
+    tbl_g = reinterpret_cast<const uint8_t*>(lds_u64(ctx + CTX_OFF(table))) + ch.table_byte;
+    row_bytes = (int32_t)lds_u32(ctx + CTX_OFF(row_bytes));
+  }
+  int r = sub;
+  for (; r + (U - 1) * rpp < rows; r += U * rpp) {  // full passes: no predicates
+    Chunk<VEC> v[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int rr = min(r + k * rpp, rows - 1);  // clamped: the loads of a ragged tail are dropped
-        v[k] = lds_chunk<VEC>(tbl + (uint32_t)(lds_u32(ids + 4u * (uint32_t)rr) * row_bytes));
-      }
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        uint8_t* o = outp.next();
-        if (r + k * rpp < rows) v[k].store(o);
-      }
+    for (int k = 0; k < U; ++k) {
+      const uint32_t o = lds_u32(ids + 4u * (uint32_t)(r + k * rpp));
+      if (STAGED) v[k] = lds_chunk<VEC>(tbl_s + o);
+      else v[k].load(tbl_g + (int64_t)o * row_bytes);
     }
-  } else {
-    const uint8_t* tbl = c.table + ch.table_byte;
-    for (int r = sub; r < rows; r += U * rpp) {
-      Chunk<VEC> v[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int rr = min(r + k * rpp, rows - 1);
-        v[k].load(tbl + (int64_t)lds_u32(ids + 4u * (uint32_t)rr) * row_bytes);
-      }
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        uint8_t* o = outp.next();
-        if (r + k * rpp < rows) v[k].store(o);
-      }
-    }
+    for (int k = 0; k < U; ++k) v[k].store(outp.next());
+  }
+  for (; r < rows; r += rpp) {  // ragged tail of the run's last tile
+    const uint32_t o = lds_u32(ids + 4u * (uint32_t)r);
+    Chunk<VEC> v;
+    if (STAGED) v = lds_chunk<VEC>(tbl_s + o);
+    else v.load(tbl_g + (int64_t)o * row_bytes);
+    v.store(outp.next());
   }
 }
 
 // The 16-byte variants are the hot ones and inlined; element-wise slabs (unaligned slices) are
 // rare and kept out of line to keep the hot code small.
 template <int VEC, bool STAGED, class QT>
-__device__ __noinline__ void dense_phase2_cold(const QT Q, const ColCtx* ctx, int W,
-                                               const DevChunk& ch, int64_t b0, int rows,
-                                               const uint8_t* s_tables, const int32_t* s_ids,
-                                               int lane) {
-  dense_phase2_impl<VEC, STAGED>(Q, ctx, W, ch, b0, rows, s_tables, s_ids, lane);
+__device__ __noinline__ void fast_phase2_cold(const QT Q, uint32_t s_ctx, int W, const DevChunk ch,
+                                              int64_t b0, int rows, uint32_t s_tables,
+                                              uint32_t s_ids, int lane) {
+  fast_phase2_impl<VEC, STAGED>(Q, s_ctx, W, ch, b0, rows, s_tables, s_ids, lane);
 }
 template <int VEC, bool STAGED, class QT>
-__device__ __forceinline__ void dense_phase2(const QT& Q, const ColCtx* ctx, int W,
-                                             const DevChunk& ch, int64_t b0, int rows,
-                                             const uint8_t* s_tables, const int32_t* s_ids,
-                                             int lane) {
-  if (VEC == 16) dense_phase2_impl<VEC, STAGED>(Q, ctx, W, ch, b0, rows, s_tables, s_ids, lane);
-  else dense_phase2_cold<VEC, STAGED>(Q, ctx, W, ch, b0, rows, s_tables, s_ids, lane);
+__device__ __forceinline__ void fast_phase2(const QT& Q, uint32_t s_ctx, int W, const DevChunk& ch,
+                                            int64_t b0, int rows, uint32_t s_tables, uint32_t s_ids,
+                                            int lane) {
+  if (VEC == 16) fast_phase2_impl<VEC, STAGED>(Q, s_ctx, W, ch, b0, rows, s_tables, s_ids, lane);
+  else fast_phase2_cold<VEC, STAGED>(Q, s_ctx, W, ch, b0, rows, s_tables, s_ids, lane);
 }
 
-
+// Optional per-warp timing, compiled in only with -DRECOM_PROFILE (make prof): every warp
+// records [start, end] in globaltimer ns plus the cycles it spent per phase:
+// 0 claims / records / entry, 1 FAST phase 1, 2 FAST phase 2, 3 column tile: transform,
+// 4 column tile: gathers, 5 waits for the FAST staging.
 #ifdef RECOM_PROFILE
 __device__ __forceinline__ uint64_t gtimer() {
   uint64_t t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define PROF_DECL                                     \
-  uint32_t prof_acc[6] = {0, 0, 0, 0, 0, 0};          \
-  const uint64_t prof_t0 = gtimer();                  \
-  uint32_t prof_last = (uint32_t)clock64();
-#ifdef RECOM_PROFILE_X
-#define PROF_ON(i) ((i) == 5)
-#else
-#define PROF_ON(i) true
-#endif
+struct ProfRef {
+  uint32_t* acc;
+  uint32_t* last;
+};
+#define PROF_PARAM , ProfRef pr
+#define PROF_ARG , pr
 #define PROF_T(i)                                     \
-  if (PROF_ON(i)) {                                   \
+  {                                                   \
     const uint32_t now_ = (uint32_t)clock64();        \
-    prof_acc[i] += now_ - prof_last;                  \
-    prof_last = now_;                                 \
-  }
-#define PROF_END                                                                       \
-  if ((threadIdx.x & 31) == 0 && A.prof) {                                             \
-    uint64_t* o_ = A.prof + ((size_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * 8;    \
-    _Pragma("unroll") for (int i_ = 0; i_ < 6; ++i_) o_[i_] = prof_acc[i_];            \
-    o_[6] = prof_t0;                                                                   \
-    o_[7] = gtimer();                                                                  \
+    pr.acc[i] += now_ - *pr.last;                     \
+    *pr.last = now_;                                  \
   }
 #else
-#define PROF_DECL
+#define PROF_PARAM
+#define PROF_ARG
 #define PROF_T(i)
-#define PROF_END
 #endif
 
 // ---------------------------------------------------------------------------
@@ -1016,7 +1023,7 @@ __device__ __noinline__ int32_t note_id(const ReqRegs Q, int32_t col, int32_t ta
 // A column reading the tile's stream, resolved against the request.
 struct UserRegs {
   const uint8_t* table;
-  int32_t row_bytes, table_rows, out_byte, combiner, col, vec_bytes;
+  int32_t row_bytes, table_rows, out_byte, combiner, col, vec_bytes, hbm;
 };
 __device__ __forceinline__ UserRegs load_user(const DevPlan& P, const ReqParams& A, int32_t index) {
   const int4* q = reinterpret_cast<const int4*>(P.users + index);
@@ -1029,7 +1036,18 @@ __device__ __forceinline__ UserRegs load_user(const DevPlan& P, const ReqParams&
   u.combiner = b.x;
   u.col = b.y;
   u.vec_bytes = b.z;
+  u.hbm = b.w;
   return u;
+}
+
+// The table rows of ids s_ids[0, n) -> L2 (tables far larger than L2: HBM latency and the page
+// walks behind it are paid once per tile, all rows in flight together, instead of once per
+// pass of the gather).
+__device__ __forceinline__ void prefetch_rows(const UserRegs& u, uint32_t s_ids, int n, int lane) {
+  for (int j = lane; j < n; j += 32) {
+    const uint8_t* row = u.table + (int64_t)lds_i32(s_ids + 4u * (uint32_t)j) * u.row_bytes;
+    for (int b = 0; b < u.row_bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+  }
 }
 
 // Where the rows a lane of a column tile stores go. Sharded output: a tile of up to 128 rows
@@ -1107,13 +1125,11 @@ __device__ __noinline__ void gather_rows_cold(const QT Q, const UserRegs u, int6
   gather_rows<VEC>(Q, u, b0, n, s_ids, lane);
 }
 
-// End of a row: combiner scaling and the row's one store. Out of line: the gather stream below
-// reaches it from every unrolled slot, and inlining it there would multiply the code size.
+// End of a row: combiner scaling (TF-CPU: segment_reduction_ops_impl.h:619-629,765-770 - n < 10
+// multiplies by 1/m, n >= 10 divides by m; m = n or sqrt(n)) and the row's one store.
 template <int VEC, bool BF16>
-__device__ __noinline__ void flush_row(Acc<VEC, BF16> acc, int32_t n, int combiner, uint8_t* outp) {
+__device__ __forceinline__ void flush_row(Acc<VEC, BF16>& acc, int32_t n, int combiner, uint8_t* outp) {
   if (n > 1 && combiner != RECOM_COMBINE_SUM) {
-    // TF-CPU scaling (segment_reduction_ops_impl.h:619-629,765-770):
-    // n < 10 multiplies by 1/m, n >= 10 divides by m; m = n or sqrt(n).
     const float m = combiner == RECOM_COMBINE_MEAN ? (float)n : (float)__dsqrt_rn((double)n);
     if (n < 10) acc.mul(__fdiv_rn(1.0f, m));
     else acc.div(m);
@@ -1121,73 +1137,55 @@ __device__ __noinline__ void flush_row(Acc<VEC, BF16> acc, int32_t n, int combin
   acc.pack().store(outp);
 }
 
+// Rows with more ids than this are summed by all lane groups together (coop_row).
+constexpr int kCoopRowIds = 64;
+
 // Multi-hot rows [b0, b0 + rows): row r owns ids [sp[r], sp[r + 1]) of the stream, held in
-// s_ids[e - e_base]. The lane walks the ids of its rows as ONE stream with up to U independent
-// row gathers in flight across row boundaries, fp32 accumulation in stream order (the order of
-// the TF-CPU kernel), one store per row; empty rows store zeros.
+// s_ids[e - e_base]. lane = (lane group, chunk); a lane group takes the rows sub, sub + rpp, ...
+// one at a time: up to U independent row gathers in flight, fp32 accumulation in id order (the
+// order of the TF-CPU kernel: bit-identical sums), one store per row; empty rows store zeros.
+// Rows longer than kCoopRowIds are left to coop_row.
 template <int VEC, bool BF16, class QT>
 __device__ __forceinline__ void sparse_rows(const QT& Q, const UserRegs& u, int64_t b0, int rows,
                                             uint32_t s_sp, uint32_t s_ids, int32_t e_base, int lane) {
   const int C = u.row_bytes / VEC;
   const bool hook = Q.check | (Q.ids_out != nullptr);
   constexpr int U = BF16 ? 4 : 8;
+  const uint32_t ids0 = s_ids - 4u * (uint32_t)e_base;
   for (int c0 = 0; c0 < C; c0 += 32) {
     const int W = min(32, C - c0);
     const int rpp = 32 / W, sub = lane / W;
     if (sub >= rpp) continue;
-    const int rps = (rows + rpp - 1) / rpp;  // rows of this lane group
-    int r = sub * rps;
-    const int r_end = min(rows, r + rps);
-    if (r >= r_end) continue;
     const int chb = (c0 + lane - sub * W) * VEC;
     const uint8_t* tbl = u.table + chb;
     const int64_t row_bytes = u.row_bytes;
-    const int combiner = u.combiner;
     const int32_t hook_col = chb == 0 ? u.col : -1;
-    ColCursor<QT::kSharded> outp(Q, b0, r, 1, u.out_byte + chb);
-    int32_t e = lds_i32(s_sp + 4u * (uint32_t)r);
-    const int32_t e_end = lds_i32(s_sp + 4u * (uint32_t)r_end);
-    int32_t row_beg = e, row_end = lds_i32(s_sp + 4u * (uint32_t)(r + 1));
-    Acc<VEC, BF16> acc;
-    acc.clear();
-    auto flush = [&]() { flush_row<VEC, BF16>(acc, row_end - row_beg, combiner, outp.next()); };
-    const uint32_t ids0 = s_ids - 4u * (uint32_t)e_base;
-    while (e < e_end) {
-      int32_t id[U];
-#pragma unroll
-      for (int k = 0; k < U; ++k) id[k] = e + k < e_end ? lds_i32(ids0 + 4u * (uint32_t)(e + k)) : 0;
-      if (hook) {
-#pragma unroll
-        for (int k = 0; k < U; ++k)
-          if (e + k < e_end) id[k] = note_id(Q, hook_col, u.table_rows, e + k, id[k]);
-      }
-      Chunk<VEC> v[U];
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        if (e + k < e_end) v[k].load(tbl + (int64_t)id[k] * row_bytes);
-        else v[k].zero();
-      }
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        if (e + k < e_end) {
-          while (e + k >= row_end) {  // the stream enters the next (possibly empty) row
-            flush();
-            ++r;
-            row_beg = row_end;
-            row_end = lds_i32(s_sp + 4u * (uint32_t)(r + 1));
-            acc.clear();
-          }
-          acc.add(v[k]);
-        }
-      }
-      e += U;
-    }
-    for (;;) {  // the row being accumulated, then the empty rows after the last id
-      flush();
-      if (++r >= r_end) break;
-      row_beg = row_end;
-      row_end = lds_i32(s_sp + 4u * (uint32_t)(r + 1));
+    ColCursor<QT::kSharded> outp(Q, b0, sub, rpp, u.out_byte + chb);
+    for (int r = sub; r < rows; r += rpp) {
+      const int32_t e0 = lds_i32(s_sp + 4u * (uint32_t)r), e1 = lds_i32(s_sp + 4u * (uint32_t)(r + 1));
+      uint8_t* o = outp.next();
+      if (e1 - e0 > kCoopRowIds) continue;
+      Acc<VEC, BF16> acc;
       acc.clear();
+      for (int32_t e = e0; e < e1; e += U) {
+        int32_t id[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) id[k] = e + k < e1 ? lds_i32(ids0 + 4u * (uint32_t)(e + k)) : 0;
+        if (hook) {
+#pragma unroll
+          for (int k = 0; k < U; ++k)
+            if (e + k < e1) id[k] = note_id(Q, hook_col, u.table_rows, e + k, id[k]);
+        }
+        Chunk<VEC> v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          if (e + k < e1) v[k].load(tbl + (int64_t)id[k] * row_bytes);
+          else v[k].zero();
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) acc.add(v[k]);  // + 0.0f for the slots past the row's end
+      }
+      flush_row<VEC, BF16>(acc, e1 - e0, u.combiner, o);
     }
   }
 }
@@ -1197,80 +1195,122 @@ __device__ __noinline__ void sparse_rows_cold(const QT Q, const UserRegs u, int6
   sparse_rows<VEC, BF16>(Q, u, b0, rows, s_sp, s_ids, e_base, lane);
 }
 
-// A row with more ids than the scratch holds (long tails of variable-length features): the
-// ids are transformed `cap` at a time; the lane groups take alternate ids, and their partial
-// sums meet in shared memory. (Another summation order than the stream's: within the fp32
-// tolerance, not bit-identical to a sequential sum.)
+// The partial sums of a long row, accumulated over the ids s_ids[0, cn) (stream positions
+// e_first + j): the lane groups take alternate ids. (Another summation order than the stream's:
+// within the fp32 tolerance, not bit-identical to a sequential sum.)
 template <int VEC, bool BF16, class QT>
-__device__ __noinline__ void long_row(const DevPlan& P, const QT Q, const ColItem it,
-                                      const UserRegs u, const uint8_t* values, const uint8_t* bytes,
-                                      int64_t row, int32_t e0, int32_t e1, uint32_t s_ids, int cap,
-                                      int lane) {
-  constexpr int NE = Acc<VEC, BF16>::kFloats;
-  const int C = u.row_bytes / VEC;
+__device__ __forceinline__ void coop_accumulate(const QT& Q, const UserRegs& u, Acc<VEC, BF16>& acc,
+                                                const uint8_t* tbl, int32_t hook_col, int rpp, int sub,
+                                                uint32_t s_ids, int32_t cn, int32_t e_first) {
   const bool hook = Q.check | (Q.ids_out != nullptr);
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    const int W = min(32, C - c0);
-    const int rpp = 32 / W, sub = lane / W;
-    const bool active = sub < rpp;
-    const int chb = (c0 + lane - sub * W) * VEC;
-    const uint8_t* tbl = u.table + chb;
-    const int32_t hook_col = chb == 0 ? u.col : -1;
-    Acc<VEC, BF16> acc;
-    acc.clear();
-    for (int32_t cb = e0; cb < e1; cb += cap) {
-      const int32_t cn = min(e1 - cb, cap);
-      transform_ids(P, it, values, bytes, cb, cb + cn, s_ids, lane);
-      __syncwarp();
-      if (active) {
-        for (int32_t j = sub; j < cn; j += 4 * rpp) {
-          int32_t id[4];
+  for (int32_t j = sub; j < cn; j += 4 * rpp) {
+    int32_t id[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) id[k] = j + k * rpp < cn ? lds_i32(s_ids + 4u * (uint32_t)(j + k * rpp)) : 0;
-          if (hook) {
+    for (int k = 0; k < 4; ++k) id[k] = j + k * rpp < cn ? lds_i32(s_ids + 4u * (uint32_t)(j + k * rpp)) : 0;
+    if (hook) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (j + k * rpp < cn) id[k] = note_id(Q, hook_col, u.table_rows, cb + j + k * rpp, id[k]);
-          }
-          Chunk<VEC> v[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (j + k * rpp < cn) v[k].load(tbl + (int64_t)id[k] * u.row_bytes);
-            else v[k].zero();
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) acc.add(v[k]);
-        }
-      }
-      __syncwarp();
+      for (int k = 0; k < 4; ++k)
+        if (j + k * rpp < cn) id[k] = note_id(Q, hook_col, u.table_rows, e_first + j + k * rpp, id[k]);
     }
-    // the partial sums of the lane groups -> group 0
+    Chunk<VEC> v[4];
 #pragma unroll
-    for (int i = 0; i < NE; ++i)
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_ids + 4u * (uint32_t)(lane * NE + i)), "f"(acc.at(i))
-                   : "memory");
-    __syncwarp();
-    if (sub == 0) {
-      for (int s = 1; s < rpp; ++s) {
-#pragma unroll
-        for (int i = 0; i < NE; ++i) acc.at(i) += lds_f32(s_ids + 4u * (uint32_t)((s * W + lane) * NE + i));
-      }
-      ColCursor<QT::kSharded> outp(Q, row, 0, 1, u.out_byte + chb);
-      flush_row<VEC, BF16>(acc, e1 - e0, u.combiner, outp.next());
+    for (int k = 0; k < 4; ++k) {
+      if (j + k * rpp < cn) v[k].load(tbl + (int64_t)id[k] * u.row_bytes);
+      else v[k].zero();
     }
-    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc.add(v[k]);
+  }
+}
+// ... and their meeting in shared memory (s_tmp: 32 * kFloats floats), scaling and store by
+// lane group 0.
+template <int VEC, bool BF16, class QT>
+__device__ __forceinline__ void coop_finish(const QT& Q, const UserRegs& u, Acc<VEC, BF16>& acc,
+                                            int W, int rpp, int sub, int chb, int64_t row, int32_t n,
+                                            uint32_t s_tmp, int lane) {
+  constexpr int NE = Acc<VEC, BF16>::kFloats;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NE; ++i)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_tmp + 4u * (uint32_t)(lane * NE + i)), "f"(acc.at(i))
+                 : "memory");
+  __syncwarp();
+  if (sub == 0) {
+    for (int s = 1; s < rpp; ++s) {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) acc.at(i) += lds_f32(s_tmp + 4u * (uint32_t)((s * W + lane) * NE + i));
+    }
+    ColCursor<QT::kSharded> outp(Q, row, 0, 1, u.out_byte + chb);
+    flush_row<VEC, BF16>(acc, n, u.combiner, outp.next());
+  }
+  __syncwarp();
+}
+
+// The rows of a tile with more than kCoopRowIds ids (ids in the scratch): all lane groups sum
+// one row together. s_tmp: scratch behind the tile's ids.
+template <int VEC, bool BF16, class QT>
+__device__ __noinline__ void coop_rows(const QT Q, const UserRegs u, int64_t b0, int rows,
+                                       uint32_t s_sp, uint32_t s_ids, int32_t e_base, uint32_t s_tmp,
+                                       int lane) {
+  const int C = u.row_bytes / VEC;
+  for (int r = 0; r < rows; ++r) {
+    const int32_t e0 = lds_i32(s_sp + 4u * (uint32_t)r), e1 = lds_i32(s_sp + 4u * (uint32_t)(r + 1));
+    if (e1 - e0 <= kCoopRowIds) continue;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int W = min(32, C - c0);
+      const int rpp = 32 / W, sub = lane / W;
+      const int chb = (c0 + lane - sub * W) * VEC;
+      Acc<VEC, BF16> acc;
+      acc.clear();
+      if (sub < rpp)
+        coop_accumulate<VEC, BF16>(Q, u, acc, u.table + chb, chb == 0 ? u.col : -1, rpp, sub,
+                                   s_ids + 4u * (uint32_t)(e0 - e_base), e1 - e0, e0);
+      coop_finish<VEC, BF16>(Q, u, acc, W, rpp, sub, chb, b0 + r, e1 - e0, s_tmp, lane);
+    }
   }
 }
 
-// Rows [r_lo, r_hi) of a multi-hot tile whose ids are in the scratch: every column of the stream.
+// A row with more ids than the scratch holds (long tails of variable-length features): the
+// ids are transformed `cap` at a time.
+template <int VEC, bool BF16, class QT>
+__device__ __noinline__ void long_row(const DevPlan& P, const QT Q, const ColItem it,
+                                      const UserRegs u, const uint8_t* values, const uint8_t* bytes,
+                                      int64_t row, int32_t e0, int32_t e1, uint32_t s_ids, int capc,
+                                      uint32_t s_tmp, int lane) {
+  const int C = u.row_bytes / VEC;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int W = min(32, C - c0);
+    const int rpp = 32 / W, sub = lane / W;
+    const int chb = (c0 + lane - sub * W) * VEC;
+    Acc<VEC, BF16> acc;
+    acc.clear();
+    for (int32_t cb = e0; cb < e1; cb += capc) {
+      const int32_t cn = min(e1 - cb, capc);
+      transform_ids(P, it, values, bytes, cb, cb + cn, s_ids, lane);
+      __syncwarp();
+      if (sub < rpp)
+        coop_accumulate<VEC, BF16>(Q, u, acc, u.table + chb, chb == 0 ? u.col : -1, rpp, sub, s_ids, cn, cb);
+      __syncwarp();
+    }
+    coop_finish<VEC, BF16>(Q, u, acc, W, rpp, sub, chb, row, e1 - e0, s_tmp, lane);
+  }
+}
+
+// Rows [b0, b0 + rows) of a multi-hot tile whose ids are in the scratch: every column of the
+// stream. `any_long`: some row has more than kCoopRowIds ids.
 template <bool BF16, class QT>
 __device__ __forceinline__ void sparse_users(const DevPlan& P, const ReqParams& A, const QT& Q,
                                              const ColItem& it, UserRegs u, int64_t b0, int rows,
-                                             uint32_t s_sp, uint32_t s_ids, int32_t e_base, int lane) {
+                                             uint32_t s_sp, uint32_t s_ids, int32_t e_base,
+                                             bool any_long, uint32_t s_tmp, int lane) {
   constexpr int ELEM = BF16 ? 2 : 4;
   for (int ui = 0;;) {
     if (u.vec_bytes == 16) sparse_rows<16, BF16>(Q, u, b0, rows, s_sp, s_ids, e_base, lane);
     else sparse_rows_cold<ELEM, BF16>(Q, u, b0, rows, s_sp, s_ids, e_base, lane);
+    if (any_long) {
+      if (u.vec_bytes == 16) coop_rows<16, BF16>(Q, u, b0, rows, s_sp, s_ids, e_base, s_tmp, lane);
+      else coop_rows<ELEM, BF16>(Q, u, b0, rows, s_sp, s_ids, e_base, s_tmp, lane);
+    }
     if (++ui >= it.num_users) break;
     u = load_user(P, A, it.first_user + ui);
   }
@@ -1282,7 +1322,7 @@ template <bool BF16, class QT>
 __device__ __noinline__ void sparse_tile_overflow(const DevPlan& P, const ReqParams& A, const QT Q,
                                                   const ColItem it, const uint8_t* values,
                                                   const uint8_t* bytes, uint32_t s_sp,
-                                                  uint32_t s_ids, int cap, int lane) {
+                                                  uint32_t s_ids, int cap, uint32_t s_tmp, int lane) {
   constexpr int ELEM = BF16 ? 2 : 4;
   const int R = it.count;
   int r_lo = 0;
@@ -1295,9 +1335,9 @@ __device__ __noinline__ void sparse_tile_overflow(const DevPlan& P, const ReqPar
       for (int ui = 0; ui < it.num_users; ++ui) {
         const UserRegs u = load_user(P, A, it.first_user + ui);
         if (u.vec_bytes == 16)
-          long_row<16, BF16>(P, Q, it, u, values, bytes, (int64_t)it.begin + r_lo, e_lo, e_hi, s_ids, cap, lane);
+          long_row<16, BF16>(P, Q, it, u, values, bytes, (int64_t)it.begin + r_lo, e_lo, e_hi, s_ids, cap, s_tmp, lane);
         else
-          long_row<ELEM, BF16>(P, Q, it, u, values, bytes, (int64_t)it.begin + r_lo, e_lo, e_hi, s_ids, cap, lane);
+          long_row<ELEM, BF16>(P, Q, it, u, values, bytes, (int64_t)it.begin + r_lo, e_lo, e_hi, s_ids, cap, s_tmp, lane);
       }
       ++r_lo;
       continue;
@@ -1306,7 +1346,7 @@ __device__ __noinline__ void sparse_tile_overflow(const DevPlan& P, const ReqPar
     transform_ids(P, it, values, bytes, e_lo, e_hi, s_ids, lane);
     __syncwarp();
     sparse_users<BF16>(P, A, Q, it, load_user(P, A, it.first_user), (int64_t)it.begin + r_lo,
-                       r_hi - r_lo, s_sp + 4u * (uint32_t)r_lo, s_ids, e_lo, lane);
+                       r_hi - r_lo, s_sp + 4u * (uint32_t)r_lo, s_ids, e_lo, true, s_tmp, lane);
     __syncwarp();
     r_lo = r_hi;
   }
@@ -1320,18 +1360,10 @@ __device__ __forceinline__ void load_item(const ColItem* p, ColItem& it) {
   for (int k = 0; k < 4; ++k) d[k] = __ldg(q + k);
 }
 
-#ifdef RECOM_PROFILE
-#define TILE_PROF_PARAMS , uint32_t (&prof_acc)[6], uint32_t& prof_last
-#define TILE_PROF_ARGS , prof_acc, prof_last
-#else
-#define TILE_PROF_PARAMS
-#define TILE_PROF_ARGS
-#endif
-
 template <bool BF16, class QT>
 __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A, const QT& Q,
-                                            const ColItem& it, uint8_t* scratch, int lane
-                                            TILE_PROF_PARAMS) {
+                                            const ColItem& it, uint32_t s_scratch, int lane
+                                            PROF_PARAM) {
   constexpr int ELEM = BF16 ? 2 : 4;
   // resolve the stream and its first column against the request: one read of the slot offsets
   const uint8_t* values = A.blob + __ldg(A.slot_offsets + it.value_slot);
@@ -1341,13 +1373,16 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
     rs = it.coo_index >= 0 ? A.ws_row_splits + (int64_t)it.coo_index * (A.batch + 1)
                            : (const int32_t*)(A.blob + __ldg(A.slot_offsets + it.seg_slot));
   UserRegs u = load_user(P, A, it.first_user);
-  const uint32_t s_sp = smem_u32(scratch), s_ids = s_sp + kColSplitBytes;
-  const int cap = (P.scratch_bytes - kColSplitBytes) >> 2;
+  const uint32_t s_sp = s_scratch, s_ids = s_sp + kColSplitBytes;
+  // scratch: [row_splits | ids (cap) | 1 KB for the partial sums of long rows]
+  const int cap = (P.scratch_bytes - kColSplitBytes - 1024) >> 2;
+  const uint32_t s_tmp = s_sp + (uint32_t)P.scratch_bytes - 1024u;
   if (it.seg_slot < 0) {
     // one id per row; the schedule keeps count <= cap
     const int n = it.count;
     transform_ids(P, it, values, bytes, it.begin, (int64_t)it.begin + n, s_ids, lane);
     __syncwarp();
+    if (u.hbm && !Q.check) prefetch_rows(u, s_ids, n, lane);
     PROF_T(3)
     for (int ui = 0;;) {
       if (u.vec_bytes == 16) gather_rows<16>(Q, u, it.begin, n, s_ids, lane);
@@ -1363,14 +1398,18 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
     sts_i32(s_sp + 4u * (uint32_t)lane, lane < R ? v : e_end);
     if (lane == 0) sts_i32(s_sp + 4u * 32u, e_end);
     const int32_t e0 = __shfl_sync(0xffffffffu, v, 0);
+    const int32_t v_next = __shfl_down_sync(0xffffffffu, v, 1);
+    const int32_t n_row = lane < R ? (lane == R - 1 ? e_end : v_next) - v : 0;
+    const bool any_long = __any_sync(0xffffffffu, n_row > kCoopRowIds);
     __syncwarp();
     if (e_end - e0 <= cap) {
       transform_ids(P, it, values, bytes, e0, e_end, s_ids, lane);
       __syncwarp();
+      if (u.hbm && !Q.check) prefetch_rows(u, s_ids, e_end - e0, lane);
       PROF_T(3)
-      sparse_users<BF16>(P, A, Q, it, u, it.begin, R, s_sp, s_ids, e0, lane);
+      sparse_users<BF16>(P, A, Q, it, u, it.begin, R, s_sp, s_ids, e0, any_long, s_tmp, lane);
     } else {
-      sparse_tile_overflow<BF16>(P, A, Q, it, values, bytes, s_sp, s_ids, cap, lane);
+      sparse_tile_overflow<BF16>(P, A, Q, it, values, bytes, s_sp, s_ids, cap, s_tmp, lane);
     }
     PROF_T(4)
   }
@@ -1381,6 +1420,158 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
 // ---------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------
+// What warp 0 publishes about the CTA's current FAST run (shared memory, guarded by mbar_ctx).
+struct RunShared {
+  Tile run;
+  DevChunk chunks[32];  // lane -> its chunk of the slab's span
+  int32_t nruns;        // FAST runs of this CTA
+  int32_t first_run;    // index of the CTA's first run in Sched::runs
+  int32_t keep_bnd;     // the run's single boundary set is already resident
+  int32_t staged_bnd;   // (warp 0) pool offset of the single boundary set resident in smem, or -1
+};
+
+// The CTA's shared state outside the dynamic region.
+struct CtaShared {
+  uint64_t mbar_tbl;    // tables of the staged slab have landed
+  uint64_t mbar_bnd;    // boundaries of the staged slab have landed
+  uint64_t mbar_ctx;    // the run's record and column contexts are in shared memory
+  int next_fast[2];     // next FAST tile of the run (alternating between runs)
+  int next_col;         // next column tile of the CTA
+  int pad;
+  RunShared rs;
+};
+
+// Shared addresses of the dynamic region's parts.
+struct SmemMap {
+  uint32_t tables, bnd, ctx, scratch;  // scratch: this warp's
+};
+
+// Warp 0: record, column contexts and TMA staging of the CTA's run `ri`.
+__device__ __noinline__ void setup_run(const DevPlan& P, const Sched& S, const ReqParams& A,
+                                       CtaShared* cs, uint8_t* smem, int ri, int lane) {
+  const Tile run = S.runs[cs->rs.first_run + ri];
+  const int staged_bnd = cs->rs.staged_bnd;
+  const bool keep = ri > 0 && run.slab.num_bnds == 1 && run.slab.first_bnd_pool == staged_bnd;
+  cs->rs.chunks[lane] = P.chunks[run.slab.first_chunk + lane % run.slab.num_chunks];
+  __syncwarp();
+  if (lane == 0) {
+    cs->rs.run = run;
+    cs->rs.keep_bnd = keep ? 1 : 0;
+    if (run.slab.num_bnds == 1) cs->rs.staged_bnd = run.slab.first_bnd_pool;
+    else if (run.slab.num_bnds > 1) cs->rs.staged_bnd = -1;
+    cs->next_fast[ri & 1] = 0;
+  }
+  enter_run(P, A, run, reinterpret_cast<ColCtx*>(smem + P.smem_off_ctx), smem,
+            reinterpret_cast<float*>(smem + P.smem_off_bnd), keep, &cs->mbar_tbl, &cs->mbar_bnd);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&cs->mbar_ctx);
+}
+
+// The CTA's column tiles, taken from the counter in shared memory (k >= 0: the warp's static
+// first tile).
+template <bool BF16, class QT>
+__device__ __noinline__ void column_section(const DevPlan& P, const ReqParams& A, const QT Q,
+                                            const ColItem* q_items, int q_count, int k,
+                                            int* next_col, uint32_t s_scratch, int lane PROF_PARAM) {
+  auto claim = [&]() {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(next_col, 1);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  if (k < 0) k = claim();
+  ColItem it;
+  if (k < q_count) load_item(q_items + k, it);
+  while (k < q_count) {
+    PROF_T(0)
+    column_tile<BF16>(P, A, Q, it, s_scratch, lane PROF_ARG);
+    k = claim();
+    if (k < q_count) load_item(q_items + k, it);
+  }
+}
+
+// The CTA's FAST runs: every warp takes tiles from the run's counter.
+template <bool BF16, class QT>
+__device__ __noinline__ void fast_section(const DevPlan& P, const Sched& S, const ReqParams& A,
+                                          const QT Q, CtaShared* cs, uint8_t* smem, SmemMap sm,
+                                          int warp, int lane PROF_PARAM) {
+  constexpr int ELEM = BF16 ? 2 : 4;
+  uint32_t tbl_par = 0, bnd_par = 0, ctx_par = 0;
+  const uint32_t s_ids = sm.scratch;
+  mbar_wait(&cs->mbar_ctx, ctx_par);
+  ctx_par ^= 1;
+  const int nruns = cs->rs.nruns;
+  for (int ri = 0; ri < nruns; ++ri) {
+    if (ri > 0) {
+      __syncthreads();  // every warp is done with the previous run's tables and contexts
+      if (warp == 0) setup_run(P, S, A, cs, smem, ri, lane);
+      mbar_wait(&cs->mbar_ctx, ctx_par);
+      ctx_par ^= 1;
+    }
+    const DevSlab slab = cs->rs.run.slab;
+    const int run_rows = cs->rs.run.rows;
+    const int64_t run_begin = cs->rs.run.row_begin;
+    const bool staged = cs->rs.run.stage != 0 && slab.stage_bytes > 0;
+    const bool wait_bnd = !cs->rs.keep_bnd && slab.bnd_bytes > 0;
+    const DevChunk ch = cs->rs.chunks[lane];
+    PROF_T(5)
+    bool bnd_ready = !wait_bnd;
+    bool tbl_ready = !staged;
+    const int TR = slab.tile_rows;  // 16 or 32 rows
+    const int ntiles = (run_rows + TR - 1) / TR;
+    int* ctr = &cs->next_fast[ri & 1];
+    auto claim = [&]() {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(ctr, 1);
+      return __shfl_sync(0xffffffffu, t, 0);
+    };
+    // two value buffers behind the tile's row ids: the raw values of the warp's next tile are
+    // requested (asynchronous copies) before this tile is worked on
+    const uint32_t val_bytes = 4u * (uint32_t)(slab.num_cols * TR);
+    uint32_t s_val = s_ids + 4u * (uint32_t)(slab.num_cols * kIdPitch), s_val_next = s_val + val_bytes;
+    int t = claim();
+    if (t < ntiles) fast_prefetch(sm.ctx, slab, run_begin + (int64_t)t * TR, min(TR, run_rows - t * TR), s_val, lane);
+    while (t < ntiles) {
+      const int64_t b0 = run_begin + (int64_t)t * TR;
+      const int rows = min(TR, run_rows - t * TR);
+      const int tn = claim();
+      if (tn < ntiles) {
+        fast_prefetch(sm.ctx, slab, run_begin + (int64_t)tn * TR, min(TR, run_rows - tn * TR), s_val_next, lane);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      if (!bnd_ready) {
+        mbar_wait(&cs->mbar_bnd, bnd_par);
+        bnd_ready = true;
+      }
+      if (staged) fast_phase1<true>(Q, sm.ctx, slab, b0, rows, sm.bnd, s_ids, s_val, lane);
+      else fast_phase1<false>(Q, sm.ctx, slab, b0, rows, sm.bnd, s_ids, s_val, lane);
+      __syncwarp();
+      PROF_T(1)
+      if (!tbl_ready) {
+        mbar_wait(&cs->mbar_tbl, tbl_par);
+        tbl_ready = true;
+      }
+      if (staged) {
+        if (slab.vec_bytes == 16) fast_phase2<16, true>(Q, sm.ctx, slab.num_chunks, ch, b0, rows, sm.tables, s_ids, lane);
+        else fast_phase2<ELEM, true>(Q, sm.ctx, slab.num_chunks, ch, b0, rows, sm.tables, s_ids, lane);
+      } else {
+        if (slab.vec_bytes == 16) fast_phase2<16, false>(Q, sm.ctx, slab.num_chunks, ch, b0, rows, sm.tables, s_ids, lane);
+        else fast_phase2<ELEM, false>(Q, sm.ctx, slab.num_chunks, ch, b0, rows, sm.tables, s_ids, lane);
+      }
+      __syncwarp();
+      PROF_T(2)
+      const uint32_t tmp = s_val;
+      s_val = s_val_next;
+      s_val_next = tmp;
+      t = tn;
+    }
+    // a warp without tiles must still consume the phases it would have waited for
+    if (wait_bnd) bnd_par ^= 1;
+    if (staged) tbl_par ^= 1;
+  }
+}
+
 template <bool BF16, bool SH>
 #ifndef RECOM_MIN_BLOCKS
 #define RECOM_MIN_BLOCKS 2
@@ -1389,16 +1580,59 @@ __global__ void __launch_bounds__(kThreads, RECOM_MIN_BLOCKS)
 fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ Sched S,
                      const __grid_constant__ ReqParams A) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t mbar_tbl;  // tables of the staged slab have landed
-  __shared__ uint64_t mbar_bnd;  // boundaries of the staged slab have landed
-  __shared__ uint64_t mbar_ctx;  // the run's column contexts are in shared memory
-  __shared__ int s_next[2];      // next FAST tile of the run (alternating between runs)
-  constexpr int ELEM = BF16 ? 2 : 4;
+  __shared__ __align__(16) CtaShared cs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* s_tables = smem;
-  float* s_bnd = reinterpret_cast<float*>(smem + P.smem_off_bnd);
-  ColCtx* s_ctx = reinterpret_cast<ColCtx*>(smem + P.smem_off_ctx);
-  uint8_t* scratch = smem + P.smem_off_scratch + warp * P.scratch_bytes;
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+#ifdef RECOM_PROFILE
+  uint32_t prof_acc[6] = {0, 0, 0, 0, 0, 0};
+  const uint64_t prof_t0 = gtimer();
+  uint32_t prof_last = (uint32_t)clock64();
+  ProfRef pr{prof_acc, &prof_last};
+#endif
+
+  // The whole request blob -> L2 while the grid starts up (one 128-byte line per thread and
+  // pass): HBM is idle then, and every later input load of the launch is an L2 hit.
+  for (int64_t o = ((int64_t)cta * kThreads + threadIdx.x) * 128; o < A.blob_bytes;
+       o += (int64_t)G * kThreads * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.blob + o));
+
+  if (threadIdx.x == 0) {
+    mbar_init(&cs.mbar_tbl, 1);
+    mbar_init(&cs.mbar_bnd, 1);
+    mbar_init(&cs.mbar_ctx, 1);
+    cs.next_fast[0] = 0;
+    cs.next_fast[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  // ---- the CTA's column tiles: the cost-sorted queue was dealt round robin, the cc-th CTA that
+  // holds column tiles has tiles cc, cc + Gc, ... contiguously. Warps [fast_warps, kWarps)
+  // start with one each. ----
+  const bool excl = S.fast_ctas >= 0;
+  const int Gc = excl ? G - S.fast_ctas : G;       // CTAs that hold column tiles
+  const int cc = excl ? cta - S.fast_ctas : cta;   // this CTA's rank among them (< 0: none)
+  const int q_base = Gc > 0 ? S.num_queue / Gc : 0, q_rem = S.num_queue - q_base * Gc;
+  const int q_count = cc < 0 ? 0 : q_base + (cc < q_rem ? 1 : 0);
+  const ColItem* q_items = S.queue + ((int64_t)max(cc, 0) * q_base + min(max(cc, 0), q_rem));
+  const int fast_warps = excl ? (cc < 0 ? kWarps : 0) : S.fast_warps;
+  const bool fast_first = warp < fast_warps;
+  if (threadIdx.x == 0) cs.next_col = kWarps - fast_warps;  // the static first tiles are taken
+  __syncthreads();
+
+  // ---- warp 0: the CTA's first FAST run - record, contexts, TMA staging - in flight while
+  // the other warps start on their column tiles ----
+  if (warp == 0) {
+    const CtaWork cw = S.cta[cta];
+    if (lane == 0) {
+      cs.rs.nruns = cw.count;
+      cs.rs.first_run = cw.first;
+      cs.rs.staged_bnd = -1;
+    }
+    __syncwarp();
+    if (cw.count > 0) setup_run(P, S, A, &cs, smem, 0, lane);
+    else if (lane == 0) mbar_arrive(&cs.mbar_ctx);
+  }
+
   ReqRegsT<SH> Q;
   Q.out = A.out;
   Q.bind(A);
@@ -1407,138 +1641,17 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
   Q.ids_out = A.ids_out;
   Q.ids_base = A.ids_base;
   Q.check = P.check_ids != 0;
-  PROF_DECL
+  SmemMap sm;
+  sm.tables = smem_u32(smem);
+  sm.bnd = sm.tables + (uint32_t)P.smem_off_bnd;
+  sm.ctx = sm.tables + (uint32_t)P.smem_off_ctx;
+  sm.scratch = sm.tables + (uint32_t)P.smem_off_scratch + (uint32_t)(warp * P.scratch_bytes);
 
-  // ---- the record of the warp's first column tile: requested before anything else ----
-  const int gw = (int)blockIdx.x + (int)gridDim.x * warp;  // tiles are dealt CTA by CTA
-  const int GW = (int)gridDim.x * kWarps;
-  ColItem it;
-  if (gw < S.num_queue) load_item(S.queue + gw, it);
-
-  // The whole request blob -> L2 while the grid starts up (one 128-byte line per thread and
-  // pass): HBM is idle then, and every later input load of the launch is an L2 hit.
-  for (int64_t o = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 128; o < A.blob_bytes;
-       o += (int64_t)gridDim.x * kThreads * 128)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.blob + o));
-
-  if (threadIdx.x == 0) {
-    mbar_init(&mbar_tbl, 1);
-    mbar_init(&mbar_bnd, 1);
-    mbar_init(&mbar_ctx, 1);
-    s_next[0] = 0;
-    s_next[1] = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  // ---- the CTA's first FAST run: contexts and TMA staging in flight while the warps work on
-  // their column tiles ----
-  const CtaWork cw = S.cta[blockIdx.x];
-  Tile run;
-  run.slab_id = -1;
-  int staged_bnd = -1;  // pool offset of the single boundary set resident in smem, or -1
-  bool keep_bnd = false;
-  if (cw.count > 0) {
-    run = S.runs[cw.first];
-    if (run.slab.num_bnds == 1) staged_bnd = run.slab.first_bnd_pool;
-    if (warp == 0) {
-      enter_run(P, A, run, s_ctx, s_tables, s_bnd, false, &mbar_tbl, &mbar_bnd);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&mbar_ctx);
-    }
-  }
-
-  // ---- column tiles: t = gw, gw + GW, ... (static; the next record is requested while this
-  // tile is worked on) ----
-  for (int t = gw; t < S.num_queue; t += GW) {
-    ColItem nx;
-    const bool more = t + GW < S.num_queue;
-    if (more) load_item(S.queue + t + GW, nx);
-    PROF_T(0)
-    column_tile<BF16>(P, A, Q, it, scratch, lane TILE_PROF_ARGS);
-    if (more) it = nx;
-  }
-
-  // ---- FAST runs: every warp of the CTA takes 16-row tiles from the run's counter ----
-  {
-    uint32_t tbl_par = 0, bnd_par = 0, ctx_par = 0;
-    int32_t* s_ids = reinterpret_cast<int32_t*>(scratch);
-    for (int ri = 0; ri < cw.count; ++ri) {
-      if (ri > 0) {
-        __syncthreads();  // every warp is done with the previous run's tables and contexts
-        run = S.runs[cw.first + ri];
-        // a run whose only boundary set is already resident keeps it (model E/F: one set for all)
-        keep_bnd = run.slab.num_bnds == 1 && run.slab.first_bnd_pool == staged_bnd;
-        if (run.slab.num_bnds == 1) staged_bnd = run.slab.first_bnd_pool;
-        else if (run.slab.num_bnds > 1) staged_bnd = -1;
-        if (warp == 0) {
-          if (lane == 0) s_next[ri & 1] = 0;
-          enter_run(P, A, run, s_ctx, s_tables, s_bnd, keep_bnd, &mbar_tbl, &mbar_bnd);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&mbar_ctx);
-        }
-      }
-      const DevSlab& slab = run.slab;
-      const bool wait_bnd = !keep_bnd && slab.bnd_bytes > 0;
-      const bool staged = run.stage != 0 && slab.stage_bytes > 0;
-      const DevChunk ch = P.chunks[slab.first_chunk + lane % slab.num_chunks];
-      mbar_wait(&mbar_ctx, ctx_par);
-      ctx_par ^= 1;
-      PROF_T(5)
-      bool bnd_ready = !wait_bnd;
-      bool tbl_ready = !staged;
-      const int TR = slab.tile_rows;  // 16 or 32 rows
-      const int ntiles = (run.rows + TR - 1) / TR;
-      const int frow = lane & (TR - 1), fcg = lane / TR;
-      int* ctr = &s_next[ri & 1];
-      auto claim = [&]() {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(ctr, 1);
-        return __shfl_sync(0xffffffffu, t, 0);
-      };
-      // the raw values of the warp's next tile are requested before this tile is worked on
-      float v[8];
-      int t = claim();
-      if (t < ntiles)
-        fast_load(s_ctx, fcg * 8, (int64_t)run.row_begin + (int64_t)t * TR + frow,
-                  fcg * 8 < slab.num_cols && frow < min(TR, run.rows - t * TR), v);
-      while (t < ntiles) {
-        const int64_t b0 = (int64_t)run.row_begin + (int64_t)t * TR;
-        const int rows = min(TR, run.rows - t * TR);
-        float vn[8];
-        const int tn = claim();
-        if (tn < ntiles)
-          fast_load(s_ctx, fcg * 8, (int64_t)run.row_begin + (int64_t)tn * TR + frow,
-                    fcg * 8 < slab.num_cols && frow < min(TR, run.rows - tn * TR), vn);
-        if (!bnd_ready) {
-          mbar_wait(&mbar_bnd, bnd_par);
-          bnd_ready = true;
-        }
-        dense_phase1_fast(Q, s_ctx, slab, b0, rows, s_bnd, s_ids, lane, v);
-        __syncwarp();
-        PROF_T(1)
-        if (!tbl_ready) {
-          mbar_wait(&mbar_tbl, tbl_par);
-          tbl_ready = true;
-        }
-        if (staged) {
-          if (slab.vec_bytes == 16) dense_phase2<16, true>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
-          else dense_phase2<ELEM, true>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
-        } else {
-          if (slab.vec_bytes == 16) dense_phase2<16, false>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
-          else dense_phase2<ELEM, false>(Q, s_ctx, slab.num_chunks, ch, b0, rows, s_tables, s_ids, lane);
-        }
-        __syncwarp();
-        PROF_T(2)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = vn[k];
-        t = tn;
-      }
-      // a warp without tiles must still consume the phases it would have waited for
-      if (wait_bnd) bnd_par ^= 1;
-      if (staged) tbl_par ^= 1;
-    }
-  }
+  if (!fast_first)
+    column_section<BF16>(P, A, Q, q_items, q_count, warp - fast_warps, &cs.next_col, sm.scratch, lane PROF_ARG);
+  fast_section<BF16>(P, S, A, Q, &cs, smem, sm, warp, lane PROF_ARG);
+  if (fast_first)
+    column_section<BF16>(P, A, Q, q_items, q_count, -1, &cs.next_col, sm.scratch, lane PROF_ARG);
 
   // ---- sharded output: the last warp of the grid tells every peer that this rank's slices
   // of its rows are in place (and, with the barrier inside the kernel, waits for theirs) ----
@@ -1547,7 +1660,7 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
     bool last = false;
     if (lane == 0) {
       __threadfence_system();
-      last = atomicAdd(A.counters, 1) == GW - 1;
+      last = atomicAdd(A.counters, 1) == G * kWarps - 1;
       if (last) {
         A.counters[0] = 0;
         __threadfence();
@@ -1567,7 +1680,15 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
         wait_flag(A.peer_flags[A.rank], lane, A.epoch, A.wait_timeout_ms);
     }
   }
-  PROF_END
+#ifdef RECOM_PROFILE
+  if (lane == 0 && A.prof) {
+    uint64_t* o_ = A.prof + ((size_t)blockIdx.x * kWarps + warp) * 8;
+#pragma unroll
+    for (int i_ = 0; i_ < 6; ++i_) o_[i_] = prof_acc[i_];
+    o_[6] = prof_t0;
+    o_[7] = gtimer();
+  }
+#endif
 }
 
 

@@ -135,7 +135,8 @@ struct ColUser {
   int32_t combiner;
   int32_t col;         // global column index (ids_out hook)
   int32_t vec_bytes;   // 16, or the element size when the slice is not 16-byte aligned
-  int32_t pad;
+  int32_t hbm;         // 1: the table is far larger than L2: its rows are prefetched into L2 as
+                       // soon as the tile's ids are known (one round trip instead of one per pass)
 };
 static_assert(sizeof(ColUser) == 32, "ColUser layout");
 
@@ -236,29 +237,37 @@ struct Tile {
 };
 static_assert(sizeof(Tile) == 80, "Tile layout");
 
-// The DENSE runs of a CTA: runs[first, first + count), walked in order.
+// The work of a CTA: FAST runs runs[first, first + count), walked in order, and column tiles
+// queue[q_first, q_first + q_count), most expensive first.
 struct CtaWork {
   int32_t first;
   int32_t count;
+  int32_t q_first;
+  int32_t q_count;
 };
 
-// The schedule of a batch size (cached on the device by the plan); a kernel parameter. Fully
-// static: no claim counters, no atomics, no fences inside a launch (measured: an atomic claim
-// costs a warp 1-2 us, a gpu-scope release 2-6 us under load - as much as the work of a tile).
+// The schedule of a batch size (cached on the device by the plan); a kernel parameter. Static
+// per CTA: no global claim counters, no atomics on global memory, no fences inside a launch
+// (measured: an atomic claim costs a warp 1-2 us, a gpu-scope release 2-6 us under load - as much
+// as the work of a tile).
 //   * Column tiles (the queue): everything that is not a FAST slab - hashed, multi-hot, unstaged.
-//     Tile t belongs to global warp t mod (grid * kWarps), global warp = blockIdx.x + grid *
-//     warp, so the tiles of the (cost-sorted) queue are dealt CTA by CTA. A warp works on its
-//     column tiles first: they are chains of dependent loads, and start while the CTA's FAST
-//     staging is in flight.
+//     The cost-sorted tiles are dealt to the CTAs round robin; a CTA's tiles are contiguous in
+//     `queue` (CtaWork::q_first) and taken by its warps from a counter in shared memory.
 //   * FAST runs (slabs made of fast bucketize groups, tables staged in shared memory by TMA): every
-//     CTA owns the runs cta[c] (usually one: a row range of one slab); all warps of the CTA
-//     take its 16-row tiles from a counter in shared memory as they become free, so a warp
-//     with a long column tile simply takes fewer of them.
+//     CTA owns the runs cta[c] (usually one: a row range of one slab); its warps take the run's
+//     16-row tiles from another shared-memory counter.
+//   * Warps [0, fast_warps) of a CTA start with the FAST tiles and go on with column tiles, the
+//     others the other way round: the bandwidth-bound store stream of the FAST tiles and the
+//     latency-bound chains of the column tiles overlap on every SM from the first microsecond,
+//     and whoever runs out of its own kind of work takes the other.
 struct Sched {
   const Tile* runs;          // FAST runs, grouped by CTA
   const CtaWork* cta;        // [grid]
-  const ColItem* queue;      // [num_queue] column tiles
+  const ColItem* queue;      // [num_queue] column tiles, grouped by CTA
   int32_t num_queue;
+  int32_t fast_warps;
+  int32_t fast_ctas;         // >= 0: exclusive roles - CTAs [0, fast_ctas) own all FAST runs and no
+                             // column tiles, the others the column tiles and no FAST run; -1: mixed
   int32_t pad;
 };
 
