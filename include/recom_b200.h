@@ -184,6 +184,28 @@ RECOM_API recom_status recom_plan_create_from_blob(const void *buf, size_t bytes
 RECOM_API recom_status recom_plan_num_columns(const recom_plan *plan, int32_t *out);
 RECOM_API recom_status recom_plan_out_width(const recom_plan *plan, int32_t *out);
 
+/* What an op kernel with the reference's signature (Addons>FeatureColumnProcess[WithSymbols],
+ * feature_column_process_op_gpu.cu.cc:140-175) needs to turn its inputs into a recom_request and
+ * its result into the reference's outputs:
+ *   recom_plan_slot_layout   per blob slot: rank of the host tensor ConcatInputs packed (its dims in
+ *                            `concated_shapes`: 1, or 2 for SparseTensor.indices) and element size;
+ *   recom_plan_infer_batch   the batch size from the slots' element counts (the reference's
+ *                            generated code reads it from the same shapes);
+ *   recom_plan_output_shapes `output_shapes`: [batch, dim] per column, concat order;
+ *   recom_plan_output_ptrs   `output_ptrs`: device int64[num_columns], the address of every
+ *                            column's slice in row 0 of the concat tensor at `out` (row pitch
+ *                            out_width elements: the columns are already in place, what
+ *                            Addons>ConcatOutputs would have produced; one tiny kernel on `stream`). */
+RECOM_API recom_status recom_plan_num_slots(const recom_plan *plan, int32_t *out);
+RECOM_API recom_status recom_plan_slot_layout(const recom_plan *plan, int32_t *ranks,
+                                    int32_t *elem_bytes);
+RECOM_API recom_status recom_plan_infer_batch(const recom_plan *plan, const int64_t *slot_elems,
+                                    int64_t *batch);
+RECOM_API recom_status recom_plan_output_shapes(const recom_plan *plan, int64_t batch,
+                                      int32_t *shapes);
+RECOM_API recom_status recom_plan_output_ptrs(const recom_plan *plan, void *out, int64_t *ptrs_dev,
+                                    recom_stream_t stream);
+
 /* Upper bound of the per-request scratch for a batch of `batch` rows carrying
  * `total_ids` ids over all non-DENSE columns. */
 RECOM_API recom_status recom_plan_workspace_bytes(const recom_plan *plan, int64_t batch,
@@ -261,6 +283,16 @@ RECOM_API recom_status recom_scatter_columns(const void *const *cols,
                                    int64_t batch, int32_t out_width,
                                    int32_t elem_bytes, void *out,
                                    recom_stream_t stream);
+
+/* The same for columns that live in HOST memory (Addons>ConcatOutputs' `host_inputs`,
+ * concat_outputs_op_gpu.cu.cc:186-232): uploaded into `d_scratch` (device, 16-byte aligned, the
+ * columns' bytes rounded up to 16 each), then scattered. */
+RECOM_API recom_status recom_scatter_host_columns(const void *const *host_cols,
+                                        const int32_t *col_dims,
+                                        const int32_t *col_offsets, int32_t num_cols,
+                                        int64_t batch, int32_t out_width,
+                                        int32_t elem_bytes, void *out, void *d_scratch,
+                                        recom_stream_t stream);
 
 /* Sorted COO row ids (int64, stride in int64s) -> int32 row_splits[batch+1]. */
 RECOM_API recom_status recom_segment_ids_to_row_splits(const int64_t *coo, int64_t nnz,

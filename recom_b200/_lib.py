@@ -60,8 +60,9 @@ class RecomError(RuntimeError):
 EXPORTS = [
     "recom_last_error", "recom_abi_version", "recom_plan_create", "recom_plan_destroy",
     "recom_plan_serialize", "recom_plan_create_from_blob", "recom_plan_num_columns",
-    "recom_plan_out_width", "recom_plan_workspace_bytes", "recom_plan_run",
-    "recom_last_launch_count", "recom_plan_algorithmic_bytes", "recom_scatter_columns",
+    "recom_plan_out_width", "recom_plan_num_slots", "recom_plan_slot_layout", "recom_plan_infer_batch",
+    "recom_plan_output_shapes", "recom_plan_output_ptrs", "recom_plan_workspace_bytes", "recom_plan_run",
+    "recom_last_launch_count", "recom_plan_algorithmic_bytes", "recom_scatter_columns", "recom_scatter_host_columns",
     "recom_segment_ids_to_row_splits", "recom_string_to_hash_bucket_fast", "recom_fingerprint64",
     "recom_concat_inputs", "recom_concat_inputs_with_args", "recom_shape_construct_create", "recom_shape_construct_eval",
     "recom_shape_construct_destroy", "recom_plan_run_sharded", "recom_ipc_alloc", "recom_ipc_open",
@@ -88,6 +89,11 @@ def _load() -> C.CDLL:
         "recom_plan_create_from_blob": [vp, sz, i32, C.POINTER(vp)],
         "recom_plan_num_columns": [vp, C.POINTER(i32)],
         "recom_plan_out_width": [vp, C.POINTER(i32)],
+        "recom_plan_num_slots": [vp, C.POINTER(i32)],
+        "recom_plan_slot_layout": [vp, vp, vp],
+        "recom_plan_infer_batch": [vp, vp, C.POINTER(i64)],
+        "recom_plan_output_shapes": [vp, i64, vp],
+        "recom_plan_output_ptrs": [vp, vp, vp, vp],
         "recom_plan_workspace_bytes": [vp, i64, i64, C.POINTER(sz)],
         "recom_plan_run": [vp, C.POINTER(Request)],
         "recom_plan_run_sharded": [vp, C.POINTER(Request), C.POINTER(ShardOut)],
@@ -97,6 +103,7 @@ def _load() -> C.CDLL:
         "recom_ipc_close": [vp],
         "recom_ipc_free": [vp],
         "recom_plan_algorithmic_bytes": [vp, C.POINTER(Request), C.POINTER(i64)],
+        "recom_scatter_host_columns": [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp],
         "recom_scatter_columns": [vp, vp, vp, i32, i64, i32, i32, vp, vp],
         "recom_segment_ids_to_row_splits": [vp, i64, i32, i64, vp, vp],
         "recom_string_to_hash_bucket_fast": [vp, vp, i64, i64, vp, vp],

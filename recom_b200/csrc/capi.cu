@@ -164,6 +164,7 @@ struct recom_plan {
   // device
   void* d_block = nullptr;
   DevPlan dev{};
+  const int32_t* d_out_offsets = nullptr;  // [num_cols] element offset of every column's slice
   int elem_bytes = 4;
   int num_sms = 148;
   int ctas_per_sm = 2;
@@ -704,6 +705,7 @@ void build_layout(recom_plan* p) {
       }
       double g = 0;
       for (const ColUser& cu : unit_users[ui]) {
+        if (&cu == &unit_users[ui][0]) u.u0 = cu;
         g += (cu.hbm ? 2.0 : 1.0) * (1.0 + cu.row_bytes / 64.0);
         p->unit_hbm[ui] = p->unit_hbm[ui] || cu.hbm;
         p->users.push_back(cu);
@@ -882,7 +884,9 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   if (fast.empty()) tt->fast_warps = 0;
   else if (qs.empty()) tt->fast_warps = kWarps;
   else
-    tt->fast_warps = std::max(1, std::min(kWarps - 1, (int)(kWarps * fast_cost / (fast_cost + queue_cost) + 0.5)));
+    // (measured on models E / F: a column tile costs a warp about three times its estimate
+    // relative to a FAST tile - chains of dependent loads against a store stream)
+    tt->fast_warps = std::max(1, std::min(kWarps - 1, (int)(kWarps * fast_cost / (fast_cost + 3.0 * queue_cost) + 0.5)));
   if (p->force_fast_warps >= 0 && !fast.empty() && !qs.empty())
     tt->fast_warps = std::max(1, std::min(kWarps - 1, p->force_fast_warps));
   return tt;
@@ -925,7 +929,9 @@ recom_status upload_plan(recom_plan* p) {
     size_t bytes;
     size_t off;
   };
-  Part parts[8] = {
+  std::vector<int32_t> out_offsets;
+  for (const recom_column_desc& d : p->descs) out_offsets.push_back(d.out_offset);
+  Part parts[9] = {
       {p->cols.data(), p->cols.size() * sizeof(DevColumn), 0},
       {p->slabs.data(), p->slabs.size() * sizeof(DevSlab), 0},
       {p->chunks.data(), p->chunks.size() * sizeof(DevChunk), 0},
@@ -934,6 +940,7 @@ recom_status upload_plan(recom_plan* p) {
       {p->boundary_pool.data(), p->boundary_pool.size() * sizeof(float), 0},
       {p->users.data(), p->users.size() * sizeof(ColUser), 0},
       {p->coos.data(), p->coos.size() * sizeof(DevCoo), 0},
+      {out_offsets.data(), out_offsets.size() * sizeof(int32_t), 0},
   };
   size_t total = 0;
   for (Part& pt : parts) {
@@ -954,6 +961,7 @@ recom_status upload_plan(recom_plan* p) {
   p->dev.boundaries = (const float*)(base + parts[5].off);
   p->dev.users = (const ColUser*)(base + parts[6].off);
   p->dev.coos = (const DevCoo*)(base + parts[7].off);
+  p->d_out_offsets = (const int32_t*)(base + parts[8].off);
   p->dev.num_coo = (int32_t)p->coos.size();
   p->dev.num_cols = (int32_t)p->cols.size();
   p->dev.num_slabs = (int32_t)p->slabs.size();
@@ -1231,6 +1239,88 @@ recom_status recom_plan_out_width(const recom_plan* p, int32_t* out) {
   return RECOM_OK;
 }
 
+}  // extern "C"
+namespace {
+// The plan's allocations, cached uploads and launches belong to cfg.device; the caller's current
+// device may be another one (multi-GPU hosts). Switch for the duration of the call only.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess || prev == device) return e;
+    switched = true;
+    return cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+extern "C" {
+
+recom_status recom_plan_num_slots(const recom_plan* p, int32_t* out) {
+  if (!p || !out) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  *out = p->cfg.num_slots;
+  return RECOM_OK;
+}
+
+recom_status recom_plan_slot_layout(const recom_plan* p, int32_t* ranks, int32_t* elem_bytes) {
+  if (!p || !ranks || !elem_bytes) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  for (int s = 0; s < p->cfg.num_slots; ++s) {
+    ranks[s] = 1;
+    elem_bytes[s] = 1;
+  }
+  for (const recom_column_desc& d : p->descs) {
+    elem_bytes[d.value_slot] = dtype_bytes(d.value_dtype);
+    if (d.value_dtype == RECOM_STR && d.bytes_slot >= 0) elem_bytes[d.bytes_slot] = 1;
+    if (d.lookup != RECOM_LOOKUP_DENSE && d.seg_slot >= 0) {
+      const bool coo = d.seg_format == RECOM_SEG_COO_I64;
+      elem_bytes[d.seg_slot] = coo ? 8 : 4;
+      ranks[d.seg_slot] = coo ? 2 : 1;  // SparseTensor.indices: [nnz, rank]
+    }
+  }
+  return RECOM_OK;
+}
+
+recom_status recom_plan_infer_batch(const recom_plan* p, const int64_t* slot_elems, int64_t* batch) {
+  if (!p || !slot_elems || !batch) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  for (const recom_column_desc& d : p->descs) {
+    if (d.lookup == RECOM_LOOKUP_DENSE) {
+      *batch = slot_elems[d.value_slot] - (d.value_dtype == RECOM_STR ? 1 : 0);
+      return RECOM_OK;
+    }
+    if (d.seg_format == RECOM_SEG_ROW_SPLITS_I32) {
+      *batch = slot_elems[d.seg_slot] - 1;
+      return RECOM_OK;
+    }
+  }
+  return fail(RECOM_ERR_UNSUPPORTED,
+              "no column carries the batch size (COO-only plans: pass it through the symbols input)");
+}
+
+recom_status recom_plan_output_shapes(const recom_plan* p, int64_t batch, int32_t* shapes) {
+  if (!p || !shapes || batch < 0 || batch > 0x7fffffffLL)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  for (size_t i = 0; i < p->descs.size(); ++i) {
+    shapes[2 * i] = (int32_t)batch;
+    shapes[2 * i + 1] = p->descs[i].dim;
+  }
+  return RECOM_OK;
+}
+
+recom_status recom_plan_output_ptrs(const recom_plan* p, void* out, int64_t* ptrs_dev,
+                                    recom_stream_t stream) {
+  if (!p || !out || !ptrs_dev) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard;
+  CUDA_TRY(guard.enter(p->cfg.device));
+  launch_output_ptrs((int32_t)p->descs.size(), p->d_out_offsets, p->elem_bytes, out, ptrs_dev,
+                     (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "output_ptrs launch: %s", cudaGetErrorString(e));
+  return RECOM_OK;
+}
+
 // Bytes of the argument data staged per request when it does not travel inside the blob:
 // slot offsets, slot element counts, (ids_out hook only) the per-column id prefix, and the table
 // pointers when the plan's table-set cache is full.
@@ -1284,21 +1374,6 @@ struct HostProf {
 };
 HostProf g_host_prof;
 
-// The plan's allocations, cached uploads and launches belong to cfg.device; the caller's current
-// device may be another one (multi-GPU hosts). Switch for the duration of the call only.
-struct DeviceGuard {
-  int prev = -1;
-  bool switched = false;
-  cudaError_t enter(int device) {
-    cudaError_t e = cudaGetDevice(&prev);
-    if (e != cudaSuccess || prev == device) return e;
-    switched = true;
-    return cudaSetDevice(device);
-  }
-  ~DeviceGuard() {
-    if (switched) cudaSetDevice(prev);
-  }
-};
 
 // Device copy of the request's table pointer array: the plan's cached copy when this very set
 // of addresses was seen before (every request of a serving process), a new published copy
@@ -1644,6 +1719,31 @@ recom_status recom_scatter_columns(const void* const* cols, const int32_t* col_d
   cudaFreeAsync(d, stream);
   if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "scatter launch failed: %s", cudaGetErrorString(e));
   return RECOM_OK;
+}
+
+// Addons>ConcatOutputs' host_inputs (concat_outputs_op_gpu.cu.cc:186-232): the columns live in
+// host memory; they are uploaded into `d_scratch` (their bytes + 24 per column) and scattered.
+recom_status recom_scatter_host_columns(const void* const* host_cols, const int32_t* col_dims,
+                                        const int32_t* col_offsets, int32_t num_cols, int64_t batch,
+                                        int32_t out_width, int32_t elem_bytes, void* out,
+                                        void* d_scratch, recom_stream_t stream_) {
+  if (num_cols == 0 || batch == 0) return RECOM_OK;
+  if (!host_cols || !col_dims || !col_offsets || !out || !d_scratch || num_cols < 0 || batch < 0 ||
+      (elem_bytes != 4 && elem_bytes != 2) || ((uintptr_t)d_scratch & 15))
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  std::vector<const void*> dev(num_cols);
+  uint8_t* d = (uint8_t*)d_scratch;
+  for (int i = 0; i < num_cols; ++i) {
+    if (!host_cols[i] || col_dims[i] <= 0) return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: bad pointer/dim", i);
+    const size_t bytes = (size_t)batch * col_dims[i] * elem_bytes;
+    CUDA_TRY(cudaMemcpyAsync(d, host_cols[i], bytes, cudaMemcpyHostToDevice, stream));
+    dev[i] = d;
+    d += align_up(bytes, 16);
+  }
+  // (pageable sources: the copies above have been staged when cudaMemcpyAsync returns)
+  return recom_scatter_columns(dev.data(), col_dims, col_offsets, num_cols, batch, out_width,
+                               elem_bytes, out, stream_);
 }
 
 recom_status recom_segment_ids_to_row_splits(const int64_t* coo, int64_t nnz, int32_t stride,

@@ -995,6 +995,22 @@ struct ProfRef {
 #define PROF_ARG
 #define PROF_T(i)
 #endif
+// -DRECOM_PROFILE_COL (with -DRECOM_PROFILE): level timers of the column tiles instead - 0 claim +
+// record, 1 slot offsets / column record, 2 row_splits, 3 transform, 4 gathers; a lap waits for
+// the value `dep` (what the level's loads produce).
+#if defined(RECOM_PROFILE) && defined(RECOM_PROFILE_COL)
+#define PROF_C(i, dep)                                                                   \
+  {                                                                                      \
+    uint32_t now_;                                                                       \
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(now_) : "r"((uint32_t)(dep)) : "memory"); \
+    pr.acc[i] += now_ - *pr.last;                                                        \
+    *pr.last = now_;                                                                     \
+  }
+#undef PROF_T
+#define PROF_T(i)
+#else
+#define PROF_C(i, dep)
+#endif
 
 // ---------------------------------------------------------------------------
 // column tiles (the queue): one warp, rows [begin, begin + count) of one id stream.
@@ -1037,6 +1053,19 @@ __device__ __forceinline__ UserRegs load_user(const DevPlan& P, const ReqParams&
   u.col = b.y;
   u.vec_bytes = b.z;
   u.hbm = b.w;
+  return u;
+}
+
+__device__ __forceinline__ UserRegs first_user(const ReqParams& A, const ColItem& it) {
+  UserRegs u;
+  u.table = (const uint8_t*)A.tables[it.u0.table];
+  u.row_bytes = it.u0.row_bytes;
+  u.table_rows = it.u0.table_rows;
+  u.out_byte = it.u0.out_byte;
+  u.combiner = it.u0.combiner;
+  u.col = it.u0.col;
+  u.vec_bytes = it.u0.vec_bytes;
+  u.hbm = it.u0.hbm;
   return u;
 }
 
@@ -1345,20 +1374,21 @@ __device__ __noinline__ void sparse_tile_overflow(const DevPlan& P, const ReqPar
     const int32_t e_hi = lds_i32(s_sp + 4u * (uint32_t)r_hi);
     transform_ids(P, it, values, bytes, e_lo, e_hi, s_ids, lane);
     __syncwarp();
-    sparse_users<BF16>(P, A, Q, it, load_user(P, A, it.first_user), (int64_t)it.begin + r_lo,
+    sparse_users<BF16>(P, A, Q, it, first_user(A, it), (int64_t)it.begin + r_lo,
                        r_hi - r_lo, s_sp + 4u * (uint32_t)r_lo, s_ids, e_lo, true, s_tmp, lane);
     __syncwarp();
     r_lo = r_hi;
   }
 }
 
-// The record of a column tile: 64 bytes, four 128-bit loads (lane-uniform address).
+// The record of a column tile: 96 bytes, six 128-bit loads (lane-uniform address).
 __device__ __forceinline__ void load_item(const ColItem* p, ColItem& it) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4* d = reinterpret_cast<uint4*>(&it);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) d[k] = __ldg(q + k);
+  for (int k = 0; k < 6; ++k) d[k] = __ldg(q + k);
 }
+
 
 template <bool BF16, class QT>
 __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A, const QT& Q,
@@ -1372,7 +1402,8 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
   if (it.seg_slot >= 0)
     rs = it.coo_index >= 0 ? A.ws_row_splits + (int64_t)it.coo_index * (A.batch + 1)
                            : (const int32_t*)(A.blob + __ldg(A.slot_offsets + it.seg_slot));
-  UserRegs u = load_user(P, A, it.first_user);
+  UserRegs u = first_user(A, it);
+  PROF_C(1, (uintptr_t)values + (uintptr_t)bytes + (uintptr_t)rs + (uintptr_t)u.table + u.row_bytes)
   const uint32_t s_sp = s_scratch, s_ids = s_sp + kColSplitBytes;
   // scratch: [row_splits | ids (cap) | 1 KB for the partial sums of long rows]
   const int cap = (P.scratch_bytes - kColSplitBytes - 1024) >> 2;
@@ -1384,6 +1415,7 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
     __syncwarp();
     if (u.hbm && !Q.check) prefetch_rows(u, s_ids, n, lane);
     PROF_T(3)
+    PROF_C(3, lds_i32(s_ids))
     for (int ui = 0;;) {
       if (u.vec_bytes == 16) gather_rows<16>(Q, u, it.begin, n, s_ids, lane);
       else gather_rows_cold<ELEM>(Q, u, it.begin, n, s_ids, lane);
@@ -1391,6 +1423,7 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
       u = load_user(P, A, it.first_user + ui);
     }
     PROF_T(4)
+    PROF_C(4, 0)
   } else {
     const int R = it.count;  // <= 32
     const int32_t v = lane < R ? __ldg(rs + it.begin + lane) : 0;
@@ -1402,16 +1435,19 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
     const int32_t n_row = lane < R ? (lane == R - 1 ? e_end : v_next) - v : 0;
     const bool any_long = __any_sync(0xffffffffu, n_row > kCoopRowIds);
     __syncwarp();
+    PROF_C(2, e0 + e_end)
     if (e_end - e0 <= cap) {
       transform_ids(P, it, values, bytes, e0, e_end, s_ids, lane);
       __syncwarp();
       if (u.hbm && !Q.check) prefetch_rows(u, s_ids, e_end - e0, lane);
       PROF_T(3)
+      PROF_C(3, lds_i32(s_ids))
       sparse_users<BF16>(P, A, Q, it, u, it.begin, R, s_sp, s_ids, e0, any_long, s_tmp, lane);
     } else {
       sparse_tile_overflow<BF16>(P, A, Q, it, values, bytes, s_sp, s_ids, cap, s_tmp, lane);
     }
     PROF_T(4)
+    PROF_C(4, 0)
   }
   __syncwarp();  // everybody is done with the scratch
 }
@@ -1467,22 +1503,26 @@ __device__ __noinline__ void setup_run(const DevPlan& P, const Sched& S, const R
   if (lane == 0) mbar_arrive(&cs->mbar_ctx);
 }
 
-// The CTA's column tiles, taken from the counter in shared memory (k >= 0: the warp's static
-// first tile).
+// The CTA's column tiles, taken from the counter in shared memory as the warps become free
+// (k >= 0: the warp's static first tile, its record `it` requested at kernel entry). Measured:
+// a static deal of the tiles to the warps costs more in balance (mixed1000 156 -> 227 us) than
+// the exposed load of a claimed tile's record.
 template <bool BF16, class QT>
 __device__ __noinline__ void column_section(const DevPlan& P, const ReqParams& A, const QT Q,
-                                            const ColItem* q_items, int q_count, int k,
+                                            const ColItem* q_items, int q_count, int k, ColItem it,
                                             int* next_col, uint32_t s_scratch, int lane PROF_PARAM) {
   auto claim = [&]() {
     int t = 0;
     if (lane == 0) t = atomicAdd(next_col, 1);
     return __shfl_sync(0xffffffffu, t, 0);
   };
-  if (k < 0) k = claim();
-  ColItem it;
-  if (k < q_count) load_item(q_items + k, it);
+  if (k < 0) {
+    k = claim();
+    if (k < q_count) load_item(q_items + k, it);
+  }
   while (k < q_count) {
     PROF_T(0)
+    PROF_C(0, it.begin + it.count)
     column_tile<BF16>(P, A, Q, it, s_scratch, lane PROF_ARG);
     k = claim();
     if (k < q_count) load_item(q_items + k, it);
@@ -1616,6 +1656,10 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
   const ColItem* q_items = S.queue + ((int64_t)max(cc, 0) * q_base + min(max(cc, 0), q_rem));
   const int fast_warps = excl ? (cc < 0 ? kWarps : 0) : S.fast_warps;
   const bool fast_first = warp < fast_warps;
+  // the column-first warps' first tile is static: its record is requested before anything else
+  const int k0 = fast_first ? -1 : warp - fast_warps;
+  ColItem it;
+  if (k0 >= 0 && k0 < q_count) load_item(q_items + k0, it);
   if (threadIdx.x == 0) cs.next_col = kWarps - fast_warps;  // the static first tiles are taken
   __syncthreads();
 
@@ -1648,10 +1692,10 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
   sm.scratch = sm.tables + (uint32_t)P.smem_off_scratch + (uint32_t)(warp * P.scratch_bytes);
 
   if (!fast_first)
-    column_section<BF16>(P, A, Q, q_items, q_count, warp - fast_warps, &cs.next_col, sm.scratch, lane PROF_ARG);
+    column_section<BF16>(P, A, Q, q_items, q_count, k0, it, &cs.next_col, sm.scratch, lane PROF_ARG);
   fast_section<BF16>(P, S, A, Q, &cs, smem, sm, warp, lane PROF_ARG);
   if (fast_first)
-    column_section<BF16>(P, A, Q, q_items, q_count, -1, &cs.next_col, sm.scratch, lane PROF_ARG);
+    column_section<BF16>(P, A, Q, q_items, q_count, k0, it, &cs.next_col, sm.scratch, lane PROF_ARG);
 
   // ---- sharded output: the last warp of the grid tells every peer that this rank's slices
   // of its rows are in place (and, with the barrier inside the kernel, waits for theirs) ----
@@ -1823,6 +1867,24 @@ void launch_scatter_columns(const void* const* d_cols, const int32_t* d_dims,
   dim3 grid(64, (unsigned)num_cols);
   scatter_columns_kernel<<<grid, 256, 0, stream>>>(d_cols, d_dims, d_offsets, batch, out_width,
                                                   elem_bytes, (uint8_t*)out);
+}
+
+// ---------------------------------------------------------------------------
+// `output_ptrs` of the reference's op (feature_column_process_op_gpu.cu.cc:118-121 uploads them
+// and synchronises): the address of every column's slice in row 0 of the concat tensor.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+output_ptrs_kernel(int32_t num_cols, const int32_t* __restrict__ out_offsets, int32_t elem_bytes,
+                   uint8_t* out, long long* __restrict__ ptrs) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_cols; i += gridDim.x * blockDim.x)
+    ptrs[i] = (long long)(uintptr_t)(out + (int64_t)out_offsets[i] * elem_bytes);
+}
+
+void launch_output_ptrs(int32_t num_cols, const int32_t* d_out_offsets, int32_t elem_bytes, void* out,
+                        int64_t* ptrs_dev, cudaStream_t stream) {
+  const int bx = (num_cols + 255) / 256;
+  output_ptrs_kernel<<<bx < 1 ? 1 : bx, 256, 0, stream>>>(num_cols, d_out_offsets, elem_bytes,
+                                                        (uint8_t*)out, (long long*)ptrs_dev);
 }
 
 // ---------------------------------------------------------------------------

@@ -100,6 +100,20 @@ struct DevSlabCol {
   int32_t pad0, pad1;
 };
 
+// A column reading an id stream.
+struct ColUser {
+  int32_t table;       // index into the request's table pointer array
+  int32_t row_bytes;
+  int32_t table_rows;
+  int32_t out_byte;    // byte offset of the column's slice inside an output row
+  int32_t combiner;
+  int32_t col;         // global column index (ids_out hook)
+  int32_t vec_bytes;   // 16, or the element size when the slice is not 16-byte aligned
+  int32_t hbm;         // 1: the table is far larger than L2: its rows are prefetched into L2 as
+                       // soon as the tile's ids are known (one round trip instead of one per pass)
+};
+static_assert(sizeof(ColUser) == 32, "ColUser layout");
+
 // A column tile of the queue: rows [begin, begin + count) of ONE id stream - a distinct (input,
 // transform) pair - worked on by one warp: raw values -> row ids (hash / bucketize / none; every
 // lane runs the same transform on consecutive ids: coalesced, no divergence) -> for every column
@@ -123,22 +137,11 @@ struct ColItem {
   int32_t first_user;         // into the ColUser array
   int32_t num_users;
   int32_t pad;
+  ColUser u0;                 // = users[first_user]: the common case of one column per stream
+                              // needs no second record
 };
-static_assert(sizeof(ColItem) == 64, "ColItem layout");
+static_assert(sizeof(ColItem) == 96, "ColItem layout");
 
-// A column reading an id stream.
-struct ColUser {
-  int32_t table;       // index into the request's table pointer array
-  int32_t row_bytes;
-  int32_t table_rows;
-  int32_t out_byte;    // byte offset of the column's slice inside an output row
-  int32_t combiner;
-  int32_t col;         // global column index (ids_out hook)
-  int32_t vec_bytes;   // 16, or the element size when the slice is not 16-byte aligned
-  int32_t hbm;         // 1: the table is far larger than L2: its rows are prefetched into L2 as
-                       // soon as the tile's ids are known (one round trip instead of one per pass)
-};
-static_assert(sizeof(ColUser) == 32, "ColUser layout");
 
 // A COO input (SparseTensor.indices) whose row ids are turned into row_splits in the workspace.
 struct DevCoo {
@@ -330,6 +333,8 @@ void launch_scatter_columns(const void* const* d_cols, const int32_t* d_dims,
 void launch_segment_ids_to_row_splits(const int64_t* coo, int64_t nnz, int32_t stride,
                                       int64_t batch, int32_t* row_splits,
                                       cudaStream_t stream);
+void launch_output_ptrs(int32_t num_cols, const int32_t* d_out_offsets, int32_t elem_bytes, void* out,
+                        int64_t* ptrs_dev, cudaStream_t stream);
 void launch_fingerprint64(const uint8_t* bytes, const int32_t* offsets, int64_t n,
                           int64_t num_buckets, uint64_t* out, cudaStream_t stream);
 // configures the dynamic shared memory of the fused kernel; returns resident CTAs per SM
