@@ -58,7 +58,7 @@ def parse_args():
                              # other BASELINE.json configurations (informational lines)
                              "model_E_bf16", "mixed1000", "mixed1000_bf16", "production2000"])
     ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--sets", type=int, default=4, help="rotating request/output buffer sets")
+    ap.add_argument("--sets", type=int, default=8, help="distinct requests / rotating output buffer sets")
     ap.add_argument("--lt-columns", dest="lt_columns", type=int, default=0, help="large_table: columns")
     ap.add_argument("--lt-rows", dest="lt_rows", type=int, default=0, help="large_table: rows per table")
     ap.add_argument("--lt-exchange", dest="lt_exchange", default="fused",
@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--lt-lag", dest="lt_lag", type=int, default=0,
                     help="large_table, fused exchange: steps the launch stream may run ahead of the waits")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of a timed request")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the large-table (sharded) measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -88,7 +90,7 @@ def build_model(workload: str, world: int = 1, rank: int = 0):
     if workload == "model_E_sparse":
         return synth.dlrm_model(0, 0, 0, 15, 5, name="E_sparse"), 2048
     # informational lines (parity-tested configurations of BASELINE.json, not the headline)
-    from recom_b200 import _lib as L
+    from recom_b200 import consts as L
     if workload == "model_E_bf16":
         return synth.model_E(out_dtype=L.BF16), 2048
     if workload == "mixed1000":      # config 2 extension: dims 8-64, sum / mean / sqrtn
@@ -186,7 +188,7 @@ def time_oracle(model, batch, n_sets, seconds, warmup, steps=None):
     descs, bnd = model.descs()
     tabs = host_tables(model)
     ptrs = np.array([t.ctypes.data for t in tabs], dtype=np.uint64)
-    reqs = [pack_request(model, batch, synth.make_features(model, batch, seed=100 + s))
+    reqs = [pack_request(model, batch, synth.make_features(model, batch, seed=s))
             for s in range(n_sets)]
     out = np.zeros((batch, model.out_width), np.float32)
     # all the host cores this process may use; torchrun exports OMP_NUM_THREADS=1 to its
@@ -224,16 +226,39 @@ def time_oracle(model, batch, n_sets, seconds, warmup, steps=None):
     lat_ms = np.array(lat) * 1e3
     return {"samples_per_s": batch * len(lat) / total, "steps": len(lat), "cores": threads,
             "ms_per_step": total / len(lat) * 1e3, "p50_ms": float(np.percentile(lat_ms, 50)),
-            "p99_ms": float(np.percentile(lat_ms, 99))}
+            "p99_ms": float(np.percentile(lat_ms, 99)),
+            "rot_mb": (sum(r.blob.nbytes for r in reqs) + n_sets * out.nbytes) / 1e6}
+
+
+def _package_without_library():
+    """The reference arm needs the synthetic models and the request packer (pure numpy) but must
+    not map the product's shared library: register the package without running its __init__."""
+    import types
+
+    if "recom_b200" not in sys.modules:
+        pkg = types.ModuleType("recom_b200")
+        pkg.__path__ = [os.path.join(ROOT, "recom_b200")]
+        sys.modules["recom_b200"] = pkg
+
+
+def config_of(workload, model, batch, world, rot_mb=None, sets=None):
+    """The same keys on both arms (the driver compares the two `config` dicts)."""
+    return {"workload": f"{workload}_b{batch}", "columns": len(model.columns), "batch": batch,
+            "out_width": model.out_width, "table_bytes": model.table_bytes(),
+            "parallelism": f"replicas x{world}",
+            "l2": f"rotating {sets} distinct requests / output sets = {rot_mb:.0f} MB > 126 MB L2",
+            "hashing": "fused (Fingerprint64 of the raw strings / integers inside the stage)",
+            "segments": "int32 row_splits"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _package_without_library()
     model, batch = build_model(args.workload)
     batch = args.batch or batch
-    r = time_oracle(model, batch, args.sets, 0.0, args.warmup, steps=args.steps)
+    r = time_oracle(model, batch, max(args.sets, 2), 0.0, args.warmup, steps=args.steps)
     sample = f"{r['steps']} batches of {batch} samples of {args.workload}, all {len(model.columns)} columns"
     line = {
         "impl": "reference", "metric": METRIC, "value": r["samples_per_s"], "unit": UNIT,
@@ -241,8 +266,7 @@ def run_reference(args):
         "ms_per_step": r["ms_per_step"], "p50_ms": r["p50_ms"], "p99_ms": r["p99_ms"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}_b{batch}", "columns": len(model.columns),
-                   "batch": batch, "out_width": model.out_width},
+        "config": config_of(args.workload, model, batch, 1, r["rot_mb"], max(args.sets, 2)),
         "cpu_baseline": {"value": r["samples_per_s"], "unit": UNIT, "cores": r["cores"],
                          "kind": "port", "sample": sample},
         "e2e": {"value": r["samples_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0,
@@ -253,15 +277,43 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def check_parity(model, batch, req, tables, out, launch, stream):
+    """Runs `req` on the device and through the CPU oracle (test infrastructure, the checker only)
+    on the same tables; embeddings within north_star's tolerance (1e-5 relative for fp32, 1e-2 for
+    bf16; against the summed magnitudes for multi-hot rows), copies bit-exact. -> summary dict."""
+    import torch
+
+    from oracle import oracle as O
+    from recom_b200 import consts as K
+
+    bf16 = model.out_dtype == K.BF16
+    with torch.cuda.stream(stream):
+        launch()
+    stream.synchronize()
+    got = out.float().cpu().numpy()
+    if bf16:
+        host = [t.view(torch.int16).cpu().numpy().view(np.uint16) for t in tables]
+    else:
+        host = [t.cpu().numpy() for t in tables]
+    descs, bnd = model.descs()
+    ref, _ = O.run_model(descs, bnd, model.out_width, model.out_dtype, batch, req.blob, req.slot_offsets,
+                         req.slot_elems, host, req.total_ids, O.num_threads())
+    rtol, atol = (1e-2, 1e-5) if bf16 else (1e-5, 1e-6)
+    bad = ~np.isclose(got, ref, rtol=rtol, atol=atol)
+    exact_cols = 0
+    for c in model.columns:
+        if c.lookup != K.LOOKUP_SEGMENT:
+            sl = slice(c.out_offset, c.out_offset + c.dim)
+            assert np.array_equal(got[:, sl], ref[:, sl]), f"column {c.name}: copy is not bit-exact"
+            exact_cols += 1
+    assert not bad.any(), f"{int(bad.sum())} elements outside rtol={rtol} atol={atol}"
+    return {"checked": True, "against": "CPU oracle (oracle/recom_oracle.c)", "rtol": rtol, "atol": atol,
+            "max_abs_err": float(np.abs(got - ref).max()), "bit_exact_columns": exact_cols,
+            "columns": len(model.columns)}
+
+
 def run_ours(args):
     import ctypes as C
-
-    if args.workload == "large_table" and not os.environ.get("RECOM_B200_LIB"):
-        # multi-hot columns over large tables: the 12-warps-per-CTA flavour of the library
-        # (recom_b200/_lib.py); must be chosen before the package loads its library
-        w12 = os.path.join(ROOT, "recom_b200", "librecom_b200_w12.so")
-        if os.path.exists(w12):
-            os.environ["RECOM_B200_LIB"] = w12
 
     import torch
     import torch.distributed as dist
@@ -285,13 +337,16 @@ def run_ours(args):
 
     model, batch = build_model(args.workload)
     batch = args.batch or batch
+    # S distinct requests (own ids, own row lengths, hence own slot offsets each): nothing in the
+    # timed loop is served from a cache of earlier requests - the argument data of a request
+    # travels inside its blob
     K, W, S = args.steps, max(args.warmup, 3), max(args.sets, 2)
 
     plan = R.Plan(model, device=local)
     tables = R.make_tables(model, device=local, seed=0)
     ptrs = R.table_pointers(tables)
     reqs = [pack_request(model, batch, synth.make_features(model, batch, seed=1000 * rank + s))
-            for s in range(S)]
+            for s in range(S)]  # (the reference arm packs the same S requests of rank 0)
     blobs = [R.upload_blob(r, local) for r in reqs]
     outs = [plan.alloc_out(batch) for _ in range(S)]
     wss = [plan.alloc_workspace(batch, r.sparse_ids) for r in reqs]
@@ -317,6 +372,12 @@ def run_ours(args):
             L.check(run(h, refs[i % S]))
     launches_per_step = plan.last_launch_count()
     barrier()
+
+    # ---- parity of what is timed: one of the timed requests against the CPU oracle ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = check_parity(model, batch, reqs[0], tables, outs[0], lambda: L.check(run(h, refs[0])), stream)
+        torch.cuda.synchronize(local)
 
     # ---- device-resident timing: K back-to-back steps -----------------------------
     sampler = ClockSampler(local)
@@ -400,29 +461,24 @@ def run_ours(args):
     peak, peak_src = peaks()
     mean_alg = float(np.mean(alg_bytes))
     achieved = mean_alg / (ms_per_step * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as f:
-            traffic = json.load(f).get(f"{args.workload}_b{batch}")
-
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "p50_ms": float(np.percentile(lat, 50)),
         "p99_ms": float(np.percentile(lat, 99)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if outs[0].element_size() == 2 else "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}_b{batch}", "columns": len(model.columns),
-                   "batch": batch, "out_width": model.out_width,
-                   "table_bytes": model.table_bytes(), "parallelism": f"replicas x{world}",
-                   "l2": f"rotating {S} request/output sets = {rot_bytes / 1e6:.0f} MB > 126 MB L2",
-                   "hashing": "fused on device (Fingerprint64)", "segments": "int32 row_splits"},
+        "config": config_of(args.workload, model, batch, world, rot_bytes / 1e6, S),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": mean_alg, "kernel": "fused_columns_kernel"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,
+        "parity_checked": bool(parity and parity["checked"]), "parity": parity,
+        "requests": f"{S} distinct requests (own ids and row lengths each); per-request argument data "
+                    "travels inside the blob: no argument cache, no host->device copy besides the blob",
+        "e2e_note": "d2h = the last output row (the consumer of the concat tensor is the GPU MLP); "
+                    "h2d = the whole request blob from pinned memory, every step",
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -435,6 +491,32 @@ def run_ours(args):
             "sample": f"{r['steps']} batches of {batch} samples of {args.workload} "
                       f"(all {len(model.columns)} columns), {args.cpu_seconds:.0f} s of CPU work",
         }
+    if world > 1 and not args.no_sharded:
+        # The configuration that needs more than one GPU (BASELINE config 4: 1000 multi-hot columns
+        # over 192 GB of tables), column-group sharded over the same ranks with the exchange fused
+        # into the kernel; its one-GPU equivalent (tables cut to fit one GPU) is measured first,
+        # on rank 0, in this very run. Same library as the headline.
+        from recom_b200 import sharding
+
+        del tables, blobs, outs, wss, plan
+        torch.cuda.empty_cache()
+        lt_steps = min(K, 100)
+        one = None
+        if rank == 0:
+            one = sharding.measure_large_table(args, 1, 0, local, rows=1_300_000, steps=lt_steps)
+        barrier()
+        sh = sharding.measure_large_table(args, world, rank, local, steps=lt_steps)
+        if rank == 0:
+            line["sharded"] = {
+                "workload": sh.get("config", {}).get("workload"), "ms_per_step": sh.get("ms_per_step"),
+                "value": sh.get("value"), "unit": UNIT, "n_gpus": world, "scaling": "strong",
+                "exchange": sh.get("exchange"), "parity_vs_all_to_all": sh.get("parity_vs_all_to_all"),
+                "one_gpu_equiv_ms_per_step": one.get("ms_per_step"),
+                "one_gpu_equiv": one.get("config", {}).get("workload"),
+                "speedup_vs_1gpu_equiv": (one["ms_per_step"] / sh["ms_per_step"]
+                                          if one.get("ms_per_step") and sh.get("ms_per_step") else None),
+                "library": sh.get("config", {}).get("library"), "unavailable": sh.get("unavailable"),
+            }
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

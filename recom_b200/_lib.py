@@ -13,10 +13,6 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # RECOM_B200_LIB selects another build of the same library (e.g. the phase-timer build)
 LIB_PATH = os.environ.get("RECOM_B200_LIB") or os.path.join(_HERE, "librecom_b200.so")
-# The 12-warps-per-CTA flavour of the same source (csrc/Makefile): plans that are one long HBM
-# gather stream (multi-hot columns over large tables) run ~6 % faster with it, everything else
-# ~6 % slower. One flavour per process.
-LIB_PATH_W12 = os.path.join(_HERE, "librecom_b200_w12.so")
 
 from .consts import *  # noqa: F401,F403  (enums, COLUMN_DESC, DTYPE_BYTES)
 from .consts import COLUMN_DESC, DTYPE_BYTES  # noqa: F401

@@ -347,8 +347,23 @@ def combine_scale(combiner: int, counts: np.ndarray) -> np.ndarray:
 # bench leg: the >180 GB large-table configuration (BASELINE.json config 4)
 # ---------------------------------------------------------------------------------------
 def bench_large_table(args, world: int, rank: int, local: int):
-    """1000 multi-hot mean columns over [rows, 32] fp32 tables, column-group sharded over
-    `world` GPUs, NCCL all-gather of the slices. Prints one JSON line on rank 0."""
+    """`bench.py --workload large_table`: prints one JSON line on rank 0."""
+    import json
+
+    import torch.distributed as dist
+
+    line = measure_large_table(args, world, rank, local)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_large_table(args, world: int, rank: int, local: int, rows: int = 0, steps: int = 0):
+    """BASELINE config 4: 1000 multi-hot mean columns over [rows, 32] fp32 tables (192 GB),
+    column-group sharded over `world` GPUs, the exchange fused into the kernel (or an NCCL
+    exchange). Collective over the `world` ranks of the default process group (world == 1: no
+    collective is called). -> the JSON line (dict) on every rank."""
     import ctypes as C
     import json
     import time
@@ -361,21 +376,19 @@ def bench_large_table(args, world: int, rank: int, local: int):
     from .schema import algorithmic_bytes, pack_request
 
     n_cols = int(getattr(args, "lt_columns", 0) or 1000)
-    rows = int(getattr(args, "lt_rows", 0) or 1_500_000)
+    rows = int(rows or getattr(args, "lt_rows", 0) or 1_500_000)
     batch = args.batch or 2048
     model = synth.large_table_model(n_cols, rows, 32)
     per_gpu_budget = 170 << 30
     if model.table_bytes() / world > per_gpu_budget:
-        if rank == 0:
-            print(json.dumps({"metric": "embedding_column_stage_samples_per_sec", "unavailable":
-                              f"{model.table_bytes() / 1e9:.0f} GB of tables need more than {world} GPU(s)"}))
-        return
+        return {"metric": "embedding_column_stage_samples_per_sec", "unavailable":
+                f"{model.table_bytes() / 1e9:.0f} GB of tables need more than {world} GPU(s)"}
     shards = partition_columns(model, world)
     sh = shards[rank]
     plan = R.Plan(sh.model, device=local)
     tables = R.make_tables(sh.model, device=local, seed=rank)
     ptrs = R.table_pointers(tables)
-    K, W, S = args.steps, max(args.warmup, 3), max(args.sets, 2)
+    K, W, S = int(steps or args.steps), max(args.warmup, 3), max(args.sets, 2)
     reqs = []
     for s in range(S):
         feats = synth.make_features(model, batch, seed=100 + s)  # replicated inputs, same on all ranks
@@ -476,33 +489,36 @@ def bench_large_table(args, world: int, rank: int, local: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(alg_t, op=dist.ReduceOp.SUM)
     ms = float(t[0]) / K
-    if rank == 0:
-        print(json.dumps({
-            "metric": "embedding_column_stage_samples_per_sec", "value": batch / (ms * 1e-3),
-            "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"large_table_{n_cols}x{rows}x32_b{batch}", "columns": n_cols,
-                       "batch": batch, "table_bytes": model.table_bytes(),
-                       "parallelism": (f"column-group x{world}, exchange fused into the kernel: rows stored straight into the "
-                                       f"owners' [B/{world}, sum D] tensors over NVLink (IPC peer memory); completion "
-                                       f"flags stored to every peer by the kernel's last warp, " +
-                                       ("which also waits for all ranks' flags: compute, exchange and barrier in one kernel"
-                                        if wait_mode == "kernel" else
-                                        f"one-warp wait kernel {'on the launch stream' if lag == 0 else f'on a second stream, launches run {lag} step(s) ahead'}") +
-                                       " (no NCCL call in the step)" if exchange == "fused" else
-                                       f"column-group x{world}, NCCL all-gather of [B, W_g] slices" if exchange == "all_gather"
-                                       else f"column-group x{world}, NCCL all-to-all of [B/{world}, W_g] row blocks "
-                                            f"(every rank keeps its B/{world} rows of the concat tensor)"),
-                       "l2": f"rotating {S} request/output sets",
-                       "library": os.path.basename(L.LIB_PATH)},
-            "roofline": {"bound": "hbm", "achieved": float(alg_t[0]) / (ms * 1e-3) / 1e9,
-                         "unit": "GB/s", "note": "aggregate algorithmic bytes over all ranks / step time"},
-            "gpu_launches": (plan.last_launch_count() + (1 if exchange == "fused" and wait_mode != "kernel" else 0)) * K,
-        }), flush=True)
+    line = {
+        "metric": "embedding_column_stage_samples_per_sec", "value": batch / (ms * 1e-3),
+        "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"large_table_{n_cols}x{rows}x32_b{batch}", "columns": n_cols,
+                   "batch": batch, "table_bytes": model.table_bytes(),
+                   "parallelism": (f"column-group x{world}, exchange fused into the kernel: rows stored straight into the "
+                                   f"owners' [B/{world}, sum D] tensors over NVLink (IPC peer memory); completion "
+                                   f"flags stored to every peer by the kernel's last warp, " +
+                                   ("which also waits for all ranks' flags: compute, exchange and barrier in one kernel"
+                                    if wait_mode == "kernel" else
+                                    f"one-warp wait kernel {'on the launch stream' if lag == 0 else f'on a second stream, launches run {lag} step(s) ahead'}") +
+                                   " (no NCCL call in the step)" if exchange == "fused" else
+                                   f"column-group x{world}, NCCL all-gather of [B, W_g] slices" if exchange == "all_gather"
+                                   else f"column-group x{world}, NCCL all-to-all of [B/{world}, W_g] row blocks "
+                                        f"(every rank keeps its B/{world} rows of the concat tensor)"),
+                   "l2": f"rotating {S} request/output sets",
+                   "library": os.path.basename(L.LIB_PATH)},
+        "roofline": {"bound": "hbm", "achieved": float(alg_t[0]) / (ms * 1e-3) / 1e9,
+                     "unit": "GB/s", "note": "aggregate algorithmic bytes over all ranks / step time"},
+        "gpu_launches": (plan.last_launch_count() + (1 if exchange == "fused" and wait_mode != "kernel" else 0)) * K,
+        "exchange": exchange,
+        # the fused exchange was compared (torch.equal) with the NCCL all-to-all of the same slices
+        "parity_vs_all_to_all": exchange == "fused",
+    }
     if peers:
         barrier()
         for p in peers:
             p.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del tables, blobs, outs, wss, plan
+    torch.cuda.empty_cache()
+    return line
