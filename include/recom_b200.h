@@ -137,7 +137,14 @@ typedef struct recom_plan_config {
                            raise the request's status word */
   int32_t device;       /* CUDA device ordinal */
   int32_t max_ctas_per_sm; /* 0 = library default */
-  int32_t reserved;
+  int32_t row_shard;    /* Mode B, 0 = whole tables: world | rank << 16. The rows of every table are
+                           sharded over `world` ranks - row r lives on rank r % world at local row
+                           r / world, and recom_request.tables point to this rank's shards. The
+                           plan then writes PARTIAL SUMS over the rows it owns (every combiner
+                           acts as SUM, rows of other ranks contribute zeros); the caller reduces
+                           the [batch, out_width] tensors over the ranks (ncclReduceScatter) and
+                           calls recom_plan_scale_rows on the rows it keeps. Descriptors keep
+                           the GLOBAL table_rows. */
 } recom_plan_config;
 
 typedef struct recom_plan recom_plan;
@@ -203,6 +210,12 @@ RECOM_API recom_status recom_plan_infer_batch(const recom_plan *plan, const int6
                                     int64_t *batch);
 RECOM_API recom_status recom_plan_output_shapes(const recom_plan *plan, int64_t batch,
                                       int32_t *shapes);
+/* Mode B (recom_plan_config.row_shard), after the cross-rank reduction: applies the mean /
+ * sqrtn scaling (TF-CPU rule: x 1/m below 10 ids, / m otherwise) to rows [row_begin, row_begin +
+ * rows) of the summed concat tensor; out_rows = address of row `row_begin`. `req`: the request the
+ * partial sums were computed from (blob with the argument trailer, stream, workspace). */
+RECOM_API recom_status recom_plan_scale_rows(const recom_plan *plan, const recom_request *req,
+                                   int64_t row_begin, int64_t rows, void *out_rows);
 RECOM_API recom_status recom_plan_output_ptrs(const recom_plan *plan, void *out, int64_t *ptrs_dev,
                                     recom_stream_t stream);
 

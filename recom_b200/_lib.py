@@ -22,7 +22,7 @@ class PlanConfig(C.Structure):
     _fields_ = [
         ("out_dtype", C.c_int32), ("out_width", C.c_int32), ("num_slots", C.c_int32),
         ("num_tables", C.c_int32), ("check_ids", C.c_int32), ("device", C.c_int32),
-        ("max_ctas_per_sm", C.c_int32), ("reserved", C.c_int32),
+        ("max_ctas_per_sm", C.c_int32), ("row_shard", C.c_int32),
     ]
 
 
@@ -57,7 +57,7 @@ EXPORTS = [
     "recom_last_error", "recom_abi_version", "recom_plan_create", "recom_plan_destroy",
     "recom_plan_serialize", "recom_plan_create_from_blob", "recom_plan_num_columns",
     "recom_plan_out_width", "recom_plan_num_slots", "recom_plan_slot_layout", "recom_plan_infer_batch",
-    "recom_plan_output_shapes", "recom_plan_output_ptrs", "recom_plan_workspace_bytes", "recom_plan_run",
+    "recom_plan_output_shapes", "recom_plan_output_ptrs", "recom_plan_scale_rows", "recom_plan_workspace_bytes", "recom_plan_run",
     "recom_last_launch_count", "recom_plan_algorithmic_bytes", "recom_scatter_columns", "recom_scatter_host_columns",
     "recom_segment_ids_to_row_splits", "recom_string_to_hash_bucket_fast", "recom_fingerprint64",
     "recom_concat_inputs", "recom_concat_inputs_with_args", "recom_shape_construct_create", "recom_shape_construct_eval",
@@ -90,6 +90,7 @@ def _load() -> C.CDLL:
         "recom_plan_infer_batch": [vp, vp, C.POINTER(i64)],
         "recom_plan_output_shapes": [vp, i64, vp],
         "recom_plan_output_ptrs": [vp, vp, vp, vp],
+        "recom_plan_scale_rows": [vp, C.POINTER(Request), i64, i64, vp],
         "recom_plan_workspace_bytes": [vp, i64, i64, C.POINTER(sz)],
         "recom_plan_run": [vp, C.POINTER(Request)],
         "recom_plan_run_sharded": [vp, C.POINTER(Request), C.POINTER(ShardOut)],

@@ -137,6 +137,7 @@ struct TileTable {
     s.num_queue = (int32_t)queue.size();
     s.fast_warps = fast_warps;
     s.fast_ctas = fast_ctas;
+    for (size_t c = 0; c < cta.size() && c < (size_t)kMaxParamCtas; ++c) s.cta_param[c] = cta[c];
     return s;
   }
 };
@@ -168,6 +169,7 @@ struct recom_plan {
   int elem_bytes = 4;
   int num_sms = 148;
   int ctas_per_sm = 2;
+  int shard_world = 1, shard_rank = 0;  // Mode B: rows of every table sharded over ranks
   bool exclusive = false;      // FAST runs and column tiles on disjoint CTAs
   double col_weight = 1.0;     // scales the column tiles' cost in that split
   int force_fast_warps = -1;  // >= 0: override the cost-proportional split (experiments)
@@ -621,7 +623,7 @@ void build_layout(recom_plan* p) {
         if (uni) sl.uni8_mask |= 1u << g;
       }
     }
-    if (sl.cls == kSlabDenseStaged && sl.num_cols >= 8 && sl.num_cols % 8 == 0 &&
+    if (p->shard_world <= 1 && sl.cls == kSlabDenseStaged && sl.num_cols >= 8 && sl.num_cols % 8 == 0 &&
         sl.fast8_mask == (uint32_t)((1ull << (sl.num_cols / 8)) - 1ull)) {
       sl.all_fast = 1;  // a FAST slab: scheduled statically, everything else goes to the queue
       if (sl.num_cols >= 16) sl.tile_rows = kFastTileRows;
@@ -682,7 +684,7 @@ void build_layout(recom_plan* p) {
         cu.row_bytes = d.dim * es;
         cu.table_rows = (int32_t)d.table_rows;
         cu.out_byte = d.out_offset * es;
-        cu.combiner = d.combiner;
+        cu.combiner = p->shard_world > 1 ? (int32_t)RECOM_COMBINE_SUM : d.combiner;  // Mode B: partial sums
         cu.col = sc.col;
         cu.vec_bytes = sl.vec_bytes;
         cu.hbm = d.table_rows * (int64_t)d.dim * es > kHbmTableBytes ? 1 : 0;
@@ -789,12 +791,20 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   };
   std::vector<Costed> qs;
   double queue_cost = 0;
+  bool long_queue;
+  {
+    int64_t n = 0;
+    for (const ColItem& u : p->units)
+      n += u.seg_slot >= 0 ? (B + rows_sparse - 1) / rows_sparse : (B + rows_dense - 1) / rows_dense;
+    long_queue = n > 4 * warps;
+  }
   for (size_t ui = 0; ui < p->units.size(); ++ui) {
     const ColItem& u = p->units[ui];
     const int64_t full = u.seg_slot >= 0 ? kColTileRowsSparse : kColTileRowsDense;
     int64_t step = u.seg_slot >= 0 ? rows_sparse : rows_dense;
-    // rows gathered from HBM-resident tables: a quarter of the rows, four times the tiles in flight
-    if (p->unit_hbm[ui]) step = std::max<int64_t>(u.seg_slot >= 0 ? 4 : 32, step / 4);
+    // rows gathered from HBM-resident tables: a quarter of the rows, four times the tiles in
+    // flight - unless the queue is long anyway (every tile pays its chain of dependent loads)
+    if (p->unit_hbm[ui] && !long_queue) step = std::max<int64_t>(u.seg_slot >= 0 ? 4 : 32, step / 4);
     for (int64_t b = 0; b < B; b += step) {
       ColItem it = u;
       it.begin = (int32_t)b;
@@ -868,17 +878,38 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     }
   }
   tt->cta.assign(grid, CtaWork{0, 0, 0, 0});
+  // The cost-sorted column tiles go to the least loaded CTA that holds column tiles (all of
+  // them, or those behind the FAST CTAs); a CTA's load starts with its FAST runs (55 slabs over
+  // 296 CTAs: some CTAs own a fifth more rows than others), column tiles weighted as in the
+  // split of the warps below.
+  const int first_c = tt->fast_ctas >= 0 ? tt->fast_ctas : 0;
+  std::vector<std::vector<int>> q_of(grid);
+  {
+    using Load = std::pair<double, int>;
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (int c = first_c; c < grid; ++c) {
+      double l = 0;
+      for (const Tile& t : per_cta[c]) {
+        const DevSlab& sl = t.slab;
+        l += (double)t.slab.run_tiles * 2.0 * (sl.tile_rows * sl.num_chunks * sl.vec_bytes) / 8192.0;
+      }
+      heap.push({l, c});
+    }
+    for (size_t i = 0; i < qs.size(); ++i) {
+      Load top = heap.top();
+      heap.pop();
+      q_of[top.second].push_back((int)i);
+      top.first += 3.0 * qs[i].cost;
+      heap.push(top);
+    }
+  }
   for (int c = 0; c < grid; ++c) {
     tt->cta[c].first = (int32_t)tt->runs.size();
     tt->cta[c].count = (int32_t)per_cta[c].size();
     for (Tile& t : per_cta[c]) tt->runs.push_back(t);
-    // the cost-sorted column tiles, dealt round robin over the CTAs that hold column tiles
-    // (all of them, or those behind the FAST CTAs): the cc-th of them gets tiles cc, cc + gc, ...
     tt->cta[c].q_first = (int32_t)tt->queue.size();
-    const int first_c = tt->fast_ctas >= 0 ? tt->fast_ctas : 0, gc = grid - first_c;
-    if (c >= first_c)
-      for (size_t i = (size_t)(c - first_c); i < qs.size(); i += (size_t)gc) tt->queue.push_back(qs[i].it);
-    tt->cta[c].q_count = (int32_t)tt->queue.size() - tt->cta[c].q_first;
+    for (int i : q_of[c]) tt->queue.push_back(qs[i].it);
+    tt->cta[c].q_count = (int32_t)q_of[c].size();
   }
   // warps that start with the FAST tiles: in proportion to the estimated cost of the two kinds
   if (fast.empty()) tt->fast_warps = 0;
@@ -967,6 +998,8 @@ recom_status upload_plan(recom_plan* p) {
   p->dev.num_slabs = (int32_t)p->slabs.size();
   p->dev.elem_bytes = p->elem_bytes;
   p->dev.check_ids = p->cfg.check_ids;
+  p->dev.shard_world = p->shard_world;
+  p->dev.shard_rank = p->shard_rank;
   return RECOM_OK;
 }
 
@@ -1081,6 +1114,15 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
   recom_plan* p = new (std::nothrow) recom_plan();
   if (!p) return fail(RECOM_ERR_OUT_OF_MEMORY, "host allocation failed");
   p->cfg = *cfg;
+  // row_shard: world | rank << 16 (0: whole tables)
+  p->shard_world = std::max(1, cfg->row_shard & 0xffff);
+  p->shard_rank = (cfg->row_shard >> 16) & 0xffff;
+  if (p->shard_rank >= p->shard_world) {
+    delete p;
+    cudaSetDevice(prev_dev);
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "row_shard: rank %d outside world %d", (cfg->row_shard >> 16) & 0xffff,
+                cfg->row_shard & 0xffff);
+  }
   p->descs.assign(cols, cols + num_cols);
   if (num_boundaries) p->boundaries_in.assign(boundaries, boundaries + num_boundaries);
   p->elem_bytes = cfg->out_dtype == RECOM_BF16 ? 2 : 4;
@@ -1259,6 +1301,8 @@ struct DeviceGuard {
 }  // namespace
 extern "C" {
 
+static size_t max_sched_bytes_of(const recom_plan* p, int64_t batch);
+
 recom_status recom_plan_num_slots(const recom_plan* p, int32_t* out) {
   if (!p || !out) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
   *out = p->cfg.num_slots;
@@ -1309,6 +1353,37 @@ recom_status recom_plan_output_shapes(const recom_plan* p, int64_t batch, int32_
   return RECOM_OK;
 }
 
+recom_status recom_plan_scale_rows(const recom_plan* p, const recom_request* req, int64_t row_begin,
+                                   int64_t rows, void* out_rows) {
+  if (!p || !req || !out_rows || row_begin < 0 || rows < 0 || row_begin + rows > req->batch)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
+  if (rows == 0) return RECOM_OK;
+  if (req->args_offset < 0)
+    return fail(RECOM_ERR_UNSUPPORTED, "recom_plan_scale_rows needs a blob with the argument trailer");
+  DeviceGuard guard;
+  CUDA_TRY(guard.enter(p->cfg.device));
+  ReqParams A{};
+  A.blob = (const uint8_t*)req->blob;
+  A.slot_offsets = (const int64_t*)((const uint8_t*)req->blob + req->args_offset + 16);
+  A.batch = req->batch;
+  // row_splits built from COO inputs live where recom_plan_run of the same request put them
+  size_t off = 0;
+  {
+    size_t b = 2 * align_up((size_t)p->cfg.num_slots * 8, 16);
+    b += align_up((p->descs.size() + 1) * 4, 16);
+    b += align_up((size_t)p->cfg.num_tables * 8, 16);
+    off = align_up(align_up(b, 64) + max_sched_bytes_of(p, req->batch), 256);
+  }
+  A.ws_row_splits = req->workspace ? (int32_t*)((uint8_t*)req->workspace + off) : nullptr;
+  if (!p->coos.empty() && !req->workspace)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "COO inputs: pass the workspace recom_plan_run used");
+  launch_scale_rows(p->dev, p->d_out_offsets, A, row_begin, rows, p->cfg.out_width, out_rows,
+                    p->elem_bytes == 2, (cudaStream_t)req->stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(RECOM_ERR_CUDA, "scale_rows launch: %s", cudaGetErrorString(e));
+  return RECOM_OK;
+}
+
 recom_status recom_plan_output_ptrs(const recom_plan* p, void* out, int64_t* ptrs_dev,
                                     recom_stream_t stream) {
   if (!p || !out || !ptrs_dev) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
@@ -1331,6 +1406,8 @@ static size_t arg_block_bytes(const recom_plan* p) {
   return align_up(b, 64);
 }
 
+static size_t max_sched_bytes(const recom_plan* p, int64_t batch);
+static size_t max_sched_bytes_of(const recom_plan* p, int64_t batch) { return max_sched_bytes(p, batch); }
 static size_t max_sched_bytes(const recom_plan* p, int64_t batch) {
   // only used when the schedule cache is full and the schedule travels with the request
   const size_t ctas = (size_t)p->num_sms * p->ctas_per_sm;

@@ -613,6 +613,10 @@ struct ReqRegs {
   int32_t* ids_out;
   const int32_t* ids_base;
   bool check;
+  // Mode B (table rows sharded over `shard_world` ranks, row r on rank r % world at local row
+  // r / world): ids of other ranks' rows are skipped, the plan's combiners are SUM and the
+  // caller scales after its cross-rank reduction. 1: whole tables.
+  int32_t shard_world, shard_rank;
 };
 
 template <bool SH>
@@ -872,7 +876,7 @@ __device__ __forceinline__ void fast_phase1(const ReqRegs& Q, uint32_t s_ctx, co
   const int row = lane & (TR - 1), cg = lane / TR, ncg = 32 / TR;
   const bool valid = row < rows;
   const int64_t i = b0 + row;
-  const bool hook = Q.check | (Q.ids_out != nullptr);
+  const bool hook = Q.check | (Q.ids_out != nullptr) | (Q.shard_world > 1);
   for (int cbase = cg * 8; cbase < nc; cbase += ncg * 8) {
     const uint32_t ctx = s_ctx + (uint32_t)cbase * (uint32_t)sizeof(ColCtx);
     float v[8];
@@ -1033,6 +1037,8 @@ __device__ __noinline__ int32_t note_id(const ReqRegs Q, int32_t col, int32_t ta
                                         int32_t id) {
   if (Q.check) id = checked_id(id, table_rows, Q.status);
   if (Q.ids_out && col >= 0) Q.ids_out[Q.ids_base[col] + i] = id;
+  if (Q.shard_world > 1)  // -1: another rank's row (the caller skips the gather)
+    id = id % Q.shard_world == Q.shard_rank ? id / Q.shard_world : -1;
   return id;
 }
 
@@ -1117,7 +1123,7 @@ template <int VEC, class QT>
 __device__ __forceinline__ void gather_rows(const QT& Q, const UserRegs& u, int64_t b0, int n,
                                             uint32_t s_ids, int lane) {
   const int C = u.row_bytes / VEC;
-  const bool hook = Q.check | (Q.ids_out != nullptr);
+  const bool hook = Q.check | (Q.ids_out != nullptr) | (Q.shard_world > 1);
   constexpr int U = 8;
   for (int c0 = 0; c0 < C; c0 += 32) {  // rows wider than 32 chunks: 32 chunks at a time
     const int W = min(32, C - c0);
@@ -1138,8 +1144,10 @@ __device__ __forceinline__ void gather_rows(const QT& Q, const UserRegs& u, int6
       }
       Chunk<VEC> v[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k)
-        if (r + k * rpp < n) v[k].load(tbl + (int64_t)id[k] * u.row_bytes);
+      for (int k = 0; k < U; ++k) {
+        if (r + k * rpp < n && id[k] >= 0) v[k].load(tbl + (int64_t)id[k] * u.row_bytes);
+        else v[k].zero();  // (row-sharded tables: another rank's row)
+      }
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         uint8_t* o = outp.next();
@@ -1178,7 +1186,7 @@ template <int VEC, bool BF16, class QT>
 __device__ __forceinline__ void sparse_rows(const QT& Q, const UserRegs& u, int64_t b0, int rows,
                                             uint32_t s_sp, uint32_t s_ids, int32_t e_base, int lane) {
   const int C = u.row_bytes / VEC;
-  const bool hook = Q.check | (Q.ids_out != nullptr);
+  const bool hook = Q.check | (Q.ids_out != nullptr) | (Q.shard_world > 1);
   constexpr int U = BF16 ? 4 : 8;
   const uint32_t ids0 = s_ids - 4u * (uint32_t)e_base;
   for (int c0 = 0; c0 < C; c0 += 32) {
@@ -1208,7 +1216,7 @@ __device__ __forceinline__ void sparse_rows(const QT& Q, const UserRegs& u, int6
         Chunk<VEC> v[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-          if (e + k < e1) v[k].load(tbl + (int64_t)id[k] * row_bytes);
+          if (e + k < e1 && id[k] >= 0) v[k].load(tbl + (int64_t)id[k] * row_bytes);
           else v[k].zero();
         }
 #pragma unroll
@@ -1231,7 +1239,7 @@ template <int VEC, bool BF16, class QT>
 __device__ __forceinline__ void coop_accumulate(const QT& Q, const UserRegs& u, Acc<VEC, BF16>& acc,
                                                 const uint8_t* tbl, int32_t hook_col, int rpp, int sub,
                                                 uint32_t s_ids, int32_t cn, int32_t e_first) {
-  const bool hook = Q.check | (Q.ids_out != nullptr);
+  const bool hook = Q.check | (Q.ids_out != nullptr) | (Q.shard_world > 1);
   for (int32_t j = sub; j < cn; j += 4 * rpp) {
     int32_t id[4];
 #pragma unroll
@@ -1244,7 +1252,7 @@ __device__ __forceinline__ void coop_accumulate(const QT& Q, const UserRegs& u, 
     Chunk<VEC> v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (j + k * rpp < cn) v[k].load(tbl + (int64_t)id[k] * u.row_bytes);
+      if (j + k * rpp < cn && id[k] >= 0) v[k].load(tbl + (int64_t)id[k] * u.row_bytes);
       else v[k].zero();
     }
 #pragma unroll
@@ -1413,7 +1421,7 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
     const int n = it.count;
     transform_ids(P, it, values, bytes, it.begin, (int64_t)it.begin + n, s_ids, lane);
     __syncwarp();
-    if (u.hbm && !Q.check) prefetch_rows(u, s_ids, n, lane);
+    if (u.hbm && !Q.check && Q.shard_world <= 1) prefetch_rows(u, s_ids, n, lane);
     PROF_T(3)
     PROF_C(3, lds_i32(s_ids))
     for (int ui = 0;;) {
@@ -1439,7 +1447,7 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
     if (e_end - e0 <= cap) {
       transform_ids(P, it, values, bytes, e0, e_end, s_ids, lane);
       __syncwarp();
-      if (u.hbm && !Q.check) prefetch_rows(u, s_ids, e_end - e0, lane);
+      if (u.hbm && !Q.check && Q.shard_world <= 1) prefetch_rows(u, s_ids, e_end - e0, lane);
       PROF_T(3)
       PROF_C(3, lds_i32(s_ids))
       sparse_users<BF16>(P, A, Q, it, u, it.begin, R, s_sp, s_ids, e0, any_long, s_tmp, lane);
@@ -1645,16 +1653,13 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
-  // ---- the CTA's column tiles: the cost-sorted queue was dealt round robin, the cc-th CTA that
-  // holds column tiles has tiles cc, cc + Gc, ... contiguously. Warps [fast_warps, kWarps)
-  // start with one each. ----
+  // ---- the CTA's work: FAST runs and column tiles (contiguous in the queue, most expensive
+  // first). Warps [fast_warps, kWarps) start with one column tile each. ----
+  const CtaWork cw = G <= kMaxParamCtas ? S.cta_param[cta] : S.cta[cta];
+  const int q_count = cw.q_count;
+  const ColItem* q_items = S.queue + cw.q_first;
   const bool excl = S.fast_ctas >= 0;
-  const int Gc = excl ? G - S.fast_ctas : G;       // CTAs that hold column tiles
-  const int cc = excl ? cta - S.fast_ctas : cta;   // this CTA's rank among them (< 0: none)
-  const int q_base = Gc > 0 ? S.num_queue / Gc : 0, q_rem = S.num_queue - q_base * Gc;
-  const int q_count = cc < 0 ? 0 : q_base + (cc < q_rem ? 1 : 0);
-  const ColItem* q_items = S.queue + ((int64_t)max(cc, 0) * q_base + min(max(cc, 0), q_rem));
-  const int fast_warps = excl ? (cc < 0 ? kWarps : 0) : S.fast_warps;
+  const int fast_warps = excl ? (cta < S.fast_ctas ? kWarps : 0) : S.fast_warps;
   const bool fast_first = warp < fast_warps;
   // the column-first warps' first tile is static: its record is requested before anything else
   const int k0 = fast_first ? -1 : warp - fast_warps;
@@ -1666,7 +1671,6 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
   // ---- warp 0: the CTA's first FAST run - record, contexts, TMA staging - in flight while
   // the other warps start on their column tiles ----
   if (warp == 0) {
-    const CtaWork cw = S.cta[cta];
     if (lane == 0) {
       cs.rs.nruns = cw.count;
       cs.rs.first_run = cw.first;
@@ -1685,6 +1689,8 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
   Q.ids_out = A.ids_out;
   Q.ids_base = A.ids_base;
   Q.check = P.check_ids != 0;
+  Q.shard_world = P.shard_world;
+  Q.shard_rank = P.shard_rank;
   SmemMap sm;
   sm.tables = smem_u32(smem);
   sm.bnd = sm.tables + (uint32_t)P.smem_off_bnd;
@@ -1867,6 +1873,61 @@ void launch_scatter_columns(const void* const* d_cols, const int32_t* d_dims,
   dim3 grid(64, (unsigned)num_cols);
   scatter_columns_kernel<<<grid, 256, 0, stream>>>(d_cols, d_dims, d_offsets, batch, out_width,
                                                   elem_bytes, (uint8_t*)out);
+}
+
+// ---------------------------------------------------------------------------
+// Mode B, after the cross-rank reduction of the partial sums: the mean / sqrtn scaling of rows
+// [row_begin, row_begin + rows) of the summed concat tensor at `out` (row 0 of `out` = row
+// row_begin). One thread per (row, column); n = the row's id count from the request's
+// row_splits. TF-CPU scaling as in flush_row.
+// ---------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const DevColumn* __restrict__ cols, const int32_t* __restrict__ out_offsets,
+                  int32_t num_cols, const uint8_t* __restrict__ blob,
+                  const int64_t* __restrict__ slot_offsets, const int32_t* __restrict__ ws_row_splits,
+                  int64_t batch, int64_t row_begin, int64_t rows, int32_t out_width, uint8_t* out) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < rows * num_cols;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % num_cols);
+    const int64_t r = t / num_cols;
+    const DevColumn col = cols[c];
+    if (col.lookup != RECOM_LOOKUP_SEGMENT || col.combiner == RECOM_COMBINE_SUM) continue;
+    const int32_t* rs = col.coo_index >= 0 ? ws_row_splits + (int64_t)col.coo_index * (batch + 1)
+                                           : (const int32_t*)(blob + slot_offsets[col.seg_slot]);
+    const int32_t n = rs[row_begin + r + 1] - rs[row_begin + r];
+    if (n <= 1) continue;
+    const float m = col.combiner == RECOM_COMBINE_MEAN ? (float)n : (float)__dsqrt_rn((double)n);
+    const float inv = __fdiv_rn(1.0f, m);
+    uint8_t* p = out + (r * out_width + out_offsets[c]) * (BF16 ? 2 : 4);
+    for (int e = 0; e < col.dim; ++e) {
+      if (BF16) {
+        uint16_t* q = (uint16_t*)p + e;
+        float x = bf16_lo((uint32_t)*q);
+        x = n < 10 ? x * inv : __fdiv_rn(x, m);
+        *q = (uint16_t)(pack_bf16(x, 0.f) & 0xffffu);
+      } else {
+        float* q = (float*)p + e;
+        *q = n < 10 ? *q * inv : __fdiv_rn(*q, m);
+      }
+    }
+  }
+}
+
+void launch_scale_rows(const DevPlan& plan, const int32_t* d_out_offsets, const ReqParams& req,
+                       int64_t row_begin, int64_t rows, int32_t out_width, void* out, bool bf16,
+                       cudaStream_t stream) {
+  int64_t bx = (rows * plan.num_cols + 255) / 256;
+  if (bx > 148 * 16) bx = 148 * 16;
+  if (bx < 1) bx = 1;
+  if (bf16)
+    scale_rows_kernel<true><<<(unsigned)bx, 256, 0, stream>>>(plan.cols, d_out_offsets, plan.num_cols, req.blob,
+                                                             req.slot_offsets, req.ws_row_splits, req.batch,
+                                                             row_begin, rows, out_width, (uint8_t*)out);
+  else
+    scale_rows_kernel<false><<<(unsigned)bx, 256, 0, stream>>>(plan.cols, d_out_offsets, plan.num_cols, req.blob,
+                                                              req.slot_offsets, req.ws_row_splits, req.batch,
+                                                              row_begin, rows, out_width, (uint8_t*)out);
 }
 
 // ---------------------------------------------------------------------------

@@ -219,6 +219,8 @@ struct DevPlan {
   int32_t num_slabs;
   int32_t elem_bytes;   // 4 (fp32) or 2 (bf16): table and output element size
   int32_t check_ids;
+  int32_t shard_world;  // Mode B: table rows sharded over this many ranks (1: whole tables)
+  int32_t shard_rank;
   // dynamic shared memory layout (bytes from the start):
   // [staged tables | staged boundaries | FAST column contexts | kWarps x warp scratch]
   int32_t smem_off_bnd;
@@ -263,15 +265,20 @@ struct CtaWork {
 //     others the other way round: the bandwidth-bound store stream of the FAST tiles and the
 //     latency-bound chains of the column tiles overlap on every SM from the first microsecond,
 //     and whoever runs out of its own kind of work takes the other.
+constexpr int kMaxParamCtas = 320;  // CTAs whose work record travels in the kernel parameters
+
 struct Sched {
   const Tile* runs;          // FAST runs, grouped by CTA
-  const CtaWork* cta;        // [grid]
+  const CtaWork* cta;        // [grid] (device copy: grids beyond kMaxParamCtas)
   const ColItem* queue;      // [num_queue] column tiles, grouped by CTA
   int32_t num_queue;
   int32_t fast_warps;
   int32_t fast_ctas;         // >= 0: exclusive roles - CTAs [0, fast_ctas) own all FAST runs and no
                              // column tiles, the others the column tiles and no FAST run; -1: mixed
   int32_t pad;
+  // the CTAs' work records, in the parameter space (constant bank): a warp requests the record
+  // of its first column tile with its very first global load, no dependent load in front of it
+  CtaWork cta_param[kMaxParamCtas];
 };
 
 // Per-request values known on the host at launch; a kernel parameter (no dependent loads).
@@ -333,6 +340,9 @@ void launch_scatter_columns(const void* const* d_cols, const int32_t* d_dims,
 void launch_segment_ids_to_row_splits(const int64_t* coo, int64_t nnz, int32_t stride,
                                       int64_t batch, int32_t* row_splits,
                                       cudaStream_t stream);
+void launch_scale_rows(const DevPlan& plan, const int32_t* d_out_offsets, const ReqParams& req,
+                       int64_t row_begin, int64_t rows, int32_t out_width, void* out, bool bf16,
+                       cudaStream_t stream);
 void launch_output_ptrs(int32_t num_cols, const int32_t* d_out_offsets, int32_t elem_bytes, void* out,
                         int64_t* ptrs_dev, cudaStream_t stream);
 void launch_fingerprint64(const uint8_t* bytes, const int32_t* offsets, int64_t n,

@@ -21,7 +21,10 @@ class Plan:
     feature_column_process_op_gpu.cu.cc:51-62)."""
 
     def __init__(self, model: Model, device: int = 0, check_ids: bool = False,
-                 max_ctas_per_sm: int = 0):
+                 max_ctas_per_sm: int = 0, row_shard: Optional[tuple] = None):
+        """row_shard = (world, rank): Mode B - the tables passed to run() are this rank's row shards
+        (row r on rank r % world at local row r // world), the plan writes partial sums, and
+        scale_rows() finishes the rows this rank keeps after the cross-rank reduction."""
         self.model = model
         self.device = device
         descs, boundaries = model.descs()
@@ -29,7 +32,8 @@ class Plan:
         cfg = L.PlanConfig(out_dtype=model.out_dtype, out_width=model.out_width,
                            num_slots=model.num_slots, num_tables=len(model.table_shapes),
                            check_ids=int(check_ids), device=device,
-                           max_ctas_per_sm=max_ctas_per_sm, reserved=0)
+                           max_ctas_per_sm=max_ctas_per_sm,
+                           row_shard=(row_shard[0] | (row_shard[1] << 16)) if row_shard else 0)
         h = C.c_void_p()
         L.check(L.lib.recom_plan_create(descs.ctypes.data, len(descs),
                                         boundaries.ctypes.data if boundaries.size else None,
@@ -100,6 +104,14 @@ class Plan:
         r = self._request(req, blob_dev, tables_ptrs, workspace, workspace, None, None, stream)
         r.out = None
         L.check(L.lib.recom_plan_run_sharded(self._h, C.byref(r), C.byref(shard_out)))
+
+    def scale_rows(self, req: PackedRequest, blob_dev: torch.Tensor, tables_ptrs: np.ndarray,
+                   workspace: torch.Tensor, rows_tensor: torch.Tensor, row_begin: int, stream=None) -> None:
+        """Mode B: mean / sqrtn scaling of rows [row_begin, row_begin + len(rows_tensor)) of the
+        cross-rank sum (rows_tensor: [rows, out_width], contiguous), in place."""
+        r = self._request(req, blob_dev, tables_ptrs, rows_tensor, workspace, None, None, stream)
+        L.check(L.lib.recom_plan_scale_rows(self._h, C.byref(r), int(row_begin), int(rows_tensor.shape[0]),
+                                            rows_tensor.data_ptr()))
 
     def algorithmic_bytes(self, req: PackedRequest, blob_dev, tables_ptrs, out, workspace) -> int:
         r = self._request(req, blob_dev, tables_ptrs, out, workspace, None, None, None)

@@ -332,6 +332,52 @@ class RowShard:
         return Feature(lids, row_splits=rs), total
 
 
+class RowShardedStage:
+    """Mode B on the device: this rank's share of a model whose TABLE ROWS are sharded over
+    `world` ranks (row r on rank r % world, local row r // world). Inputs are replicated; every
+    rank runs the whole fused stage over the rows it owns (the kernel skips ids of other ranks'
+    rows after the hash / bucketize, plan option row_shard), the [batch, out_width] partial sums
+    are reduce-scattered over the ranks (NCCL), and every rank scales the batch/world rows it keeps
+    (recom_plan_scale_rows). The nearest logic in the reference is its CPU spill of tables above
+    256 MiB (cuda_emitter.cc:1080-1094)."""
+
+    def __init__(self, model: Model, world: int, rank: int, device: int = 0):
+        from . import runtime as R
+
+        self.model, self.world, self.rank, self.device = model, world, rank, device
+        self.plan = R.Plan(model, device=device, row_shard=(world, rank))
+
+    def local_tables(self, tables_np):
+        """Host tables -> this rank's row shards on the device."""
+        from . import runtime as R
+
+        return R.tables_from_numpy(self.model, [np.ascontiguousarray(t[self.rank::self.world]) if t.shape[0] > self.rank
+                                                else np.zeros((1, t.shape[1]), t.dtype) for t in tables_np],
+                                   self.device)
+
+    def partial(self, req, blob_dev, ptrs, out, ws, stream=None):
+        """-> out: [batch, out_width] partial sums over this rank's rows."""
+        self.plan.run(req, blob_dev, ptrs, out, ws, stream=stream)
+        return out
+
+    def finish(self, req, blob_dev, ptrs, ws, partial, process_group=None):
+        """reduce-scatter of the partial sums over the ranks, then the scaling of the rows this
+        rank keeps. -> ([rows_per_rank, out_width] tensor, first row). batch % world must be 0."""
+        import torch
+        import torch.distributed as dist
+
+        B = partial.shape[0]
+        assert B % self.world == 0, "Mode B keeps batch / world rows per rank"
+        rpr = B // self.world
+        mine = torch.empty((rpr, partial.shape[1]), dtype=partial.dtype, device=partial.device)
+        if self.world > 1:
+            dist.reduce_scatter_tensor(mine, partial, op=dist.ReduceOp.SUM, group=process_group)
+        else:
+            mine.copy_(partial)
+        self.plan.scale_rows(req, blob_dev, ptrs, ws, mine, self.rank * rpr)
+        return mine, self.rank * rpr
+
+
 def combine_scale(combiner: int, counts: np.ndarray) -> np.ndarray:
     """Per-sample factor applied after the partial sums were reduced (TF semantics:
     mean divides by n, sqrtn by sqrt(n); empty rows stay 0)."""

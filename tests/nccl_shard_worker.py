@@ -67,8 +67,23 @@ def main():
     np.testing.assert_array_equal(got.cpu().numpy()[: hi - lo], full.cpu().numpy()[lo:hi])
     peers.close()
     dist.barrier()
+    # Mode B: table rows sharded over the ranks, partial sums reduce-scattered (NCCL), scaled after
+    stage = sharding.RowShardedStage(m, world, rank, local)
+    tabs_b = stage.local_tables(tables)
+    ptrs_b = R.table_pointers(tabs_b)
+    req_b = pack_request(m, batch, feats)
+    blob_b = R.upload_blob(req_b, local)
+    out_b = stage.plan.alloc_out(batch)
+    ws_b = stage.plan.alloc_workspace(batch, req_b.sparse_ids)
+    stage.partial(req_b, blob_b, ptrs_b, out_b, ws_b)
+    mine_b, row0 = stage.finish(req_b, blob_b, ptrs_b, ws_b, out_b)
+    torch.cuda.synchronize()
+    want = ref[row0:row0 + mine_b.shape[0]]
+    err = np.abs(mine_b.cpu().numpy() - want)
+    assert np.all(err <= 2e-5 * np.maximum(np.abs(want), 1.0)), float(err.max())
+    dist.barrier()
     if rank == 0:
-        print("SHARD_OK")
+        print("SHARD_OK MODE_B_OK")
     dist.destroy_process_group()
 
 

@@ -63,7 +63,7 @@ def test_invalid_descriptors_are_rejected_before_touching_the_device():
     m = synth.microbenchmark_model(4)
     descs, bnd = m.descs()
     cfg = L.PlanConfig(out_dtype=L.F32, out_width=m.out_width, num_slots=m.num_slots,
-                       num_tables=len(m.table_shapes), check_ids=0, device=0, max_ctas_per_sm=0, reserved=0)
+                       num_tables=len(m.table_shapes), check_ids=0, device=0, max_ctas_per_sm=0, row_shard=0)
     h = C.c_void_p()
 
     def create(d, b=bnd, cfg=cfg):
