@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define RECOM_B200_ABI_VERSION 2
+#define RECOM_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RECOM_API __attribute__((visibility("default")))
@@ -128,6 +128,41 @@ typedef struct recom_column_desc {
   int64_t num_buckets;       /* HASH_* only */
 } recom_column_desc;
 
+/* Pre-lookup id filtering fused into the stage. The reference's
+ * pre_lookup_optimizer.cc:66-123,413-478 folds the graph's comparison / tf.where chains on the ids
+ * into interval sets and emits three TF-CPU ops; here the same decisions are taken per id inside
+ * the kernel, in front of the transform:
+ *   RECOM_FILTER_KEEP     Addons>GatherIndiceValue (gather_indice_value_ops.cc:33-70): an id whose
+ *                         raw value lies in none of the closed intervals [lo_i, hi_i] is dropped -
+ *                         not gathered, not counted by mean / sqrtn. (The reference's comparator
+ *                         `x >= l || x <= r` is always true; the documented intent - and the graph
+ *                         it replaces, e.g. sparse.retain(ids, ids >= 0) - is `l <= x <= r`.)
+ *   RECOM_FILTER_SELECT   Addons>SelectValue (select_value_ops.cc:33-56): such an id's raw value
+ *                         is replaced by `substitute`.
+ *   RECOM_FILTER_STR_NE   Addons>GatherStrValueGenIndice (gather_str_value_gen_indice_ops.cc:31-58):
+ *                         a string equal to `not_equal` (usually "") is dropped.
+ * KEEP / SELECT apply to I32 / I64 values, STR_NE to STR values. A one-id-per-row column whose id
+ * is dropped writes a zero row. */
+typedef enum recom_filter_kind {
+  RECOM_FILTER_NONE = 0,
+  RECOM_FILTER_KEEP = 1,
+  RECOM_FILTER_SELECT = 2,
+  RECOM_FILTER_STR_NE = 3
+} recom_filter_kind;
+
+#define RECOM_MAX_INTERVALS 4
+
+typedef struct recom_column_filter {
+  int32_t kind;          /* recom_filter_kind */
+  int32_t num_intervals; /* KEEP / SELECT: 1..RECOM_MAX_INTERVALS */
+  int64_t lo[RECOM_MAX_INTERVALS];
+  int64_t hi[RECOM_MAX_INTERVALS];
+  int64_t substitute;    /* SELECT */
+  int32_t not_equal_len; /* STR_NE: 0..16 */
+  uint8_t not_equal[16];
+  int32_t pad;
+} recom_column_filter;
+
 typedef struct recom_plan_config {
   int32_t out_dtype;    /* RECOM_F32 or RECOM_BF16: dtype of the concat tensor */
   int32_t out_width;    /* sum of dims (row length of the concat tensor), elements */
@@ -180,6 +215,11 @@ RECOM_API int recom_abi_version(void);
 RECOM_API recom_status recom_plan_create(const recom_column_desc *cols, int32_t num_cols,
                                const float *boundaries, int64_t num_boundaries,
                                const recom_plan_config *cfg, recom_plan **out);
+/* The same with one recom_column_filter per column (`filters` may be null: no filtering). */
+RECOM_API recom_status recom_plan_create_filtered(const recom_column_desc *cols, int32_t num_cols,
+                                        const float *boundaries, int64_t num_boundaries,
+                                        const recom_column_filter *filters,
+                                        const recom_plan_config *cfg, recom_plan **out);
 RECOM_API recom_status recom_plan_destroy(recom_plan *plan);
 
 /* Serialized plan: the payload that replaces the reference's `dlpath` attr. */

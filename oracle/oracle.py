@@ -199,3 +199,40 @@ def run_model(descs: np.ndarray, boundaries: np.ndarray, out_width: int, out_dty
 
 def num_threads() -> int:
     return int(lib.oracle_num_threads())
+
+
+# ---------------------------------------------------------------------------------------
+# The reference's pre-lookup filter ops, restated. TEST INFRASTRUCTURE ONLY.
+# The comparator of the reference kernels reads `x >= l || x <= r`, which holds for every x; the
+# interval sets the graph pass hands them (pre_lookup_optimizer.cc:66-123: GreaterEqual -> [c, MAX],
+# LessEqual -> [MIN, c], ...) and the graph they replace (tf.where / sparse.retain) mean
+# `l <= x <= r`: that is what is restated here.
+# ---------------------------------------------------------------------------------------
+def _in_intervals(values: np.ndarray, intervals) -> np.ndarray:
+    keep = np.zeros(values.shape, bool)
+    for lo, hi in intervals:
+        keep |= (values >= lo) & (values <= hi)
+    return keep
+
+
+def gather_indice_value(indices: np.ndarray, values: np.ndarray, intervals):
+    """Addons>GatherIndiceValue (custom_ops/gather_indice_value/gather_indice_value_ops.cc:33-70):
+    (indices [nnz, rank], values [nnz]) -> the entries whose value lies in the interval set."""
+    keep = _in_intervals(values, intervals)
+    return indices[keep], values[keep]
+
+
+def select_value(values: np.ndarray, intervals, substitute):
+    """Addons>SelectValue (custom_ops/select_value/select_value_ops.cc:33-56): values outside the
+    interval set are replaced by `substitute`."""
+    return np.where(_in_intervals(values, intervals), values, np.asarray(substitute, values.dtype))
+
+
+def gather_str_value_gen_indice(strings, not_equal: bytes, dense_rank: int = 2):
+    """Addons>GatherStrValueGenIndice (custom_ops/gather_str_value_gen_indice/
+    gather_str_value_gen_indice_ops.cc:31-58): (strings [n]) -> (indices [m, dense_rank] = [i, 0..],
+    the strings != not_equal)."""
+    keep = [i for i, s in enumerate(strings) if s != not_equal]
+    idx = np.zeros((len(keep), dense_rank), np.int64)
+    idx[:, 0] = keep
+    return idx, [strings[i] for i in keep]

@@ -54,7 +54,7 @@ class RecomError(RuntimeError):
 
 
 EXPORTS = [
-    "recom_last_error", "recom_abi_version", "recom_plan_create", "recom_plan_destroy",
+    "recom_last_error", "recom_abi_version", "recom_plan_create", "recom_plan_create_filtered", "recom_plan_destroy",
     "recom_plan_serialize", "recom_plan_create_from_blob", "recom_plan_num_columns",
     "recom_plan_out_width", "recom_plan_num_slots", "recom_plan_slot_layout", "recom_plan_infer_batch",
     "recom_plan_output_shapes", "recom_plan_output_ptrs", "recom_plan_scale_rows", "recom_plan_workspace_bytes", "recom_plan_run",
@@ -80,6 +80,7 @@ def _load() -> C.CDLL:
     vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
     sigs = {
         "recom_plan_create": [vp, i32, vp, i64, C.POINTER(PlanConfig), C.POINTER(vp)],
+        "recom_plan_create_filtered": [vp, i32, vp, i64, vp, C.POINTER(PlanConfig), C.POINTER(vp)],
         "recom_plan_destroy": [vp],
         "recom_plan_serialize": [vp, vp, sz, C.POINTER(sz)],
         "recom_plan_create_from_blob": [vp, sz, i32, C.POINTER(vp)],

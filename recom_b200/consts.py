@@ -34,3 +34,16 @@ COLUMN_DESC = np.dtype(
 assert COLUMN_DESC.itemsize == 80
 
 
+
+# pre-lookup id filters (recom_column_filter)
+FILTER_NONE, FILTER_KEEP, FILTER_SELECT, FILTER_STR_NE = 0, 1, 2, 3
+MAX_INTERVALS = 4
+COLUMN_FILTER = np.dtype(
+    [
+        ("kind", "<i4"), ("num_intervals", "<i4"), ("lo", "<i8", (MAX_INTERVALS,)),
+        ("hi", "<i8", (MAX_INTERVALS,)), ("substitute", "<i8"), ("not_equal_len", "<i4"),
+        ("not_equal", "u1", (16,)), ("pad", "<i4"),
+    ],
+    align=True,
+)
+assert COLUMN_FILTER.itemsize == 104

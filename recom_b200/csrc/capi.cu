@@ -148,6 +148,8 @@ struct recom_plan {
   recom_plan_config cfg{};
   std::vector<recom_column_desc> descs;  // as given (for serialisation)
   std::vector<float> boundaries_in;      // as given
+  std::vector<recom_column_filter> filters_in;  // as given, one per column (empty: none)
+  std::vector<DevFilter> dev_filters;    // distinct filters in use
   // host mirrors of the device arrays
   std::vector<DevColumn> cols;
   std::vector<DevSlab> slabs;
@@ -610,7 +612,7 @@ void build_layout(recom_plan* p) {
       for (int k = 0; k < 8; ++k) {
         const DevSlabCol& sc = p->slab_cols[sl.first_col + g * 8 + k];
         fast = fast && sc.transform == RECOM_XFORM_BUCKETIZE && sc.value_dtype == RECOM_F32 &&
-               sc.bnd_off >= 0 && sc.num_boundaries > 0;
+               sc.bnd_off >= 0 && sc.num_boundaries > 0;  // (float values: no filter applies)
       }
       if (fast) {
         sl.fast8_mask |= 1u << g;
@@ -661,7 +663,20 @@ void build_layout(recom_plan* p) {
         key.v[7] = sparse ? 1 : 0;
         key.v[8] = sparse ? d.seg_slot : -1;
         key.v[9] = sparse ? c.coo_index : -1;
-        key.v[10] = 0;
+        // the stream's filter: distinct filters are numbered by content
+        int32_t fidx = -1;
+        if (!p->filters_in.empty() && p->filters_in[sc.col].kind != RECOM_FILTER_NONE) {
+          const recom_column_filter& f = p->filters_in[sc.col];
+          for (size_t q = 0; q < p->dev_filters.size() && fidx < 0; ++q)
+            if (memcmp(&p->dev_filters[q], &f, sizeof f) == 0) fidx = (int32_t)q;
+          if (fidx < 0) {
+            DevFilter df;
+            memcpy(&df, &f, sizeof f);
+            fidx = (int32_t)p->dev_filters.size();
+            p->dev_filters.push_back(df);
+          }
+        }
+        key.v[10] = fidx;
         auto it = index.find(key);
         if (it == index.end()) {
           ColItem u{};
@@ -675,6 +690,7 @@ void build_layout(recom_plan* p) {
           u.coo_index = sparse ? c.coo_index : -1;
           u.boundaries_offset = c.boundaries_offset;
           u.num_boundaries = c.num_boundaries;
+          u.filter = fidx;
           it = index.emplace(key, (int32_t)p->units.size()).first;
           p->units.push_back(u);
           unit_users.emplace_back();
@@ -962,7 +978,7 @@ recom_status upload_plan(recom_plan* p) {
   };
   std::vector<int32_t> out_offsets;
   for (const recom_column_desc& d : p->descs) out_offsets.push_back(d.out_offset);
-  Part parts[9] = {
+  Part parts[10] = {
       {p->cols.data(), p->cols.size() * sizeof(DevColumn), 0},
       {p->slabs.data(), p->slabs.size() * sizeof(DevSlab), 0},
       {p->chunks.data(), p->chunks.size() * sizeof(DevChunk), 0},
@@ -972,6 +988,7 @@ recom_status upload_plan(recom_plan* p) {
       {p->users.data(), p->users.size() * sizeof(ColUser), 0},
       {p->coos.data(), p->coos.size() * sizeof(DevCoo), 0},
       {out_offsets.data(), out_offsets.size() * sizeof(int32_t), 0},
+      {p->dev_filters.data(), p->dev_filters.size() * sizeof(DevFilter), 0},
   };
   size_t total = 0;
   for (Part& pt : parts) {
@@ -993,6 +1010,7 @@ recom_status upload_plan(recom_plan* p) {
   p->dev.users = (const ColUser*)(base + parts[6].off);
   p->dev.coos = (const DevCoo*)(base + parts[7].off);
   p->d_out_offsets = (const int32_t*)(base + parts[8].off);
+  p->dev.filters = (const DevFilter*)(base + parts[9].off);
   p->dev.num_coo = (int32_t)p->coos.size();
   p->dev.num_cols = (int32_t)p->cols.size();
   p->dev.num_slabs = (int32_t)p->slabs.size();
@@ -1090,12 +1108,37 @@ int recom_last_launch_count(void) { return g_last_launches; }
 recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
                                const float* boundaries, int64_t num_boundaries,
                                const recom_plan_config* cfg, recom_plan** out) {
+  return recom_plan_create_filtered(cols, num_cols, boundaries, num_boundaries, nullptr, cfg, out);
+}
+
+recom_status recom_plan_create_filtered(const recom_column_desc* cols, int32_t num_cols,
+                                        const float* boundaries, int64_t num_boundaries,
+                                        const recom_column_filter* filters,
+                                        const recom_plan_config* cfg, recom_plan** out) {
   if (!cols || num_cols <= 0 || !cfg || !out)
     return fail(RECOM_ERR_INVALID_ARGUMENT, "null or empty argument");
   if (num_boundaries < 0 || (num_boundaries > 0 && !boundaries))
     return fail(RECOM_ERR_INVALID_ARGUMENT, "bad boundaries array");
   recom_status st = validate_columns(cols, num_cols, *cfg, num_boundaries);
   if (st != RECOM_OK) return st;
+  for (int32_t i = 0; filters && i < num_cols; ++i) {
+    const recom_column_filter& f = filters[i];
+    if (f.kind == RECOM_FILTER_NONE) continue;
+    if (f.kind == RECOM_FILTER_KEEP || f.kind == RECOM_FILTER_SELECT) {
+      if (f.num_intervals < 1 || f.num_intervals > RECOM_MAX_INTERVALS)
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: filter needs 1..%d intervals", i, RECOM_MAX_INTERVALS);
+      if (cols[i].value_dtype != RECOM_I32 && cols[i].value_dtype != RECOM_I64)
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: KEEP / SELECT filters need I32 or I64 values", i);
+    } else if (f.kind == RECOM_FILTER_STR_NE) {
+      if (cols[i].value_dtype != RECOM_STR || f.not_equal_len < 0 || f.not_equal_len > 16)
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: STR_NE filter needs STR values and a constant of <= 16 bytes", i);
+    } else {
+      return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: unknown filter kind %d", i, f.kind);
+    }
+    if ((cfg->row_shard & 0xffff) > 1 && f.kind != RECOM_FILTER_SELECT)
+      return fail(RECOM_ERR_UNSUPPORTED, "column %d: dropping filters and row-sharded tables (the counts "
+                  "recom_plan_scale_rows divides by come from the row_splits)", i);
+  }
   for (int32_t i = 0; i < num_cols; ++i) {
     if (cols[i].transform != RECOM_XFORM_BUCKETIZE) continue;
     const float* b = boundaries + cols[i].boundaries_offset;
@@ -1124,6 +1167,7 @@ recom_status recom_plan_create(const recom_column_desc* cols, int32_t num_cols,
                 cfg->row_shard & 0xffff);
   }
   p->descs.assign(cols, cols + num_cols);
+  if (filters) p->filters_in.assign(filters, filters + num_cols);
   if (num_boundaries) p->boundaries_in.assign(boundaries, boundaries + num_boundaries);
   p->elem_bytes = cfg->out_dtype == RECOM_BF16 ? 2 : 4;
   // tuning knobs (the reference's counterpart: its RECOM_* env flags, fc_optimize_pass.cc:41-69)
@@ -1220,13 +1264,14 @@ struct BlobHeader {
   int64_t num_boundaries;
   recom_plan_config cfg;
   int32_t desc_bytes;
-  int32_t pad;
+  int32_t has_filters;  // one recom_column_filter per column follows the boundaries
 };
 
 recom_status recom_plan_serialize(const recom_plan* p, void* buf, size_t buf_bytes, size_t* needed) {
   if (!p || !needed) return fail(RECOM_ERR_INVALID_ARGUMENT, "null argument");
   const size_t total = sizeof(BlobHeader) + p->descs.size() * sizeof(recom_column_desc) +
-                       p->boundaries_in.size() * sizeof(float);
+                       p->boundaries_in.size() * sizeof(float) +
+                       p->filters_in.size() * sizeof(recom_column_filter);
   *needed = total;
   if (!buf) return RECOM_OK;
   if (buf_bytes < total) return fail(RECOM_ERR_INVALID_ARGUMENT, "buffer too small");
@@ -1237,6 +1282,7 @@ recom_status recom_plan_serialize(const recom_plan* p, void* buf, size_t buf_byt
   h.num_boundaries = (int64_t)p->boundaries_in.size();
   h.cfg = p->cfg;
   h.desc_bytes = (int32_t)sizeof(recom_column_desc);
+  h.has_filters = p->filters_in.empty() ? 0 : 1;
   uint8_t* o = (uint8_t*)buf;
   memcpy(o, &h, sizeof h);
   o += sizeof h;
@@ -1244,6 +1290,9 @@ recom_status recom_plan_serialize(const recom_plan* p, void* buf, size_t buf_byt
   o += p->descs.size() * sizeof(recom_column_desc);
   if (!p->boundaries_in.empty())
     memcpy(o, p->boundaries_in.data(), p->boundaries_in.size() * sizeof(float));
+  o += p->boundaries_in.size() * sizeof(float);
+  if (!p->filters_in.empty())
+    memcpy(o, p->filters_in.data(), p->filters_in.size() * sizeof(recom_column_filter));
   return RECOM_OK;
 }
 
@@ -1257,7 +1306,8 @@ recom_status recom_plan_create_from_blob(const void* buf, size_t bytes, int32_t 
       h.desc_bytes != (int32_t)sizeof(recom_column_desc) || h.num_cols <= 0 || h.num_boundaries < 0)
     return fail(RECOM_ERR_INVALID_ARGUMENT, "not a recom_b200 plan blob (or ABI mismatch)");
   const size_t want = sizeof(BlobHeader) + (size_t)h.num_cols * sizeof(recom_column_desc) +
-                      (size_t)h.num_boundaries * sizeof(float);
+                      (size_t)h.num_boundaries * sizeof(float) +
+                      (h.has_filters ? (size_t)h.num_cols * sizeof(recom_column_filter) : 0);
   if (bytes < want) return fail(RECOM_ERR_INVALID_ARGUMENT, "plan blob truncated");
   std::vector<recom_column_desc> descs(h.num_cols);
   std::vector<float> bnd((size_t)h.num_boundaries);
@@ -1265,9 +1315,16 @@ recom_status recom_plan_create_from_blob(const void* buf, size_t bytes, int32_t 
   memcpy(descs.data(), o, descs.size() * sizeof(recom_column_desc));
   o += descs.size() * sizeof(recom_column_desc);
   if (!bnd.empty()) memcpy(bnd.data(), o, bnd.size() * sizeof(float));
+  o += bnd.size() * sizeof(float);
+  std::vector<recom_column_filter> flt;
+  if (h.has_filters) {
+    flt.resize(h.num_cols);
+    memcpy(flt.data(), o, flt.size() * sizeof(recom_column_filter));
+  }
   recom_plan_config cfg = h.cfg;
   cfg.device = device;
-  return recom_plan_create(descs.data(), h.num_cols, bnd.data(), h.num_boundaries, &cfg, out);
+  return recom_plan_create_filtered(descs.data(), h.num_cols, bnd.data(), h.num_boundaries,
+                                    flt.empty() ? nullptr : flt.data(), &cfg, out);
 }
 
 recom_status recom_plan_num_columns(const recom_plan* p, int32_t* out) {

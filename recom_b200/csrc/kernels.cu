@@ -369,12 +369,37 @@ __device__ __forceinline__ void sts_i32(uint32_t addr, int32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// Pre-lookup filters on raw integer values (recom_column_filter; the reference's
+// Addons>GatherIndiceValue / Addons>SelectValue, gather_indice_value_ops.cc:33-70,
+// select_value_ops.cc:33-56). -> false: the id is dropped. `f` is warp uniform (one stream per
+// tile), null for no filter.
+__device__ __forceinline__ bool in_intervals(const DevFilter* f, long long v) {
+  bool in = false;
+  for (int i = 0; i < f->num_intervals; ++i) in = in || (v >= f->lo[i] && v <= f->hi[i]);
+  return in;
+}
+template <typename T>
+__device__ __forceinline__ bool filter_value(const DevFilter* f, T& v) {
+  if (!f) return true;
+  if (f->kind == RECOM_FILTER_KEEP) return in_intervals(f, (long long)v);
+  if (f->kind == RECOM_FILTER_SELECT && !in_intervals(f, (long long)v)) v = (T)f->substitute;
+  return true;
+}
+// Addons>GatherStrValueGenIndice (gather_str_value_gen_indice_ops.cc:31-58): drop the strings equal
+// to the filter's constant.
+__device__ __noinline__ bool string_equals(const DevFilter* f, const uint8_t* p, uint32_t len) {
+  if ((int32_t)len != f->not_equal_len) return false;
+  for (uint32_t i = 0; i < len; ++i)
+    if (__ldg(p + i) != f->not_equal[i]) return false;
+  return true;
+}
+
 // TF StringToHashBucketFast over ids [e0, e1) of a packed string slot. s_ids: shared-memory
 // address of the id of e0.
 __device__ __forceinline__ void xform_hash_str(const uint32_t* __restrict__ off,
                                                const uint8_t* __restrict__ bytes, uint32_t nbk,
-                                               uint64_t magic, int64_t e0, int64_t e1,
-                                               uint32_t s_ids, int lane) {
+                                               uint64_t magic, const DevFilter* flt, int64_t e0,
+                                               int64_t e1, uint32_t s_ids, int lane) {
   for (int64_t base = e0 + lane; base < e1 + lane; base += 128) {
     uint32_t o0[4], len[4];
     uint32_t okmask = 0;
@@ -411,16 +436,19 @@ __device__ __forceinline__ void xform_hash_str(const uint32_t* __restrict__ off,
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if ((okmask >> k) & 1u)
-        sts_i32(s_ids + 4u * (uint32_t)(base + 32 * k - e0), (int32_t)fh::mod_bucket(h[k], nbk, magic));
+      if ((okmask >> k) & 1u) {
+        int32_t id = (int32_t)fh::mod_bucket(h[k], nbk, magic);
+        if (flt && flt->kind == RECOM_FILTER_STR_NE && string_equals(flt, bytes + o0[k], len[k])) id = kDroppedId;
+        sts_i32(s_ids + 4u * (uint32_t)(base + 32 * k - e0), id);
+      }
   }
 }
 
 // AsString(int) + StringToHashBucketFast (feature_column_v2.py:3414-3419).
 template <typename T>
 __device__ __forceinline__ void xform_hash_int(const T* __restrict__ vals, uint32_t nbk,
-                                               uint64_t magic, int64_t e0, int64_t e1,
-                                               uint32_t s_ids, int lane) {
+                                               uint64_t magic, const DevFilter* flt, int64_t e0,
+                                               int64_t e1, uint32_t s_ids, int lane) {
   for (int64_t base = e0 + lane; base < e1 + lane; base += 128) {
     T v[4];
 #pragma unroll
@@ -428,6 +456,10 @@ __device__ __forceinline__ void xform_hash_int(const T* __restrict__ vals, uint3
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (base + 32 * k >= e1) continue;
+      if (!filter_value(flt, v[k])) {
+        sts_i32(s_ids + 4u * (uint32_t)(base + 32 * k - e0), kDroppedId);
+        continue;
+      }
       const uint64_t h = (v[k] >= 0 && v[k] < 100000000)
                              ? fh::fingerprint64_of_decimal_u32small((uint32_t)v[k])
                              : fh::fingerprint64_of_decimal((int64_t)v[k]);
@@ -471,7 +503,8 @@ __device__ __forceinline__ void bucket_grid4(const float* __restrict__ bnd, int3
 template <typename T>
 __device__ __forceinline__ void xform_bucketize(const T* __restrict__ vals,
                                                 const float* __restrict__ bnd, int32_t nb,
-                                                int64_t e0, int64_t e1, uint32_t s_ids, int lane) {
+                                                const DevFilter* flt, int64_t e0, int64_t e1,
+                                                uint32_t s_ids, int lane) {
   const float* hdr = bnd + ((nb + 3) & ~3);
   float b0 = 0.f, inv = 0.f;
   int32_t cells = 0;
@@ -484,6 +517,11 @@ __device__ __forceinline__ void xform_bucketize(const T* __restrict__ vals,
     T v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = base + 32 * k < e1 ? __ldg(vals + base + 32 * k) : (T)0;
+    bool keep[4] = {true, true, true, true};
+    if (flt && (std::is_same<T, int32_t>::value || std::is_same<T, long long>::value)) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) keep[k] = filter_value(flt, v[k]);
+    }
     int32_t id[4];
     if (std::is_same<T, double>::value) {
 #pragma unroll
@@ -499,70 +537,74 @@ __device__ __forceinline__ void xform_bucketize(const T* __restrict__ vals,
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (base + 32 * k < e1) sts_i32(s_ids + 4u * (uint32_t)(base + 32 * k - e0), id[k]);
+      if (base + 32 * k < e1) sts_i32(s_ids + 4u * (uint32_t)(base + 32 * k - e0), keep[k] ? id[k] : kDroppedId);
   }
 }
 
 // Transform NONE: the values are the ids.
 template <typename T>
-__device__ __forceinline__ void xform_copy(const T* __restrict__ vals, int64_t e0, int64_t e1,
-                                           uint32_t s_ids, int lane) {
+__device__ __forceinline__ void xform_copy(const T* __restrict__ vals, const DevFilter* flt, int64_t e0,
+                                           int64_t e1, uint32_t s_ids, int lane) {
   for (int64_t base = e0 + lane; base < e1 + lane; base += 128) {
     T v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = base + 32 * k < e1 ? __ldg(vals + base + 32 * k) : (T)0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (base + 32 * k < e1) sts_i32(s_ids + 4u * (uint32_t)(base + 32 * k - e0), (int32_t)v[k]);
+      if (base + 32 * k < e1) {
+        const bool keep = filter_value(flt, v[k]);
+        sts_i32(s_ids + 4u * (uint32_t)(base + 32 * k - e0), keep ? (int32_t)v[k] : kDroppedId);
+      }
   }
 }
 
 // ids [e0, e1) of the tile's stream -> s_ids[0, e1 - e0). The kinds are out of line: a warp
 // runs exactly one of them per tile, and the hot code stays small.
 __device__ __noinline__ void run_hash_str(const uint8_t* values, const uint8_t* bytes, uint32_t nbk,
-                                          uint64_t magic, int64_t e0, int64_t e1, uint32_t s_ids,
-                                          int lane) {
-  xform_hash_str((const uint32_t*)values, bytes, nbk, magic, e0, e1, s_ids, lane);
+                                          uint64_t magic, const DevFilter* flt, int64_t e0, int64_t e1,
+                                          uint32_t s_ids, int lane) {
+  xform_hash_str((const uint32_t*)values, bytes, nbk, magic, flt, e0, e1, s_ids, lane);
 }
 __device__ __noinline__ void run_hash_int(const uint8_t* values, bool i64, uint32_t nbk,
-                                          uint64_t magic, int64_t e0, int64_t e1, uint32_t s_ids,
-                                          int lane) {
-  if (i64) xform_hash_int((const long long*)values, nbk, magic, e0, e1, s_ids, lane);
-  else xform_hash_int((const int32_t*)values, nbk, magic, e0, e1, s_ids, lane);
+                                          uint64_t magic, const DevFilter* flt, int64_t e0, int64_t e1,
+                                          uint32_t s_ids, int lane) {
+  if (i64) xform_hash_int((const long long*)values, nbk, magic, flt, e0, e1, s_ids, lane);
+  else xform_hash_int((const int32_t*)values, nbk, magic, flt, e0, e1, s_ids, lane);
 }
 __device__ __noinline__ void run_bucketize(const uint8_t* values, int32_t dtype, const float* bnd,
-                                           int32_t nb, int64_t e0, int64_t e1, uint32_t s_ids,
-                                           int lane) {
+                                           int32_t nb, const DevFilter* flt, int64_t e0, int64_t e1,
+                                           uint32_t s_ids, int lane) {
   switch (dtype) {
-    case RECOM_F32: xform_bucketize((const float*)values, bnd, nb, e0, e1, s_ids, lane); break;
-    case RECOM_I32: xform_bucketize((const int32_t*)values, bnd, nb, e0, e1, s_ids, lane); break;
-    case RECOM_I64: xform_bucketize((const long long*)values, bnd, nb, e0, e1, s_ids, lane); break;
-    default: xform_bucketize((const double*)values, bnd, nb, e0, e1, s_ids, lane); break;
+    case RECOM_F32: xform_bucketize((const float*)values, bnd, nb, flt, e0, e1, s_ids, lane); break;
+    case RECOM_I32: xform_bucketize((const int32_t*)values, bnd, nb, flt, e0, e1, s_ids, lane); break;
+    case RECOM_I64: xform_bucketize((const long long*)values, bnd, nb, flt, e0, e1, s_ids, lane); break;
+    default: xform_bucketize((const double*)values, bnd, nb, flt, e0, e1, s_ids, lane); break;
   }
 }
-__device__ __noinline__ void run_copy(const uint8_t* values, bool i64, int64_t e0, int64_t e1,
-                                      uint32_t s_ids, int lane) {
-  if (i64) xform_copy((const long long*)values, e0, e1, s_ids, lane);
-  else xform_copy((const int32_t*)values, e0, e1, s_ids, lane);
+__device__ __noinline__ void run_copy(const uint8_t* values, bool i64, const DevFilter* flt, int64_t e0,
+                                      int64_t e1, uint32_t s_ids, int lane) {
+  if (i64) xform_copy((const long long*)values, flt, e0, e1, s_ids, lane);
+  else xform_copy((const int32_t*)values, flt, e0, e1, s_ids, lane);
 }
 
 __device__ __forceinline__ void transform_ids(const DevPlan& P, const ColItem& it,
                                               const uint8_t* values, const uint8_t* bytes,
                                               int64_t e0, int64_t e1, uint32_t s_ids, int lane) {
+  const DevFilter* flt = it.filter >= 0 ? P.filters + it.filter : nullptr;
   switch (it.transform) {
     case RECOM_XFORM_HASH_STR:
-      run_hash_str(values, bytes, (uint32_t)it.num_buckets, it.bucket_magic, e0, e1, s_ids, lane);
+      run_hash_str(values, bytes, (uint32_t)it.num_buckets, it.bucket_magic, flt, e0, e1, s_ids, lane);
       break;
     case RECOM_XFORM_HASH_INT:
       run_hash_int(values, it.value_dtype == RECOM_I64, (uint32_t)it.num_buckets, it.bucket_magic,
-                   e0, e1, s_ids, lane);
+                   flt, e0, e1, s_ids, lane);
       break;
     case RECOM_XFORM_BUCKETIZE:
       run_bucketize(values, it.value_dtype, P.boundaries + it.boundaries_offset,
-                    it.num_boundaries, e0, e1, s_ids, lane);
+                    it.num_boundaries, flt, e0, e1, s_ids, lane);
       break;
     default:
-      run_copy(values, it.value_dtype == RECOM_I64, e0, e1, s_ids, lane);
+      run_copy(values, it.value_dtype == RECOM_I64, flt, e0, e1, s_ids, lane);
       break;
   }
 }
@@ -1035,6 +1077,7 @@ __device__ __forceinline__ int32_t lds_i32(uint32_t addr) {
 // Bounds check and the ids_out parity hook, off the fast path.
 __device__ __noinline__ int32_t note_id(const ReqRegs Q, int32_t col, int32_t table_rows, int64_t i,
                                         int32_t id) {
+  if (id == kDroppedId) return id;  // dropped by the stream's filter
   if (Q.check) id = checked_id(id, table_rows, Q.status);
   if (Q.ids_out && col >= 0) Q.ids_out[Q.ids_base[col] + i] = id;
   if (Q.shard_world > 1)  // -1: another rank's row (the caller skips the gather)
@@ -1080,7 +1123,9 @@ __device__ __forceinline__ UserRegs first_user(const ReqParams& A, const ColItem
 // pass of the gather).
 __device__ __forceinline__ void prefetch_rows(const UserRegs& u, uint32_t s_ids, int n, int lane) {
   for (int j = lane; j < n; j += 32) {
-    const uint8_t* row = u.table + (int64_t)lds_i32(s_ids + 4u * (uint32_t)j) * u.row_bytes;
+    const int32_t id = lds_i32(s_ids + 4u * (uint32_t)j);
+    if (id < 0) continue;  // dropped by the stream's filter
+    const uint8_t* row = u.table + (int64_t)id * u.row_bytes;
     for (int b = 0; b < u.row_bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
   }
 }
@@ -1204,10 +1249,14 @@ __device__ __forceinline__ void sparse_rows(const QT& Q, const UserRegs& u, int6
       if (e1 - e0 > kCoopRowIds) continue;
       Acc<VEC, BF16> acc;
       acc.clear();
+      int32_t kept = 0;  // ids the stream's filter did not drop
       for (int32_t e = e0; e < e1; e += U) {
         int32_t id[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) id[k] = e + k < e1 ? lds_i32(ids0 + 4u * (uint32_t)(e + k)) : 0;
+        for (int k = 0; k < U; ++k) {
+          id[k] = e + k < e1 ? lds_i32(ids0 + 4u * (uint32_t)(e + k)) : kDroppedId;
+          kept += id[k] != kDroppedId;
+        }
         if (hook) {
 #pragma unroll
           for (int k = 0; k < U; ++k)
@@ -1222,7 +1271,7 @@ __device__ __forceinline__ void sparse_rows(const QT& Q, const UserRegs& u, int6
 #pragma unroll
         for (int k = 0; k < U; ++k) acc.add(v[k]);  // + 0.0f for the slots past the row's end
       }
-      flush_row<VEC, BF16>(acc, e1 - e0, u.combiner, o);
+      flush_row<VEC, BF16>(acc, kept, u.combiner, o);
     }
   }
 }
@@ -1230,6 +1279,13 @@ template <int VEC, bool BF16, class QT>
 __device__ __noinline__ void sparse_rows_cold(const QT Q, const UserRegs u, int64_t b0, int rows,
                                               uint32_t s_sp, uint32_t s_ids, int32_t e_base, int lane) {
   sparse_rows<VEC, BF16>(Q, u, b0, rows, s_sp, s_ids, e_base, lane);
+}
+
+// Ids of s_ids[0, n) the stream's filter kept (warp uniform).
+__device__ __forceinline__ int32_t count_kept(uint32_t s_ids, int32_t n, int lane) {
+  int32_t c = 0;
+  for (int32_t j = lane; j < n; j += 32) c += lds_i32(s_ids + 4u * (uint32_t)j) != kDroppedId;
+  return __reduce_add_sync(0xffffffffu, c);
 }
 
 // The partial sums of a long row, accumulated over the ids s_ids[0, cn) (stream positions
@@ -1299,10 +1355,11 @@ __device__ __noinline__ void coop_rows(const QT Q, const UserRegs u, int64_t b0,
       const int chb = (c0 + lane - sub * W) * VEC;
       Acc<VEC, BF16> acc;
       acc.clear();
+      const int32_t kept = count_kept(s_ids + 4u * (uint32_t)(e0 - e_base), e1 - e0, lane);
       if (sub < rpp)
         coop_accumulate<VEC, BF16>(Q, u, acc, u.table + chb, chb == 0 ? u.col : -1, rpp, sub,
                                    s_ids + 4u * (uint32_t)(e0 - e_base), e1 - e0, e0);
-      coop_finish<VEC, BF16>(Q, u, acc, W, rpp, sub, chb, b0 + r, e1 - e0, s_tmp, lane);
+      coop_finish<VEC, BF16>(Q, u, acc, W, rpp, sub, chb, b0 + r, kept, s_tmp, lane);
     }
   }
 }
@@ -1321,15 +1378,17 @@ __device__ __noinline__ void long_row(const DevPlan& P, const QT Q, const ColIte
     const int chb = (c0 + lane - sub * W) * VEC;
     Acc<VEC, BF16> acc;
     acc.clear();
+    int32_t kept = 0;
     for (int32_t cb = e0; cb < e1; cb += capc) {
       const int32_t cn = min(e1 - cb, capc);
       transform_ids(P, it, values, bytes, cb, cb + cn, s_ids, lane);
       __syncwarp();
+      kept += count_kept(s_ids, cn, lane);
       if (sub < rpp)
         coop_accumulate<VEC, BF16>(Q, u, acc, u.table + chb, chb == 0 ? u.col : -1, rpp, sub, s_ids, cn, cb);
       __syncwarp();
     }
-    coop_finish<VEC, BF16>(Q, u, acc, W, rpp, sub, chb, row, e1 - e0, s_tmp, lane);
+    coop_finish<VEC, BF16>(Q, u, acc, W, rpp, sub, chb, row, kept, s_tmp, lane);
   }
 }
 

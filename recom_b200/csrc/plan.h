@@ -114,6 +114,22 @@ struct ColUser {
 };
 static_assert(sizeof(ColUser) == 32, "ColUser layout");
 
+// An id the stream's filter dropped (recom_column_filter): not gathered, not counted.
+constexpr int32_t kDroppedId = (int32_t)0x80000000;
+
+// A stream's pre-lookup filter (recom_column_filter), device resident.
+struct DevFilter {
+  int32_t kind;
+  int32_t num_intervals;
+  int64_t lo[RECOM_MAX_INTERVALS];
+  int64_t hi[RECOM_MAX_INTERVALS];
+  int64_t substitute;
+  int32_t not_equal_len;
+  uint8_t not_equal[16];
+  int32_t pad;
+};
+static_assert(sizeof(DevFilter) == sizeof(recom_column_filter), "DevFilter layout");
+
 // A column tile of the queue: rows [begin, begin + count) of ONE id stream - a distinct (input,
 // transform) pair - worked on by one warp: raw values -> row ids (hash / bucketize / none; every
 // lane runs the same transform on consecutive ids: coalesced, no divergence) -> for every column
@@ -136,7 +152,7 @@ struct ColItem {
   int32_t count;              // rows
   int32_t first_user;         // into the ColUser array
   int32_t num_users;
-  int32_t pad;
+  int32_t filter;             // index into the plan's filters, -1: none
   ColUser u0;                 // = users[first_user]: the common case of one column per stream
                               // needs no second record
 };
@@ -213,6 +229,7 @@ struct DevPlan {
   const DevSlabBnd* slab_bnds;
   const float* boundaries;
   const ColUser* users;
+  const DevFilter* filters;
   const DevCoo* coos;
   int32_t num_coo;
   int32_t num_cols;

@@ -35,9 +35,12 @@ class Plan:
                            max_ctas_per_sm=max_ctas_per_sm,
                            row_shard=(row_shard[0] | (row_shard[1] << 16)) if row_shard else 0)
         h = C.c_void_p()
-        L.check(L.lib.recom_plan_create(descs.ctypes.data, len(descs),
-                                        boundaries.ctypes.data if boundaries.size else None,
-                                        boundaries.size, C.byref(cfg), C.byref(h)))
+        flt = model.filters()
+        self._filters = flt
+        L.check(L.lib.recom_plan_create_filtered(descs.ctypes.data, len(descs),
+                                                 boundaries.ctypes.data if boundaries.size else None,
+                                                 boundaries.size, flt.ctypes.data if flt is not None else None,
+                                                 C.byref(cfg), C.byref(h)))
         self._h = h
 
     @classmethod

@@ -26,6 +26,18 @@ NP_OF = {L.F32: np.float32, L.I32: np.int32, L.I64: np.int64, L.F64: np.float64}
 
 
 @dataclass
+class Filter:
+    """Pre-lookup id filter of a column (include/recom_b200.h: recom_column_filter). kind KEEP /
+    SELECT: `intervals` = closed [lo, hi] pairs over the raw integer values; SELECT replaces the
+    values outside by `substitute`, KEEP drops them. STR_NE drops the strings equal to `not_equal`."""
+
+    kind: int
+    intervals: Sequence[Tuple[int, int]] = ()
+    substitute: int = 0
+    not_equal: bytes = b""
+
+
+@dataclass
 class Column:
     """One embedding column (the reference's "FC", graph_info.h:41-42)."""
 
@@ -42,6 +54,7 @@ class Column:
     seg_format: int = L.SEG_NONE
     seg_stride: int = 2  # COO only
     input_key: Optional[str] = None  # columns with the same key share input slots
+    filter: Optional[Filter] = None  # pre-lookup id filter
     # assigned by Model.finalize()
     out_offset: int = -1
     value_slot: int = -1
@@ -120,6 +133,25 @@ class Model:
                 boff += b.size
         boundaries = np.concatenate(bnd) if bnd else np.zeros(0, np.float32)
         return d, boundaries
+
+    def filters(self) -> Optional[np.ndarray]:
+        """-> recom_column_filter[num_cols], or None when no column has a filter."""
+        if not any(c.filter for c in self.columns):
+            return None
+        f = np.zeros(len(self.columns), dtype=L.COLUMN_FILTER)
+        for i, c in enumerate(self.columns):
+            if not c.filter:
+                continue
+            f[i]["kind"] = c.filter.kind
+            iv = list(c.filter.intervals)
+            f[i]["num_intervals"] = len(iv)
+            for k, (lo, hi) in enumerate(iv):
+                f[i]["lo"][k], f[i]["hi"][k] = lo, hi
+            f[i]["substitute"] = c.filter.substitute
+            ne = bytes(c.filter.not_equal)
+            f[i]["not_equal_len"] = len(ne)
+            f[i]["not_equal"][:len(ne)] = np.frombuffer(ne, np.uint8)
+        return f
 
     def table_bytes(self) -> int:
         es = 2 if self.out_dtype == L.BF16 else 4
