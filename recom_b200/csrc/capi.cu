@@ -812,7 +812,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     int64_t n = 0;
     for (const ColItem& u : p->units)
       n += u.seg_slot >= 0 ? (B + rows_sparse - 1) / rows_sparse : (B + rows_dense - 1) / rows_dense;
-    long_queue = n > 4 * warps;
+    long_queue = n > warps;
   }
   for (size_t ui = 0; ui < p->units.size(); ++ui) {
     const ColItem& u = p->units[ui];
