@@ -359,6 +359,18 @@ __device__ __forceinline__ fh::RegBytes short_bytes(const StrWords& w, const uin
   return s;
 }
 
+// The hashes themselves live out of line, ONE copy each: inlined into the four unrolled chains
+// of a transform they were 13 KB of straight-line code that every warp runs once per tile - a
+// quarter of the kernel's stall samples were instruction-cache misses (no_instruction) there.
+// The loads in front of them stay batched; 20 warps per SM interleave the multiply chains.
+__device__ __noinline__ uint64_t hash_8_16_ool(uint64_t first, uint64_t last, uint32_t len) {
+  return fh::hash_len_8_16(first, last, len);
+}
+__device__ __noinline__ uint64_t hash_decimal_small_ool(uint32_t v) {
+  return fh::fingerprint64_of_decimal_u32small(v);
+}
+__device__ __noinline__ uint64_t hash_decimal_ool(long long v) { return fh::fingerprint64_of_decimal((int64_t)v); }
+
 // Any length (rare path of the string transform, out of line).
 __device__ __noinline__ uint64_t hash_any(const uint8_t* p, uint32_t len, const StrWords sw) {
   if (len - 1u < 16u) return fh::hash_len_0_16(short_bytes(sw, p), len);
@@ -427,7 +439,7 @@ __device__ __forceinline__ void xform_hash_str(const uint32_t* __restrict__ off,
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const fh::RegBytes sb = short_bytes(sw[k], bytes + o0[k]);
-        h[k] = fh::hash_len_8_16(sb.w0, sb.fetch64(len[k] - 8), len[k]);
+        h[k] = hash_8_16_ool(sb.w0, sb.fetch64(len[k] - 8), len[k]);
       }
     } else {
 #pragma unroll
@@ -460,9 +472,8 @@ __device__ __forceinline__ void xform_hash_int(const T* __restrict__ vals, uint3
         sts_i32(s_ids + 4u * (uint32_t)(base + 32 * k - e0), kDroppedId);
         continue;
       }
-      const uint64_t h = (v[k] >= 0 && v[k] < 100000000)
-                             ? fh::fingerprint64_of_decimal_u32small((uint32_t)v[k])
-                             : fh::fingerprint64_of_decimal((int64_t)v[k]);
+      const uint64_t h = (v[k] >= 0 && v[k] < 100000000) ? hash_decimal_small_ool((uint32_t)v[k])
+                                                         : hash_decimal_ool((long long)v[k]);
       sts_i32(s_ids + 4u * (uint32_t)(base + 32 * k - e0), (int32_t)fh::mod_bucket(h, nbk, magic));
     }
   }
