@@ -102,10 +102,22 @@ typedef enum recom_transform {
 typedef enum recom_seg_format {
   RECOM_SEG_NONE = 0,
   RECOM_SEG_ROW_SPLITS_I32 = 1, /* int32[batch+1], CSR */
-  RECOM_SEG_COO_I64 = 2 /* int64[nnz, seg_stride] SparseTensor.indices, row id in
+  RECOM_SEG_COO_I64 = 2, /* int64[nnz, seg_stride] SparseTensor.indices, row id in
                            column 0, row-major sorted: what the reference reads in
                            place (cuda_emitter.cc:1836-1873) */
+  RECOM_SEG_SPLIT_STR = 3 /* the values are ONE string per row (STR: int32
+                           offsets[batch+1] + payload) and the row's ids are the tokens of
+                           tf.strings.split(row, delimiter) (StringSplit, string_split_op.cc:37-99,
+                           162-170; the reference's model E joins its ids with ';',
+                           examples/python/dlrm.py:49-53), hashed with StringToHashBucketFast.
+                           transform must be HASH_STR, seg_slot -1, and seg_stride holds the
+                           delimiter: RECOM_SPLIT_SPEC(d0, d1, d2, n, skip_empty) - any of the n <= 3
+                           characters splits (n == 0: every character is a token), empty tokens
+                           are skipped when skip_empty (TF's default). */
 } recom_seg_format;
+#define RECOM_SPLIT_SPEC(d0, d1, d2, n, skip_empty)                                        \
+  ((int32_t)((uint32_t)(uint8_t)(d0) | (uint32_t)(uint8_t)(d1) << 8 | (uint32_t)(uint8_t)(d2) << 16 | \
+             (uint32_t)(n) << 24 | (uint32_t)((skip_empty) ? 1 : 0) << 28))
 
 /* One embedding column ("FC" in the reference, graph_info.h:41-42). */
 typedef struct recom_column_desc {

@@ -236,3 +236,28 @@ def gather_str_value_gen_indice(strings, not_equal: bytes, dense_rank: int = 2):
     idx = np.zeros((len(keep), dense_rank), np.int64)
     idx[:, 0] = keep
     return idx, [strings[i] for i in keep]
+
+
+def string_split(strings, delimiter: bytes, skip_empty: bool = True):
+    """tf.strings.split / StringSplit restated (TF/tensorflow/core/kernels/string_split_op.cc:37-99:
+    SplitOnChar / SplitOnCharSet / Split; :162-170 skip_empty defaults to true). An empty string has
+    no tokens; an empty delimiter splits character by character; otherwise ANY character of
+    `delimiter` splits, and empty tokens are dropped when skip_empty.
+    -> (tokens: list of bytes, row_splits int32[len(strings) + 1])."""
+    tokens, rs = [], [0]
+    for s in strings:
+        s = bytes(s)
+        if len(s) == 0:
+            pass
+        elif len(delimiter) == 0:
+            tokens.extend(bytes([c]) for c in s)
+        else:
+            start = 0
+            for i in range(len(s) + 1):
+                if i == len(s) or s[i] in delimiter:
+                    tok = s[start:i]
+                    if not skip_empty or len(tok) > 0:
+                        tokens.append(tok)
+                    start = i + 1
+        rs.append(len(tokens))
+    return tokens, np.asarray(rs, np.int32)

@@ -16,7 +16,7 @@ F32, BF16, I32, I64, STR, F64 = 0, 1, 2, 3, 4, 5
 LOOKUP_DENSE, LOOKUP_GATHER_SCATTER, LOOKUP_SEGMENT = 0, 1, 2
 COMBINE_SUM, COMBINE_MEAN, COMBINE_SQRTN = 0, 1, 2
 XFORM_NONE, XFORM_BUCKETIZE, XFORM_HASH_STR, XFORM_HASH_INT = 0, 1, 2, 3
-SEG_NONE, SEG_ROW_SPLITS_I32, SEG_COO_I64 = 0, 1, 2
+SEG_NONE, SEG_ROW_SPLITS_I32, SEG_COO_I64, SEG_SPLIT_STR = 0, 1, 2, 3
 
 DTYPE_BYTES = {F32: 4, BF16: 2, I32: 4, I64: 8, STR: 4, F64: 8}
 
@@ -47,3 +47,11 @@ COLUMN_FILTER = np.dtype(
     align=True,
 )
 assert COLUMN_FILTER.itemsize == 104
+
+
+def split_spec(delimiter: bytes, skip_empty: bool = True) -> int:
+    """RECOM_SPLIT_SPEC of include/recom_b200.h: up to 3 delimiter characters."""
+    d = bytes(delimiter)
+    assert len(d) <= 3
+    d3 = d + b"\0" * (3 - len(d))
+    return d3[0] | d3[1] << 8 | d3[2] << 16 | len(d) << 24 | (1 if skip_empty else 0) << 28

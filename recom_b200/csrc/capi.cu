@@ -164,6 +164,8 @@ struct recom_plan {
   std::vector<double> unit_cost;     // estimated cost of a full tile of a unit (a FAST tile = 2)
   std::vector<char> unit_hbm;        // a user's table is HBM resident: smaller tiles
   std::vector<DevCoo> coos;          // distinct COO inputs
+  std::vector<DevSplit> splits;      // distinct string inputs split on the device
+  std::vector<int32_t> split_of_col; // [num_cols] index into splits, -1
   // device
   void* d_block = nullptr;
   DevPlan dev{};
@@ -272,9 +274,15 @@ recom_status validate_columns(const recom_column_desc* cols, int32_t n, const re
     if (c.lookup == RECOM_LOOKUP_DENSE) {
       // nothing
     } else if (c.lookup == RECOM_LOOKUP_GATHER_SCATTER || c.lookup == RECOM_LOOKUP_SEGMENT) {
-      if (c.seg_slot < 0 || c.seg_slot >= cfg.num_slots)
+      if (c.seg_format == RECOM_SEG_SPLIT_STR) {
+        if (c.transform != RECOM_XFORM_HASH_STR || c.seg_slot != -1 || ((c.seg_stride >> 24) & 15) > 3)
+          return fail(RECOM_ERR_INVALID_ARGUMENT,
+                      "column %d: SPLIT_STR needs transform HASH_STR, seg_slot -1 and a RECOM_SPLIT_SPEC", i);
+      } else if (c.seg_slot < 0 || c.seg_slot >= cfg.num_slots)
         return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: seg_slot out of range", i);
-      if (c.seg_format == RECOM_SEG_COO_I64) {
+      if (c.seg_format == RECOM_SEG_SPLIT_STR) {
+        // checked above
+      } else if (c.seg_format == RECOM_SEG_COO_I64) {
         if (c.seg_stride < 1)
           return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: COO seg_stride must be >= 1", i);
       } else if (c.seg_format != RECOM_SEG_ROW_SPLITS_I32) {
@@ -421,6 +429,7 @@ void build_layout(recom_plan* p) {
   const int es = p->elem_bytes;
   std::map<std::vector<float>, int32_t> pool_index;  // dedup identical boundary sets
   p->cols.resize(n);
+  p->split_of_col.assign(n, -1);
   for (int i = 0; i < n; ++i) {
     const recom_column_desc& d = p->descs[i];
     DevColumn& c = p->cols[i];
@@ -455,6 +464,13 @@ void build_layout(recom_plan* p) {
           if (p->coos[k].seg_slot == d.seg_slot && p->coos[k].seg_stride == d.seg_stride) break;
         if (k == (int32_t)p->coos.size()) p->coos.push_back(DevCoo{d.seg_slot, d.seg_stride});
         c.coo_index = k;
+      } else if (d.seg_format == RECOM_SEG_SPLIT_STR) {
+        DevSplit sp{c.bucket_magic, (int32_t)d.num_buckets, d.value_slot, d.bytes_slot, d.seg_stride};
+        int32_t k = 0;
+        for (; k < (int32_t)p->splits.size(); ++k)
+          if (memcmp(&p->splits[k], &sp, sizeof sp) == 0) break;
+        if (k == (int32_t)p->splits.size()) p->splits.push_back(sp);
+        p->split_of_col[i] = k;
       }
     }
     if (d.transform == RECOM_XFORM_BUCKETIZE) {
@@ -474,6 +490,9 @@ void build_layout(recom_plan* p) {
     }
   }
   while (p->boundary_pool.size() < 4) p->boundary_pool.push_back(0.f);
+  // the row_splits of split string inputs are built in the workspace, behind the COO inputs'
+  for (int i = 0; i < n; ++i)
+    if (p->split_of_col[i] >= 0) p->cols[i].coo_index = (int32_t)p->coos.size() + p->split_of_col[i];
 
   // slabs: walk columns in concat order, group same-class neighbours up to 32 chunks
   std::vector<int> order(n);
@@ -652,8 +671,9 @@ void build_layout(recom_plan* p) {
         const bool sparse = d.lookup != RECOM_LOOKUP_DENSE;
         const bool bkt = d.transform == RECOM_XFORM_BUCKETIZE;
         const bool hashed = d.transform == RECOM_XFORM_HASH_STR || d.transform == RECOM_XFORM_HASH_INT;
+        const int32_t split = p->split_of_col[sc.col];  // >= 0: ids = hashed tokens in the workspace
         Key key{};
-        key.v[0] = d.value_slot;
+        key.v[0] = split >= 0 ? -1 - split : d.value_slot;
         key.v[1] = d.value_dtype == RECOM_STR ? d.bytes_slot : -1;
         key.v[2] = d.transform;
         key.v[3] = d.value_dtype;
@@ -691,6 +711,15 @@ void build_layout(recom_plan* p) {
           u.boundaries_offset = c.boundaries_offset;
           u.num_boundaries = c.num_boundaries;
           u.filter = fidx;
+          if (split >= 0) {
+            // the split kernel has hashed the tokens: this stream reads int32 ids from the workspace
+            u.transform = RECOM_XFORM_NONE;
+            u.value_dtype = RECOM_I32;
+            u.value_slot = -1 - split;
+            u.bytes_slot = -1;
+            u.seg_slot = 0;  // (multi-hot; its row_splits come from coo_index)
+            u.num_buckets = 0;
+          }
           it = index.emplace(key, (int32_t)p->units.size()).first;
           p->units.push_back(u);
           unit_users.emplace_back();
@@ -978,7 +1007,7 @@ recom_status upload_plan(recom_plan* p) {
   };
   std::vector<int32_t> out_offsets;
   for (const recom_column_desc& d : p->descs) out_offsets.push_back(d.out_offset);
-  Part parts[10] = {
+  Part parts[11] = {
       {p->cols.data(), p->cols.size() * sizeof(DevColumn), 0},
       {p->slabs.data(), p->slabs.size() * sizeof(DevSlab), 0},
       {p->chunks.data(), p->chunks.size() * sizeof(DevChunk), 0},
@@ -989,6 +1018,7 @@ recom_status upload_plan(recom_plan* p) {
       {p->coos.data(), p->coos.size() * sizeof(DevCoo), 0},
       {out_offsets.data(), out_offsets.size() * sizeof(int32_t), 0},
       {p->dev_filters.data(), p->dev_filters.size() * sizeof(DevFilter), 0},
+      {p->splits.data(), p->splits.size() * sizeof(DevSplit), 0},
   };
   size_t total = 0;
   for (Part& pt : parts) {
@@ -1011,6 +1041,8 @@ recom_status upload_plan(recom_plan* p) {
   p->dev.coos = (const DevCoo*)(base + parts[7].off);
   p->d_out_offsets = (const int32_t*)(base + parts[8].off);
   p->dev.filters = (const DevFilter*)(base + parts[9].off);
+  p->dev.splits = (const DevSplit*)(base + parts[10].off);
+  p->dev.num_splits = (int32_t)p->splits.size();
   p->dev.num_coo = (int32_t)p->coos.size();
   p->dev.num_cols = (int32_t)p->cols.size();
   p->dev.num_slabs = (int32_t)p->slabs.size();
@@ -1041,6 +1073,7 @@ int64_t blob_extent(const recom_plan* p, const recom_request* req) {
 int64_t column_num_ids(const recom_plan* p, int ci, const recom_request* req) {
   const recom_column_desc& d = p->descs[ci];
   if (d.lookup == RECOM_LOOKUP_DENSE) return req->batch;
+  if (d.seg_format == RECOM_SEG_SPLIT_STR) return 0;  // tokens are counted on the device
   const int64_t e = req->slot_elems[d.value_slot];
   return d.value_dtype == RECOM_STR ? e - 1 : e;
 }
@@ -1076,6 +1109,10 @@ recom_status validate_request(const recom_plan* p, const recom_request* req) {
       if (velems != want)
         return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: value slot has %lld elements, want %lld",
                     i, (long long)velems, (long long)want);
+    } else if (d.seg_format == RECOM_SEG_SPLIT_STR) {
+      if (velems != req->batch + 1)
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: a split string input holds batch+1 offsets (has %lld)",
+                    i, (long long)velems);
     } else {
       const int64_t nnz = d.value_dtype == RECOM_STR ? velems - 1 : velems;
       if (nnz < 0) return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: empty STR offsets slot", i);
@@ -1395,6 +1432,10 @@ recom_status recom_plan_infer_batch(const recom_plan* p, const int64_t* slot_ele
       *batch = slot_elems[d.seg_slot] - 1;
       return RECOM_OK;
     }
+    if (d.seg_format == RECOM_SEG_SPLIT_STR) {
+      *batch = slot_elems[d.value_slot] - 1;
+      return RECOM_OK;
+    }
   }
   return fail(RECOM_ERR_UNSUPPORTED,
               "no column carries the batch size (COO-only plans: pass it through the symbols input)");
@@ -1432,8 +1473,8 @@ recom_status recom_plan_scale_rows(const recom_plan* p, const recom_request* req
     off = align_up(align_up(b, 64) + max_sched_bytes_of(p, req->batch), 256);
   }
   A.ws_row_splits = req->workspace ? (int32_t*)((uint8_t*)req->workspace + off) : nullptr;
-  if (!p->coos.empty() && !req->workspace)
-    return fail(RECOM_ERR_INVALID_ARGUMENT, "COO inputs: pass the workspace recom_plan_run used");
+  if ((!p->coos.empty() || !p->splits.empty()) && !req->workspace)
+    return fail(RECOM_ERR_INVALID_ARGUMENT, "COO / split inputs: pass the workspace recom_plan_run used");
   launch_scale_rows(p->dev, p->d_out_offsets, A, row_begin, rows, p->cfg.out_width, out_rows,
                     p->elem_bytes == 2, (cudaStream_t)req->stream);
   cudaError_t e = cudaGetLastError();
@@ -1479,9 +1520,11 @@ recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int6
                                         size_t* out) {
   if (!p || !out || batch < 0 || total_ids < 0)
     return fail(RECOM_ERR_INVALID_ARGUMENT, "bad argument");
-  // [argument block + schedule (upload path only) | row_splits built from COO inputs]
+  // [argument block + schedule (upload path only) | row_splits built from COO / split inputs |
+  //  hashed tokens of the split inputs: total_ids must cover their payload bytes + batch + 1 each]
   size_t b = align_up(arg_block_bytes(p) + max_sched_bytes(p, batch), 256);
-  b += align_up(p->coos.size() * (size_t)(batch + 1) * 4 + 16, 256);
+  b += align_up((p->coos.size() + p->splits.size()) * (size_t)(batch + 1) * 4 + 16, 256);
+  if (!p->splits.empty()) b += align_up((size_t)total_ids * 4 + 16, 256);
   *out = b;
   return RECOM_OK;
 }
@@ -1610,7 +1653,16 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   // workspace: [argument block + schedule (upload path only) | ws_row_splits]
   size_t off = align_up(arg_block_bytes(p) + max_sched_bytes(p, B), 256);
   const size_t off_rs = off;
-  off += align_up(p->coos.size() * (size_t)(B + 1) * 4 + 16, 256);
+  off += align_up((p->coos.size() + p->splits.size()) * (size_t)(B + 1) * 4 + 16, 256);
+  const size_t off_split = off;
+  if (!p->splits.empty()) {
+    if (req->ids_out)
+      return fail(RECOM_ERR_UNSUPPORTED, "ids_out with string inputs split on the device (their token count "
+                  "is not known on the host)");
+    size_t ids = 0;
+    for (const DevSplit& sp : p->splits) ids += (size_t)req->slot_elems[sp.bytes_slot] + (size_t)B + 1;
+    off += align_up(ids * 4 + 16, 256);
+  }
   if (!req->workspace || req->workspace_bytes < off)
     return fail(RECOM_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes, got %zu", off,
                 req->workspace_bytes);
@@ -1705,6 +1757,7 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   A.ids_out = req->ids_out;
   A.status = req->status_out;
   A.ws_row_splits = (int32_t*)(ws + off_rs);
+  A.ws_split_ids = (int32_t*)(ws + off_split);
   A.slot_offsets = d_slot_offsets;
   A.slot_elems = d_slot_elems;
   A.tables = d_tables;
@@ -1740,6 +1793,10 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
 
   if (!p->coos.empty()) {
     launch_coo_to_row_splits(p->dev, A, max_coo_nnz, stream);
+    g_last_launches++;
+  }
+  if (!p->splits.empty()) {
+    launch_split_hash(p->dev, A, stream);
     g_last_launches++;
   }
   launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream);
@@ -1811,7 +1868,9 @@ recom_status recom_plan_algorithmic_bytes(const recom_plan* p, const recom_reque
     const recom_column_desc& d = p->descs[i];
     const int64_t nnz = column_num_ids(p, (int)i, req);
     int64_t in_bytes;
-    if (d.value_dtype == RECOM_STR)
+    if (d.seg_format == RECOM_SEG_SPLIT_STR && d.lookup != RECOM_LOOKUP_DENSE)
+      in_bytes = 4 * (B + 1) + req->slot_elems[d.bytes_slot];  // (token count unknown here: no table term)
+    else if (d.value_dtype == RECOM_STR)
       in_bytes = 4 * (nnz + 1) + req->slot_elems[d.bytes_slot];
     else
       in_bytes = (int64_t)dtype_bytes(d.value_dtype) * nnz;

@@ -1459,6 +1459,17 @@ __device__ __noinline__ void sparse_tile_overflow(const DevPlan& P, const ReqPar
   }
 }
 
+// Where the hashed tokens of split input k start in ws_split_ids (in ids): input k' < k takes
+// payload bytes + batch + 1 slots, an upper bound of its tokens whatever the delimiter. Warp
+// collective (lanes stride over k').
+__device__ __forceinline__ int64_t split_ids_offset(const DevPlan& P, const ReqParams& A, int k, int lane) {
+  int64_t s = 0;
+  for (int j = lane; j < k; j += 32) s += A.slot_elems[P.splits[j].bytes_slot] + A.batch + 1;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  return s;
+}
+
 // The record of a column tile: 96 bytes, six 128-bit loads (lane-uniform address).
 __device__ __forceinline__ void load_item(const ColItem* p, ColItem& it) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -1474,7 +1485,11 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
                                             PROF_PARAM) {
   constexpr int ELEM = BF16 ? 2 : 4;
   // resolve the stream and its first column against the request: one read of the slot offsets
-  const uint8_t* values = A.blob + __ldg(A.slot_offsets + it.value_slot);
+  // (value_slot < 0: the ids are the hashed tokens of split input -1 - value_slot, written into the
+  // workspace by the split kernel in front of this launch)
+  const uint8_t* values =
+      it.value_slot >= 0 ? A.blob + __ldg(A.slot_offsets + it.value_slot)
+                         : (const uint8_t*)(A.ws_split_ids + split_ids_offset(P, A, -1 - it.value_slot, lane));
   const uint8_t* bytes = it.bytes_slot >= 0 ? A.blob + __ldg(A.slot_offsets + it.bytes_slot) : nullptr;
   const int32_t* rs = nullptr;
   if (it.seg_slot >= 0)
@@ -1857,6 +1872,101 @@ shard_wait_kernel(uint32_t* flags, int world, uint32_t epoch, uint32_t timeout_m
 void launch_shard_wait(uint32_t* local_flags, int world, uint32_t epoch, uint32_t timeout_ms,
                        cudaStream_t stream) {
   shard_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, epoch, timeout_ms);
+}
+
+// ---------------------------------------------------------------------------
+// tf.strings.split + StringToHashBucketFast of a string input (RECOM_SEG_SPLIT_STR; StringSplit:
+// string_split_op.cc:37-99 - SplitOnChar / SplitOnCharSet, skip_empty - and :162-170). One block per
+// split input: thread = row. Pass 1 counts the row's tokens, a block scan turns the counts into
+// row_splits, pass 2 hashes every token (Fingerprint64 of the bytes where they lie) into its slot.
+// ---------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ int32_t for_each_token(const uint8_t* __restrict__ p, int32_t len, int32_t spec, F f) {
+  const int nd = (spec >> 24) & 15;
+  const bool skip_empty = (spec >> 28) & 1;
+  const uint32_t d0 = spec & 0xff, d1 = (spec >> 8) & 0xff, d2 = (spec >> 16) & 0xff;
+  int32_t n = 0;
+  if (len == 0) return 0;  // Split(): an empty string has no tokens
+  if (nd == 0) {           // empty delimiter: character by character
+    for (int32_t i = 0; i < len; ++i) f(n++, i, 1);
+    return n;
+  }
+  int32_t start = 0;
+  for (int32_t i = 0; i <= len; ++i) {
+    bool cut = i == len;
+    if (!cut) {
+      const uint32_t ch = __ldg(p + i);
+      cut = ch == d0 || (nd > 1 && ch == d1) || (nd > 2 && ch == d2);
+    }
+    if (cut) {
+      if (!skip_empty || i > start) f(n++, start, i - start);
+      start = i + 1;
+    }
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(1024)
+split_hash_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ReqParams A) {
+  __shared__ int32_t s_warp[32];
+  __shared__ int32_t s_carry;
+  const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const DevSplit sp = P.splits[k];
+  const int32_t* off = (const int32_t*)(A.blob + A.slot_offsets[sp.value_slot]);
+  const uint8_t* bytes = A.blob + A.slot_offsets[sp.bytes_slot];
+  int32_t* rs = A.ws_row_splits + (int64_t)(P.num_coo + k) * (A.batch + 1);
+  int32_t* ids = A.ws_split_ids + split_ids_offset(P, A, k, lane);
+  const int64_t B = A.batch;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  // pass 1 + scan, 1024 rows at a time: rs[r] = tokens in front of row r
+  for (int64_t base = 0; base < B; base += 1024) {
+    const int64_t r = base + tid;
+    int32_t cnt = 0;
+    if (r < B) {
+      const int32_t o0 = off[r];
+      cnt = for_each_token(bytes + o0, off[r + 1] - o0, sp.spec, [](int32_t, int32_t, int32_t) {});
+    }
+    int32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = s_warp[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += t;
+      }
+      s_warp[lane] = wi - w;  // exclusive prefix of the warps
+    }
+    __syncthreads();
+    const int32_t excl = s_carry + s_warp[warp] + incl - cnt;
+    if (r < B) rs[r] = excl;
+    __syncthreads();
+    if (tid == 1023) s_carry = excl + cnt;
+    __syncthreads();
+  }
+  if (tid == 0) rs[B] = s_carry;
+  __syncthreads();
+  // pass 2: hash every token into its slot
+  const uint32_t nbk = (uint32_t)sp.num_buckets;
+  for (int64_t r = tid; r < B; r += 1024) {
+    const int32_t o0 = off[r];
+    int32_t* dst = ids + rs[r];
+    const uint8_t* p = bytes + o0;
+    for_each_token(p, off[r + 1] - o0, sp.spec, [&](int32_t j, int32_t b, int32_t n) {
+      dst[j] = (int32_t)fh::mod_bucket(fh::fingerprint64(p + b, (uint32_t)n), nbk, sp.bucket_magic);
+    });
+  }
+}
+
+void launch_split_hash(const DevPlan& plan, const ReqParams& req, cudaStream_t stream) {
+  split_hash_kernel<<<(unsigned)plan.num_splits, 1024, 0, stream>>>(plan, req);
 }
 
 // ---------------------------------------------------------------------------

@@ -165,6 +165,18 @@ struct DevCoo {
   int32_t seg_stride;
 };
 
+// A string input that is split into tokens on the device (RECOM_SEG_SPLIT_STR): a helper kernel
+// in front of the fused one writes its row_splits (ws_row_splits, behind the COO inputs') and the
+// hashed tokens (int32 bucket ids, ws_split_ids) into the workspace.
+struct DevSplit {
+  uint64_t bucket_magic;
+  int32_t num_buckets;
+  int32_t value_slot;   // int32 offsets[batch + 1]
+  int32_t bytes_slot;
+  int32_t spec;         // RECOM_SPLIT_SPEC
+};
+static_assert(sizeof(DevSplit) == 24, "DevSplit layout");
+
 // The same column resolved against one request; lives in shared memory while a CTA (DENSE
 // run) or a warp (SPARSE tile) works on the slab.
 struct ColCtx {
@@ -231,7 +243,9 @@ struct DevPlan {
   const ColUser* users;
   const DevFilter* filters;
   const DevCoo* coos;
+  const DevSplit* splits;
   int32_t num_coo;
+  int32_t num_splits;
   int32_t num_cols;
   int32_t num_slabs;
   int32_t elem_bytes;   // 4 (fp32) or 2 (bf16): table and output element size
@@ -304,7 +318,9 @@ struct ReqParams {
   uint8_t* out;
   int32_t* ids_out;        // may be null
   int32_t* status;         // may be null
-  int32_t* ws_row_splits;  // workspace: row_splits built from COO inputs, [num_coo][batch + 1]
+  int32_t* ws_row_splits;  // workspace: row_splits built from COO inputs and split string inputs,
+                           // [num_coo + num_splits][batch + 1]
+  int32_t* ws_split_ids;   // workspace: hashed tokens of the split inputs, input k at split_ids_offset(k)
   // arrays of the request's argument block (device addresses)
   const int64_t* slot_offsets;  // [num_slots]
   const int64_t* slot_elems;    // [num_slots]
@@ -348,6 +364,7 @@ void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqPara
                           bool bf16, cudaStream_t stream);
 void launch_shard_wait(uint32_t* local_flags, int world, uint32_t epoch, uint32_t timeout_ms,
                        cudaStream_t stream);
+void launch_split_hash(const DevPlan& plan, const ReqParams& req, cudaStream_t stream);
 void launch_coo_to_row_splits(const DevPlan& plan, const ReqParams& req, int64_t max_nnz,
                               cudaStream_t stream);
 void launch_scatter_columns(const void* const* d_cols, const int32_t* d_dims,

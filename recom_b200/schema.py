@@ -52,7 +52,7 @@ class Column:
     boundaries: Optional[np.ndarray] = None  # float32, BUCKETIZE only
     num_buckets: int = 0  # HASH_* only
     seg_format: int = L.SEG_NONE
-    seg_stride: int = 2  # COO only
+    seg_stride: int = 2  # COO: int64s per entry; SPLIT_STR: consts.split_spec(delimiter, skip_empty)
     input_key: Optional[str] = None  # columns with the same key share input slots
     filter: Optional[Filter] = None  # pre-lookup id filter
     # assigned by Model.finalize()
@@ -95,7 +95,7 @@ class Model:
                 c.bytes_slot = slot
                 slot += 1
             c.seg_slot = -1
-            if c.lookup != L.LOOKUP_DENSE:
+            if c.lookup != L.LOOKUP_DENSE and c.seg_format != L.SEG_SPLIT_STR:
                 c.seg_slot = slot
                 slot += 1
             self.slot_of_key[c.key] = (c.value_slot, c.bytes_slot, c.seg_slot)
@@ -234,7 +234,7 @@ def pack_request(model: Model, batch: int, features: Dict[str, Feature],
             slot_arrays[c.bytes_slot] = np.ascontiguousarray(f.values.data, np.uint8)
         else:
             slot_arrays[c.value_slot] = np.ascontiguousarray(f.values, NP_OF[c.value_dtype])
-        if c.lookup != L.LOOKUP_DENSE:
+        if c.lookup != L.LOOKUP_DENSE and c.seg_format != L.SEG_SPLIT_STR:
             if c.seg_format == L.SEG_ROW_SPLITS_I32:
                 assert f.row_splits is not None, c.name
                 slot_arrays[c.seg_slot] = np.ascontiguousarray(f.row_splits, np.int32)
@@ -266,6 +266,10 @@ def pack_request(model: Model, batch: int, features: Dict[str, Feature],
     for i, c in enumerate(model.columns):
         if c.lookup == L.LOOKUP_DENSE:
             n = batch
+        elif c.seg_format == L.SEG_SPLIT_STR:
+            # tokens are counted on the device; the workspace holds payload bytes + batch + 1 ids
+            n = 0
+            sparse += int(elems[c.bytes_slot]) + batch + 1
         else:
             n = int(elems[c.value_slot]) - (1 if c.value_dtype == L.STR else 0)
             sparse += n
@@ -281,6 +285,10 @@ def algorithmic_bytes(model: Model, req: PackedRequest) -> int:
     total = 0
     for i, c in enumerate(model.columns):
         nnz = int(req.ids_base[i + 1] - req.ids_base[i])
+        if c.lookup != L.LOOKUP_DENSE and c.seg_format == L.SEG_SPLIT_STR:
+            # mirror of the C side: offsets + payload, no table term (token count unknown on the host)
+            total += 4 * (req.batch + 1) + int(req.slot_elems[c.bytes_slot]) + c.dim * es * req.batch
+            continue
         if c.value_dtype == L.STR:
             inb = 4 * (nnz + 1) + int(req.slot_elems[c.bytes_slot])
         else:
