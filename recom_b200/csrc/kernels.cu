@@ -1593,7 +1593,7 @@ __device__ __noinline__ void setup_run(const DevPlan& P, const Sched& S, const R
   enter_run(P, A, run, reinterpret_cast<ColCtx*>(smem + P.smem_off_ctx), smem,
             reinterpret_cast<float*>(smem + P.smem_off_bnd), keep, &cs->mbar_tbl, &cs->mbar_bnd);
   __syncwarp();
-  if (lane == 0) mbar_arrive(&cs->mbar_ctx);
+  mbar_arrive(&cs->mbar_ctx);
 }
 
 // The CTA's column tiles, taken from the counter in shared memory as the warps become free
@@ -1732,7 +1732,7 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
   if (threadIdx.x == 0) {
     mbar_init(&cs.mbar_tbl, 1);
     mbar_init(&cs.mbar_bnd, 1);
-    mbar_init(&cs.mbar_ctx, 1);
+    mbar_init(&cs.mbar_ctx, 32);  // every lane of warp 0 arrives: each releases its own writes
     cs.next_fast[0] = 0;
     cs.next_fast[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1763,7 +1763,7 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
     }
     __syncwarp();
     if (cw.count > 0) setup_run(P, S, A, &cs, smem, 0, lane);
-    else if (lane == 0) mbar_arrive(&cs.mbar_ctx);
+    else mbar_arrive(&cs.mbar_ctx);
   }
 
   ReqRegsT<SH> Q;
