@@ -80,6 +80,10 @@ def build_model(workload: str, world: int = 1, rank: int = 0):
     from recom_b200 import synth
 
     if workload == "model_E":
+        # RECOM_BENCH_LARGE_ROWS: diagnostic only (rows of the five 2^23-row tables; the line's
+        # config.table_bytes shows it) - how much of a launch is the random walk over 5 GB of HBM
+        if os.environ.get("RECOM_BENCH_LARGE_ROWS"):
+            return synth.model_E(large_rows=int(os.environ["RECOM_BENCH_LARGE_ROWS"])), 2048
         return synth.model_E(), 2048
     if workload == "model_F":
         return synth.model_F(), 2048
@@ -90,7 +94,8 @@ def build_model(workload: str, world: int = 1, rank: int = 0):
     if workload == "model_E_bucketize":
         return synth.dlrm_model(880, 0, 0, 0, 0, name="E_bucketize"), 2048
     if workload == "model_E_sparse":
-        return synth.dlrm_model(0, 0, 0, 15, 5, name="E_sparse"), 2048
+        return synth.dlrm_model(0, 0, 0, 15, 5, name="E_sparse",
+                                large_rows=int(os.environ.get("RECOM_BENCH_LARGE_ROWS", synth.LARGE_ROWS))), 2048
     # informational lines (parity-tested configurations of BASELINE.json, not the headline)
     from recom_b200 import consts as L
     if workload == "model_E_bf16":
@@ -486,7 +491,12 @@ def run_ours(args):
         "config": config_of(args.workload, model, batch, world, rot_bytes / 1e6, S),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": mean_alg, "kernel": "fused_columns_kernel"},
+                     "algorithmic_bytes_per_launch": mean_alg,
+                     # one launch per step: the fused persistent kernel; two: the flat kernel of the
+                     # column tiles + the persistent kernel of the FAST runs (capi.cu prefer_flat) -
+                     # `achieved` is then the step's bytes over the step's duration (both launches)
+                     "kernel": "fused_columns_kernel" if launches_per_step == 1 and not os.environ.get("RECOM_B200_FLAT")
+                               else f"{launches_per_step} launches per step (column_tiles_kernel / fused_columns_kernel)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
         "gpu_launches": launches_per_step * K,

@@ -113,6 +113,7 @@ struct TileTable {
   std::vector<Tile> runs;        // FAST runs grouped by CTA
   std::vector<ColItem> queue;    // column tiles
   std::vector<CtaWork> cta;      // [grid]
+  std::vector<ColItem> flat;     // column tiles of the flat kernel (one warp each), by descending cost
   int grid = 1;
   int fast_warps = 0;
   int fast_ctas = -1;
@@ -122,11 +123,17 @@ struct TileTable {
   }
   size_t runs_bytes() const { return align_up(runs.size() * sizeof(Tile), 16); }
   size_t queue_bytes() const { return align_up(queue.size() * sizeof(ColItem), 16); }
-  size_t bytes() const { return runs_bytes() + queue_bytes() + cta.size() * sizeof(CtaWork); }
+  size_t cta_bytes() const { return align_up(cta.size() * sizeof(CtaWork), 16); }
+  size_t bytes() const { return runs_bytes() + queue_bytes() + cta_bytes() + flat.size() * sizeof(ColItem); }
+  const ColItem* flat_items(const void* base) const {
+    return (const ColItem*)((const uint8_t*)base + runs_bytes() + queue_bytes() + cta_bytes());
+  }
   void write(uint8_t* dst) const {
     if (!runs.empty()) memcpy(dst, runs.data(), runs.size() * sizeof(Tile));
     if (!queue.empty()) memcpy(dst + runs_bytes(), queue.data(), queue.size() * sizeof(ColItem));
     memcpy(dst + runs_bytes() + queue_bytes(), cta.data(), cta.size() * sizeof(CtaWork));
+    if (!flat.empty())
+      memcpy(dst + runs_bytes() + queue_bytes() + cta_bytes(), flat.data(), flat.size() * sizeof(ColItem));
   }
   Sched sched(const void* base) const {
     Sched s{};
@@ -179,9 +186,17 @@ struct recom_plan {
   int force_fast_warps = -1;  // >= 0: override the cost-proportional split (experiments)
   int col_rows_dense = kColTileRowsDense;    // rows of a column tile, one id per row (<= 128)
   int col_rows_sparse = kColTileRowsSparse;  // rows of a multi-hot column tile (<= 32)
+  // The flat kernel of the column tiles (one warp per tile, in front of the persistent kernel,
+  // which then keeps the FAST runs only): plain and Mode-B requests; the fused Mode-A exchange
+  // (sharded output) stays in the persistent kernel, whose last warp signals the peers.
+  int flat_mode = -1;          // RECOM_B200_FLAT: 1 always, 0 never, unset: by cost (prefer_flat)
+  bool flat_pdl = true;        // the persistent kernel starts while the flat one drains
+  int flat_ctas_per_sm = 8;    // resident CTAs (4 warps each) of the flat kernel
+  int flat_warps_target = 0;   // tiles are cut finer until there are about this many (0: resident warps)
+  DevPlan dev_flat{};          // = dev with the flat kernel's warp scratch
   // tile tables depend only on the batch size: cached (read-mostly)
   std::mutex tiles_mu;
-  std::map<int64_t, std::shared_ptr<const TileTable>> tiles_by_batch;
+  std::map<int64_t, std::shared_ptr<const TileTable>> tiles_by_batch;  // key: batch * 2 + flat
   bool stage_tables = true;
   // profiling builds only (RECOM_B200_PROF_DUMP=<file>): per-CTA phase timers of the last run
   uint64_t* d_prof = nullptr;
@@ -791,7 +806,24 @@ void build_layout(recom_plan* p) {
 //   * Everything else is cut into column tiles (one unit = one id stream, kColTileRowsDense /
 //     kColTileRowsSparse rows; fewer for small batches, until there is about one tile per
 //     resident warp), sorted by descending cost and dealt to the global warps round robin.
-std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
+// Flat or fused? (RECOM_B200_FLAT unset.) Measured on B200 at batch 2048: with the column tiles
+// in their own one-warp-per-tile kernel, mixed1000 (no FAST slab) runs in 123 instead of 155 us,
+// production2000 (column tiles 5.3x the FAST cost) in 102 instead of 111, the 20 multi-hot
+// columns of model E alone in 16 instead of 25; models E and F (1.8x / 1.2x) lose 4-5 us, the
+// 980 one-id columns of E (0.5x) 9 us: two launches do not overlap the way the fused kernel's
+// warps do. Flat when the column tiles weigh at least three times the FAST slabs.
+bool prefer_flat(const recom_plan* p, int64_t B) {
+  if (p->flat_mode >= 0) return p->flat_mode != 0;
+  double fast_cost = 0, col_cost = 0;
+  for (const DevSlab& sl : p->slabs)
+    if (sl.cls == kSlabDenseStaged && sl.all_fast)
+      fast_cost += (double)((B + sl.tile_rows - 1) / sl.tile_rows) * 2.0 * (sl.tile_rows * sl.num_chunks * sl.vec_bytes) / 8192.0;
+  for (size_t ui = 0; ui < p->units.size(); ++ui)
+    col_cost += p->unit_cost[ui] * (double)B / (p->units[ui].seg_slot >= 0 ? kColTileRowsSparse : kColTileRowsDense);
+  return col_cost > 0 && col_cost >= 3.0 * fast_cost;
+}
+
+std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B, bool flat) {
   const int cap_ctas = std::max(1, p->num_sms * p->ctas_per_sm);
   auto tt = std::make_shared<TileTable>();
   auto make = [&](int s, int64_t b, int64_t rows) {
@@ -816,7 +848,9 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   // rows per tile: the fewer tiles than warps, the finer (a launch lasts as long as its longest
   // chain of dependent loads, and a tile's chain does not get shorter with fewer rows - but the
   // transform and gather passes behind it do)
-  const int64_t warps = (int64_t)cap_ctas * kWarps;
+  const int64_t warps = !flat ? (int64_t)cap_ctas * kWarps
+                         : p->flat_warps_target > 0 ? p->flat_warps_target
+                                                    : (int64_t)p->num_sms * p->flat_ctas_per_sm * 4;
   int rows_dense = std::min(kColTileRowsDense, p->col_rows_dense);
   int rows_sparse = std::min(kColTileRowsSparse, p->col_rows_sparse);
   {
@@ -835,7 +869,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     ColItem it;
   };
   std::vector<Costed> qs;
-  double queue_cost = 0;
+  double queue_cost = 0, flat_cost = 0;
   bool long_queue;
   {
     int64_t n = 0;
@@ -860,6 +894,12 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     }
   }
   std::stable_sort(qs.begin(), qs.end(), [](const Costed& a, const Costed& b) { return a.cost > b.cost; });
+  if (flat) {  // every column tile gets its own warp of the flat kernel; the persistent one keeps the FAST runs
+    for (const Costed& c : qs) tt->flat.push_back(c.it);
+    qs.clear();
+    flat_cost = queue_cost;
+    queue_cost = 0;
+  }
 
   // ---- FAST runs ----
   std::vector<double> cost(fast.size());
@@ -877,7 +917,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
   units = std::max<int64_t>(units, std::min<int64_t>((int64_t)fast.size(), cap_ctas));
   if (units > p->num_sms) units = (units + p->num_sms - 1) / p->num_sms * p->num_sms;
   const int grid = (int)std::min<int64_t>(cap_ctas, units);
-  tt->grid = grid;
+  tt->grid = fast.empty() && qs.empty() ? 0 : grid;  // 0: no persistent launch (flat tiles only)
 
   // Exclusive roles (RECOM_B200_EXCLUSIVE): the FAST runs go to the first `nf` CTAs only, the
   // column tiles to the others, in proportion to the estimated cost of the two kinds of work.
@@ -963,6 +1003,10 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B) {
     // (measured on models E / F: a column tile costs a warp about three times its estimate
     // relative to a FAST tile - chains of dependent loads against a store stream)
     tt->fast_warps = std::max(1, std::min(kWarps - 1, (int)(kWarps * fast_cost / (fast_cost + 3.0 * queue_cost) + 0.5)));
+  if (getenv("RECOM_B200_DEBUG_SCHED"))
+    fprintf(stderr, "[recom sched] batch %lld flat %d: fast slabs %zu tiles %lld cost %.0f | column tiles %zu cost %.0f | grid %d\n",
+            (long long)B, (int)flat, fast.size(), (long long)fast_tiles, fast_cost, flat ? tt->flat.size() : qs.size(),
+            flat ? flat_cost : queue_cost, tt->grid);
   if (p->force_fast_warps >= 0 && !fast.empty() && !qs.empty())
     tt->fast_warps = std::max(1, std::min(kWarps - 1, p->force_fast_warps));
   return tt;
@@ -980,13 +1024,14 @@ cudaError_t blocking_upload(recom_plan* p, void* dst, const void* src, size_t by
 
 // Cached (device resident) schedule of a batch size, or nullptr when the cache is full:
 // the caller then ships the schedule inside the request's argument block.
-std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, recom_status* st) {
+std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, bool flat, recom_status* st) {
   *st = RECOM_OK;
   std::lock_guard<std::mutex> lock(p->tiles_mu);
-  auto it = p->tiles_by_batch.find(B);
+  const int64_t key = B * 2 + (flat ? 1 : 0);
+  auto it = p->tiles_by_batch.find(key);
   if (it != p->tiles_by_batch.end()) return it->second;
   if (p->tiles_by_batch.size() >= kMaxCachedTileTables) return nullptr;
-  std::shared_ptr<TileTable> tt = build_tiles(p, B);
+  std::shared_ptr<TileTable> tt = build_tiles(p, B, flat);
   std::vector<uint8_t> host(tt->bytes() + 64, 0);
   tt->write(host.data());
   // first use of a batch size (warm-up): a blocking allocation + copy
@@ -995,7 +1040,7 @@ std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, recom_st
     *st = fail(RECOM_ERR_CUDA, "tile table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     return nullptr;
   }
-  p->tiles_by_batch[B] = tt;
+  p->tiles_by_batch[key] = tt;
   return tt;
 }
 
@@ -1221,11 +1266,21 @@ recom_status recom_plan_create_filtered(const recom_column_desc* cols, int32_t n
   if (const char* e = getenv("RECOM_B200_COL_WEIGHT")) p->col_weight = atof(e);
   p->col_rows_dense = pow2_env("RECOM_B200_COL_ROWS_DENSE", 32, kColTileRowsDense, kColTileRowsDense);
   p->col_rows_sparse = pow2_env("RECOM_B200_COL_ROWS_SPARSE", 4, kColTileRowsSparse, kColTileRowsSparse);
+  if (const char* e = getenv("RECOM_B200_FLAT")) p->flat_mode = atoi(e) != 0;
+  if (const char* e = getenv("RECOM_B200_FLAT_PDL")) p->flat_pdl = atoi(e) != 0;
+  if (const char* e = getenv("RECOM_B200_FLAT_WARPS")) p->flat_warps_target = atoi(e);
   build_layout(p);
   st = upload_plan(p);
   if (st == RECOM_OK) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) p->num_sms = prop.multiProcessorCount;
+    p->dev_flat = p->dev;
+    p->dev_flat.scratch_bytes = kFlatScratchBytes;
+    if (p->flat_mode != 0) {
+      const int occ_flat = column_tiles_configure(p->elem_bytes == 2, 4 * kFlatScratchBytes);
+      if (occ_flat < 1) st = fail(RECOM_ERR_CUDA, "flat kernel does not fit: %s", cudaGetErrorString(cudaGetLastError()));
+      else p->flat_ctas_per_sm = occ_flat;
+    }
     int occ = fused_kernel_configure(p->elem_bytes == 2, p->dev.smem_bytes);
     if (occ < 1) {
       st = fail(RECOM_ERR_CUDA, "fused kernel does not fit (smem %d bytes): %s", p->dev.smem_bytes,
@@ -1635,11 +1690,12 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   cudaStream_t stream = (cudaStream_t)req->stream;
 
   g_host_prof.lap(0);
-  std::shared_ptr<const TileTable> tt = cached_tiles(p, B, &st);
+  const bool flat = !so && prefer_flat(p, B);
+  std::shared_ptr<const TileTable> tt = cached_tiles(p, B, flat, &st);
   if (st != RECOM_OK) return st;
   g_host_prof.lap(1);
   const bool sched_in_args = !tt;
-  if (sched_in_args) tt = build_tiles(p, B);
+  if (sched_in_args) tt = build_tiles(p, B, flat);
   const int grid = tt->grid;
 
   st = validate_request(p, req);
@@ -1686,6 +1742,7 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     d_slot_elems = d_slot_offsets + num_slots;
   }
   Sched sched = sched_in_args ? Sched{} : tt->sched(tt->d_block);
+  const ColItem* d_flat = sched_in_args ? nullptr : tt->flat_items(tt->d_block);
   ArgSlot* slot = nullptr;
   std::unique_lock<std::mutex> slot_lock;
   if (!trailer || req->ids_out || !d_tables || sched_in_args) {
@@ -1723,6 +1780,7 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     if (sched_in_args) {
       tt->write(h + args_bytes);
       sched = tt->sched(ws + args_bytes);
+      d_flat = tt->flat_items(ws + args_bytes);
     }
     CUDA_TRY(cudaMemcpyAsync(ws, h, up_bytes, cudaMemcpyHostToDevice, stream));
     if (!trailer) {
@@ -1799,8 +1857,26 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     launch_split_hash(p->dev, A, stream);
     g_last_launches++;
   }
-  launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream);
-  g_last_launches++;
+  const bool has_flat = !tt->flat.empty();
+  if (has_flat) {
+    // profiling builds: RECOM_B200_PROF_FLAT=1 times the flat kernel's warps instead of the persistent one's
+    static const bool prof_flat = getenv("RECOM_B200_PROF_FLAT") != nullptr;
+    ReqParams F = A;
+    F.prof = nullptr;
+    if (p->d_prof && prof_flat) {
+      const int cap_rows = p->num_sms * 4 * kWarps;
+      F.prof = p->d_prof;
+      F.pad0 = std::min<int>(cap_rows, (int)tt->flat.size());
+      A.prof = nullptr;
+      p->prof_grid = F.pad0 / kWarps;
+    }
+    launch_column_tiles(p->dev_flat, F, d_flat, (int)tt->flat.size(), p->elem_bytes == 2, stream);
+    g_last_launches++;
+  }
+  if (grid > 0) {
+    launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream, has_flat && p->flat_pdl);
+    g_last_launches++;
+  }
   cudaError_t e = cudaGetLastError();
   if (slot) {
     cudaEventRecord(slot->done, stream);

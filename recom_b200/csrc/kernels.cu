@@ -438,6 +438,8 @@ __device__ __forceinline__ void xform_hash_str(const uint32_t* __restrict__ off,
     if (__all_sync(0xffffffffu, all816)) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        h[k] = 0ull;
+        if (base - lane + 32 * k >= e1) continue;  // (warp uniform) a short tile: no live string in this chain
         const fh::RegBytes sb = short_bytes(sw[k], bytes + o0[k]);
         h[k] = hash_8_16_ool(sb.w0, sb.fetch64(len[k] - 8), len[k]);
       }
@@ -1815,6 +1817,9 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
         wait_flag(A.peer_flags[A.rank], lane, A.epoch, A.wait_timeout_ms);
     }
   }
+  // launched behind the flat kernel of the column tiles with programmatic serialization: this
+  // grid is complete only when that one is (no-op otherwise)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef RECOM_PROFILE
   if (lane == 0 && A.prof) {
     uint64_t* o_ = A.prof + ((size_t)blockIdx.x * kWarps + warp) * 8;
@@ -1846,20 +1851,126 @@ int fused_kernel_configure(bool bf16, int smem_bytes) {
 }
 
 void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqParams& req, int grid,
-                          bool bf16, cudaStream_t stream) {
+                          bool bf16, cudaStream_t stream, bool pdl) {
   const size_t sm = (size_t)plan.smem_bytes;
 #ifdef RECOM_TEST_NOLAUNCH
-  (void)sm; (void)sched; (void)req; (void)grid; (void)stream; (void)bf16;
+  (void)sm; (void)sched; (void)req; (void)grid; (void)stream; (void)bf16; (void)pdl;
   return;
 #endif
   const bool sh = req.world > 0;  // sharded output: rows stored into their owners' tensors
+  // pdl: programmatic dependent launch behind the flat kernel of the column tiles - this grid's
+  // CTAs may start while that one drains (neither reads what the other writes; every thread of
+  // this kernel executes griddepcontrol.wait before it exits, so this launch - and with it the
+  // request - is complete only when the flat kernel is).
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = sm;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   if (bf16) {
-    if (sh) fused_columns_kernel<true, true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
-    else fused_columns_kernel<true, false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+    if (sh) cudaLaunchKernelEx(&cfg, fused_columns_kernel<true, true>, plan, sched, req);
+    else cudaLaunchKernelEx(&cfg, fused_columns_kernel<true, false>, plan, sched, req);
   } else {
-    if (sh) fused_columns_kernel<false, true><<<grid, kThreads, sm, stream>>>(plan, sched, req);
-    else fused_columns_kernel<false, false><<<grid, kThreads, sm, stream>>>(plan, sched, req);
+    if (sh) cudaLaunchKernelEx(&cfg, fused_columns_kernel<false, true>, plan, sched, req);
+    else cudaLaunchKernelEx(&cfg, fused_columns_kernel<false, false>, plan, sched, req);
   }
+}
+
+// ---------------------------------------------------------------------------
+// the flat kernel of the column tiles: ONE WARP PER TILE, no persistence
+// ---------------------------------------------------------------------------
+// A column tile is a chain of dependent loads (record -> slot offsets -> row_splits -> string
+// offsets -> string bytes -> table rows); inside the persistent kernel a warp walks several of
+// them one after the other next to its FAST tiles, at 20 warps per SM, and the launch lasts as
+// long as the sum. Here every tile has its own warp, the grid holds as many warps as there are
+// tiles (most expensive first: `items` is sorted by cost), the CTAs are small (4 warps, scratch
+// only) and 12 - 16 of them are resident per SM: the chains of ALL tiles overlap, and the launch
+// lasts about as long as one of them. The persistent kernel behind it keeps the FAST runs only.
+// With programmatic dependent launch (`pdl`) the persistent kernel's CTAs become resident as
+// this kernel's last wave drains; the two write disjoint slices of the concat rows.
+constexpr int kFlatWarps = 4;
+#ifndef RECOM_FLAT_MIN_BLOCKS
+#define RECOM_FLAT_MIN_BLOCKS 8
+#endif
+template <bool BF16>
+__global__ void __launch_bounds__(kFlatWarps * 32, RECOM_FLAT_MIN_BLOCKS)
+column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ReqParams A,
+                    const ColItem* __restrict__ items, int num_items) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = (int)blockIdx.x * kFlatWarps + warp;
+  // let the dependent launch (the persistent kernel of the FAST runs) become resident as soon
+  // as every CTA of this grid has started
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // the whole request blob -> L2 (one 128-byte line per thread and pass): the tiles' second and
+  // later levels of dependent loads (string bytes behind their offsets, ...) are L2 hits
+  for (int64_t o = ((int64_t)blockIdx.x * (kFlatWarps * 32) + threadIdx.x) * 128; o < A.blob_bytes;
+       o += (int64_t)gridDim.x * (kFlatWarps * 32) * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.blob + o));
+  if (k >= num_items) return;
+  ColItem it;
+  load_item(items + k, it);
+#ifdef RECOM_PROFILE
+  uint32_t prof_acc[6] = {0, 0, 0, 0, 0, 0};
+  const uint64_t prof_t0 = gtimer();
+  uint32_t prof_last = (uint32_t)clock64();
+  ProfRef pr{prof_acc, &prof_last};
+#endif
+  ReqRegsT<false> Q;
+  Q.out = A.out;
+  Q.bind(A);
+  Q.out_row_bytes = A.out_row_bytes;
+  Q.status = A.status;
+  Q.ids_out = A.ids_out;
+  Q.ids_base = A.ids_base;
+  Q.check = P.check_ids != 0;
+  Q.shard_world = P.shard_world;
+  Q.shard_rank = P.shard_rank;
+  PROF_T(0)
+  PROF_C(0, it.begin + it.count)
+  column_tile<BF16>(P, A, Q, it, smem_u32(smem) + (uint32_t)(warp * P.scratch_bytes), lane PROF_ARG);
+#ifdef RECOM_PROFILE
+  if (lane == 0 && A.prof && k < A.pad0) {  // (pad0: rows of the timer buffer)
+    uint64_t* o_ = A.prof + (size_t)k * 8;
+#pragma unroll
+    for (int i_ = 0; i_ < 6; ++i_) o_[i_] = prof_acc[i_];
+    o_[6] = prof_t0;
+    o_[7] = gtimer();
+  }
+#endif
+}
+
+int column_tiles_configure(bool bf16, int smem_bytes) {
+  int n = 0;
+  cudaError_t e;
+  if (bf16) {
+    e = cudaFuncSetAttribute(column_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, column_tiles_kernel<true>, kFlatWarps * 32, smem_bytes);
+  } else {
+    e = cudaFuncSetAttribute(column_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, column_tiles_kernel<false>, kFlatWarps * 32, smem_bytes);
+  }
+  return e == cudaSuccess ? n : -1;
+}
+
+void launch_column_tiles(const DevPlan& plan, const ReqParams& req, const ColItem* items, int num_items,
+                         bool bf16, cudaStream_t stream) {
+#ifdef RECOM_TEST_NOLAUNCH
+  (void)plan; (void)req; (void)items; (void)num_items; (void)bf16; (void)stream;
+  return;
+#endif
+  if (num_items <= 0) return;
+  const int grid = (num_items + kFlatWarps - 1) / kFlatWarps;
+  const size_t sm = (size_t)kFlatWarps * plan.scratch_bytes;
+  if (bf16) column_tiles_kernel<true><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
+  else column_tiles_kernel<false><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
 }
 
 // Stream-side end of the fused exchange: lane g waits for rank g's completion signal.

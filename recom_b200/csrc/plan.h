@@ -28,6 +28,7 @@ constexpr int kSparseRowsPerSub = 4;   // SPARSE warp tile: rows per lane group 
 constexpr int kSparseRowsPerSubHash = 2;  // ... when the ids are hashed on the fly
 constexpr int kSparseIdsPerRow = 8;    // smem budget of a SPARSE warp tile, ids per (column, row)
 constexpr int kWarpScratchBytes = 4 << 10;  // per warp: row_splits + row ids of a column tile
+constexpr int kFlatScratchBytes = 3 << 10;  // ... of the flat kernel: row_splits + 472 row ids + 1 KB
 constexpr int kColTileRowsDense = 128;     // rows of a column tile with one id per row
 constexpr int kColTileRowsSparse = 32;     // rows of a multi-hot column tile
 constexpr int64_t kHbmTableBytes = 32ll << 20;  // a table beyond this is "HBM resident"
@@ -361,7 +362,11 @@ constexpr uint64_t kArgsMagic = 0x5247524132304252ull;  // trailer: {magic, num_
 
 // kernels.cu
 void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqParams& req, int grid,
-                          bool bf16, cudaStream_t stream);
+                          bool bf16, cudaStream_t stream, bool pdl);
+// the flat kernel of the column tiles (one warp per tile); `plan.scratch_bytes` = its warp scratch
+void launch_column_tiles(const DevPlan& plan, const ReqParams& req, const ColItem* items, int num_items,
+                         bool bf16, cudaStream_t stream);
+int column_tiles_configure(bool bf16, int smem_bytes);
 void launch_shard_wait(uint32_t* local_flags, int world, uint32_t epoch, uint32_t timeout_ms,
                        cudaStream_t stream);
 void launch_split_hash(const DevPlan& plan, const ReqParams& req, cudaStream_t stream);
