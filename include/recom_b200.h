@@ -105,7 +105,7 @@ typedef enum recom_seg_format {
   RECOM_SEG_COO_I64 = 2, /* int64[nnz, seg_stride] SparseTensor.indices, row id in
                            column 0, row-major sorted: what the reference reads in
                            place (cuda_emitter.cc:1836-1873) */
-  RECOM_SEG_SPLIT_STR = 3 /* the values are ONE string per row (STR: int32
+  RECOM_SEG_SPLIT_STR = 3, /* the values are ONE string per row (STR: int32
                            offsets[batch+1] + payload) and the row's ids are the tokens of
                            tf.strings.split(row, delimiter) (StringSplit, string_split_op.cc:37-99,
                            162-170; the reference's model E joins its ids with ';',
@@ -114,7 +114,24 @@ typedef enum recom_seg_format {
                            delimiter: RECOM_SPLIT_SPEC(d0, d1, d2, n, skip_empty) - any of the n <= 3
                            characters splits (n == 0: every character is a token), empty tokens
                            are skipped when skip_empty (TF's default). */
+  RECOM_SEG_COO_RESHAPE_I64 = 4, /* SparseTensor.indices of rank R behind a SparseReshape, inlined
+                           into the load of the row id the way the reference's EmitInputInline does
+                           (cuda_emitter.cc:1874-1922: linearise with the input shape, divide by
+                           the trailing output dimensions): seg_slot = int64[nnz, R] indices,
+                           seg_slot + 1 = int64[R] dense_shape, and - with has_new_shape -
+                           seg_slot + 2 = int64[Ro] new shape (one entry may be -1, inferred like
+                           SparseReshape does); without it the new shape is
+                           [prod(shape[:-1]), shape[-1]], the reshape of
+                           safe_embedding_lookup_sparse (embedding_ops.py:882-941). The id's row is
+                           column 0 of the reshaped indices: linear(e) / prod(new_shape[1:]).
+                           seg_stride = RECOM_RESHAPE_SPEC(R, has_new_shape), 1 <= R, Ro <= 8. */
+  RECOM_SEG_FIXED = 5      /* every row owns the same number T of consecutive ids: the values are
+                           a dense [batch, T] tensor and the column is Sum(axis=1) over the gathered
+                           [batch, T, D] rows - the reference's EmitBatchColReduction
+                           (cuda_emitter.cc:1180-1244) fused with the gather in front of it.
+                           seg_slot -1; seg_stride = T, or 0: T = value elements / batch. */
 } recom_seg_format;
+#define RECOM_RESHAPE_SPEC(rank, has_new_shape) ((int32_t)((rank) | ((has_new_shape) ? 256 : 0)))
 #define RECOM_SPLIT_SPEC(d0, d1, d2, n, skip_empty)                                        \
   ((int32_t)((uint32_t)(uint8_t)(d0) | (uint32_t)(uint8_t)(d1) << 8 | (uint32_t)(uint8_t)(d2) << 16 | \
              (uint32_t)(n) << 24 | (uint32_t)((skip_empty) ? 1 : 0) << 28))

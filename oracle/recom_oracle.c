@@ -636,8 +636,39 @@ ORACLE_API int oracle_run_model(const recom_column_desc *cols, int32_t num_cols,
     int rc = column_ids(c, blob, slot_offsets, slot_elems, boundaries, ids, n);
     if (rc == 0 && c->lookup != RECOM_LOOKUP_DENSE) {
       row_of = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
-      const uint8_t *seg = blob + slot_offsets[c->seg_slot];
-      if (c->seg_format == RECOM_SEG_ROW_SPLITS_I32) {
+      const uint8_t *seg = c->seg_slot >= 0 ? blob + slot_offsets[c->seg_slot] : NULL;
+      if (c->seg_format == RECOM_SEG_FIXED) {
+        /* Sum(axis=1) over the gathered [batch, T, D] tensor: EmitBatchColReduction,
+         * cuda_emitter.cc:1180-1244 (out[b, c] = sum_j in[b, j, c]); T = seg_stride or n / batch */
+        const int64_t T = c->seg_stride > 0 ? c->seg_stride : (batch > 0 ? n / batch : 0);
+        if (n != T * batch) rc = -1;
+        for (int64_t i = 0; rc == 0 && i < n; ++i) row_of[i] = i / T;
+      } else if (c->seg_format == RECOM_SEG_COO_RESHAPE_I64) {
+        /* SparseReshape (TF sparse_reshape_op: linearise with the input shape, re-split with the
+         * output shape, -1 inferred) followed by reading column 0 - what EmitInputInline turns into
+         * ((i0 * s1 + i1) * s2 + ...) / (o_last) / ... (cuda_emitter.cc:1874-1922). */
+        const int rank = c->seg_stride & 255;
+        const int64_t *coo = (const int64_t *)seg;
+        const int64_t *shape = (const int64_t *)(blob + slot_offsets[c->seg_slot + 1]);
+        int64_t total = 1;
+        for (int j = 0; j < rank; ++j) total *= shape[j];
+        int64_t div = shape[rank - 1] > 0 ? shape[rank - 1] : 1;
+        if (c->seg_stride & 256) {
+          const int64_t *ns = (const int64_t *)(blob + slot_offsets[c->seg_slot + 2]);
+          const int ro = (int)slot_elems[c->seg_slot + 2];
+          int64_t known = 1;
+          for (int j = 0; j < ro; ++j)
+            if (ns[j] >= 0) known *= ns[j];
+          div = 1;
+          for (int j = 1; j < ro; ++j) div *= ns[j] < 0 ? (known > 0 ? total / known : 0) : ns[j];
+          if (div <= 0) div = 1;
+        }
+        for (int64_t i = 0; i < n; ++i) {
+          int64_t lin = 0;
+          for (int j = 0; j < rank; ++j) lin = lin * shape[j] + coo[i * rank + j];
+          row_of[i] = lin / div;
+        }
+      } else if (c->seg_format == RECOM_SEG_ROW_SPLITS_I32) {
         const int32_t *rs = (const int32_t *)seg;
         if (slot_elems[c->seg_slot] != batch + 1 || rs[0] != 0 || rs[batch] != n) rc = -1;
         if (rc == 0)

@@ -17,6 +17,12 @@ LOOKUP_DENSE, LOOKUP_GATHER_SCATTER, LOOKUP_SEGMENT = 0, 1, 2
 COMBINE_SUM, COMBINE_MEAN, COMBINE_SQRTN = 0, 1, 2
 XFORM_NONE, XFORM_BUCKETIZE, XFORM_HASH_STR, XFORM_HASH_INT = 0, 1, 2, 3
 SEG_NONE, SEG_ROW_SPLITS_I32, SEG_COO_I64, SEG_SPLIT_STR = 0, 1, 2, 3
+SEG_COO_RESHAPE_I64, SEG_FIXED = 4, 5
+
+
+def reshape_spec(rank: int, has_new_shape: bool = False) -> int:
+    """RECOM_RESHAPE_SPEC (include/recom_b200.h)."""
+    return rank | (256 if has_new_shape else 0)
 
 DTYPE_BYTES = {F32: 4, BF16: 2, I32: 4, I64: 8, STR: 4, F64: 8}
 

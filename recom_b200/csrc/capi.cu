@@ -293,10 +293,20 @@ recom_status validate_columns(const recom_column_desc* cols, int32_t n, const re
         if (c.transform != RECOM_XFORM_HASH_STR || c.seg_slot != -1 || ((c.seg_stride >> 24) & 15) > 3)
           return fail(RECOM_ERR_INVALID_ARGUMENT,
                       "column %d: SPLIT_STR needs transform HASH_STR, seg_slot -1 and a RECOM_SPLIT_SPEC", i);
+      } else if (c.seg_format == RECOM_SEG_FIXED) {
+        if (c.seg_slot != -1 || c.seg_stride < 0 || c.lookup != RECOM_LOOKUP_SEGMENT)
+          return fail(RECOM_ERR_INVALID_ARGUMENT,
+                      "column %d: SEG_FIXED needs lookup SEGMENT, seg_slot -1 and seg_stride >= 0", i);
       } else if (c.seg_slot < 0 || c.seg_slot >= cfg.num_slots)
         return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: seg_slot out of range", i);
-      if (c.seg_format == RECOM_SEG_SPLIT_STR) {
+      if (c.seg_format == RECOM_SEG_SPLIT_STR || c.seg_format == RECOM_SEG_FIXED) {
         // checked above
+      } else if (c.seg_format == RECOM_SEG_COO_RESHAPE_I64) {
+        const int rank = c.seg_stride & 255, extra = (c.seg_stride & 256) ? 2 : 1;
+        if (rank < 1 || rank > 8 || (c.seg_stride & ~511) || c.seg_slot + extra >= cfg.num_slots)
+          return fail(RECOM_ERR_INVALID_ARGUMENT,
+                      "column %d: COO_RESHAPE needs RECOM_RESHAPE_SPEC(rank 1..8, has_new_shape) and the shape "
+                      "slots behind seg_slot", i);
       } else if (c.seg_format == RECOM_SEG_COO_I64) {
         if (c.seg_stride < 1)
           return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: COO seg_stride must be >= 1", i);
@@ -473,11 +483,26 @@ void build_layout(recom_plan* p) {
     if (d.lookup != RECOM_LOOKUP_DENSE) {
       c.sparse_index = (int32_t)p->sparse_cols.size();
       p->sparse_cols.push_back(i);
-      if (d.seg_format == RECOM_SEG_COO_I64) {
+      if (d.seg_format == RECOM_SEG_COO_I64 || d.seg_format == RECOM_SEG_COO_RESHAPE_I64 ||
+          d.seg_format == RECOM_SEG_FIXED) {
+        DevCoo dc{};
+        dc.seg_slot = d.seg_slot;
+        dc.seg_stride = d.seg_stride;
+        if (d.seg_format == RECOM_SEG_COO_RESHAPE_I64) {
+          dc.kind = 1;
+          dc.seg_stride = d.seg_stride & 255;
+          dc.has_new_shape = (d.seg_stride & 256) ? 1 : 0;
+        } else if (d.seg_format == RECOM_SEG_FIXED) {
+          dc.kind = 2;
+          dc.value_slot = d.value_slot;
+          dc.value_str = d.value_dtype == RECOM_STR ? 1 : 0;
+          // the units below read "multi-hot" off seg_slot >= 0; the row_splits come from coo_index
+          c.seg_slot = 0;
+        }
         int32_t k = 0;
         for (; k < (int32_t)p->coos.size(); ++k)
-          if (p->coos[k].seg_slot == d.seg_slot && p->coos[k].seg_stride == d.seg_stride) break;
-        if (k == (int32_t)p->coos.size()) p->coos.push_back(DevCoo{d.seg_slot, d.seg_stride});
+          if (memcmp(&p->coos[k], &dc, sizeof dc) == 0) break;
+        if (k == (int32_t)p->coos.size()) p->coos.push_back(dc);
         c.coo_index = k;
       } else if (d.seg_format == RECOM_SEG_SPLIT_STR) {
         DevSplit sp{c.bucket_magic, (int32_t)d.num_buckets, d.value_slot, d.bytes_slot, d.seg_stride};
@@ -721,7 +746,7 @@ void build_layout(recom_plan* p) {
           u.value_dtype = d.value_dtype;
           u.value_slot = d.value_slot;
           u.bytes_slot = d.value_dtype == RECOM_STR ? d.bytes_slot : -1;
-          u.seg_slot = sparse ? d.seg_slot : -1;
+          u.seg_slot = !sparse ? -1 : d.seg_format == RECOM_SEG_FIXED ? 0 : d.seg_slot;  // (FIXED: row_splits from coo_index)
           u.coo_index = sparse ? c.coo_index : -1;
           u.boundaries_offset = c.boundaries_offset;
           u.num_boundaries = c.num_boundaries;
@@ -1107,10 +1132,13 @@ int64_t blob_extent(const recom_plan* p, const recom_request* req) {
                             req->slot_elems[d.value_slot] * dtype_bytes(d.value_dtype));
     if (d.value_dtype == RECOM_STR && d.bytes_slot >= 0)
       end = std::max(end, req->slot_offsets[d.bytes_slot] + req->slot_elems[d.bytes_slot]);
-    if (d.lookup != RECOM_LOOKUP_DENSE && d.seg_slot >= 0)
-      end = std::max(end, req->slot_offsets[d.seg_slot] +
-                              req->slot_elems[d.seg_slot] *
-                                  (d.seg_format == RECOM_SEG_COO_I64 ? 8 : 4));
+    if (d.lookup != RECOM_LOOKUP_DENSE && d.seg_slot >= 0) {
+      const bool coo = d.seg_format == RECOM_SEG_COO_I64 || d.seg_format == RECOM_SEG_COO_RESHAPE_I64;
+      end = std::max(end, req->slot_offsets[d.seg_slot] + req->slot_elems[d.seg_slot] * (coo ? 8 : 4));
+      if (d.seg_format == RECOM_SEG_COO_RESHAPE_I64)
+        for (int k = 1; k <= ((d.seg_stride & 256) ? 2 : 1); ++k)
+          end = std::max(end, req->slot_offsets[d.seg_slot + k] + req->slot_elems[d.seg_slot + k] * 8);
+    }
   }
   return end;
 }
@@ -1158,6 +1186,12 @@ recom_status validate_request(const recom_plan* p, const recom_request* req) {
       if (velems != req->batch + 1)
         return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: a split string input holds batch+1 offsets (has %lld)",
                     i, (long long)velems);
+    } else if (d.seg_format == RECOM_SEG_FIXED) {
+      const int64_t nnz = d.value_dtype == RECOM_STR ? velems - 1 : velems;
+      const int64_t T = d.seg_stride > 0 ? d.seg_stride : (req->batch > 0 ? nnz / req->batch : 0);
+      if (nnz < 0 || nnz != T * req->batch)
+        return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: a [batch, T] input holds %lld values for batch %lld, T %lld",
+                    i, (long long)nnz, (long long)req->batch, (long long)T);
     } else {
       const int64_t nnz = d.value_dtype == RECOM_STR ? velems - 1 : velems;
       if (nnz < 0) return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: empty STR offsets slot", i);
@@ -1169,10 +1203,21 @@ recom_status validate_request(const recom_plan* p, const recom_request* req) {
                       "column %d: row_splits slot must hold batch+1 int32 (has %lld)", i,
                       (long long)selems);
       } else {
-        if (soff % 8 || selems != nnz * d.seg_stride)
+        const int64_t stride = d.seg_format == RECOM_SEG_COO_RESHAPE_I64 ? (d.seg_stride & 255) : d.seg_stride;
+        if (soff % 8 || selems != nnz * stride)
           return fail(RECOM_ERR_INVALID_ARGUMENT,
                       "column %d: COO slot must hold nnz*stride int64 (has %lld, nnz %lld)", i,
                       (long long)selems, (long long)nnz);
+        if (d.seg_format == RECOM_SEG_COO_RESHAPE_I64) {
+          // dense_shape (int64[rank]) and, when given, the new shape (int64[1..8]) behind the indices
+          if (req->slot_offsets[d.seg_slot + 1] % 8 || req->slot_elems[d.seg_slot + 1] != stride)
+            return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: slot %d must hold the int64[%lld] dense_shape",
+                        i, d.seg_slot + 1, (long long)stride);
+          if ((d.seg_stride & 256) && (req->slot_offsets[d.seg_slot + 2] % 8 || req->slot_elems[d.seg_slot + 2] < 1 ||
+                                       req->slot_elems[d.seg_slot + 2] > 8))
+            return fail(RECOM_ERR_INVALID_ARGUMENT, "column %d: slot %d must hold the int64[1..8] new shape",
+                        i, d.seg_slot + 2);
+        }
       }
     }
   }
@@ -1468,9 +1513,11 @@ recom_status recom_plan_slot_layout(const recom_plan* p, int32_t* ranks, int32_t
     elem_bytes[d.value_slot] = dtype_bytes(d.value_dtype);
     if (d.value_dtype == RECOM_STR && d.bytes_slot >= 0) elem_bytes[d.bytes_slot] = 1;
     if (d.lookup != RECOM_LOOKUP_DENSE && d.seg_slot >= 0) {
-      const bool coo = d.seg_format == RECOM_SEG_COO_I64;
+      const bool coo = d.seg_format == RECOM_SEG_COO_I64 || d.seg_format == RECOM_SEG_COO_RESHAPE_I64;
       elem_bytes[d.seg_slot] = coo ? 8 : 4;
       ranks[d.seg_slot] = coo ? 2 : 1;  // SparseTensor.indices: [nnz, rank]
+      if (d.seg_format == RECOM_SEG_COO_RESHAPE_I64)
+        for (int k = 1; k <= ((d.seg_stride & 256) ? 2 : 1); ++k) elem_bytes[d.seg_slot + k] = 8;  // int64 shapes
     }
   }
   return RECOM_OK;
@@ -1489,6 +1536,10 @@ recom_status recom_plan_infer_batch(const recom_plan* p, const int64_t* slot_ele
     }
     if (d.seg_format == RECOM_SEG_SPLIT_STR) {
       *batch = slot_elems[d.value_slot] - 1;
+      return RECOM_OK;
+    }
+    if (d.seg_format == RECOM_SEG_FIXED && d.seg_stride > 0) {
+      *batch = (slot_elems[d.value_slot] - (d.value_dtype == RECOM_STR ? 1 : 0)) / d.seg_stride;
       return RECOM_OK;
     }
   }
@@ -1703,7 +1754,7 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   // longest COO input (grid of the helper kernel)
   int64_t max_coo_nnz = 0;
   for (const DevCoo& c : p->coos)
-    max_coo_nnz = std::max<int64_t>(max_coo_nnz, req->slot_elems[c.seg_slot] / c.seg_stride);
+    max_coo_nnz = std::max<int64_t>(max_coo_nnz, c.kind == 2 ? B : req->slot_elems[c.seg_slot] / c.seg_stride);
   g_host_prof.lap(2);
 
   // workspace: [argument block + schedule (upload path only) | ws_row_splits]

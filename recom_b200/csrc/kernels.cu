@@ -2085,11 +2085,24 @@ void launch_split_hash(const DevPlan& plan, const ReqParams& req, cudaStream_t s
 // cuda_emitter.cc:768-818, which walks tiles serially in one block).
 // Every boundary i in [0, nnz] fills row_splits for the rows in (row[i-1], row[i]].
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void fill_row_splits(const long long* __restrict__ coo, int64_t nnz,
-                                                int32_t stride, int64_t batch,
+// Row id of entry i of a COO input. kind 1: SparseReshape inlined (cuda_emitter.cc:1874-1922).
+struct CooRows {
+  const long long* coo;
+  int32_t stride;
+  int32_t rank;        // > 0: reshape - linear = sum_j idx[j] * mul[j]; row = linear / div
+  long long mul[8];
+  long long div;
+  __device__ __forceinline__ int64_t row(int64_t i) const {
+    if (rank == 0) return (int64_t)__ldg(coo + i * stride);
+    long long lin = 0;
+    for (int j = 0; j < rank; ++j) lin += __ldg(coo + i * stride + j) * mul[j];
+    return (int64_t)(lin / div);
+  }
+};
+__device__ __forceinline__ void fill_row_splits(const CooRows& c, int64_t nnz, int64_t batch,
                                                 int32_t* __restrict__ rs, int64_t i) {
-  const int64_t prev = i == 0 ? -1 : (int64_t)__ldg(coo + (i - 1) * stride);
-  int64_t cur = i == nnz ? batch : (int64_t)__ldg(coo + i * stride);
+  const int64_t prev = i == 0 ? -1 : c.row(i - 1);
+  int64_t cur = i == nnz ? batch : c.row(i);
   if (cur > batch) cur = batch;
   for (int64_t r = prev + 1; r <= cur; ++r) rs[r] = (int32_t)i;
 }
@@ -2100,12 +2113,48 @@ coo_to_row_splits_kernel(const DevCoo* __restrict__ coos, const int64_t* __restr
                          int64_t batch, int32_t* __restrict__ ws_row_splits) {
   const int k = blockIdx.y;
   const DevCoo c = coos[k];
-  const int64_t nnz = slot_elems[c.seg_slot] / c.seg_stride;
-  const long long* coo = (const long long*)(blob + slot_offsets[c.seg_slot]);
   int32_t* rs = ws_row_splits + (int64_t)k * (batch + 1);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz;
-       i += (int64_t)gridDim.x * blockDim.x)
-    fill_row_splits(coo, nnz, c.seg_stride, batch, rs, i);
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, dt = (int64_t)gridDim.x * blockDim.x;
+  if (c.kind == 2) {  // fixed row length: Sum(axis=1) over [batch, T, D]
+    const int64_t n = slot_elems[c.value_slot] - (c.value_str ? 1 : 0);
+    const int64_t T = c.seg_stride > 0 ? c.seg_stride : (batch > 0 ? n / batch : 0);
+    for (int64_t r = t0; r <= batch; r += dt) rs[r] = (int32_t)(r * T);
+    return;
+  }
+  CooRows R;
+  R.coo = (const long long*)(blob + slot_offsets[c.seg_slot]);
+  R.stride = c.seg_stride;
+  R.rank = 0;
+  R.div = 1;
+  const int64_t nnz = slot_elems[c.seg_slot] / c.seg_stride;
+  if (c.kind == 1) {
+    const int rank = c.seg_stride;
+    const long long* shape = (const long long*)(blob + slot_offsets[c.seg_slot + 1]);
+    R.rank = rank;
+    long long m = 1;
+    for (int j = rank - 1; j >= 0; --j) {
+      R.mul[j] = m;
+      m *= __ldg(shape + j);
+    }
+    if (c.has_new_shape) {
+      // row = linear / prod(new_shape[1:]); a -1 entry is the quotient of the total by the others
+      const long long* ns = (const long long*)(blob + slot_offsets[c.seg_slot + 2]);
+      const int ro = (int)slot_elems[c.seg_slot + 2];
+      long long known = 1, tail = 1;
+      for (int j = 0; j < ro; ++j) {
+        const long long d = __ldg(ns + j);
+        if (d >= 0) known *= d;
+      }
+      for (int j = 1; j < ro; ++j) {
+        const long long d = __ldg(ns + j);
+        tail *= d < 0 ? (known > 0 ? m / known : 0) : d;
+      }
+      R.div = tail > 0 ? tail : 1;
+    } else {
+      R.div = max(1ll, __ldg(shape + rank - 1));
+    }
+  }
+  for (int64_t i = t0; i <= nnz; i += dt) fill_row_splits(R, nnz, batch, rs, i);
 }
 
 void launch_coo_to_row_splits(const DevPlan& plan, const ReqParams& req, int64_t max_nnz,
@@ -2121,9 +2170,14 @@ void launch_coo_to_row_splits(const DevPlan& plan, const ReqParams& req, int64_t
 __global__ void __launch_bounds__(256)
 segment_ids_to_row_splits_kernel(const long long* __restrict__ coo, int64_t nnz, int32_t stride,
                                  int64_t batch, int32_t* __restrict__ rs) {
+  CooRows R;
+  R.coo = coo;
+  R.stride = stride;
+  R.rank = 0;
+  R.div = 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz;
        i += (int64_t)gridDim.x * blockDim.x)
-    fill_row_splits(coo, nnz, stride, batch, rs, i);
+    fill_row_splits(R, nnz, batch, rs, i);
 }
 
 void launch_segment_ids_to_row_splits(const int64_t* coo, int64_t nnz, int32_t stride,

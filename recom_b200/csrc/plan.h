@@ -161,9 +161,18 @@ static_assert(sizeof(ColItem) == 96, "ColItem layout");
 
 
 // A COO input (SparseTensor.indices) whose row ids are turned into row_splits in the workspace.
+// kind 0: row id = indices[e * seg_stride]; 1 (RECOM_SEG_COO_RESHAPE_I64): the indices of rank
+// seg_stride are linearised with the dense_shape in slot seg_slot + 1 and divided by the trailing
+// dimensions of the new shape (slot seg_slot + 2, or [prod(shape[:-1]), shape[-1]]); 2
+// (RECOM_SEG_FIXED): no indices - row r owns ids [r * T, (r + 1) * T), T = seg_stride or
+// elements of `value_slot` (minus one for strings) / batch.
 struct DevCoo {
   int32_t seg_slot;
   int32_t seg_stride;
+  int32_t kind;
+  int32_t has_new_shape;
+  int32_t value_slot;
+  int32_t value_str;
 };
 
 // A string input that is split into tokens on the device (RECOM_SEG_SPLIT_STR): a helper kernel

@@ -95,9 +95,11 @@ class Model:
                 c.bytes_slot = slot
                 slot += 1
             c.seg_slot = -1
-            if c.lookup != L.LOOKUP_DENSE and c.seg_format != L.SEG_SPLIT_STR:
+            if c.lookup != L.LOOKUP_DENSE and c.seg_format not in (L.SEG_SPLIT_STR, L.SEG_FIXED):
                 c.seg_slot = slot
                 slot += 1
+                if c.seg_format == L.SEG_COO_RESHAPE_I64:  # dense_shape (+ new shape) behind the indices
+                    slot += 2 if c.seg_stride & 256 else 1
             self.slot_of_key[c.key] = (c.value_slot, c.bytes_slot, c.seg_slot)
         self.out_width = off
         self.num_slots = slot
@@ -194,6 +196,8 @@ class Feature:
     values: Union[np.ndarray, Strings]
     row_splits: Optional[np.ndarray] = None
     coo: Optional[np.ndarray] = None
+    dense_shape: Optional[np.ndarray] = None  # SEG_COO_RESHAPE_I64: int64[rank] of the SparseTensor
+    new_shape: Optional[np.ndarray] = None    # ... and the SparseReshape target, when the column gives one
 
 
 @dataclass
@@ -234,10 +238,17 @@ def pack_request(model: Model, batch: int, features: Dict[str, Feature],
             slot_arrays[c.bytes_slot] = np.ascontiguousarray(f.values.data, np.uint8)
         else:
             slot_arrays[c.value_slot] = np.ascontiguousarray(f.values, NP_OF[c.value_dtype])
-        if c.lookup != L.LOOKUP_DENSE and c.seg_format != L.SEG_SPLIT_STR:
+        if c.lookup != L.LOOKUP_DENSE and c.seg_format not in (L.SEG_SPLIT_STR, L.SEG_FIXED):
             if c.seg_format == L.SEG_ROW_SPLITS_I32:
                 assert f.row_splits is not None, c.name
                 slot_arrays[c.seg_slot] = np.ascontiguousarray(f.row_splits, np.int32)
+            elif c.seg_format == L.SEG_COO_RESHAPE_I64:
+                assert f.coo is not None and f.dense_shape is not None, c.name
+                slot_arrays[c.seg_slot] = np.ascontiguousarray(f.coo, np.int64).reshape(-1)
+                slot_arrays[c.seg_slot + 1] = np.ascontiguousarray(f.dense_shape, np.int64)
+                if c.seg_stride & 256:
+                    assert f.new_shape is not None, c.name
+                    slot_arrays[c.seg_slot + 2] = np.ascontiguousarray(f.new_shape, np.int64)
             else:
                 assert f.coo is not None, c.name
                 slot_arrays[c.seg_slot] = np.ascontiguousarray(f.coo, np.int64).reshape(-1)
