@@ -187,8 +187,8 @@ struct recom_plan {
   int col_rows_dense = kColTileRowsDense;    // rows of a column tile, one id per row (<= 128)
   int col_rows_sparse = kColTileRowsSparse;  // rows of a multi-hot column tile (<= 32)
   // The flat kernel of the column tiles (one warp per tile, in front of the persistent kernel,
-  // which then keeps the FAST runs only): plain and Mode-B requests; the fused Mode-A exchange
-  // (sharded output) stays in the persistent kernel, whose last warp signals the peers.
+  // which then keeps the FAST runs only): plain, Mode-B and Mode-A requests alike (sharded output:
+  // the warps of both launches count themselves, the last one signals the peers).
   int flat_mode = -1;          // RECOM_B200_FLAT: 1 always, 0 never, unset: by cost (prefer_flat)
   bool flat_pdl = true;        // the persistent kernel starts while the flat one drains
   int flat_ctas_per_sm = 8;    // resident CTAs (4 warps each) of the flat kernel
@@ -1741,7 +1741,7 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   cudaStream_t stream = (cudaStream_t)req->stream;
 
   g_host_prof.lap(0);
-  const bool flat = !so && prefer_flat(p, B);
+  const bool flat = prefer_flat(p, B);
   std::shared_ptr<const TileTable> tt = cached_tiles(p, B, flat, &st);
   if (st != RECOM_OK) return st;
   g_host_prof.lap(1);
@@ -1909,6 +1909,7 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     g_last_launches++;
   }
   const bool has_flat = !tt->flat.empty();
+  A.total_warps = grid * kWarps + (has_flat ? column_tiles_grid((int)tt->flat.size()) * 4 : 0);
   if (has_flat) {
     // profiling builds: RECOM_B200_PROF_FLAT=1 times the flat kernel's warps instead of the persistent one's
     static const bool prof_flat = getenv("RECOM_B200_PROF_FLAT") != nullptr;

@@ -1707,6 +1707,36 @@ __device__ __noinline__ void fast_section(const DevPlan& P, const Sched& S, cons
   }
 }
 
+// Sharded output (Mode A, fused exchange): every warp of the request's launches counts itself
+// when its rows are stored; the last one tells every peer that this rank's slices of its rows
+// are in place (and, with the barrier inside the kernel, waits for theirs).
+__device__ __forceinline__ void signal_peers(const ReqParams& A, int lane) {
+  if (A.peer_flags[0] == nullptr) return;
+  __syncwarp();  // the lanes' row stores are ordered before lane 0's fence
+  bool last = false;
+  if (lane == 0) {
+    __threadfence_system();
+    last = atomicAdd(A.counters, 1) == A.total_warps - 1;
+    if (last) {
+      A.counters[0] = 0;
+      __threadfence();
+      // the slot may be handed to another request (host side check in recom_plan_run)
+      if (A.done_seq) *(volatile uint32_t*)A.done_seq = A.seq;
+    }
+  }
+  if (__shfl_sync(0xffffffffu, (int)last, 0)) {
+    __threadfence_system();
+    if (lane < A.world)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peer_flags[lane] + A.rank),
+                   "r"(A.epoch)
+                   : "memory");
+    // the barrier inside the kernel: this launch ends when every rank's slices of this
+    // rank's rows have landed (lane g watches rank g's word of the local flag array)
+    if (A.wait_in_kernel && lane < A.world)
+      wait_flag(A.peer_flags[A.rank], lane, A.epoch, A.wait_timeout_ms);
+  }
+}
+
 template <bool BF16, bool SH>
 #ifndef RECOM_MIN_BLOCKS
 #define RECOM_MIN_BLOCKS 2
@@ -1790,33 +1820,9 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
   if (fast_first)
     column_section<BF16>(P, A, Q, q_items, q_count, k0, it, &cs.next_col, sm.scratch, lane PROF_ARG);
 
-  // ---- sharded output: the last warp of the grid tells every peer that this rank's slices
-  // of its rows are in place (and, with the barrier inside the kernel, waits for theirs) ----
-  if (SH && A.peer_flags[0] != nullptr) {
-    __syncwarp();  // the lanes' row stores are ordered before lane 0's fence
-    bool last = false;
-    if (lane == 0) {
-      __threadfence_system();
-      last = atomicAdd(A.counters, 1) == G * kWarps - 1;
-      if (last) {
-        A.counters[0] = 0;
-        __threadfence();
-        // the slot may be handed to another request (host side check in recom_plan_run)
-        if (A.done_seq) *(volatile uint32_t*)A.done_seq = A.seq;
-      }
-    }
-    if (__shfl_sync(0xffffffffu, (int)last, 0)) {
-      __threadfence_system();
-      if (lane < A.world)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peer_flags[lane] + A.rank),
-                     "r"(A.epoch)
-                     : "memory");
-      // the barrier inside the kernel: this launch ends when every rank's slices of this
-      // rank's rows have landed (lane g watches rank g's word of the local flag array)
-      if (A.wait_in_kernel && lane < A.world)
-        wait_flag(A.peer_flags[A.rank], lane, A.epoch, A.wait_timeout_ms);
-    }
-  }
+  // ---- sharded output: the last warp of the request (this grid's and the flat kernel's) tells
+  // every peer that this rank's slices of its rows are in place ----
+  if (SH) signal_peers(A, lane);
   // launched behind the flat kernel of the column tiles with programmatic serialization: this
   // grid is complete only when that one is (no-op otherwise)
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1897,7 +1903,7 @@ constexpr int kFlatWarps = 4;
 #ifndef RECOM_FLAT_MIN_BLOCKS
 #define RECOM_FLAT_MIN_BLOCKS 8
 #endif
-template <bool BF16>
+template <bool BF16, bool SH>
 __global__ void __launch_bounds__(kFlatWarps * 32, RECOM_FLAT_MIN_BLOCKS)
 column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ReqParams A,
                     const ColItem* __restrict__ items, int num_items) {
@@ -1912,7 +1918,10 @@ column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ R
   for (int64_t o = ((int64_t)blockIdx.x * (kFlatWarps * 32) + threadIdx.x) * 128; o < A.blob_bytes;
        o += (int64_t)gridDim.x * (kFlatWarps * 32) * 128)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(A.blob + o));
-  if (k >= num_items) return;
+  if (k >= num_items) {
+    if (SH) signal_peers(A, lane);
+    return;
+  }
   ColItem it;
   load_item(items + k, it);
 #ifdef RECOM_PROFILE
@@ -1921,7 +1930,7 @@ column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ R
   uint32_t prof_last = (uint32_t)clock64();
   ProfRef pr{prof_acc, &prof_last};
 #endif
-  ReqRegsT<false> Q;
+  ReqRegsT<SH> Q;
   Q.out = A.out;
   Q.bind(A);
   Q.out_row_bytes = A.out_row_bytes;
@@ -1934,6 +1943,7 @@ column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ R
   PROF_T(0)
   PROF_C(0, it.begin + it.count)
   column_tile<BF16>(P, A, Q, it, smem_u32(smem) + (uint32_t)(warp * P.scratch_bytes), lane PROF_ARG);
+  if (SH) signal_peers(A, lane);
 #ifdef RECOM_PROFILE
   if (lane == 0 && A.prof && k < A.pad0) {  // (pad0: rows of the timer buffer)
     uint64_t* o_ = A.prof + (size_t)k * 8;
@@ -1945,20 +1955,19 @@ column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ R
 #endif
 }
 
-int column_tiles_configure(bool bf16, int smem_bytes) {
+template <bool BF16>
+static int configure_flat(int smem_bytes) {
   int n = 0;
-  cudaError_t e;
-  if (bf16) {
-    e = cudaFuncSetAttribute(column_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, column_tiles_kernel<true>, kFlatWarps * 32, smem_bytes);
-  } else {
-    e = cudaFuncSetAttribute(column_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, column_tiles_kernel<false>, kFlatWarps * 32, smem_bytes);
-  }
-  return e == cudaSuccess ? n : -1;
+  if (cudaFuncSetAttribute(column_tiles_kernel<BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+      cudaFuncSetAttribute(column_tiles_kernel<BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, column_tiles_kernel<BF16, false>, kFlatWarps * 32, smem_bytes) != cudaSuccess)
+    return -1;
+  return n;
 }
+int column_tiles_configure(bool bf16, int smem_bytes) {
+  return bf16 ? configure_flat<true>(smem_bytes) : configure_flat<false>(smem_bytes);
+}
+int column_tiles_grid(int num_items) { return (num_items + kFlatWarps - 1) / kFlatWarps; }
 
 void launch_column_tiles(const DevPlan& plan, const ReqParams& req, const ColItem* items, int num_items,
                          bool bf16, cudaStream_t stream) {
@@ -1969,8 +1978,14 @@ void launch_column_tiles(const DevPlan& plan, const ReqParams& req, const ColIte
   if (num_items <= 0) return;
   const int grid = (num_items + kFlatWarps - 1) / kFlatWarps;
   const size_t sm = (size_t)kFlatWarps * plan.scratch_bytes;
-  if (bf16) column_tiles_kernel<true><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
-  else column_tiles_kernel<false><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
+  const bool sh = req.world > 0;  // sharded output: rows stored into their owners' tensors
+  if (bf16) {
+    if (sh) column_tiles_kernel<true, true><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
+    else column_tiles_kernel<true, false><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
+  } else {
+    if (sh) column_tiles_kernel<false, true><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
+    else column_tiles_kernel<false, false><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
+  }
 }
 
 // Stream-side end of the fused exchange: lane g waits for rank g's completion signal.

@@ -340,7 +340,10 @@ struct ReqParams {
                                 // (the last one signals the peers and resets it)
   uint32_t* done_seq;           // host-mapped word of this slot: receives `seq` when the launch ends
   uint32_t seq;
-  int32_t pad0;
+  int32_t pad0;                 // (profiling builds: rows of the flat kernel's timer buffer)
+  int32_t total_warps;          // sharded output only: warps of all launches of this request (what
+                                // `counters` counts up to)
+  int32_t pad1;
   int64_t blob_bytes;           // extent of the blob (L2 prefetch at kernel entry), 0: unknown
   // Sharded output (Mode A, fused exchange): rows [g * rows_per_rank, (g + 1) * rows_per_rank)
   // are stored into peer_out[g] (rank g's [rows_per_rank, global width] tensor, peer mapped);
@@ -376,6 +379,7 @@ void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqPara
 void launch_column_tiles(const DevPlan& plan, const ReqParams& req, const ColItem* items, int num_items,
                          bool bf16, cudaStream_t stream);
 int column_tiles_configure(bool bf16, int smem_bytes);
+int column_tiles_grid(int num_items);  // CTAs (of 4 warps) the flat kernel launches for `num_items` tiles
 void launch_shard_wait(uint32_t* local_flags, int world, uint32_t epoch, uint32_t timeout_ms,
                        cudaStream_t stream);
 void launch_split_hash(const DevPlan& plan, const ReqParams& req, cudaStream_t stream);
