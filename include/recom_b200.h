@@ -24,6 +24,7 @@
  *        concat_outputs_op_gpu.cu.cc:133-140): it writes the final row-major
  *       [batch, out_width] tensor directly, stream ordered, no host sync.
  *   recom_scatter_columns
+ *   recom_dense_relu            (8(f) N4: the first dense layer behind the concat, tcgen05)
  *       keeps ConcatOutputs' `host_inputs` capability
  *       (concat_outputs_op_gpu.cu.cc:186-232): columns computed elsewhere are
  *       scattered into their concat slices.
@@ -369,6 +370,17 @@ RECOM_API recom_status recom_scatter_columns(const void *const *cols,
 /* The same for columns that live in HOST memory (Addons>ConcatOutputs' `host_inputs`,
  * concat_outputs_op_gpu.cu.cc:186-232): uploaded into `d_scratch` (device, 16-byte aligned, the
  * columns' bytes rounded up to 16 each), then scattered. */
+/* SURVEY 8(f) N4 - the layer on the far side of the path: out[m, n] = relu(A[m, k] * W[n, k]^T +
+ * bias[n]), the first dense layer of the top MLP behind the concat (examples/python/dlrm.py:175-182:
+ * tf.layers.dense(units, relu); the reference leaves it to TF's MatMul / BiasAdd / Relu). A is the
+ * bf16 concat tensor a RECOM_BF16 plan has just written (row stride lda elements), W the layer's
+ * kernel stored [n, k] (K-major: TF's [k, n] kernel transposed once at load time), both device
+ * pointers, 16-byte aligned, k and lda multiples of 8; bias (fp32[n], device) may be null; out is
+ * fp32 [m, n]. One tcgen05 / TMA kernel on `stream` (csrc/dense_layer.cu). */
+RECOM_API recom_status recom_dense_relu(const void *a_bf16, int64_t m, int32_t k, int64_t lda,
+                                        const void *w_nk_bf16, int32_t n, const float *bias,
+                                        int32_t relu, float *out, recom_stream_t stream);
+
 RECOM_API recom_status recom_scatter_host_columns(const void *const *host_cols,
                                         const int32_t *col_dims,
                                         const int32_t *col_offsets, int32_t num_cols,

@@ -2011,6 +2011,17 @@ recom_status recom_plan_algorithmic_bytes(const recom_plan* p, const recom_reque
   return RECOM_OK;
 }
 
+recom_status recom_dense_relu(const void* a_bf16, int64_t m, int32_t k, int64_t lda, const void* w_nk_bf16,
+                              int32_t n, const float* bias, int32_t relu, float* out, recom_stream_t stream) {
+  const char* why = "";
+  const int rc = launch_dense_relu(a_bf16, m, k, lda, w_nk_bf16, n, bias, relu, out, (cudaStream_t)stream, &why);
+  if (rc == 0) {
+    g_last_launches = 1;
+    return RECOM_OK;
+  }
+  return fail(rc == 1 ? RECOM_ERR_INVALID_ARGUMENT : RECOM_ERR_CUDA, "recom_dense_relu: %s", why);
+}
+
 recom_status recom_scatter_columns(const void* const* cols, const int32_t* col_dims,
                                    const int32_t* col_offsets, int32_t num_cols, int64_t batch,
                                    int32_t out_width, int32_t elem_bytes, void* out,

@@ -399,6 +399,9 @@ void launch_output_ptrs(int32_t num_cols, const int32_t* d_out_offsets, int32_t 
                         int64_t* ptrs_dev, cudaStream_t stream);
 void launch_fingerprint64(const uint8_t* bytes, const int32_t* offsets, int64_t n,
                           int64_t num_buckets, uint64_t* out, cudaStream_t stream);
+// dense_layer.cu: out = relu(A W^T + bias) on the tcgen05 tensor cores
+int launch_dense_relu(const void* a, int64_t M, int32_t K, int64_t lda, const void* w, int32_t N,
+                      const float* bias, int relu, float* out, cudaStream_t stream, const char** why);
 // configures the dynamic shared memory of the fused kernel; returns resident CTAs per SM
 int fused_kernel_configure(bool bf16, int smem_bytes);
 

@@ -192,3 +192,25 @@ def string_to_hash_bucket_fast(bytes_dev: torch.Tensor, offsets_dev: torch.Tenso
     L.check(L.lib.recom_string_to_hash_bucket_fast(bytes_dev.data_ptr(), offsets_dev.data_ptr(), n,
                                                    num_buckets, out.data_ptr(), s.cuda_stream))
     return out
+
+
+def dense_relu(a: torch.Tensor, w_nk: torch.Tensor, bias: Optional[torch.Tensor] = None,
+               relu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = relu(a @ w_nk.T + bias) on the tcgen05 tensor cores (recom_dense_relu,
+    csrc/dense_layer.cu). a: bf16 [M, K] (row stride a.stride(0): the concat tensor of a bf16 plan),
+    w_nk: bf16 [N, K] contiguous (the layer's [K, N] kernel transposed once), bias: fp32 [N] or None.
+    -> fp32 [M, N]."""
+    assert a.is_cuda and a.dtype == torch.bfloat16 and a.dim() == 2 and a.stride(1) == 1
+    assert w_nk.is_cuda and w_nk.dtype == torch.bfloat16 and w_nk.is_contiguous() and w_nk.shape[1] == a.shape[1]
+    m, k = a.shape
+    n = w_nk.shape[0]
+    if bias is not None:
+        assert bias.is_cuda and bias.dtype == torch.float32 and bias.numel() == n and bias.is_contiguous()
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (m, n)
+    s = torch.cuda.current_stream(a.device)
+    L.check(L.lib.recom_dense_relu(a.data_ptr(), m, k, a.stride(0), w_nk.data_ptr(), n,
+                                   bias.data_ptr() if bias is not None else None, 1 if relu else 0,
+                                   out.data_ptr(), s.cuda_stream))
+    return out
