@@ -28,11 +28,20 @@
 namespace recom {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, kStages = 4, kUmmaK = 16;
-constexpr int kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
+// Two tile shapes: 128 x 128 with a 6-stage ring (small M x N: more CTAs than a 128 x 256 grid
+// would give), 128 x 256 with 4 stages (large grids: a quarter less operand traffic per flop out
+// of L2, which is what bounds a 128 x 128 tile at a third of the tensor peak).
+constexpr int BM = 128, BK = 64, kUmmaK = 16;
+constexpr int kStageBytesA = BM * BK * 2;
 constexpr int kDenseThreads = 192;
-constexpr int kTmemCols = 128;
-constexpr int kDenseSmem = kStages * (kStageBytesA + kStageBytesB) + 256 + 1024;  // + barriers + alignment slack
+template <int BN, int STAGES>
+struct DenseCfg {
+  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kSmem = STAGES * (kStageBytesA + kStageBytesB) + 256 + 1024;  // + barriers + alignment slack
+  // D fp32, A / B bf16, both K-major, M = 128, N = BN (cute::UMMA::InstrDescriptor)
+  static constexpr uint32_t kInstrDesc =
+      (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -70,15 +79,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// D fp32, A / B bf16, both K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-      ::"r"(tmem_d), "l"(a), "l"(b), "r"(kInstrDesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -98,11 +104,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <int BN, int kStages>
 __global__ void __launch_bounds__(kDenseThreads, 1)
 dense_relu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const float* __restrict__ bias, float* __restrict__ out, int M, int N, int K, int relu) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);  // the swizzle atoms are 1024-byte aligned
+  constexpr int kStageBytesB = DenseCfg<BN, kStages>::kStageBytesB;
+  constexpr int kTmemCols = BN;
   const uint32_t s_a = s32(smem), s_b = s_a + kStages * kStageBytesA;
   uint8_t* ctl = smem + kStages * (kStageBytesA + kStageBytesB);
   const uint32_t s_full = s32(ctl), s_empty = s_full + 8 * kStages, s_tfull = s_empty + 8 * kStages;
@@ -150,7 +159,7 @@ dense_relu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int k = 0; k < BK / kUmmaK; ++k) {
         const uint64_t da = umma_desc(s_a + s * kStageBytesA + k * kUmmaK * 2);
         const uint64_t db = umma_desc(s_b + s * kStageBytesB + k * kUmmaK * 2);
-        umma_f16(tmem, da, db, (kb | k) != 0 ? 1u : 0u);
+        umma_f16(tmem, da, db, DenseCfg<BN, kStages>::kInstrDesc, (kb | k) != 0 ? 1u : 0u);
       }
       umma_commit(s_empty + 8 * s);  // the stage is free once these MMAs have read it
     }
@@ -210,13 +219,13 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows, K] bf16, row stride `ld` elements, boxes of 128 rows x 64 columns, 128-byte swizzle
-bool make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K, int64_t ld) {
+// [rows, K] bf16, row stride `ld` elements, boxes of box_rows rows x 64 columns, 128-byte swizzle
+bool make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t es[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -236,18 +245,29 @@ int launch_dense_relu(const void* a, int64_t M, int32_t K, int64_t lda, const vo
     *why = msg[1];
     return 1;
   }
+  // 128 x 256 tiles when they still fill most of the GPU, else 128 x 128
+  const int64_t tiles_m = (M + BM - 1) / BM;
+  const bool wide = N >= 256 && tiles_m * ((N + 255) / 256) >= 120;
+  const int bn = wide ? 256 : 128;
   CUtensorMap ma, mw;
-  if (!make_map(&ma, a, M, K, lda) || !make_map(&mw, w, N, K, K)) {
+  if (!make_map(&ma, a, M, K, lda, BM) || !make_map(&mw, w, N, K, K, bn)) {
     *why = msg[2];
     return 2;
   }
-  if (cudaFuncSetAttribute(dense_relu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) {
-    *why = msg[3];
-    return 3;
+  dim3 grid((unsigned)tiles_m, (unsigned)((N + bn - 1) / bn));
+  cudaError_t e;
+  if (wide) {
+    auto fn = dense_relu_kernel<256, 4>;
+    constexpr int smem = DenseCfg<256, 4>::kSmem;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) fn<<<grid, kDenseThreads, smem, stream>>>(ma, mw, bias, out, (int)M, N, K, relu);
+  } else {
+    auto fn = dense_relu_kernel<128, 6>;
+    constexpr int smem = DenseCfg<128, 6>::kSmem;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) fn<<<grid, kDenseThreads, smem, stream>>>(ma, mw, bias, out, (int)M, N, K, relu);
   }
-  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
-  dense_relu_kernel<<<grid, kDenseThreads, kDenseSmem, stream>>>(ma, mw, bias, out, (int)M, N, K, relu);
-  if (cudaGetLastError() != cudaSuccess) {
+  if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
     *why = msg[3];
     return 3;
   }

@@ -21,7 +21,9 @@ def _reference(a, w, bias, relu):
 
 
 @pytest.mark.parametrize("m,k,n", [(128, 64, 128), (128, 256, 128), (2048, 8120, 1024), (300, 520, 200),
-                                   (1, 8, 1), (129, 72, 130), (257, 4096, 16)])
+                                   (1, 8, 1), (129, 72, 130), (257, 4096, 16),
+                                   # 128 x 256 tiles (grids that still fill the GPU), full and ragged in N
+                                   (4096, 520, 1024), (5000, 264, 600)])
 @pytest.mark.parametrize("relu", [True, False])
 def test_dense_relu_matches_fp32_reference(m, k, n, relu):
     import torch
