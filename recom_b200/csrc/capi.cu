@@ -192,11 +192,13 @@ struct recom_plan {
   int flat_mode = -1;          // RECOM_B200_FLAT: 1 always, 0 never, unset: by cost (prefer_flat)
   bool flat_pdl = true;        // the persistent kernel starts while the flat one drains
   int flat_ctas_per_sm = 8;    // resident CTAs (4 warps each) of the flat kernel
+  int defer_ids = kDeferIds;   // RECOM_B200_DEFER_IDS (>= kDeferIds: the workspace bound assumes it)
+  int long_ctas_per_sm = 8;    // RECOM_B200_LONG_CTAS (measured on config 3, B = 2048: 2 / 4 / 8 CTAs per SM 177 / 156 / 148 us)
   int flat_warps_target = 0;   // tiles are cut finer until there are about this many (0: resident warps)
   DevPlan dev_flat{};          // = dev with the flat kernel's warp scratch
   // tile tables depend only on the batch size: cached (read-mostly)
   std::mutex tiles_mu;
-  std::map<int64_t, std::shared_ptr<const TileTable>> tiles_by_batch;  // key: batch * 2 + flat
+  std::map<int64_t, std::shared_ptr<const TileTable>> tiles_by_batch;  // key: (batch * 2 + flat) * 4 + density class
   bool stage_tables = true;
   // profiling builds only (RECOM_B200_PROF_DUMP=<file>): per-CTA phase timers of the last run
   uint64_t* d_prof = nullptr;
@@ -848,7 +850,25 @@ bool prefer_flat(const recom_plan* p, int64_t B) {
   return col_cost > 0 && col_cost >= 3.0 * fast_cost;
 }
 
-std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B, bool flat) {
+// Density class of a request: multi-hot tiles are cut by rows, but their cost goes with their
+// ids - with long rows (config 3: zipf lengths, mean 60 ids per row) a 32-row tile holds
+// thousands of ids and the launch lasts as long as its fullest tile. Class c halves the rows per
+// multi-hot tile c times (32 -> 16 -> 8 -> 4) so that a tile holds ~256 ids on average. The
+// schedule cache is keyed by (batch, schedule, class).
+int density_class(const recom_plan* p, const recom_request* req) {
+  if (req->batch <= 0) return 0;
+  int64_t worst = 0;
+  for (const ColItem& u : p->units) {
+    if (u.seg_slot < 0 || u.value_slot < 0) continue;
+    const int64_t nnz = req->slot_elems[u.value_slot] - (u.value_dtype == RECOM_STR ? 1 : 0);
+    worst = std::max(worst, nnz / req->batch);
+  }
+  int c = 0;
+  while (c < 3 && worst >= (16ll << c)) ++c;
+  return c;
+}
+
+std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B, bool flat, int dens) {
   const int cap_ctas = std::max(1, p->num_sms * p->ctas_per_sm);
   auto tt = std::make_shared<TileTable>();
   auto make = [&](int s, int64_t b, int64_t rows) {
@@ -877,7 +897,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B, bool flat
                          : p->flat_warps_target > 0 ? p->flat_warps_target
                                                     : (int64_t)p->num_sms * p->flat_ctas_per_sm * 4;
   int rows_dense = std::min(kColTileRowsDense, p->col_rows_dense);
-  int rows_sparse = std::min(kColTileRowsSparse, p->col_rows_sparse);
+  int rows_sparse = std::max(4, std::min(kColTileRowsSparse, p->col_rows_sparse) >> dens);
   {
     auto count = [&](int rd, int rs) {
       int64_t n = 0;
@@ -1049,14 +1069,14 @@ cudaError_t blocking_upload(recom_plan* p, void* dst, const void* src, size_t by
 
 // Cached (device resident) schedule of a batch size, or nullptr when the cache is full:
 // the caller then ships the schedule inside the request's argument block.
-std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, bool flat, recom_status* st) {
+std::shared_ptr<const TileTable> cached_tiles(recom_plan* p, int64_t B, bool flat, int dens, recom_status* st) {
   *st = RECOM_OK;
   std::lock_guard<std::mutex> lock(p->tiles_mu);
-  const int64_t key = B * 2 + (flat ? 1 : 0);
+  const int64_t key = (B * 2 + (flat ? 1 : 0)) * 4 + dens;
   auto it = p->tiles_by_batch.find(key);
   if (it != p->tiles_by_batch.end()) return it->second;
   if (p->tiles_by_batch.size() >= kMaxCachedTileTables) return nullptr;
-  std::shared_ptr<TileTable> tt = build_tiles(p, B, flat);
+  std::shared_ptr<TileTable> tt = build_tiles(p, B, flat, dens);
   std::vector<uint8_t> host(tt->bytes() + 64, 0);
   tt->write(host.data());
   // first use of a batch size (warm-up): a blocking allocation + copy
@@ -1314,6 +1334,8 @@ recom_status recom_plan_create_filtered(const recom_column_desc* cols, int32_t n
   if (const char* e = getenv("RECOM_B200_FLAT")) p->flat_mode = atoi(e) != 0;
   if (const char* e = getenv("RECOM_B200_FLAT_PDL")) p->flat_pdl = atoi(e) != 0;
   if (const char* e = getenv("RECOM_B200_FLAT_WARPS")) p->flat_warps_target = atoi(e);
+  if (const char* e = getenv("RECOM_B200_DEFER_IDS")) p->defer_ids = std::max(32, atoi(e));
+  if (const char* e = getenv("RECOM_B200_LONG_CTAS")) p->long_ctas_per_sm = std::max(1, std::min(8, atoi(e)));
   build_layout(p);
   st = upload_plan(p);
   if (st == RECOM_OK) {
@@ -1325,6 +1347,7 @@ recom_status recom_plan_create_filtered(const recom_column_desc* cols, int32_t n
       const int occ_flat = column_tiles_configure(p->elem_bytes == 2, 4 * kFlatScratchBytes);
       if (occ_flat < 1) st = fail(RECOM_ERR_CUDA, "flat kernel does not fit: %s", cudaGetErrorString(cudaGetLastError()));
       else p->flat_ctas_per_sm = occ_flat;
+      long_rows_configure(p->elem_bytes == 2, kLongRowWarps * kFlatScratchBytes);
     }
     int occ = fused_kernel_configure(p->elem_bytes == 2, p->dev.smem_bytes);
     if (occ < 1) {
@@ -1631,6 +1654,8 @@ recom_status recom_plan_workspace_bytes(const recom_plan* p, int64_t batch, int6
   size_t b = align_up(arg_block_bytes(p) + max_sched_bytes(p, batch), 256);
   b += align_up((p->coos.size() + p->splits.size()) * (size_t)(batch + 1) * 4 + 16, 256);
   if (!p->splits.empty()) b += align_up((size_t)total_ids * 4 + 16, 256);
+  // the list of deferred long rows: (item, row) pairs, at most one per kDeferIds ids of a unit
+  b += align_up(((size_t)total_ids / std::min(kDeferIds, p->defer_ids) + p->units.size() + 2) * 8 + 16, 256);
   *out = b;
   return RECOM_OK;
 }
@@ -1742,11 +1767,12 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
 
   g_host_prof.lap(0);
   const bool flat = prefer_flat(p, B);
-  std::shared_ptr<const TileTable> tt = cached_tiles(p, B, flat, &st);
+  const int dens = density_class(p, req);
+  std::shared_ptr<const TileTable> tt = cached_tiles(p, B, flat, dens, &st);
   if (st != RECOM_OK) return st;
   g_host_prof.lap(1);
   const bool sched_in_args = !tt;
-  if (sched_in_args) tt = build_tiles(p, B, flat);
+  if (sched_in_args) tt = build_tiles(p, B, flat, dens);
   const int grid = tt->grid;
 
   st = validate_request(p, req);
@@ -1769,6 +1795,19 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     size_t ids = 0;
     for (const DevSplit& sp : p->splits) ids += (size_t)req->slot_elems[sp.bytes_slot] + (size_t)B + 1;
     off += align_up(ids * 4 + 16, 256);
+  }
+  // long rows of dense requests (density class >= 1) go to long_rows_kernel (flat schedule, plain output)
+  const size_t off_long = off;
+  int32_t long_cap = 0;
+  const bool defer_long = dens >= 1 && flat && !so && !tt->flat.empty();
+  if (defer_long) {
+    int64_t cap = 0;
+    for (const ColItem& u : p->units) {
+      if (u.seg_slot < 0 || u.value_slot < 0) continue;
+      cap += (req->slot_elems[u.value_slot] - (u.value_dtype == RECOM_STR ? 1 : 0)) / p->defer_ids + 1;
+    }
+    long_cap = (int32_t)std::min<int64_t>(cap, 0x3fffffff);
+    off += align_up(((size_t)long_cap + 1) * 8 + 16, 256);
   }
   if (!req->workspace || req->workspace_bytes < off)
     return fail(RECOM_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes, got %zu", off,
@@ -1908,6 +1947,12 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     launch_split_hash(p->dev, A, stream);
     g_last_launches++;
   }
+  if (defer_long) {
+    A.long_list = (int32_t*)(ws + off_long);
+    A.long_cap = long_cap;
+    A.long_ids = p->defer_ids;
+    CUDA_TRY(cudaMemsetAsync(A.long_list, 0, 8, stream));
+  }
   const bool has_flat = !tt->flat.empty();
   A.total_warps = grid * kWarps + (has_flat ? column_tiles_grid((int)tt->flat.size()) * 4 : 0);
   if (has_flat) {
@@ -1927,6 +1972,10 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   }
   if (grid > 0) {
     launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream, has_flat && p->flat_pdl);
+    g_last_launches++;
+  }
+  if (defer_long) {
+    launch_long_rows(p->dev_flat, A, d_flat, p->num_sms * p->long_ctas_per_sm, p->elem_bytes == 2, stream);
     g_last_launches++;
   }
   cudaError_t e = cudaGetLastError();

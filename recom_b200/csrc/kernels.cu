@@ -1431,14 +1431,33 @@ template <bool BF16, class QT>
 __device__ __noinline__ void sparse_tile_overflow(const DevPlan& P, const ReqParams& A, const QT Q,
                                                   const ColItem it, const uint8_t* values,
                                                   const uint8_t* bytes, uint32_t s_sp,
-                                                  uint32_t s_ids, int cap, uint32_t s_tmp, int lane) {
+                                                  uint32_t s_ids, int cap, uint32_t s_tmp, int lane,
+                                                  int item_k) {
   constexpr int ELEM = BF16 ? 2 : 4;
   const int R = it.count;
   int r_lo = 0;
+  // rows longer than kDeferIds are left to long_rows_kernel when the request has a list for them
+  auto deferred = [&](int r) {
+    return A.long_list != nullptr && item_k >= 0 &&
+           lds_i32(s_sp + 4u * (uint32_t)(r + 1)) - lds_i32(s_sp + 4u * (uint32_t)r) > A.long_ids;
+  };
   while (r_lo < R) {
     const int32_t e_lo = lds_i32(s_sp + 4u * (uint32_t)r_lo);
+    if (deferred(r_lo)) {
+      int slot = A.long_cap;
+      if (lane == 0) slot = atomicAdd(A.long_list, 1);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (slot < A.long_cap) {  // (a full list: the row is summed here after all)
+        if (lane == 0) {
+          A.long_list[2 + 2 * slot] = item_k;
+          A.long_list[3 + 2 * slot] = it.begin + r_lo;
+        }
+        ++r_lo;
+        continue;
+      }
+    }
     int r_hi = r_lo;
-    while (r_hi < R && lds_i32(s_sp + 4u * (uint32_t)(r_hi + 1)) - e_lo <= cap) ++r_hi;
+    while (r_hi < R && lds_i32(s_sp + 4u * (uint32_t)(r_hi + 1)) - e_lo <= cap && !(r_hi > r_lo && deferred(r_hi))) ++r_hi;
     if (r_hi == r_lo) {
       const int32_t e_hi = lds_i32(s_sp + 4u * (uint32_t)(r_lo + 1));
       for (int ui = 0; ui < it.num_users; ++ui) {
@@ -1483,7 +1502,7 @@ __device__ __forceinline__ void load_item(const ColItem* p, ColItem& it) {
 
 template <bool BF16, class QT>
 __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A, const QT& Q,
-                                            const ColItem& it, uint32_t s_scratch, int lane
+                                            const ColItem& it, uint32_t s_scratch, int lane, int item_k
                                             PROF_PARAM) {
   constexpr int ELEM = BF16 ? 2 : 4;
   // resolve the stream and its first column against the request: one read of the slot offsets
@@ -1529,9 +1548,10 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
     const int32_t v_next = __shfl_down_sync(0xffffffffu, v, 1);
     const int32_t n_row = lane < R ? (lane == R - 1 ? e_end : v_next) - v : 0;
     const bool any_long = __any_sync(0xffffffffu, n_row > kCoopRowIds);
+    const bool any_deferred = A.long_list != nullptr && item_k >= 0 && __any_sync(0xffffffffu, n_row > A.long_ids);
     __syncwarp();
     PROF_C(2, e0 + e_end)
-    if (e_end - e0 <= cap) {
+    if (e_end - e0 <= cap && !any_deferred) {
       transform_ids(P, it, values, bytes, e0, e_end, s_ids, lane);
       __syncwarp();
       if (u.hbm && !Q.check && Q.shard_world <= 1) prefetch_rows(u, s_ids, e_end - e0, lane);
@@ -1539,7 +1559,7 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
       PROF_C(3, lds_i32(s_ids))
       sparse_users<BF16>(P, A, Q, it, u, it.begin, R, s_sp, s_ids, e0, any_long, s_tmp, lane);
     } else {
-      sparse_tile_overflow<BF16>(P, A, Q, it, values, bytes, s_sp, s_ids, cap, s_tmp, lane);
+      sparse_tile_overflow<BF16>(P, A, Q, it, values, bytes, s_sp, s_ids, cap, s_tmp, lane, item_k);
     }
     PROF_T(4)
     PROF_C(4, 0)
@@ -1618,7 +1638,7 @@ __device__ __noinline__ void column_section(const DevPlan& P, const ReqParams& A
   while (k < q_count) {
     PROF_T(0)
     PROF_C(0, it.begin + it.count)
-    column_tile<BF16>(P, A, Q, it, s_scratch, lane PROF_ARG);
+    column_tile<BF16>(P, A, Q, it, s_scratch, lane, -1 PROF_ARG);
     k = claim();
     if (k < q_count) load_item(q_items + k, it);
   }
@@ -1942,7 +1962,7 @@ column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ R
   Q.shard_rank = P.shard_rank;
   PROF_T(0)
   PROF_C(0, it.begin + it.count)
-  column_tile<BF16>(P, A, Q, it, smem_u32(smem) + (uint32_t)(warp * P.scratch_bytes), lane PROF_ARG);
+  column_tile<BF16>(P, A, Q, it, smem_u32(smem) + (uint32_t)(warp * P.scratch_bytes), lane, SH ? -1 : k PROF_ARG);
   if (SH) signal_peers(A, lane);
 #ifdef RECOM_PROFILE
   if (lane == 0 && A.prof && k < A.pad0) {  // (pad0: rows of the timer buffer)
@@ -1953,6 +1973,135 @@ column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ R
     o_[7] = gtimer();
   }
 #endif
+}
+
+// ---------------------------------------------------------------------------
+// long rows: the rows the flat kernel deferred, one CTA (8 warps) per row at a time
+// ---------------------------------------------------------------------------
+// A row of hundreds or thousands of ids (config 3: zipf lengths) is a chain of transform passes
+// and gather rounds for the one warp of its tile, and the launch lasts as long as the longest
+// such chain. Here the row's ids are dealt to the CTA's warps in contiguous parts; every warp
+// transforms and sums its part (the same code as long_row), the partial sums meet in shared
+// memory and warp 0 adds them in warp order: deterministic, no atomics on the output.
+template <int VEC, bool BF16>
+__device__ __forceinline__ void long_row_cta(const DevPlan& P, const ReqRegsT<false>& Q, const ColItem& it,
+                                             const UserRegs& u, const uint8_t* values, const uint8_t* bytes,
+                                             int64_t row, int32_t e0, int32_t e1, uint32_t s_ids, int capc,
+                                             uint32_t s_tmp, float* s_part, int32_t* s_kept, int warp, int lane) {
+  constexpr int NE = Acc<VEC, BF16>::kFloats;
+  const int C = u.row_bytes / VEC;
+  // this warp's part of the row (multiples of 4 ids)
+  const int32_t n = e1 - e0;
+  const int32_t per = ((n + kLongRowWarps - 1) / kLongRowWarps + 3) & ~3;
+  const int32_t w0 = min(e1, e0 + warp * per), w1 = min(e1, w0 + per);
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int W = min(32, C - c0);
+    const int rpp = 32 / W, sub = lane / W;
+    const int chb = (c0 + lane - sub * W) * VEC;
+    Acc<VEC, BF16> acc;
+    acc.clear();
+    int32_t kept = 0;
+    for (int32_t cb = w0; cb < w1; cb += capc) {
+      const int32_t cn = min(w1 - cb, capc);
+      transform_ids(P, it, values, bytes, cb, cb + cn, s_ids, lane);
+      __syncwarp();
+      kept += count_kept(s_ids, cn, lane);
+      if (sub < rpp)
+        coop_accumulate<VEC, BF16>(Q, u, acc, u.table + chb, chb == 0 ? u.col : -1, rpp, sub, s_ids, cn, cb);
+      __syncwarp();
+    }
+    // the lane groups' partial sums -> lane group 0 of the warp
+#pragma unroll
+    for (int i = 0; i < NE; ++i)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_tmp + 4u * (uint32_t)(lane * NE + i)), "f"(acc.at(i)) : "memory");
+    __syncwarp();
+    if (sub == 0) {
+      for (int g = 1; g < rpp; ++g) {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) acc.at(i) += lds_f32(s_tmp + 4u * (uint32_t)((g * W + lane) * NE + i));
+      }
+#pragma unroll
+      for (int i = 0; i < NE; ++i) s_part[(warp * 32 + lane) * NE + i] = acc.at(i);
+    }
+    if (lane == 0) s_kept[warp] = kept;
+    __syncthreads();
+    if (warp == 0 && sub == 0) {
+      int32_t total = s_kept[0];
+      for (int w = 1; w < kLongRowWarps; ++w) {
+        total += s_kept[w];
+#pragma unroll
+        for (int i = 0; i < NE; ++i) acc.at(i) += s_part[(w * 32 + lane) * NE + i];
+      }
+      ColCursor<false> outp(Q, row, 0, 1, u.out_byte + chb);
+      flush_row<VEC, BF16>(acc, total, u.combiner, outp.next());
+    }
+    __syncthreads();
+  }
+}
+
+#ifndef RECOM_LONG_MIN_BLOCKS
+#define RECOM_LONG_MIN_BLOCKS 2
+#endif
+template <bool BF16>
+__global__ void __launch_bounds__(kLongRowWarps * 32, RECOM_LONG_MIN_BLOCKS)
+long_rows_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ReqParams A,
+                 const ColItem* __restrict__ items) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float s_part[kLongRowWarps * 32 * 8];
+  __shared__ int32_t s_kept[kLongRowWarps];
+  constexpr int ELEM = BF16 ? 2 : 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t count = min(A.long_list[0], A.long_cap);
+  ReqRegsT<false> Q;
+  Q.out = A.out;
+  Q.bind(A);
+  Q.out_row_bytes = A.out_row_bytes;
+  Q.status = A.status;
+  Q.ids_out = A.ids_out;
+  Q.ids_base = A.ids_base;
+  Q.check = P.check_ids != 0;
+  Q.shard_world = P.shard_world;
+  Q.shard_rank = P.shard_rank;
+  const uint32_t s_scr = smem_u32(smem) + (uint32_t)(warp * P.scratch_bytes);
+  const uint32_t s_ids = s_scr + kColSplitBytes;
+  const int cap = (P.scratch_bytes - kColSplitBytes - 1024) >> 2;
+  const uint32_t s_tmp = s_scr + (uint32_t)P.scratch_bytes - 1024u;
+  for (int32_t e = (int32_t)blockIdx.x; e < count; e += (int32_t)gridDim.x) {
+    const int32_t k = A.long_list[2 + 2 * e], row = A.long_list[3 + 2 * e];
+    ColItem it;
+    load_item(items + k, it);
+    const uint8_t* values =
+        it.value_slot >= 0 ? A.blob + __ldg(A.slot_offsets + it.value_slot)
+                           : (const uint8_t*)(A.ws_split_ids + split_ids_offset(P, A, -1 - it.value_slot, lane));
+    const uint8_t* bytes = it.bytes_slot >= 0 ? A.blob + __ldg(A.slot_offsets + it.bytes_slot) : nullptr;
+    const int32_t* rs = it.coo_index >= 0 ? A.ws_row_splits + (int64_t)it.coo_index * (A.batch + 1)
+                                          : (const int32_t*)(A.blob + __ldg(A.slot_offsets + it.seg_slot));
+    const int32_t e0 = __ldg(rs + row), e1 = __ldg(rs + row + 1);
+    for (int ui = 0; ui < it.num_users; ++ui) {
+      const UserRegs u = ui == 0 ? first_user(A, it) : load_user(P, A, it.first_user + ui);
+      if (u.vec_bytes == 16)
+        long_row_cta<16, BF16>(P, Q, it, u, values, bytes, row, e0, e1, s_ids, cap, s_tmp, s_part, s_kept, warp, lane);
+      else
+        long_row_cta<ELEM, BF16>(P, Q, it, u, values, bytes, row, e0, e1, s_ids, cap, s_tmp, s_part, s_kept, warp, lane);
+    }
+  }
+}
+
+int long_rows_configure(bool bf16, int smem_bytes) {
+  cudaError_t e = bf16 ? cudaFuncSetAttribute(long_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                       : cudaFuncSetAttribute(long_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  return e == cudaSuccess ? 0 : -1;
+}
+
+void launch_long_rows(const DevPlan& plan, const ReqParams& req, const ColItem* items, int ctas, bool bf16,
+                      cudaStream_t stream) {
+#ifdef RECOM_TEST_NOLAUNCH
+  (void)plan; (void)req; (void)items; (void)ctas; (void)bf16; (void)stream;
+  return;
+#endif
+  const size_t sm = (size_t)kLongRowWarps * plan.scratch_bytes;
+  if (bf16) long_rows_kernel<true><<<ctas, kLongRowWarps * 32, sm, stream>>>(plan, req, items);
+  else long_rows_kernel<false><<<ctas, kLongRowWarps * 32, sm, stream>>>(plan, req, items);
 }
 
 template <bool BF16>

@@ -28,6 +28,8 @@ constexpr int kSparseRowsPerSub = 4;   // SPARSE warp tile: rows per lane group 
 constexpr int kSparseRowsPerSubHash = 2;  // ... when the ids are hashed on the fly
 constexpr int kSparseIdsPerRow = 8;    // smem budget of a SPARSE warp tile, ids per (column, row)
 constexpr int kWarpScratchBytes = 4 << 10;  // per warp: row_splits + row ids of a column tile
+constexpr int kDeferIds = 256;              // rows longer than this go to long_rows_kernel (when enabled)
+constexpr int kLongRowWarps = 8;            // warps of a long_rows_kernel CTA: a row's ids are dealt to them in 8 contiguous parts
 constexpr int kFlatScratchBytes = 3 << 10;  // ... of the flat kernel: row_splits + 472 row ids + 1 KB
 constexpr int kColTileRowsDense = 128;     // rows of a column tile with one id per row
 constexpr int kColTileRowsSparse = 32;     // rows of a multi-hot column tile
@@ -344,6 +346,12 @@ struct ReqParams {
   int32_t total_warps;          // sharded output only: warps of all launches of this request (what
                                 // `counters` counts up to)
   int32_t pad1;
+  // Long rows (requests of density class >= 1, flat schedule, plain output): a multi-hot row with
+  // more than kDeferIds ids is not summed by its tile's one warp but appended to this list -
+  // [0] = count, then (item index, row) pairs - and summed by a whole CTA of long_rows_kernel.
+  int32_t* long_list;           // null: rows are never deferred
+  int32_t long_cap;             // entries the list holds
+  int32_t long_ids;             // a row with more ids than this is deferred (kDeferIds)
   int64_t blob_bytes;           // extent of the blob (L2 prefetch at kernel entry), 0: unknown
   // Sharded output (Mode A, fused exchange): rows [g * rows_per_rank, (g + 1) * rows_per_rank)
   // are stored into peer_out[g] (rank g's [rows_per_rank, global width] tensor, peer mapped);
@@ -379,7 +387,11 @@ void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqPara
 void launch_column_tiles(const DevPlan& plan, const ReqParams& req, const ColItem* items, int num_items,
                          bool bf16, cudaStream_t stream);
 int column_tiles_configure(bool bf16, int smem_bytes);
-int column_tiles_grid(int num_items);  // CTAs (of 4 warps) the flat kernel launches for `num_items` tiles
+int column_tiles_grid(int num_items);
+// the rows the flat kernel deferred (ReqParams::long_list), one CTA per row at a time
+void launch_long_rows(const DevPlan& plan, const ReqParams& req, const ColItem* items, int ctas, bool bf16,
+                      cudaStream_t stream);
+int long_rows_configure(bool bf16, int smem_bytes);  // CTAs (of 4 warps) the flat kernel launches for `num_items` tiles
 void launch_shard_wait(uint32_t* local_flags, int world, uint32_t epoch, uint32_t timeout_ms,
                        cudaStream_t stream);
 void launch_split_hash(const DevPlan& plan, const ReqParams& req, cudaStream_t stream);

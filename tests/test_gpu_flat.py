@@ -66,3 +66,28 @@ def test_cost_rule_picks_the_measured_winner():
     s = synth.dlrm_model(0, 2, 2, 3, 0, name="nofast")
     feats = synth.make_features(s, 256, seed=0)
     assert _launches(s, 256, feats, synth.make_tables_np(s)) == 1  # flat only: still one launch
+
+
+def test_long_rows_are_deferred_and_match_the_oracle():
+    """Config 3: zipf row lengths (rows of hundreds to 2000 ids). Requests of density class >= 1 hand
+    rows beyond 256 ids to long_rows_kernel (a CTA per row, partial sums added in warp order): one
+    more launch, same ids, sums within the forward bound; and with the threshold out of reach
+    (RECOM_B200_DEFER_IDS) the in-tile path gives the same result."""
+    from recom_b200.schema import pack_request
+    from tests.helpers import run_gpu
+
+    assert "RECOM_B200_FLAT" not in os.environ
+    m = synth.dlrm_model(8, 1, 1, 3, 2, large_rows=1 << 16, name="dyn_small")
+    for batch, seed in ((64, 1), (700, 2)):
+        feats = synth.make_features(m, batch, seed=seed, dist="zipf", empty_frac=0.2)
+        req, got, ref = assert_parity(m, batch, feats, synth.make_tables_np(m))
+        lengths = np.diff(next(f.row_splits for f in feats.values() if f.row_splits is not None))
+        assert lengths.max() > 256, "the case must hold a long row"
+    launches = run_gpu(m, req, synth.make_tables_np(m), want_ids=False)[3]
+    assert launches in (2, 3)  # flat tiles [+ FAST runs] + long rows
+    os.environ["RECOM_B200_DEFER_IDS"] = "1000000"
+    try:
+        got2 = run_gpu(m, req, synth.make_tables_np(m), want_ids=False)[0]
+    finally:
+        del os.environ["RECOM_B200_DEFER_IDS"]
+    np.testing.assert_allclose(got2, got, rtol=1e-4, atol=1e-4)
