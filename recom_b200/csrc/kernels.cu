@@ -1245,7 +1245,10 @@ __device__ __forceinline__ void sparse_rows(const QT& Q, const UserRegs& u, int6
                                             uint32_t s_sp, uint32_t s_ids, int32_t e_base, int lane) {
   const int C = u.row_bytes / VEC;
   const bool hook = Q.check | (Q.ids_out != nullptr) | (Q.shard_world > 1);
-  constexpr int U = BF16 ? 4 : 8;
+#ifndef RECOM_SPARSE_U
+#define RECOM_SPARSE_U 10  // rows of 9-10 ids (dlrm.py:52: 1..10 per row) in one pass: mixed1000 123.2 -> 120.5, model F 49.9 -> 48.0, E multi-hot 16.2 -> 14.5 us
+#endif
+  constexpr int U = BF16 ? 4 : RECOM_SPARSE_U;
   const uint32_t ids0 = s_ids - 4u * (uint32_t)e_base;
   for (int c0 = 0; c0 < C; c0 += 32) {
     const int W = min(32, C - c0);
