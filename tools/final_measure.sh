@@ -10,7 +10,7 @@ for w in model_E model_F model_E_bucketize model_E_dense model_E_sparse mixed100
   python bench.py --steps 200 --warmup 10 --no-cpu-baseline --workload $w 2>>$O/workloads.err | tail -1 >> $O/workloads.jsonl
 done
 # launch lists of the timed region (bench.py brackets it with cudaProfilerStart/Stop)
-for w in model_E mixed1000 production2000; do
+for w in model_E mixed1000 production2000 dynamic; do
   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$w.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-parity --workload $w > /dev/null 2>>$O/ncu.err
 done
