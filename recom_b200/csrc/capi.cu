@@ -1953,6 +1953,10 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     A.long_ids = p->defer_ids;
     CUDA_TRY(cudaMemsetAsync(A.long_list, 0, 8, stream));
   }
+  // the COO helper was the last launch: what follows may start under it (programmatic dependent
+  // launch), its tiles over COO inputs wait before they read the row_splits
+  static const bool helper_pdl_on = getenv("RECOM_B200_HELPER_PDL") == nullptr || atoi(getenv("RECOM_B200_HELPER_PDL")) != 0;
+  const bool helper_pdl = helper_pdl_on && !p->coos.empty() && p->splits.empty() && !defer_long;
   const bool has_flat = !tt->flat.empty();
   A.total_warps = grid * kWarps + (has_flat ? column_tiles_grid((int)tt->flat.size()) * 4 : 0);
   if (has_flat) {
@@ -1967,11 +1971,12 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
       A.prof = nullptr;
       p->prof_grid = F.pad0 / kWarps;
     }
-    launch_column_tiles(p->dev_flat, F, d_flat, (int)tt->flat.size(), p->elem_bytes == 2, stream);
+    launch_column_tiles(p->dev_flat, F, d_flat, (int)tt->flat.size(), p->elem_bytes == 2, stream, helper_pdl);
     g_last_launches++;
   }
   if (grid > 0) {
-    launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream, has_flat && p->flat_pdl);
+    launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream,
+                         (has_flat && p->flat_pdl) || (!has_flat && helper_pdl));
     g_last_launches++;
   }
   if (defer_long) {

@@ -1516,9 +1516,13 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
                          : (const uint8_t*)(A.ws_split_ids + split_ids_offset(P, A, -1 - it.value_slot, lane));
   const uint8_t* bytes = it.bytes_slot >= 0 ? A.blob + __ldg(A.slot_offsets + it.bytes_slot) : nullptr;
   const int32_t* rs = nullptr;
-  if (it.seg_slot >= 0)
+  if (it.seg_slot >= 0) {
     rs = it.coo_index >= 0 ? A.ws_row_splits + (int64_t)it.coo_index * (A.batch + 1)
                            : (const int32_t*)(A.blob + __ldg(A.slot_offsets + it.seg_slot));
+    // row_splits built by the helper kernel in front of this launch: when this grid was launched
+    // with programmatic serialization it started while the helper ran (no-op otherwise)
+    if (it.coo_index >= 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   UserRegs u = first_user(A, it);
   PROF_C(1, (uintptr_t)values + (uintptr_t)bytes + (uintptr_t)rs + (uintptr_t)u.table + u.row_bytes)
   const uint32_t s_sp = s_scratch, s_ids = s_sp + kColSplitBytes;
@@ -1943,6 +1947,7 @@ column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ R
     asm volatile("prefetch.global.L2 [%0];" ::"l"(A.blob + o));
   if (k >= num_items) {
     if (SH) signal_peers(A, lane);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
   ColItem it;
@@ -1967,6 +1972,8 @@ column_tiles_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ R
   PROF_C(0, it.begin + it.count)
   column_tile<BF16>(P, A, Q, it, smem_u32(smem) + (uint32_t)(warp * P.scratch_bytes), lane, SH ? -1 : k PROF_ARG);
   if (SH) signal_peers(A, lane);
+  // behind the COO helper with programmatic serialization: complete only when the helper is
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef RECOM_PROFILE
   if (lane == 0 && A.prof && k < A.pad0) {  // (pad0: rows of the timer buffer)
     uint64_t* o_ = A.prof + (size_t)k * 8;
@@ -2122,21 +2129,29 @@ int column_tiles_configure(bool bf16, int smem_bytes) {
 int column_tiles_grid(int num_items) { return (num_items + kFlatWarps - 1) / kFlatWarps; }
 
 void launch_column_tiles(const DevPlan& plan, const ReqParams& req, const ColItem* items, int num_items,
-                         bool bf16, cudaStream_t stream) {
+                         bool bf16, cudaStream_t stream, bool pdl) {
 #ifdef RECOM_TEST_NOLAUNCH
-  (void)plan; (void)req; (void)items; (void)num_items; (void)bf16; (void)stream;
+  (void)plan; (void)req; (void)items; (void)num_items; (void)bf16; (void)stream; (void)pdl;
   return;
 #endif
   if (num_items <= 0) return;
-  const int grid = (num_items + kFlatWarps - 1) / kFlatWarps;
-  const size_t sm = (size_t)kFlatWarps * plan.scratch_bytes;
   const bool sh = req.world > 0;  // sharded output: rows stored into their owners' tensors
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((num_items + kFlatWarps - 1) / kFlatWarps));
+  cfg.blockDim = dim3(kFlatWarps * 32);
+  cfg.dynamicSmemBytes = (size_t)kFlatWarps * plan.scratch_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;  // behind the COO helper: the tiles over COO inputs wait for it
   if (bf16) {
-    if (sh) column_tiles_kernel<true, true><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
-    else column_tiles_kernel<true, false><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
+    if (sh) cudaLaunchKernelEx(&cfg, column_tiles_kernel<true, true>, plan, req, items, num_items);
+    else cudaLaunchKernelEx(&cfg, column_tiles_kernel<true, false>, plan, req, items, num_items);
   } else {
-    if (sh) column_tiles_kernel<false, true><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
-    else column_tiles_kernel<false, false><<<grid, kFlatWarps * 32, sm, stream>>>(plan, req, items, num_items);
+    if (sh) cudaLaunchKernelEx(&cfg, column_tiles_kernel<false, true>, plan, req, items, num_items);
+    else cudaLaunchKernelEx(&cfg, column_tiles_kernel<false, false>, plan, req, items, num_items);
   }
 }
 
@@ -2278,6 +2293,9 @@ __global__ void __launch_bounds__(256)
 coo_to_row_splits_kernel(const DevCoo* __restrict__ coos, const int64_t* __restrict__ slot_offsets,
                          const int64_t* __restrict__ slot_elems, const uint8_t* __restrict__ blob,
                          int64_t batch, int32_t* __restrict__ ws_row_splits) {
+  // the launch behind this one may start right away (programmatic dependent launch): only its
+  // tiles over COO inputs read these row_splits, and they wait (griddepcontrol.wait) before they do
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int k = blockIdx.y;
   const DevCoo c = coos[k];
   int32_t* rs = ws_row_splits + (int64_t)k * (batch + 1);

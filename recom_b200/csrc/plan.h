@@ -385,7 +385,7 @@ void launch_fused_columns(const DevPlan& plan, const Sched& sched, const ReqPara
                           bool bf16, cudaStream_t stream, bool pdl);
 // the flat kernel of the column tiles (one warp per tile); `plan.scratch_bytes` = its warp scratch
 void launch_column_tiles(const DevPlan& plan, const ReqParams& req, const ColItem* items, int num_items,
-                         bool bf16, cudaStream_t stream);
+                         bool bf16, cudaStream_t stream, bool pdl);
 int column_tiles_configure(bool bf16, int smem_bytes);
 int column_tiles_grid(int num_items);
 // the rows the flat kernel deferred (ReqParams::long_list), one CTA per row at a time
