@@ -419,6 +419,21 @@ def run_ours(args):
     torch.cuda.profiler.stop()
     total_ms = e0.elapsed_time(e1)
 
+    # the same K steps with every launch fully ordered behind the previous one (no programmatic
+    # dependent launch between consecutive requests): what one request costs on an idle GPU
+    plan.set_request_overlap(False)
+    for i in range(3):
+        L.check(run(h, refs[i % S]))
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    for i in range(K):
+        L.check(run(h, refs[i % S]))
+    g1.record(stream)
+    barrier()
+    serialized_ms = g0.elapsed_time(g1) / K
+    plan.set_request_overlap(True)
+
     # per-step latency distribution (event pair per step)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for i in range(K):
@@ -500,6 +515,12 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
         "gpu_launches": launches_per_step * K,
+        # ms_per_step / value / roofline: K back-to-back requests on one stream, consecutive fused launches under
+        # programmatic dependent launch (the prologue of request i+1 - records, contexts, TMA staging, blob
+        # prefetch: reads only - overlaps the tail of request i; nothing of i+1 is stored before i is complete).
+        # p50 / p99: one request at a time (an event pair around each launch orders it fully).
+        "serialized": {"ms_per_step": serialized_ms, "frac": mean_alg / (serialized_ms * 1e-3) / 1e9 / peak,
+                       "note": "same K steps with recom_plan_set_request_overlap(0): every launch starts after the previous one has ended"},
         "clocks": clocks,
         "parity_checked": bool(parity and parity["checked"]), "parity": parity,
         "requests": f"{S} distinct requests (own ids and row lengths each); per-request argument data "

@@ -297,6 +297,19 @@ RECOM_API recom_status recom_plan_workspace_bytes(const recom_plan *plan, int64_
 /* Enqueue the whole fused stage on req->stream. Re-entrant per plan. */
 RECOM_API recom_status recom_plan_run(const recom_plan *plan, const recom_request *req);
 
+/* Back-to-back requests on one stream. A plain request whose stage is ONE launch (no helper kernel,
+ * no ids_out hook, a grid that fills the GPU) is launched with programmatic stream serialization:
+ * when the operation in front of it on the stream is the previous request's kernel, the new grid
+ * becomes resident while that one drains, runs its prologue (work records, column contexts, TMA
+ * staging of the small tables, L2 prefetch of ITS blob - reads of its own request and of the plan
+ * only) and executes griddepcontrol.wait before its first store, i.e. nothing of request i + 1 is
+ * written before request i is complete and flushed. In front of any other operation (a copy, an
+ * event, someone else's kernel without an early trigger) the launch is ordered as usual. The
+ * request's blob and tables must therefore be in place when the operation in front of the launch
+ * STARTS if that operation is a kernel that triggers dependents early - true for every TF / torch
+ * kernel today; pass on = 0 for a producer that does (default: on; RECOM_B200_REQUEST_PDL=0). */
+RECOM_API recom_status recom_plan_set_request_overlap(recom_plan *plan, int32_t on);
+
 /* Mode A with the exchange fused into the kernel (recom_b200/sharding.py):
  * this plan computes the columns [col_offset, col_offset + out_width) of a global concat row
  * of `global_width` elements; rows [g*rows_per_rank, (g+1)*rows_per_rank) of the batch are

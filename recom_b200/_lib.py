@@ -63,6 +63,7 @@ EXPORTS = [
     "recom_concat_inputs", "recom_concat_inputs_with_args", "recom_shape_construct_create", "recom_shape_construct_eval",
     "recom_shape_construct_destroy", "recom_plan_run_sharded", "recom_ipc_alloc", "recom_ipc_open",
     "recom_ipc_close", "recom_ipc_free", "recom_shard_wait", "recom_dense_relu",
+    "recom_plan_set_request_overlap",
 ]
 
 
@@ -104,6 +105,7 @@ def _load() -> C.CDLL:
         "recom_scatter_host_columns": [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp],
         "recom_scatter_columns": [vp, vp, vp, i32, i64, i32, i32, vp, vp],
         "recom_dense_relu": [vp, i64, i32, i64, vp, i32, vp, i32, vp, vp],
+        "recom_plan_set_request_overlap": [vp, i32],
         "recom_segment_ids_to_row_splits": [vp, i64, i32, i64, vp, vp],
         "recom_string_to_hash_bucket_fast": [vp, vp, i64, i64, vp, vp],
         "recom_fingerprint64": [vp, vp, i64, vp, vp],

@@ -660,6 +660,10 @@ __device__ __forceinline__ void wait_flag(uint32_t* flags, int g, uint32_t epoch
   }
 }
 
+// See fused_columns_kernel: with A.request_pdl this grid started under the previous request's tail.
+#define REQUEST_PDL_WAIT(A) \
+  if ((A).request_pdl) asm volatile("griddepcontrol.wait;" ::: "memory")
+
 // Request-wide values every tile needs.
 struct ReqRegs {
   uint8_t* out;
@@ -1439,6 +1443,7 @@ __device__ __noinline__ void sparse_tile_overflow(const DevPlan& P, const ReqPar
   constexpr int ELEM = BF16 ? 2 : 4;
   const int R = it.count;
   int r_lo = 0;
+  REQUEST_PDL_WAIT(A);
   // rows longer than kDeferIds are left to long_rows_kernel when the request has a list for them
   auto deferred = [&](int r) {
     return A.long_list != nullptr && item_k >= 0 &&
@@ -1534,6 +1539,7 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
     const int n = it.count;
     transform_ids(P, it, values, bytes, it.begin, (int64_t)it.begin + n, s_ids, lane);
     __syncwarp();
+    REQUEST_PDL_WAIT(A);
     if (u.hbm && !Q.check && Q.shard_world <= 1) prefetch_rows(u, s_ids, n, lane);
     PROF_T(3)
     PROF_C(3, lds_i32(s_ids))
@@ -1561,6 +1567,7 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
     if (e_end - e0 <= cap && !any_deferred) {
       transform_ids(P, it, values, bytes, e0, e_end, s_ids, lane);
       __syncwarp();
+      REQUEST_PDL_WAIT(A);
       if (u.hbm && !Q.check && Q.shard_world <= 1) prefetch_rows(u, s_ids, e_end - e0, lane);
       PROF_T(3)
       PROF_C(3, lds_i32(s_ids))
@@ -1714,6 +1721,7 @@ __device__ __noinline__ void fast_section(const DevPlan& P, const Sched& S, cons
         mbar_wait(&cs->mbar_tbl, tbl_par);
         tbl_ready = true;
       }
+      REQUEST_PDL_WAIT(A);  // phase 2 stores
       if (staged) {
         if (slab.vec_bytes == 16) fast_phase2<16, true>(Q, sm.ctx, slab.num_chunks, ch, b0, rows, sm.tables, s_ids, lane);
         else fast_phase2<ELEM, true>(Q, sm.ctx, slab.num_chunks, ch, b0, rows, sm.tables, s_ids, lane);
@@ -1782,6 +1790,12 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
   ProfRef pr{prof_acc, &prof_last};
 #endif
 
+  // Back-to-back requests on one stream (A.request_pdl, launched with programmatic stream
+  // serialization): the next request's grid may become resident while this one drains - its
+  // prologue (blob prefetch, work records, column contexts, TMA staging of the tables: reads of
+  // ITS request and of the plan only) overlaps this grid's tail, and it executes
+  // griddepcontrol.wait (below) before its first store.
+  if (A.request_pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // The whole request blob -> L2 while the grid starts up (one 128-byte line per thread and
   // pass): HBM is idle then, and every later input load of the launch is an L2 hit.
   for (int64_t o = ((int64_t)cta * kThreads + threadIdx.x) * 128; o < A.blob_bytes;
@@ -1824,6 +1838,10 @@ fused_columns_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ 
     if (cw.count > 0) setup_run(P, S, A, &cs, smem, 0, lane);
     else mbar_arrive(&cs.mbar_ctx);
   }
+
+  // (A.request_pdl: nothing is stored before the launch in front of this one - the previous request - is
+  // complete: every warp executes griddepcontrol.wait between the reads of a tile - values, bucket searches,
+  // hashes: into shared memory - and its first store: REQUEST_PDL_WAIT in fast_section / column_tile)
 
   ReqRegsT<SH> Q;
   Q.out = A.out;

@@ -352,6 +352,9 @@ struct ReqParams {
   int32_t* long_list;           // null: rows are never deferred
   int32_t long_cap;             // entries the list holds
   int32_t long_ids;             // a row with more ids than this is deferred (kDeferIds)
+  int32_t request_pdl;          // fused kernel only: overlap this grid's prologue with the tail of the launch
+                                // in front of it (the previous request), see fused_columns_kernel
+  int32_t pad3;
   int64_t blob_bytes;           // extent of the blob (L2 prefetch at kernel entry), 0: unknown
   // Sharded output (Mode A, fused exchange): rows [g * rows_per_rank, (g + 1) * rows_per_rank)
   // are stored into peer_out[g] (rank g's [rows_per_rank, global width] tensor, peer mapped);

@@ -122,6 +122,10 @@ class Plan:
         L.check(L.lib.recom_plan_algorithmic_bytes(self._h, C.byref(r), C.byref(n)))
         return n.value
 
+    def set_request_overlap(self, on: bool) -> None:
+        """Programmatic dependent launch between consecutive requests (recom_plan_set_request_overlap)."""
+        L.check(L.lib.recom_plan_set_request_overlap(self._h, 1 if on else 0))
+
     @staticmethod
     def last_launch_count() -> int:
         return L.lib.recom_last_launch_count()
