@@ -428,7 +428,9 @@ def run_ours(args):
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record(stream)
     for i in range(K):
-        L.check(run(h, refs[i % S]))
+        st = run(h, refs[i % S])
+        if st:
+            L.check(st)
     g1.record(stream)
     barrier()
     serialized_ms = g0.elapsed_time(g1) / K
