@@ -840,14 +840,16 @@ void build_layout(recom_plan* p) {
 // columns of model E alone in 16 instead of 25; models E and F (1.8x / 1.2x) lose 4-5 us, the
 // 980 one-id columns of E (0.5x) 9 us: two launches do not overlap the way the fused kernel's
 // warps do. Flat when the column tiles weigh at least three times the FAST slabs.
-bool prefer_flat(const recom_plan* p, int64_t B) {
+bool prefer_flat(const recom_plan* p, int64_t B, int dens) {
   if (p->flat_mode >= 0) return p->flat_mode != 0;
   double fast_cost = 0, col_cost = 0;
   for (const DevSlab& sl : p->slabs)
     if (sl.cls == kSlabDenseStaged && sl.all_fast)
       fast_cost += (double)((B + sl.tile_rows - 1) / sl.tile_rows) * 2.0 * (sl.tile_rows * sl.num_chunks * sl.vec_bytes) / 8192.0;
   for (size_t ui = 0; ui < p->units.size(); ++ui)
-    col_cost += p->unit_cost[ui] * (double)B / (p->units[ui].seg_slot >= 0 ? kColTileRowsSparse : kColTileRowsDense);
+    // (a request of density class c holds ~2^c times the ids per multi-hot row the cost model assumes)
+    col_cost += p->unit_cost[ui] * (double)B /
+                (p->units[ui].seg_slot >= 0 ? (double)kColTileRowsSparse / (double)(1 << dens) : (double)kColTileRowsDense);
   return col_cost > 0 && col_cost >= 3.0 * fast_cost;
 }
 
@@ -1768,8 +1770,8 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
   cudaStream_t stream = (cudaStream_t)req->stream;
 
   g_host_prof.lap(0);
-  const bool flat = prefer_flat(p, B);
   const int dens = density_class(p, req);
+  const bool flat = prefer_flat(p, B, dens);
   std::shared_ptr<const TileTable> tt = cached_tiles(p, B, flat, dens, &st);
   if (st != RECOM_OK) return st;
   g_host_prof.lap(1);
