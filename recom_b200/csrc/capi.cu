@@ -114,6 +114,7 @@ struct TileTable {
   std::vector<ColItem> queue;    // column tiles
   std::vector<CtaWork> cta;      // [grid]
   std::vector<ColItem> flat;     // column tiles of the flat kernel (one warp each), by descending cost
+  int dense_tiles = 0;           // column tiles of the persistent kernel with one id per row
   int grid = 1;
   int fast_warps = 0;
   int fast_ctas = -1;
@@ -1036,6 +1037,7 @@ std::shared_ptr<TileTable> build_tiles(const recom_plan* p, int64_t B, bool flat
       heap.push(top);
     }
   }
+  for (const Costed& c : qs) tt->dense_tiles += c.it.seg_slot < 0 ? 1 : 0;
   for (int c = 0; c < grid; ++c) {
     tt->cta[c].first = (int32_t)tt->runs.size();
     tt->cta[c].count = (int32_t)per_cta[c].size();
@@ -1985,7 +1987,10 @@ static recom_status run_impl(const recom_plan* cp, const recom_request* req, con
     const bool req_pdl = p->request_overlap.load(std::memory_order_relaxed) && !has_flat && p->coos.empty() &&
                          p->splits.empty() && !so && !req->ids_out && !req->status_out && !p->cfg.check_ids &&
                          p->shard_world <= 1 && grid >= p->num_sms;
-    A.request_pdl = req_pdl ? 1 : 0;
+    // where the column tiles wait (kernels.cu, column_tile): at their entry when the one-id-per-row tiles
+    // alone nearly fill the resident warps (model F: 3040 of them over 2960 warps), behind their transform
+    // otherwise (model E: 1600)
+    A.request_pdl = !req_pdl ? 0 : (int64_t)tt->dense_tiles * 5 > (int64_t)grid * kWarps * 4 ? 2 : 1;
     launch_fused_columns(p->dev, sched, A, grid, p->elem_bytes == 2, stream,
                          (has_flat && p->flat_pdl) || (!has_flat && helper_pdl) || req_pdl);
     g_last_launches++;

@@ -1516,9 +1516,10 @@ __device__ __forceinline__ void column_tile(const DevPlan& P, const ReqParams& A
   // resolve the stream and its first column against the request: one read of the slot offsets
   // (value_slot < 0: the ids are the hashed tokens of split input -1 - value_slot, written into the
   // workspace by the split kernel in front of this launch)
-#ifdef RECOM_PDL_COL_EARLY
-  REQUEST_PDL_WAIT(A);
-#endif
+  // request_pdl 2: the column tiles wait before they read anything (plans with more column tiles than
+  // resident warps: their transforms, run ahead of the wait, compete with the previous request's tail -
+  // model F 49.2 -> 43.9 us/step); 1: they wait behind their transform (model E 40.2 -> 37.9)
+  if (A.request_pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint8_t* values =
       it.value_slot >= 0 ? A.blob + __ldg(A.slot_offsets + it.value_slot)
                          : (const uint8_t*)(A.ws_split_ids + split_ids_offset(P, A, -1 - it.value_slot, lane));
