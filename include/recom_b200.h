@@ -50,7 +50,9 @@
 extern "C" {
 #endif
 
-#define RECOM_B200_ABI_VERSION 3
+/* 4: + RECOM_SEG_COO_RESHAPE_I64 / RECOM_SEG_FIXED, recom_dense_relu, recom_plan_set_request_overlap
+ *    (additive: every struct layout of version 3 is unchanged) */
+#define RECOM_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define RECOM_API __attribute__((visibility("default")))

@@ -43,7 +43,7 @@ def test_no_unexpected_exports():
 
 
 def test_abi_version_and_struct_layout():
-    assert L.lib.recom_abi_version() == 3
+    assert L.lib.recom_abi_version() == 4
     assert L.COLUMN_DESC.itemsize == 80
     assert C.sizeof(L.PlanConfig) == 32
     assert C.sizeof(L.Request) == 96
