@@ -60,8 +60,11 @@ def _varint(buf: bytes, pos: int) -> Tuple[int, int]:
         shift += 7
 
 
-def _fields(buf: bytes):
-    """Yield (field number, wire type, value) of one message; length-delimited values are bytes."""
+def _fields(buf):
+    """Yield (field number, wire type, value) of one message; length-delimited values are
+    memoryview slices (zero copy: a frozen graph carries its tables as Const tensors of up to GBs)."""
+    if not isinstance(buf, memoryview):
+        buf = memoryview(buf)
     pos, n = 0, len(buf)
     while pos < n:
         key, pos = _varint(buf, pos)
@@ -87,7 +90,7 @@ def _signed(v: int) -> int:
     return v - (1 << 64) if v >= (1 << 63) else v
 
 
-def _packed_varints(b: bytes) -> List[int]:
+def _packed_varints(b) -> List[int]:
     out, pos = [], 0
     while pos < len(b):
         v, pos = _varint(b, pos)
@@ -126,7 +129,7 @@ def _parse_tensor(buf: bytes) -> Optional[np.ndarray]:
         elif fno in (7, 10):  # int_val, int64_val
             vals.setdefault(fno, []).extend(_packed_varints(v) if wt == 2 else [_signed(v)])
         elif fno == 8:  # string_val
-            vals.setdefault(8, []).append(v)
+            vals.setdefault(8, []).append(bytes(v))
     if dtype == DT_STRING:
         return np.array(vals.get(8, []), dtype=object)
     np_t = _NP_OF_DT.get(dtype)
@@ -227,24 +230,24 @@ class Graph:
         return v if isinstance(v, np.ndarray) else None
 
 
-def parse_graphdef(data: bytes) -> Graph:
+def parse_graphdef(data) -> Graph:
     nodes: List[Node] = []
-    for fno, _, v in _fields(data):
+    for fno, _, v in _fields(memoryview(data)):
         if fno != 1:
             continue  # versions, library
         node = Node("", "")
         for f2, _, v2 in _fields(v):
             if f2 == 1:
-                node.name = v2.decode()
+                node.name = bytes(v2).decode()
             elif f2 == 2:
-                node.op = v2.decode()
+                node.op = bytes(v2).decode()
             elif f2 == 3:
-                node.inputs.append(v2.decode())
+                node.inputs.append(bytes(v2).decode())
             elif f2 == 5:  # map<string, AttrValue> entry
                 key, val = "", None
                 for f3, _, v3 in _fields(v2):
                     if f3 == 1:
-                        key = v3.decode()
+                        key = bytes(v3).decode()
                     elif f3 == 2:
                         val = _parse_attr(v3)
                 node.attr[key] = val
@@ -351,11 +354,27 @@ _TRANSPARENT = {"Identity", "Reshape", "ExpandDims", "Squeeze", "GatherV2", "Gat
                 "StopGradient", "SparseToDense", "Cast"}
 
 
+def table_shape(v: Node) -> Optional[Tuple[int, int]]:
+    """(rows, dim) of a table node: the VariableV2's static shape attr, or the Const tensor's shape."""
+    if v.op == "Const":
+        t = v.attr.get("value")
+        return (int(t.shape[0]), int(t.shape[1])) if isinstance(t, np.ndarray) and t.ndim == 2 else None
+    shape = v.attr.get("shape")
+    dims = shape[1] if isinstance(shape, tuple) else None
+    return (int(dims[0]), int(dims[1])) if dims and len(dims) == 2 and min(dims) > 0 else None
+
+
 def find_tables(g: Graph) -> List[Node]:
-    """graph_info.cc:209-258."""
+    """graph_info.cc:209-258 (VariableV2 at grappler time); in a FROZEN graph the variables have become
+    Const nodes (convert_variables_to_constants), which LookupOptimizer::Match accepts as weights just the
+    same (lookup_optimizer.cc:64-65, 'VariableV2,Const,VarHandleOp'): a rank-2 float Const qualifies."""
     out = []
     for v in g.nodes:
-        if v.op != "VariableV2":
+        if v.op == "Const":
+            t = v.attr.get("value")
+            if not (isinstance(t, np.ndarray) and t.ndim == 2 and t.dtype in (np.float32, np.float64)):
+                continue
+        elif v.op != "VariableV2":
             continue
         stack = [c for c, _ in g.consumers[v.name]]
         cnt, ok = 0, True
@@ -509,6 +528,9 @@ class Extracted:
     model: Model
     bindings: List[Binding]
     skipped: List[Tuple[str, str]]  # (variable, why) - tables whose column did not match
+    # the tables' values where the graph carries them (frozen graphs: Const nodes; zero-copy views of
+    # the serialized graph), None for VariableV2 tables (their values live in the checkpoint)
+    table_values: List[Optional[np.ndarray]] = field(default_factory=list)
 
 
 def extract_model(g: Graph, out_dtype: int = L.F32) -> Extracted:
@@ -520,12 +542,11 @@ def extract_model(g: Graph, out_dtype: int = L.F32) -> Extracted:
             skipped.append((t.name, "no safe_embedding_lookup_sparse pattern around a SparseSegment op"))
             continue
         seed, sfer, sel = m
-        shape = t.attr.get("shape")
-        dims = shape[1] if isinstance(shape, tuple) else None
-        if not dims or len(dims) != 2:
+        dims = table_shape(t)
+        if dims is None:
             skipped.append((t.name, "table shape is not static rank 2"))
             continue
-        rows, dim = int(dims[0]), int(dims[1])
+        rows, dim = dims
         info = _walk_values(g, g.input_node(sfer, 1), g.input_port(sfer, 1))
         ph = info["placeholder"]
         if ph is None:
@@ -580,6 +601,7 @@ def extract_model(g: Graph, out_dtype: int = L.F32) -> Extracted:
     cols: List[Column] = []
     binds: List[Binding] = []
     tables: List[Tuple[int, int]] = []
+    values: List[Optional[np.ndarray]] = []
     if by_concat:
         main = max(by_concat, key=lambda k: by_concat[k])
         for cn, ci, col, b in sorted(found, key=lambda f: f[1]):
@@ -590,8 +612,11 @@ def extract_model(g: Graph, out_dtype: int = L.F32) -> Extracted:
             tables.append((col.table_rows, col.dim))
             cols.append(col)
             binds.append(b)
+            tn = g.by_name[b.table_variable]
+            v = tn.attr.get("value") if tn.op == "Const" else None
+            values.append(v if isinstance(v, np.ndarray) else None)
     model = Model(cols, tables, out_dtype=out_dtype, name="graphdef").finalize() if cols else Model([], [])
-    return Extracted(model, binds, skipped)
+    return Extracted(model, binds, skipped, values)
 
 
 def extract_from_bytes(data: bytes, out_dtype: int = L.F32) -> Extracted:

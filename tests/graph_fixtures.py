@@ -11,8 +11,9 @@ from recom_b200 import graphdef as G
 
 
 class Builder:
-    def __init__(self):
+    def __init__(self, frozen=False):
         self.nodes = []
+        self.frozen = frozen
 
     def add(self, name, op, inputs=(), **attr):
         self.nodes.append(G.Node(name, op, list(inputs), dict(attr)))
@@ -26,10 +27,14 @@ class Builder:
     # ---- the tail shared by every embedding column ----
     def lookup(self, scope, indices, values, dense_shape, rows, dim, combiner="mean", rank=2):
         a = self.add
-        table = a(f"{scope}/embedding_weights", "VariableV2", shape=("shape", [rows, dim]), dtype=("type", G.DT_FLOAT))
-        a(f"{scope}/embedding_weights/Assign", "Assign", [table, self.const(f"{scope}/init", np.zeros((1,), np.float32))])
+        if self.frozen:  # convert_variables_to_constants: the variable has become a Const holding the table
+            rng = np.random.default_rng(len(self.nodes))
+            table = self.const(f"{scope}/embedding_weights", (rng.standard_normal((rows, dim)) / np.sqrt(dim)).astype(np.float32))
+        else:
+            table = a(f"{scope}/embedding_weights", "VariableV2", shape=("shape", [rows, dim]), dtype=("type", G.DT_FLOAT))
+            a(f"{scope}/embedding_weights/Assign", "Assign", [table, self.const(f"{scope}/init", np.zeros((1,), np.float32))])
+            a("save/SaveV2/" + scope, "SaveV2", [table])
         read = a(f"{scope}/embedding_weights/read", "Identity", [table])
-        a("save/SaveV2/" + scope, "SaveV2", [table])
         # sparse_reshape to [prod(shape[:-1]), shape[-1]]
         new_shape = a(f"{scope}/new_shape", "Pack", [dense_shape, dense_shape])
         sr = a(f"{scope}/SparseReshape", "SparseReshape", [indices, dense_shape, new_shape])
@@ -105,8 +110,9 @@ class Builder:
     def finish(self, outs, with_mlp=True):
         ax = self.const("il/concat/axis", np.int32(1))
         cc = self.add("il/concat", "ConcatV2", list(outs) + [ax], N=len(outs))
-        if with_mlp:  # a dense layer behind the stage: its kernel is a VariableV2 that is NOT a table
-            w = self.add("dense/kernel", "VariableV2", shape=("shape", [64, 16]), dtype=("type", G.DT_FLOAT))
+        if with_mlp:  # a dense layer behind the stage: its kernel is a variable (frozen: a rank-2 Const) that is NOT a table
+            w = (self.const("dense/kernel", np.zeros((64, 16), np.float32)) if self.frozen else
+                 self.add("dense/kernel", "VariableV2", shape=("shape", [64, 16]), dtype=("type", G.DT_FLOAT)))
             r = self.add("dense/kernel/read", "Identity", [w])
             self.add("dense/MatMul", "MatMul", [cc, r])
         return G.encode_graphdef(self.nodes)

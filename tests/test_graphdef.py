@@ -163,3 +163,28 @@ def test_extracted_model_gpu_parity():
         got, _, status, _ = run_gpu(m, pack_request(m, batch, feats), tables, want_ids=False)
         assert status == 0
         np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_frozen_graph_tables_are_const_nodes():
+    """convert_variables_to_constants turns every VariableV2 into a Const: the tables are found all the same
+    (LookupOptimizer::Match accepts Const weights, lookup_optimizer.cc:64-65), their values come out as views of
+    the serialized graph, and the dense layer's rank-2 Const kernel is not taken for a table."""
+    b = Builder(frozen=True)
+    outs = [b.bucketized("bucketize0", np.arange(0, 500, 5), 8),
+            b.hashed_dense("categ_hashbucket0", 1000, 8, string=True),
+            b.hashed_sparse("categ_hashbucket_sparse0", 1000, 16, rank=2, combiner="sum")]
+    data = b.finish(outs)
+    ex = G.extract_from_bytes(data)
+    assert ex.skipped == [] and [c.name for c in ex.model.columns] == ["bucketize0", "categ_hashbucket0",
+                                                                        "categ_hashbucket_sparse0/values"]
+    assert [t.shape for t in ex.table_values] == [(101, 8), (1000, 8), (1000, 16)]
+    assert all(t.dtype == np.float32 for t in ex.table_values)
+    g = G.parse_graphdef(data)
+    assert "dense/kernel" not in [t.name for t in G.find_tables(g)]
+    # the extracted tables drive the oracle directly
+    m, batch = ex.model, 32
+    feats = _features_for(ex, batch)
+    out, _ = _expected(ex, batch, feats, [np.array(t) for t in ex.table_values])
+    c = m.columns[0]
+    ids = np.searchsorted(np.arange(0, 500, 5, dtype=np.float32), feats[c.key].values, side="right")
+    np.testing.assert_array_equal(out[:, :8], ex.table_values[0][ids])
