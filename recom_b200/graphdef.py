@@ -26,7 +26,9 @@ feature_column_v2.py and embedding_ops.py:882-941):
     leaves that to Addons>GatherStrValueGenIndice / GatherIndiceValue, pre_lookup_optimizer.cc:310-347);
   * the same over a sparse placeholder triple (indices, values, dense_shape): SEGMENT lookup with
     COO segments (rank 2) or the SparseReshape inlined (rank > 2, RECOM_SEG_COO_RESHAPE_I64);
-  * categorical_column_with_identity: transform NONE.
+  * categorical_column_with_identity: transform NONE;
+  * several lookup chains over ONE variable (shared_embedding_columns; BASELINE config 5): one column each, one
+    table index for all of them.
 """
 from __future__ import annotations
 
@@ -393,8 +395,10 @@ def find_tables(g: Graph) -> List[Node]:
     return out
 
 
-def _match_seed(g: Graph, table: Node) -> Optional[Tuple[Node, Node, Node]]:
-    """lookup_optimizer.cc:62-140 -> (seed, SparseFillEmptyRows, Select) for `table`."""
+def _match_seeds(g: Graph, table: Node) -> List[Tuple[Node, Node, Node]]:
+    """lookup_optimizer.cc:62-140 -> every (seed, SparseFillEmptyRows, Select) that reads `table`: one per
+    column; shared_embedding_columns (and BASELINE config 5) put several columns on one table."""
+    found: List[Tuple[Node, Node, Node]] = []
     stack = [c for c, _ in g.consumers[table.name]]
     reads = []
     while stack:
@@ -439,8 +443,9 @@ def _match_seed(g: Graph, table: Node) -> Optional[Tuple[Node, Node, Node]]:
             rs = g.input_node(tile, 0)
             if rs is None or rs.op != "Reshape" or g.input_node(rs, 0) is not sfer:
                 continue
-            return seed, sfer, sel
-    return None
+            if all(seed is not f[0] for f in found):
+                found.append((seed, sfer, sel))
+    return found
 
 
 def _walk_values(g: Graph, n: Optional[Node], port: int):
@@ -536,12 +541,13 @@ class Extracted:
 def extract_model(g: Graph, out_dtype: int = L.F32) -> Extracted:
     found = []
     skipped: List[Tuple[str, str]] = []
+    matches = []
     for t in find_tables(g):
-        m = _match_seed(g, t)
-        if m is None:
+        ms = _match_seeds(g, t)
+        if not ms:
             skipped.append((t.name, "no safe_embedding_lookup_sparse pattern around a SparseSegment op"))
-            continue
-        seed, sfer, sel = m
+        matches.extend((t, m) for m in ms)
+    for t, (seed, sfer, sel) in matches:
         dims = table_shape(t)
         if dims is None:
             skipped.append((t.name, "table shape is not static rank 2"))
@@ -602,19 +608,23 @@ def extract_model(g: Graph, out_dtype: int = L.F32) -> Extracted:
     binds: List[Binding] = []
     tables: List[Tuple[int, int]] = []
     values: List[Optional[np.ndarray]] = []
+    table_index: Dict[str, int] = {}
     if by_concat:
         main = max(by_concat, key=lambda k: by_concat[k])
         for cn, ci, col, b in sorted(found, key=lambda f: f[1]):
             if cn != main:
                 skipped.append((b.table_variable, f"reaches another ConcatV2 ({cn})"))
                 continue
-            col.table = len(tables)
-            tables.append((col.table_rows, col.dim))
+            if b.table_variable in table_index:  # columns sharing one table (descriptor-level aliasing)
+                col.table = table_index[b.table_variable]
+            else:
+                col.table = table_index[b.table_variable] = len(tables)
+                tables.append((col.table_rows, col.dim))
+                tn = g.by_name[b.table_variable]
+                v = tn.attr.get("value") if tn.op == "Const" else None
+                values.append(v if isinstance(v, np.ndarray) else None)
             cols.append(col)
             binds.append(b)
-            tn = g.by_name[b.table_variable]
-            v = tn.attr.get("value") if tn.op == "Const" else None
-            values.append(v if isinstance(v, np.ndarray) else None)
     model = Model(cols, tables, out_dtype=out_dtype, name="graphdef").finalize() if cols else Model([], [])
     return Extracted(model, binds, skipped, values)
 

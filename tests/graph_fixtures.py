@@ -25,8 +25,10 @@ class Builder:
         return self.add(name, "Const", value=arr, dtype=("type", dt))
 
     # ---- the tail shared by every embedding column ----
-    def lookup(self, scope, indices, values, dense_shape, rows, dim, combiner="mean", rank=2):
+    def lookup(self, scope, indices, values, dense_shape, rows, dim, combiner="mean", rank=2, shared_read=None):
         a = self.add
+        if shared_read is not None:  # shared_embedding_columns: another column's table
+            return self._lookup_tail(scope, indices, values, dense_shape, dim, combiner, shared_read)
         if self.frozen:  # convert_variables_to_constants: the variable has become a Const holding the table
             rng = np.random.default_rng(len(self.nodes))
             table = self.const(f"{scope}/embedding_weights", (rng.standard_normal((rows, dim)) / np.sqrt(dim)).astype(np.float32))
@@ -35,6 +37,11 @@ class Builder:
             a(f"{scope}/embedding_weights/Assign", "Assign", [table, self.const(f"{scope}/init", np.zeros((1,), np.float32))])
             a("save/SaveV2/" + scope, "SaveV2", [table])
         read = a(f"{scope}/embedding_weights/read", "Identity", [table])
+        self.last_read = read
+        return self._lookup_tail(scope, indices, values, dense_shape, dim, combiner, read)
+
+    def _lookup_tail(self, scope, indices, values, dense_shape, dim, combiner, read):
+        a = self.add
         # sparse_reshape to [prod(shape[:-1]), shape[-1]]
         new_shape = a(f"{scope}/new_shape", "Pack", [dense_shape, dense_shape])
         sr = a(f"{scope}/SparseReshape", "SparseReshape", [indices, dense_shape, new_shape])
@@ -92,13 +99,14 @@ class Builder:
         ids = a(f"il/{key}/lookup", "StringToHashBucketFast", [vals], num_buckets=buckets)
         return self.lookup(f"il/{key}_embedding", wh, ids, shp, buckets, dim, combiner)
 
-    def hashed_sparse(self, key, buckets, dim, rank=2, combiner="sum", table_rows=None):
+    def hashed_sparse(self, key, buckets, dim, rank=2, combiner="sum", table_rows=None, shared_read=None):
         a = self.add
         idx = a(f"{key}/indices", "Placeholder", dtype=("type", G.DT_INT64), shape=("shape", [-1, rank]))
         val = a(f"{key}/values", "Placeholder", dtype=("type", G.DT_STRING), shape=("shape", [-1]))
         shp = a(f"{key}/shape", "Placeholder", dtype=("type", G.DT_INT64), shape=("shape", [rank]))
         ids = a(f"il/{key}/lookup", "StringToHashBucketFast", [val], num_buckets=buckets)
-        return self.lookup(f"il/{key}_embedding", idx, ids, shp, table_rows or buckets, dim, combiner, rank)
+        return self.lookup(f"il/{key}_embedding", idx, ids, shp, table_rows or buckets, dim, combiner, rank,
+                           shared_read=shared_read)
 
     def identity_sparse(self, key, rows, dim, combiner="sqrtn"):
         a = self.add

@@ -188,3 +188,26 @@ def test_frozen_graph_tables_are_const_nodes():
     c = m.columns[0]
     ids = np.searchsorted(np.arange(0, 500, 5, dtype=np.float32), feats[c.key].values, side="right")
     np.testing.assert_array_equal(out[:, :8], ex.table_values[0][ids])
+
+
+def test_columns_sharing_one_table():
+    """shared_embedding_columns / BASELINE config 5: several lookup chains read one variable - one column each,
+    one table index for all of them."""
+    b = Builder()
+    o0 = b.hashed_sparse("user_clicks", 5000, 16, combiner="mean")
+    read = b.last_read
+    o1 = b.hashed_sparse("user_views", 5000, 16, combiner="sum", shared_read=read)
+    o2 = b.bucketized("price", [1.0, 10.0, 100.0], 8)
+    ex = G.extract_from_bytes(b.finish([o0, o1, o2]))
+    assert ex.skipped == []
+    m = ex.model
+    assert [c.name for c in m.columns] == ["user_clicks/values", "user_views/values", "price"]
+    assert [c.table for c in m.columns] == [0, 0, 1] and m.table_shapes == [(5000, 16), (4, 8)]
+    assert [c.combiner for c in m.columns[:2]] == [L.COMBINE_MEAN, L.COMBINE_SUM]
+    assert ex.bindings[0].table_variable == ex.bindings[1].table_variable
+    # runs: both columns gather from the same table
+    batch = 16
+    feats = _features_for(ex, batch)
+    tables = synth.make_tables_np(m)
+    out, _ = run_oracle(m, pack_request(m, batch, feats), tables)
+    assert out.shape == (batch, 16 + 16 + 8) and np.isfinite(out).all()
