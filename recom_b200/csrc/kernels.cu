@@ -12,26 +12,35 @@
 //   * the TF-CPU ops the reference leaves upstream: StringToHashBucketFast and
 //     AsString.
 //
-// Work decomposition (v4): a STATIC schedule per batch size, cached on the device. A slab is
-// a run of columns whose output slices are adjacent in the concat row and at most 32 16-byte
-// chunks wide, so one warp store covers up to 512 contiguous bytes of one output row.
-// Persistent CTAs (512 threads, 2 per SM); the warps of a CTA are split into
-//   dense warps   - the CTA owns one DENSE run (a row range of one slab; more when there are
-//                   more slabs than CTAs). The run's column contexts, bucket boundaries and
-//                   small tables are staged in shared memory once (TMA bulk copies, mbarrier
-//                   completion); then every warp walks its own 32-row tiles alone:
-//                     phase 1  lane = row: coalesced input loads of 8 columns in flight, 8
-//                              upper_bound searches in lock step (or hashing, 4 chains at a
-//                              time) -> row ids in the warp's shared-memory scratch;
-//                     phase 2  lane = 16-byte chunk: 128-bit gathers from the staged tables
-//                              (or ld.global.nc), 128-bit streaming stores into the concat row.
-//   sparse warps  - a static, interleaved share of the SPARSE (multi-hot) warp tiles: row_splits
-//                   and transformed ids of all the slab's columns in the warp's scratch, then
-//                   one pipelined gather stream per lane (fp32 accumulation, TF-CPU scaling).
-// No block-wide barrier after start-up, no atomics, no per-request upload: latency-bound
-// multi-hot gathers and bandwidth-bound dense stores overlap on every SM.
+// Work decomposition (v7): a STATIC schedule per (batch size, schedule kind,
+// density class), cached on the device. A slab is a run of columns whose output slices are adjacent
+// in the concat row and at most 32 16-byte chunks wide, so one warp store covers up to 512 contiguous
+// bytes of one output row.
+//   fused_columns_kernel  persistent CTAs (320 threads, 2 per SM). Every CTA owns
+//     FAST runs    - a row range of a slab of float32-bucketize columns over small tables: column
+//                    contexts, boundary sets (with their grid index) and tables staged in shared
+//                    memory once per CTA (TMA bulk copies, mbarrier completion); the warps take 16-row
+//                    tiles from a shared-memory counter: phase 1 lane = (column group, row): values by
+//                    cp.async, 8 exact upper_bound searches in lock step -> row ids in the warp's
+//                    scratch; phase 2 lane = 16-byte chunk: 128-bit loads from the staged tables,
+//                    128-bit streaming stores into the concat row;
+//     column tiles - everything else (hashed, multi-hot, unstaged, filtered): one id stream x rows per
+//                    warp (column_tile): transform (FarmHash / decimal rendering / bucketize / filters)
+//                    -> row ids in the scratch -> 128-bit row gathers, fp32 accumulation in id order,
+//                    TF-CPU scaling, one store per row - once per column that reads the stream.
+//     No global atomics, no fences, no per-request upload.
+//   column_tiles_kernel   the flat schedule: the same column_tile code, one warp per tile, 4-warp CTAs,
+//                    in front of the persistent kernel (which then keeps the FAST runs) when the column
+//                    tiles outweigh the FAST slabs (capi.cu prefer_flat).
+//   long_rows_kernel      rows of hundreds to thousands of ids that the flat kernel defers: one 8-warp
+//                    CTA per row, partial sums added in warp order.
+// Launches are chained with programmatic dependent launch where one does not read what the other
+// writes: the persistent kernel behind the flat one, either behind the COO helper (tiles over COO
+// inputs wait), and consecutive plain requests on a stream (reads run ahead, every tile waits in
+// front of its first store: REQUEST_PDL_WAIT).
 //
-// The path is HBM / L2 bound integer+copy work: no tensor cores by design.
+// The path is HBM / L2 bound integer+copy work: no tensor cores by design (the dense layer behind the
+// concat, dense_layer.cu, is the tensor-core kernel of this library).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
